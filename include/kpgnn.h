@@ -1,0 +1,111 @@
+/* kpgnn.h -- C ABI of libkpgnn_b200.so: the B200 (sm_100a) kernels behind the K-hop aggregation path of KP-GNN.
+ *
+ * The reference (JiaruiFeng/KP-GNN) is pure Python and has no FFI; the interface these entry points replace is
+ * the body of its layer modules and of its extraction function.  Each entry cites the reference lines it
+ * replaces.  Conventions:
+ *   - every function returns 0 on success, non-zero on failure; kp_last_error() gives the message (thread-local);
+ *   - all pointers are DEVICE pointers unless the name ends in _host; the caller owns and sizes every buffer;
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it and capturable in CUDA graphs
+ *     (no allocation, no synchronisation inside), except where a function is documented as synchronising;
+ *   - no global mutable state besides the launch counter, so calls on different streams are thread-safe.
+ *   - index arrays are int32 on the device; the int64 tensors of the reference layout are converted by
+ *     kp_plan_* (aggregation) and produced by kp_extract_export (extraction).
+ */
+#ifndef KPGNN_B200_H
+#define KPGNN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KPGNN_ABI_VERSION 1
+
+const char* kp_last_error(void);
+int kp_abi_version(void);
+/* kernels launched by this library since load (monotonic; bench.py reports the per-step difference) */
+uint64_t kp_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Graph plan: (dst,hop)-sorted CSR + (src,hop)-sorted transposed CSR of the hop-labelled edge list.
+ * Replaces what PyG's propagate re-derives every layer from `edge_index [2,E]` / `edge_attr [E,K]`
+ * (layers/KPGIN.py:100, KPGINplus.py:74, KPGCN.py:85-110, KPGraphSAGE.py:86, gine.py:52).
+ *
+ * Row r = v*K + h holds the in-edges e=(u->v) with edge_attr[e,h] != 0, in ascending edge id.
+ * self_loops != 0 appends, to every row (v,h), the entry (u=v, attr=1) -- KPGCN.py:85-89 -- and fills
+ * dinv[v*K+h] = deg^-1/2 with deg counted as in KPGCN.py:11-25 (loop included).
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  const int64_t* src;      /* edge_index[0], E entries */
+  const int64_t* dst;      /* edge_index[1], E entries */
+  const int64_t* attr;     /* edge_attr, element (e,h) at attr[e*attr_stride + h] */
+  int64_t attr_stride;
+  int32_t N, E, K;
+  int32_t self_loops;
+} kp_plan_input;
+
+/* bytes of scratch kp_plan_count / kp_plan_fill need (same buffer may be reused for both) */
+int kp_plan_workspace_bytes(int32_t N, int32_t E, int32_t K, size_t* bytes);
+
+/* Pass 1.  Writes rowptr/rowptrT (N*K+1 ints each, exclusive scan; nnz = rowptr[N*K] = rowptrT[N*K]),
+ * indeg[N] (in-edges per node irrespective of hop masks; KPGraphSAGE aggr="mean"), and
+ * stats[0..3] = {nnz, max attr in hop column 0, max attr in hop columns >= 1, number of out-of-range src/dst}. */
+int kp_plan_count(const kp_plan_input* in, int32_t* rowptr, int32_t* rowptrT, int32_t* indeg, int32_t* stats,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* Pass 2.  Fills col/attr16 (by dst rows), colT (by src rows; holds dst ids) -- nnz entries each -- and, when
+ * self_loops, dinv[N*K].  Deterministic: entries of a row are in ascending edge id, loop entry last. */
+int kp_plan_fill(const kp_plan_input* in, const int32_t* rowptr, const int32_t* rowptrT, int32_t* col,
+                 uint16_t* attr16, int32_t* colT, float* dinv, void* workspace, size_t workspace_bytes,
+                 void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Per-hop masked aggregation with fused epilogue (forward) -- the message/aggregate/update of
+ * KPGIN.py:100-105,115-121; KPGINplus.py:74-78,82-88; KPGCN.py:107-126; KPGraphSAGE.py:86-89,100-106;
+ * gine.py:52-59; run_simulation.py:73-75,87-93; and GeometricCombine.forward, combine.py:43-58, when fused.
+ *
+ *   acc[v,h,:] = sum_{j in row(v,h)} wsrc[col_j,h] * ( X[col_j,h,:] + T_h[attr_j,:] )      T_0=T0, T_{h>=1}=Tk
+ *   z[v,h,:]   = act( acc * wdst[v,h] * mean_scale[v] ) + P[v,h,:] + (1+eps) * X[v,h,:]
+ *   out        = fuse ? sum_h theta[h,:] * z[v,h,:]   ([N,d])   :   z   ([N,k,d] contiguous)
+ * wsrc = wdst = dinv when dinv != NULL (else 1); mean_scale = 1/max(indeg,1) when indeg != NULL (else 1);
+ * the P term is skipped when P == NULL, the self term when eps == NULL, the tables when T0 == NULL.
+ * ---------------------------------------------------------------------------------------------------------- */
+enum { KP_ACT_NONE = 0, KP_ACT_GELU = 1, KP_ACT_RELU = 2 };
+
+typedef struct {
+  int32_t N, Kplan, k, d;          /* nodes; hop count the plan was built with; hops used (k<=Kplan); width */
+  const int32_t* rowptr;           /* N*Kplan+1 */
+  const int32_t* col;              /* nnz */
+  const uint16_t* attr16;          /* nnz */
+  const int32_t* rowptrT;          /* backward only */
+  const int32_t* colT;             /* backward only */
+  const float* dinv;               /* N*Kplan or NULL */
+  const int32_t* indeg;            /* N or NULL */
+  const float* X;  int64_t x_node_stride, x_hop_stride;      /* element strides */
+  const float* P;  int64_t p_node_stride, p_hop_stride;      /* NULL = no peripheral term */
+  const float* T0; const float* Tk; int32_t rows0, rowsk;    /* embedding tables [rows, d]; NULL = none */
+  const float* theta;              /* [k,d], required when fuse */
+  const float* eps;                /* device scalar or NULL */
+  int32_t act, fuse;
+} kp_agg_desc;
+
+int kp_agg_forward(const kp_agg_desc* desc, float* out, void* stream);
+
+/* Backward of kp_agg_forward (autograd of the same reference lines).  Deterministic, no float atomics:
+ * transposed-CSR gather for dX, owner-computes partial tables for dT0/dTk, per-CTA partials for dtheta/deps.
+ *   dOut        [N,d] if fuse else [N,k,d]
+ *   dX          [N,k,d] contiguous (written, not accumulated), may be NULL
+ *   dP          [N,k,d] contiguous or NULL (when !fuse, dP == dOut and the caller should alias instead)
+ *   dT0,dTk     [rows0,d],[rowsk,d] or NULL;  dtheta [k,d] or NULL;  deps [1] or NULL
+ *   workspace   kp_agg_backward_workspace_bytes(desc) bytes
+ */
+int kp_agg_backward_workspace_bytes(const kp_agg_desc* desc, size_t* bytes);
+int kp_agg_backward(const kp_agg_desc* desc, const float* dOut, float* dX, float* dP, float* dT0, float* dTk,
+                    float* dtheta, float* deps, void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KPGNN_B200_H */

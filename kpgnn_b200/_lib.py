@@ -1,0 +1,78 @@
+"""ctypes binding of libkpgnn_b200.so (C ABI declared in include/kpgnn.h).
+
+There is NO fallback: if the shared library is missing or fails to load, importing this module raises, and so
+does every product entry point.  The oracle under `oracle/` is never reachable from here.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libkpgnn_b200.so")
+
+ABI_VERSION = 1
+
+
+class KpError(RuntimeError):
+    pass
+
+
+class PlanInput(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("attr", C.c_void_p), ("attr_stride", C.c_int64),
+                ("N", C.c_int32), ("E", C.c_int32), ("K", C.c_int32), ("self_loops", C.c_int32)]
+
+
+class AggDesc(C.Structure):
+    _fields_ = [("N", C.c_int32), ("Kplan", C.c_int32), ("k", C.c_int32), ("d", C.c_int32),
+                ("rowptr", C.c_void_p), ("col", C.c_void_p), ("attr16", C.c_void_p),
+                ("rowptrT", C.c_void_p), ("colT", C.c_void_p), ("dinv", C.c_void_p), ("indeg", C.c_void_p),
+                ("X", C.c_void_p), ("x_node_stride", C.c_int64), ("x_hop_stride", C.c_int64),
+                ("P", C.c_void_p), ("p_node_stride", C.c_int64), ("p_hop_stride", C.c_int64),
+                ("T0", C.c_void_p), ("Tk", C.c_void_p), ("rows0", C.c_int32), ("rowsk", C.c_int32),
+                ("theta", C.c_void_p), ("eps", C.c_void_p), ("act", C.c_int32), ("fuse", C.c_int32)]
+
+
+ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
+
+# name -> (restype, argtypes); must list every symbol include/kpgnn.h declares (tests/test_abi.py checks it)
+_SIGNATURES = {
+    "kp_last_error": (C.c_char_p, []),
+    "kp_abi_version": (C.c_int, []),
+    "kp_launch_count": (C.c_uint64, []),
+    "kp_plan_workspace_bytes": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
+    "kp_plan_count": (C.c_int, [C.POINTER(PlanInput), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.c_void_p, C.c_size_t, C.c_void_p]),
+    "kp_plan_fill": (C.c_int, [C.POINTER(PlanInput), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                               C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "kp_agg_forward": (C.c_int, [C.POINTER(AggDesc), C.c_void_p, C.c_void_p]),
+    "kp_agg_backward_workspace_bytes": (C.c_int, [C.POINTER(AggDesc), C.POINTER(C.c_size_t)]),
+    "kp_agg_backward": (C.c_int, [C.POINTER(AggDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+}
+
+_lib = None
+
+
+def lib():
+    """Loads the shared library on first use; raises KpError (never falls back) if it is not there."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise KpError("libkpgnn_b200.so not built: run `python -m kpgnn_b200.build` "
+                          "(there is no CPU or PyTorch fallback for the K-hop path)")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype, fn.argtypes = res, args
+        if handle.kp_abi_version() != ABI_VERSION:
+            raise KpError("libkpgnn_b200.so ABI %d != expected %d; rebuild" % (handle.kp_abi_version(), ABI_VERSION))
+        _lib = handle
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        raise KpError("%s failed (%d): %s" % (what, rc, lib().kp_last_error().decode()))
+
+
+def launch_count():
+    return int(lib().kp_launch_count())

@@ -1,0 +1,676 @@
+// agg.cu -- per-hop masked K-hop aggregation with fused epilogue, forward and backward (sm_100a).
+//
+// Reference semantics (see include/kpgnn.h for the formula): the message/aggregate/update triple of
+// layers/KPGIN.py:100-121, KPGINplus.py:74-88, KPGCN.py:107-126, KPGraphSAGE.py:86-106, gine.py:52-59 and
+// GeometricCombine (combine.py:43-58).  The reference materialises [E_K,k,d] message tensors; here each
+// (dst,hop) row of the plan is a segment of a CSR and a GROUP of G lanes (G*VEC >= d, G<=32) owns one
+// destination node: it walks the node's hop segments, gathers source rows with VEC-wide loads (float4 when
+// aligned), applies activation / peripheral / self terms in registers and, when `fuse`, reduces over hops with
+// theta so the [N,k,d] intermediate never reaches HBM.
+//
+// Backward is three deterministic passes (no float atomics):
+//   B1 (dst rows)  recompute the pre-activation, emit Gs = dZ * act' * scale  [N,k,d], dP, dtheta/deps partials
+//   B2 (src rows)  dX = wsrc * sum over the transposed CSR of Gs  (+ self term)
+//   B3 (rows)      dT0/dTk by owner-computes partial tables in shared memory, then a fixed-order reduction
+// HBM-bound gather work: no tensor cores on purpose.
+#include "common.cuh"
+
+namespace kp {
+
+template <int VEC>
+struct Vf {
+  float v[VEC];
+};
+
+template <int VEC>
+__device__ __forceinline__ Vf<VEC> vload(const float* __restrict__ p);
+template <>
+__device__ __forceinline__ Vf<4> vload<4>(const float* __restrict__ p) {
+  float4 t = __ldg(reinterpret_cast<const float4*>(p));
+  return Vf<4>{{t.x, t.y, t.z, t.w}};
+}
+template <>
+__device__ __forceinline__ Vf<2> vload<2>(const float* __restrict__ p) {
+  float2 t = __ldg(reinterpret_cast<const float2*>(p));
+  return Vf<2>{{t.x, t.y}};
+}
+template <>
+__device__ __forceinline__ Vf<1> vload<1>(const float* __restrict__ p) {
+  return Vf<1>{{__ldg(p)}};
+}
+// streaming variants for data touched exactly once (P, dOut, outputs): keep L1/L2 for the gathered rows
+template <int VEC>
+__device__ __forceinline__ Vf<VEC> vload_stream(const float* __restrict__ p);
+template <>
+__device__ __forceinline__ Vf<4> vload_stream<4>(const float* __restrict__ p) {
+  float4 t = __ldcs(reinterpret_cast<const float4*>(p));
+  return Vf<4>{{t.x, t.y, t.z, t.w}};
+}
+template <>
+__device__ __forceinline__ Vf<2> vload_stream<2>(const float* __restrict__ p) {
+  float2 t = __ldcs(reinterpret_cast<const float2*>(p));
+  return Vf<2>{{t.x, t.y}};
+}
+template <>
+__device__ __forceinline__ Vf<1> vload_stream<1>(const float* __restrict__ p) {
+  return Vf<1>{{__ldcs(p)}};
+}
+template <int VEC>
+__device__ __forceinline__ void vstore(float* __restrict__ p, const Vf<VEC>& x);
+template <>
+__device__ __forceinline__ void vstore<4>(float* __restrict__ p, const Vf<4>& x) {
+  *reinterpret_cast<float4*>(p) = make_float4(x.v[0], x.v[1], x.v[2], x.v[3]);
+}
+template <>
+__device__ __forceinline__ void vstore<2>(float* __restrict__ p, const Vf<2>& x) {
+  *reinterpret_cast<float2*>(p) = make_float2(x.v[0], x.v[1]);
+}
+template <>
+__device__ __forceinline__ void vstore<1>(float* __restrict__ p, const Vf<1>& x) {
+  *p = x.v[0];
+}
+
+template <int ACT>
+__device__ __forceinline__ float act_fwd(float x) {
+  if (ACT == KP_ACT_GELU) return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));  // exact-erf GELU
+  if (ACT == KP_ACT_RELU) return x > 0.f ? x : 0.f;
+  return x;
+}
+template <int ACT>
+__device__ __forceinline__ float act_bwd(float x) {
+  if (ACT == KP_ACT_GELU) {
+    float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+    float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
+    return cdf + x * pdf;
+  }
+  if (ACT == KP_ACT_RELU) return x > 0.f ? 1.f : 0.f;
+  return 1.f;
+}
+
+struct AggArgs {
+  kp_agg_desc d;
+  int G;        // lanes per node group (power of two <= 32)
+  int gshift;   // log2(G)
+};
+
+// acc = sum_j wsrc * (X[col_j,h,c..] + T_h[attr_j,c..]) over row (v,h) of the plan, 4 gathers in flight
+template <int VEC>
+__device__ __forceinline__ Vf<VEC> gather_row(const kp_agg_desc& a, int v, int h, int c) {
+  Vf<VEC> acc;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) acc.v[i] = 0.f;
+  const long long r = (long long)v * a.Kplan + h;
+  const int b = __ldg(a.rowptr + r), e = __ldg(a.rowptr + r + 1);
+  const float* __restrict__ T = a.T0 ? (h == 0 ? a.T0 : a.Tk) : nullptr;
+  const float* __restrict__ Xh = a.X + (long long)h * a.x_hop_stride + c;
+  for (int j = b; j < e; j += 4) {
+    int u[4];
+    int at[4];
+    Vf<VEC> xv[4];
+    const int n = min(4, e - j);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (q < n) {
+        u[q] = __ldg(a.col + j + q);
+        at[q] = T ? (int)__ldg(a.attr16 + j + q) : 0;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (q < n) xv[q] = vload<VEC>(Xh + (long long)u[q] * a.x_node_stride);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (q < n) {
+        float w = a.dinv ? __ldg(a.dinv + (long long)u[q] * a.Kplan + h) : 1.f;
+        if (T) {
+          Vf<VEC> tv = vload<VEC>(T + (long long)at[q] * a.d + c);
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) acc.v[i] += w * (xv[q].v[i] + tv.v[i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) acc.v[i] += w * xv[q].v[i];
+        }
+      }
+    }
+  }
+  return acc;
+}
+
+__device__ __forceinline__ float row_scale(const kp_agg_desc& a, int v, int h) {
+  float s = 1.f;
+  if (a.dinv) s *= __ldg(a.dinv + (long long)v * a.Kplan + h);
+  if (a.indeg) s *= 1.f / (float)max(__ldg(a.indeg + v), 1);
+  return s;
+}
+
+template <int VEC, int ACT, bool FUSE>
+__global__ void __launch_bounds__(256) agg_fwd_kernel(const AggArgs args, float* __restrict__ out) {
+  const kp_agg_desc& a = args.d;
+  const int G = args.G;
+  const int lane = threadIdx.x & (G - 1);
+  const long long group = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> args.gshift;
+  const long long ngroups = ((long long)gridDim.x * blockDim.x) >> args.gshift;
+  const float self_c = a.eps ? 1.f + __ldg(a.eps) : 0.f;
+  for (long long v = group; v < a.N; v += ngroups) {
+    for (int c = lane * VEC; c < a.d; c += G * VEC) {
+      Vf<VEC> o;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) o.v[i] = 0.f;
+      for (int h = 0; h < a.k; ++h) {
+        Vf<VEC> z = gather_row<VEC>(a, (int)v, h, c);
+        const float s = row_scale(a, (int)v, h);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) z.v[i] = act_fwd<ACT>(z.v[i] * s);
+        if (a.P) {
+          Vf<VEC> p = vload_stream<VEC>(a.P + v * a.p_node_stride + (long long)h * a.p_hop_stride + c);
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) z.v[i] += p.v[i];
+        }
+        if (a.eps) {
+          Vf<VEC> x = vload<VEC>(a.X + v * a.x_node_stride + (long long)h * a.x_hop_stride + c);
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) z.v[i] += self_c * x.v[i];
+        }
+        if (FUSE) {
+          Vf<VEC> th = vload<VEC>(a.theta + (long long)h * a.d + c);
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) o.v[i] += th.v[i] * z.v[i];
+        } else {
+          vstore<VEC>(out + (v * a.k + h) * a.d + c, z);
+        }
+      }
+      if (FUSE) vstore<VEC>(out + v * a.d + c, o);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// B1: per destination row.  RECOMPUTE=false is the linear, unfused case where only dP/deps are wanted.
+// ---------------------------------------------------------------------------------------------------------
+template <int VEC, int ACT, bool FUSE>
+__global__ void __launch_bounds__(256)
+agg_bwd_dst_kernel(const AggArgs args, const float* __restrict__ dOut, float* __restrict__ Gs,
+                   float* __restrict__ dP, float* __restrict__ dtheta_part, float* __restrict__ deps_part) {
+  extern __shared__ float smem[];
+  const kp_agg_desc& a = args.d;
+  const int G = args.G;
+  const int lane = threadIdx.x & (G - 1);
+  const int gib = threadIdx.x >> args.gshift;                 // group index inside the block
+  const int gpb = blockDim.x >> args.gshift;                  // groups per block
+  const long long group = (long long)blockIdx.x * gpb + gib;
+  const long long ngroups = (long long)gridDim.x * gpb;
+  const float self_c = a.eps ? 1.f + __ldg(a.eps) : 0.f;
+  const int dpad = ((a.d + G * VEC - 1) / (G * VEC)) * (G * VEC);
+  // per-group private dtheta accumulators [k][dpad]; every lane owns its columns -> no races
+  float* th_acc = smem + (size_t)gib * a.k * dpad;
+  if (dtheta_part) {
+    for (int i = threadIdx.x; i < gpb * a.k * dpad; i += blockDim.x) smem[i] = 0.f;
+    __syncthreads();
+  }
+  float eps_acc = 0.f;
+  for (long long v = group; v < a.N; v += ngroups) {
+    for (int c = lane * VEC; c < a.d; c += G * VEC) {
+      Vf<VEC> go;
+      if (FUSE) go = vload_stream<VEC>(dOut + v * a.d + c);
+      for (int h = 0; h < a.k; ++h) {
+        Vf<VEC> dy;
+        if (FUSE) {
+          Vf<VEC> th = vload<VEC>(a.theta + (long long)h * a.d + c);
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) dy.v[i] = th.v[i] * go.v[i];
+        } else {
+          dy = vload_stream<VEC>(dOut + (v * a.k + h) * a.d + c);
+        }
+        if (dP) vstore<VEC>(dP + (v * a.k + h) * a.d + c, dy);
+        Vf<VEC> g = dy;
+        const float s = row_scale(a, (int)v, h);
+        if (ACT != KP_ACT_NONE || (FUSE && dtheta_part)) {
+          Vf<VEC> pre = gather_row<VEC>(a, (int)v, h, c);
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) pre.v[i] *= s;
+          if (FUSE && dtheta_part) {
+            Vf<VEC> z;
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) z.v[i] = act_fwd<ACT>(pre.v[i]);
+            if (a.P) {
+              Vf<VEC> p = vload_stream<VEC>(a.P + v * a.p_node_stride + (long long)h * a.p_hop_stride + c);
+#pragma unroll
+              for (int i = 0; i < VEC; ++i) z.v[i] += p.v[i];
+            }
+            if (a.eps) {
+              Vf<VEC> x = vload<VEC>(a.X + v * a.x_node_stride + (long long)h * a.x_hop_stride + c);
+#pragma unroll
+              for (int i = 0; i < VEC; ++i) z.v[i] += self_c * x.v[i];
+            }
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) th_acc[h * dpad + c + i] += go.v[i] * z.v[i];
+          }
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) g.v[i] *= act_bwd<ACT>(pre.v[i]);
+        }
+        if (deps_part) {
+          Vf<VEC> x = vload<VEC>(a.X + v * a.x_node_stride + (long long)h * a.x_hop_stride + c);
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) eps_acc += dy.v[i] * x.v[i];
+        }
+        if (Gs) {
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) g.v[i] *= s;
+          vstore<VEC>(Gs + (v * a.k + h) * a.d + c, g);
+        }
+      }
+    }
+  }
+  if (dtheta_part) {
+    __syncthreads();
+    // fixed-order reduction over the block's groups
+    for (int i = threadIdx.x; i < a.k * a.d; i += blockDim.x) {
+      int h = i / a.d, c = i - h * a.d;
+      float s = 0.f;
+      for (int g = 0; g < gpb; ++g) s += smem[((size_t)g * a.k + h) * dpad + c];
+      dtheta_part[(size_t)blockIdx.x * a.k * a.d + i] = s;
+    }
+  }
+  if (deps_part) {
+    __shared__ float red[256];
+    __syncthreads();
+    red[threadIdx.x] = eps_acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if ((int)threadIdx.x < o && threadIdx.x + o < blockDim.x) red[threadIdx.x] += red[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) deps_part[blockIdx.x] = red[0];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// B2: per source row, gather Gs through the transposed CSR.  Gs is [N,k,d] contiguous (or dOut itself).
+// ---------------------------------------------------------------------------------------------------------
+template <int VEC, bool FUSE>
+__global__ void __launch_bounds__(256)
+agg_bwd_src_kernel(const AggArgs args, const float* __restrict__ Gs, const float* __restrict__ dOut,
+                   float* __restrict__ dX) {
+  const kp_agg_desc& a = args.d;
+  const int G = args.G;
+  const int lane = threadIdx.x & (G - 1);
+  const long long group = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> args.gshift;
+  const long long ngroups = ((long long)gridDim.x * blockDim.x) >> args.gshift;
+  const float self_c = a.eps ? 1.f + __ldg(a.eps) : 0.f;
+  for (long long u = group; u < a.N; u += ngroups) {
+    for (int c = lane * VEC; c < a.d; c += G * VEC) {
+      for (int h = 0; h < a.k; ++h) {
+        Vf<VEC> acc;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc.v[i] = 0.f;
+        const long long r = u * a.Kplan + h;
+        const int b = __ldg(a.rowptrT + r), e = __ldg(a.rowptrT + r + 1);
+        for (int j = b; j < e; j += 4) {
+          int vv[4];
+          Vf<VEC> gv[4];
+          const int n = min(4, e - j);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (q < n) vv[q] = __ldg(a.colT + j + q);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (q < n) gv[q] = vload<VEC>(Gs + ((long long)vv[q] * a.k + h) * a.d + c);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (q < n) {
+#pragma unroll
+              for (int i = 0; i < VEC; ++i) acc.v[i] += gv[q].v[i];
+            }
+        }
+        if (a.dinv) {
+          const float w = __ldg(a.dinv + r);
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) acc.v[i] *= w;
+        }
+        if (a.eps) {
+          Vf<VEC> dy;
+          if (FUSE) {
+            Vf<VEC> go = vload<VEC>(dOut + u * a.d + c);
+            Vf<VEC> th = vload<VEC>(a.theta + (long long)h * a.d + c);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) dy.v[i] = go.v[i] * th.v[i];
+          } else {
+            dy = vload<VEC>(dOut + (u * a.k + h) * a.d + c);
+          }
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) acc.v[i] += self_c * dy.v[i];
+        }
+        vstore<VEC>(dX + (u * a.k + h) * a.d + c, acc);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// B3: embedding-table gradients.  Thread (rl, t) owns VEC columns of a row-lane-private table copy in shared
+// memory, walks its rows in a fixed order, so the float sums are reproducible without atomics.
+// ---------------------------------------------------------------------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(256)
+agg_bwd_table_kernel(const kp_agg_desc a, const float* __restrict__ Gs, int cw, int rl_count, int rows_per_block,
+                     float* __restrict__ part) {
+  extern __shared__ float smem[];
+  const int trows = a.rows0 + a.rowsk;
+  const size_t tsz = (size_t)trows * a.d;
+  for (size_t i = threadIdx.x; i < tsz * rl_count; i += blockDim.x) smem[i] = 0.f;
+  __syncthreads();
+  const int rl = threadIdx.x / cw, t = threadIdx.x - rl * cw;
+  const int c = t * VEC;
+  const long long R = (long long)a.N * a.k;
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = min(R, r0 + rows_per_block);
+  if (rl < rl_count && c < a.d) {
+    float* tab = smem + tsz * rl;
+    for (long long row = r0 + rl; row < r1; row += rl_count) {
+      const int v = (int)(row / a.k), h = (int)(row - (long long)v * a.k);
+      const long long pr = (long long)v * a.Kplan + h;
+      const int b = __ldg(a.rowptr + pr), e = __ldg(a.rowptr + pr + 1);
+      if (b == e) continue;
+      const Vf<VEC> g = vload_stream<VEC>(Gs + row * a.d + c);
+      const int base = (h == 0) ? 0 : a.rows0;
+      for (int j = b; j < e; ++j) {
+        const int at = (int)__ldg(a.attr16 + j);
+        const float w = a.dinv ? __ldg(a.dinv + (long long)__ldg(a.col + j) * a.Kplan + h) : 1.f;
+        float* dst = tab + (size_t)(base + at) * a.d + c;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) dst[i] += w * g.v[i];
+      }
+    }
+  }
+  __syncthreads();
+  for (size_t i = threadIdx.x; i < tsz; i += blockDim.x) {
+    float s = 0.f;
+    for (int q = 0; q < rl_count; ++q) s += smem[tsz * q + i];
+    part[(size_t)blockIdx.x * tsz + i] = s;
+  }
+}
+
+// fallback for tables that do not fit in shared memory: global float atomics (NOT bitwise reproducible)
+__global__ void agg_bwd_table_atomic_kernel(const kp_agg_desc a, const float* __restrict__ Gs,
+                                            float* __restrict__ dT0, float* __restrict__ dTk) {
+  const long long R = (long long)a.N * a.k;
+  const long long total = R * a.d;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / a.d;
+    const int c = (int)(i - row * a.d);
+    const int v = (int)(row / a.k), h = (int)(row - (long long)v * a.k);
+    const long long pr = (long long)v * a.Kplan + h;
+    const int b = __ldg(a.rowptr + pr), e = __ldg(a.rowptr + pr + 1);
+    if (b == e) continue;
+    const float g = Gs[i];
+    float* T = (h == 0) ? dT0 : dTk;
+    for (int j = b; j < e; ++j) {
+      const float w = a.dinv ? __ldg(a.dinv + (long long)__ldg(a.col + j) * a.Kplan + h) : 1.f;
+      atomicAdd(T + (size_t)__ldg(a.attr16 + j) * a.d + c, w * g);
+    }
+  }
+}
+
+// out[i] = sum_b part[b*n + i] in ascending b; optional second destination split at n0 (dT0 | dTk)
+__global__ void reduce_partials_kernel(const float* __restrict__ part, int nblocks, int n, int n0,
+                                       float* __restrict__ out0, float* __restrict__ out1) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int b = 0; b < nblocks; ++b) s += part[(size_t)b * n + i];
+  if (i < n0) {
+    if (out0) out0[i] = s;
+  } else {
+    if (out1) out1[i - n0] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side: configuration shared by forward, backward and the workspace-size query
+// ---------------------------------------------------------------------------------------------------------
+struct Config {
+  int vec, G, gshift;
+  int grid;         // forward / B2 grid (256 threads)
+  int grid_b1;      // B1 grid (bounded so the dtheta partials stay small)
+  size_t smem_b1;   // dynamic smem of B1 when dtheta is wanted
+  bool need_gs;     // Gs workspace needed (otherwise Gs == dOut)
+  int cw, rl, grid_b3, rows_per_block;
+  size_t smem_b3;
+  bool table_atomic;
+};
+
+static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+static bool aligned8(const void* p) { return ((uintptr_t)p & 7) == 0; }
+
+static int make_config(const kp_agg_desc& a, Config* c) {
+  KP_CHECK_ARG(a.N >= 0 && a.k >= 1 && a.k <= a.Kplan && a.d >= 1, "kp_agg: bad sizes N=%d k=%d Kplan=%d d=%d",
+               a.N, a.k, a.Kplan, a.d);
+  KP_CHECK_ARG(a.rowptr && a.col && a.X, "kp_agg: null plan or X");
+  KP_CHECK_ARG(!a.T0 || (a.attr16 && a.rows0 > 0 && (a.k == 1 || (a.Tk && a.rowsk > 0))),
+               "kp_agg: embedding tables incomplete");
+  KP_CHECK_ARG(!a.fuse || a.theta, "kp_agg: fuse requires theta");
+  KP_CHECK_ARG(a.act >= 0 && a.act <= 2, "kp_agg: bad activation %d", a.act);
+  auto ok = [&](int v) {
+    if (a.d % v) return false;
+    if (a.x_node_stride % v || a.x_hop_stride % v) return false;
+    if (a.P && (a.p_node_stride % v || a.p_hop_stride % v)) return false;
+    const void* ptrs[] = {a.X, a.P, a.T0, a.Tk, a.theta};
+    for (const void* p : ptrs)
+      if (p && !(v == 4 ? aligned16(p) : aligned8(p))) return false;
+    return true;
+  };
+  c->vec = ok(4) ? 4 : (ok(2) ? 2 : 1);
+  int lanes = (a.d + c->vec - 1) / c->vec;
+  int G = 1, sh = 0;
+  while (G < lanes && G < 32) {
+    G <<= 1;
+    ++sh;
+  }
+  c->G = G;
+  c->gshift = sh;
+  const int gpb = 256 / G;
+  long long want = ((long long)a.N + gpb - 1) / gpb;
+  c->grid = (int)(want < 1 ? 1 : (want > kNumSMs * 16 ? kNumSMs * 16 : want));
+  c->grid_b1 = (int)(want < 1 ? 1 : (want > kNumSMs * 2 ? kNumSMs * 2 : want));
+  const int dpad = ((a.d + G * c->vec - 1) / (G * c->vec)) * (G * c->vec);
+  c->smem_b1 = sizeof(float) * (size_t)gpb * a.k * dpad;
+  c->need_gs = (a.act != KP_ACT_NONE) || a.fuse || a.dinv || a.indeg;
+  // table pass
+  const int trows = a.T0 ? a.rows0 + (a.k > 1 ? a.rowsk : 0) : 0;
+  c->cw = lanes;
+  c->table_atomic = false;
+  c->rl = 0;
+  c->grid_b3 = 0;
+  c->rows_per_block = 0;
+  c->smem_b3 = 0;
+  if (trows > 0) {
+    size_t tsz = sizeof(float) * (size_t)(a.rows0 + a.rowsk) * a.d;
+    int rl = 256 / lanes;
+    if (rl > 8) rl = 8;
+    while (rl > 1 && tsz * rl > 96 * 1024) rl >>= 1;
+    if (tsz * rl > 200 * 1024 || lanes > 256) {
+      c->table_atomic = true;
+    } else {
+      c->rl = rl;
+      c->smem_b3 = tsz * rl;
+      long long R = (long long)a.N * a.k;
+      long long blocks = (R + 255) / 256;  // at least 256 rows per block keeps the partials small
+      if (blocks > kNumSMs * 2) blocks = kNumSMs * 2;
+      if (blocks < 1) blocks = 1;
+      c->grid_b3 = (int)blocks;
+      c->rows_per_block = (int)((R + blocks - 1) / blocks);
+    }
+  }
+  return 0;
+}
+
+struct WsLayout {
+  size_t gs, dtheta, deps, table, total;
+};
+
+static WsLayout ws_layout(const kp_agg_desc& a, const Config& c) {
+  WsLayout w;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += align_up(bytes, 256);
+    return o;
+  };
+  w.gs = take(c.need_gs ? sizeof(float) * (size_t)a.N * a.k * a.d : 0);
+  w.dtheta = take(sizeof(float) * (size_t)c.grid_b1 * a.k * a.d);
+  w.deps = take(sizeof(float) * (size_t)c.grid_b1);
+  w.table = take(c.grid_b3 ? sizeof(float) * (size_t)c.grid_b3 * (a.rows0 + a.rowsk) * a.d : 0);
+  w.total = off;
+  return w;
+}
+
+template <int VEC, int ACT, bool FUSE>
+static int launch_fwd(const AggArgs& args, const Config& c, float* out, cudaStream_t st) {
+  KP_LAUNCH((agg_fwd_kernel<VEC, ACT, FUSE>), c.grid, 256, 0, st, args, out);
+  return 0;
+}
+
+template <int VEC, int ACT, bool FUSE>
+static int launch_b1(const AggArgs& args, const Config& c, const float* dOut, float* Gs, float* dP,
+                     float* dth, float* dep, cudaStream_t st) {
+  size_t smem = dth ? c.smem_b1 : 0;
+  if (smem > 48 * 1024) {
+    KP_CUDA(cudaFuncSetAttribute(agg_bwd_dst_kernel<VEC, ACT, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem));
+  }
+  KP_LAUNCH((agg_bwd_dst_kernel<VEC, ACT, FUSE>), c.grid_b1, 256, smem, st, args, dOut, Gs, dP, dth, dep);
+  return 0;
+}
+
+#define KP_DISPATCH_VAF(FN, vec, act, fuse, ...)                                          \
+  do {                                                                                    \
+    int _rc = 1;                                                                          \
+    if (vec == 4) {                                                                       \
+      KP_DISPATCH_AF(FN, 4, act, fuse, __VA_ARGS__);                                      \
+    } else if (vec == 2) {                                                                \
+      KP_DISPATCH_AF(FN, 2, act, fuse, __VA_ARGS__);                                      \
+    } else {                                                                              \
+      KP_DISPATCH_AF(FN, 1, act, fuse, __VA_ARGS__);                                      \
+    }                                                                                     \
+    if (_rc) return _rc;                                                                  \
+  } while (0)
+#define KP_DISPATCH_AF(FN, V, act, fuse, ...)                                             \
+  do {                                                                                    \
+    if (act == KP_ACT_GELU) {                                                             \
+      _rc = fuse ? FN<V, KP_ACT_GELU, true>(__VA_ARGS__) : FN<V, KP_ACT_GELU, false>(__VA_ARGS__); \
+    } else if (act == KP_ACT_RELU) {                                                      \
+      _rc = fuse ? FN<V, KP_ACT_RELU, true>(__VA_ARGS__) : FN<V, KP_ACT_RELU, false>(__VA_ARGS__); \
+    } else {                                                                              \
+      _rc = fuse ? FN<V, KP_ACT_NONE, true>(__VA_ARGS__) : FN<V, KP_ACT_NONE, false>(__VA_ARGS__); \
+    }                                                                                     \
+  } while (0)
+
+}  // namespace kp
+
+extern "C" {
+
+int kp_agg_forward(const kp_agg_desc* desc, float* out, void* stream) {
+  KP_CHECK_ARG(desc && out, "kp_agg_forward: null argument");
+  kp::Config c;
+  if (kp::make_config(*desc, &c)) return 1;
+  if (desc->N == 0) return 0;
+  KP_CHECK_ARG(c.vec == 1 || (c.vec == 4 ? kp::aligned16(out) : kp::aligned8(out)),
+               "kp_agg_forward: output not aligned for %d-wide stores", c.vec);
+  kp::AggArgs args{*desc, c.G, c.gshift};
+  cudaStream_t st = (cudaStream_t)stream;
+  KP_DISPATCH_VAF(kp::launch_fwd, c.vec, desc->act, desc->fuse, args, c, out, st);
+  return 0;
+}
+
+int kp_agg_backward_workspace_bytes(const kp_agg_desc* desc, size_t* bytes) {
+  KP_CHECK_ARG(desc && bytes, "kp_agg_backward_workspace_bytes: null argument");
+  kp::Config c;
+  if (kp::make_config(*desc, &c)) return 1;
+  *bytes = kp::ws_layout(*desc, c).total;
+  return 0;
+}
+
+int kp_agg_backward(const kp_agg_desc* desc, const float* dOut, float* dX, float* dP, float* dT0, float* dTk,
+                    float* dtheta, float* deps, void* workspace, size_t workspace_bytes, void* stream) {
+  KP_CHECK_ARG(desc && dOut, "kp_agg_backward: null argument");
+  const kp_agg_desc& a = *desc;
+  kp::Config c;
+  if (kp::make_config(a, &c)) return 1;
+  KP_CHECK_ARG(a.rowptrT && a.colT, "kp_agg_backward: plan has no transposed CSR");
+  KP_CHECK_ARG(!dtheta || a.fuse, "kp_agg_backward: dtheta requires fuse");
+  KP_CHECK_ARG(!deps || a.eps, "kp_agg_backward: deps requires eps");
+  KP_CHECK_ARG((!dT0 && !dTk) || a.T0, "kp_agg_backward: table gradients requested without tables");
+  kp::WsLayout w = kp::ws_layout(a, c);
+  KP_CHECK_ARG(workspace_bytes >= w.total && (workspace || w.total == 0), "kp_agg_backward: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t tn = (size_t)(a.rows0 + a.rowsk) * a.d;
+  if (a.N == 0) {
+    if (dT0) KP_CUDA(cudaMemsetAsync(dT0, 0, sizeof(float) * (size_t)a.rows0 * a.d, st));
+    if (dTk) KP_CUDA(cudaMemsetAsync(dTk, 0, sizeof(float) * (size_t)a.rowsk * a.d, st));
+    if (dtheta) KP_CUDA(cudaMemsetAsync(dtheta, 0, sizeof(float) * (size_t)a.k * a.d, st));
+    if (deps) KP_CUDA(cudaMemsetAsync(deps, 0, sizeof(float), st));
+    return 0;
+  }
+  char* ws = (char*)workspace;
+  float* Gs = c.need_gs ? (float*)(ws + w.gs) : nullptr;
+  float* dth_part = dtheta ? (float*)(ws + w.dtheta) : nullptr;
+  float* dep_part = deps ? (float*)(ws + w.deps) : nullptr;
+  kp::AggArgs args{a, c.G, c.gshift};
+  const bool want_table = (dT0 || dTk);
+  const bool want_b1 = c.need_gs ? (dX || want_table || dP || dth_part || dep_part) : (dP || dep_part);
+  if (want_b1) {
+    float* dPk = dP;
+    if (!a.fuse && dP == dOut) dPk = nullptr;
+    KP_DISPATCH_VAF(kp::launch_b1, c.vec, a.act, a.fuse, args, c, dOut, Gs, dPk, dth_part, dep_part, st);
+  }
+  const float* Gsrc = c.need_gs ? Gs : dOut;
+  if (dX) {
+    if (c.vec == 4) {
+      if (a.fuse) KP_LAUNCH((kp::agg_bwd_src_kernel<4, true>), c.grid, 256, 0, st, args, Gsrc, dOut, dX);
+      else        KP_LAUNCH((kp::agg_bwd_src_kernel<4, false>), c.grid, 256, 0, st, args, Gsrc, dOut, dX);
+    } else if (c.vec == 2) {
+      if (a.fuse) KP_LAUNCH((kp::agg_bwd_src_kernel<2, true>), c.grid, 256, 0, st, args, Gsrc, dOut, dX);
+      else        KP_LAUNCH((kp::agg_bwd_src_kernel<2, false>), c.grid, 256, 0, st, args, Gsrc, dOut, dX);
+    } else {
+      if (a.fuse) KP_LAUNCH((kp::agg_bwd_src_kernel<1, true>), c.grid, 256, 0, st, args, Gsrc, dOut, dX);
+      else        KP_LAUNCH((kp::agg_bwd_src_kernel<1, false>), c.grid, 256, 0, st, args, Gsrc, dOut, dX);
+    }
+  }
+  if (want_table) {
+    if (c.table_atomic) {
+      if (dT0) KP_CUDA(cudaMemsetAsync(dT0, 0, sizeof(float) * (size_t)a.rows0 * a.d, st));
+      if (dTk) KP_CUDA(cudaMemsetAsync(dTk, 0, sizeof(float) * (size_t)a.rowsk * a.d, st));
+      KP_CHECK_ARG(dT0 && (dTk || a.k == 1), "kp_agg_backward: atomic table path needs both dT0 and dTk");
+      KP_LAUNCH(kp::agg_bwd_table_atomic_kernel, kp::kNumSMs * 8, 256, 0, st, a, Gsrc, dT0, dTk);
+    } else {
+      float* part = (float*)(ws + w.table);
+      const int threads = 256;
+#define KP_B3(V)                                                                                           \
+  do {                                                                                                     \
+    if (c.smem_b3 > 48 * 1024)                                                                             \
+      KP_CUDA(cudaFuncSetAttribute(kp::agg_bwd_table_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                   (int)c.smem_b3));                                                       \
+    KP_LAUNCH((kp::agg_bwd_table_kernel<V>), c.grid_b3, threads, c.smem_b3, st, a, Gsrc, c.cw, c.rl,       \
+              c.rows_per_block, part);                                                                     \
+  } while (0)
+      if (c.vec == 4) KP_B3(4);
+      else if (c.vec == 2) KP_B3(2);
+      else KP_B3(1);
+#undef KP_B3
+      KP_LAUNCH(kp::reduce_partials_kernel, kp::ceil_div((long long)tn, 256), 256, 0, st, part, c.grid_b3, (int)tn,
+                a.rows0 * a.d, dT0, dTk);
+    }
+  }
+  if (dtheta) {
+    const int n = a.k * a.d;
+    KP_LAUNCH(kp::reduce_partials_kernel, kp::ceil_div(n, 256), 256, 0, st, dth_part, c.grid_b1, n, n, dtheta,
+              (float*)nullptr);
+  }
+  if (deps) {
+    KP_LAUNCH(kp::reduce_partials_kernel, 1, 32, 0, st, dep_part, c.grid_b1, 1, 1, deps, (float*)nullptr);
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,45 @@
+// common.cuh -- shared host/device helpers for libkpgnn_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+
+#include "../../include/kpgnn.h"
+
+namespace kp {
+
+void set_error(const char* fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+
+#define KP_CHECK_ARG(cond, ...)            \
+  do {                                     \
+    if (!(cond)) {                         \
+      kp::set_error(__VA_ARGS__);          \
+      return 1;                            \
+    }                                      \
+  } while (0)
+
+#define KP_CUDA(expr)                                                                      \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      kp::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return 2;                                                                            \
+    }                                                                                      \
+  } while (0)
+
+// every kernel launch goes through this so that kp_launch_count() is the library's own evidence
+#define KP_LAUNCH(kernel, grid, block, smem, stream, ...)                                  \
+  do {                                                                                     \
+    kernel<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__);              \
+    kp::g_launches.fetch_add(1, std::memory_order_relaxed);                                \
+    KP_CUDA(cudaGetLastError());                                                           \
+  } while (0)
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+constexpr int kNumSMs = 148;  // B200
+
+}  // namespace kp

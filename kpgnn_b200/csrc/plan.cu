@@ -1,0 +1,212 @@
+// plan.cu -- graph-plan builder: int64 hop-labelled edge list -> int32 (dst,hop)-CSR + (src,hop)-CSR.
+//
+// Replaces the per-layer re-derivation PyG's propagate does from edge_index/edge_attr in the reference
+// (layers/KPGIN.py:100, KPGINplus.py:74, KPGCN.py:85-110, KPGraphSAGE.py:86, gine.py:52): built once per batch,
+// shared by every layer's forward and backward.  HBM-bound integer work: one coalesced pass over the [E,K]
+// int64 attr matrix per phase, integer atomics only (exact, order-independent), per-row ordering restored by a
+// segment sort so that the float summation order downstream is reproducible.
+#include <cub/device/device_scan.cuh>
+
+#include "common.cuh"
+
+namespace kp {
+
+__global__ void plan_count_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
+                                  const int64_t* __restrict__ attr, int64_t attr_stride, int N, int E, int K,
+                                  int* __restrict__ cnt, int* __restrict__ cntT, int* __restrict__ indeg,
+                                  int* __restrict__ stats) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)E * K;
+  int max0 = 0, maxk = 0, bad = 0;
+  if (t < total) {
+    int e = (int)(t / K), h = (int)(t - (long long)e * K);
+    long long s = src[e], d = dst[e];
+    bool ok = (s >= 0 && s < N && d >= 0 && d < N);
+    if (!ok) {
+      bad = (h == 0);
+    } else {
+      if (h == 0) atomicAdd(&indeg[d], 1);
+      long long a = attr[(long long)e * attr_stride + h];
+      if (a != 0) {
+        if (a < 0 || a > 65535) {
+          bad = 1;
+        } else {
+          atomicAdd(&cnt[(long long)d * K + h], 1);
+          atomicAdd(&cntT[(long long)s * K + h], 1);
+          if (h == 0) max0 = (int)a; else maxk = (int)a;
+        }
+      }
+    }
+  }
+  // warp-reduce the statistics before touching global memory
+  for (int o = 16; o > 0; o >>= 1) {
+    max0 = max(max0, __shfl_xor_sync(0xffffffffu, max0, o));
+    maxk = max(maxk, __shfl_xor_sync(0xffffffffu, maxk, o));
+    bad += __shfl_xor_sync(0xffffffffu, bad, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (max0) atomicMax(&stats[1], max0);
+    if (maxk) atomicMax(&stats[2], maxk);
+    if (bad) atomicAdd(&stats[3], bad);
+  }
+}
+
+__global__ void plan_add_loops_kernel(int* __restrict__ cnt, int* __restrict__ cntT, int rows) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < rows) {
+    cnt[r] += 1;
+    cntT[r] += 1;
+  }
+}
+
+__global__ void plan_nnz_kernel(const int* __restrict__ rowptr, int rows, int* __restrict__ stats) {
+  stats[0] = rowptr[rows];
+}
+
+__global__ void plan_scatter_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
+                                    const int64_t* __restrict__ attr, int64_t attr_stride, int N, int E, int K,
+                                    const int* __restrict__ rowptr, const int* __restrict__ rowptrT,
+                                    int* __restrict__ cur, int* __restrict__ curT, int* __restrict__ eid,
+                                    int* __restrict__ eidT) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)E * K) return;
+  int e = (int)(t / K), h = (int)(t - (long long)e * K);
+  long long s = src[e], d = dst[e];
+  if (s < 0 || s >= N || d < 0 || d >= N) return;
+  long long a = attr[(long long)e * attr_stride + h];
+  if (a <= 0 || a > 65535) return;
+  long long r = d * K + h, rT = s * K + h;
+  eid[rowptr[r] + atomicAdd(&cur[r], 1)] = e;
+  eidT[rowptrT[rT] + atomicAdd(&curT[rT], 1)] = e;
+}
+
+__device__ __forceinline__ void insertion_sort(int* a, int n) {
+  for (int i = 1; i < n; ++i) {
+    int key = a[i], j = i - 1;
+    while (j >= 0 && a[j] > key) {
+      a[j + 1] = a[j];
+      --j;
+    }
+    a[j + 1] = key;
+  }
+}
+
+// one thread per row: restore ascending edge id inside the row, then emit the compact arrays
+__global__ void plan_emit_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
+                                 const int64_t* __restrict__ attr, int64_t attr_stride, int N, int K,
+                                 int self_loops, const int* __restrict__ rowptr, const int* __restrict__ rowptrT,
+                                 int* __restrict__ eid, int* __restrict__ eidT, int* __restrict__ col,
+                                 uint16_t* __restrict__ attr16, int* __restrict__ colT,
+                                 float* __restrict__ dinv) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= N * K) return;
+  int v = r / K, h = r - v * K;
+  {
+    int b = rowptr[r], e = rowptr[r + 1];
+    int n = e - b - (self_loops ? 1 : 0);
+    insertion_sort(eid + b, n);
+    for (int i = 0; i < n; ++i) {
+      int id = eid[b + i];
+      col[b + i] = (int)src[id];
+      attr16[b + i] = (uint16_t)attr[(long long)id * attr_stride + h];
+    }
+    if (self_loops) {
+      col[e - 1] = v;
+      attr16[e - 1] = 1;
+    }
+    if (dinv) dinv[r] = 1.0f / sqrtf((float)(e - b));
+  }
+  {
+    int b = rowptrT[r], e = rowptrT[r + 1];
+    int n = e - b - (self_loops ? 1 : 0);
+    insertion_sort(eidT + b, n);
+    for (int i = 0; i < n; ++i) colT[b + i] = (int)dst[eidT[b + i]];
+    if (self_loops) colT[e - 1] = v;
+  }
+}
+
+static size_t scan_temp_bytes(int rows_plus_1) {
+  size_t bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, bytes, (int*)nullptr, (int*)nullptr, rows_plus_1);
+  return bytes;
+}
+
+}  // namespace kp
+
+extern "C" {
+
+int kp_plan_workspace_bytes(int32_t N, int32_t E, int32_t K, size_t* bytes) {
+  KP_CHECK_ARG(N >= 0 && E >= 0 && K >= 1 && bytes, "kp_plan_workspace_bytes: bad arguments");
+  long long rows = (long long)N * K;
+  KP_CHECK_ARG(rows + 1 < (1ll << 31) && (long long)E * K + rows < (1ll << 31),
+               "kp_plan: N*K or E*K exceeds int32 indexing");
+  size_t scan = kp::align_up(kp::scan_temp_bytes((int)rows + 1), 256);
+  // fill phase: two cursor arrays (rows) + two edge-id arrays (upper bound E*K + rows entries each)
+  size_t fill = kp::align_up(sizeof(int) * (size_t)rows, 256) * 2 +
+                kp::align_up(sizeof(int) * ((size_t)E * K + rows), 256) * 2;
+  *bytes = scan > fill ? scan : fill;
+  return 0;
+}
+
+int kp_plan_count(const kp_plan_input* in, int32_t* rowptr, int32_t* rowptrT, int32_t* indeg, int32_t* stats,
+                  void* workspace, size_t workspace_bytes, void* stream) {
+  KP_CHECK_ARG(in && rowptr && rowptrT && indeg && stats, "kp_plan_count: null argument");
+  const int N = in->N, E = in->E, K = in->K;
+  size_t need = 0;
+  if (kp_plan_workspace_bytes(N, E, K, &need)) return 1;
+  KP_CHECK_ARG(workspace_bytes >= need && (workspace || need == 0), "kp_plan_count: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  long long rows = (long long)N * K;
+  KP_CUDA(cudaMemsetAsync(rowptr, 0, sizeof(int) * (rows + 1), st));
+  KP_CUDA(cudaMemsetAsync(rowptrT, 0, sizeof(int) * (rows + 1), st));
+  KP_CUDA(cudaMemsetAsync(indeg, 0, sizeof(int) * (size_t)(N > 0 ? N : 1), st));
+  KP_CUDA(cudaMemsetAsync(stats, 0, sizeof(int) * 4, st));
+  long long total = (long long)E * K;
+  if (total > 0) {
+    KP_LAUNCH(kp::plan_count_kernel, kp::ceil_div(total, 256), 256, 0, st, in->src, in->dst, in->attr,
+              in->attr_stride, N, E, K, rowptr, rowptrT, indeg, stats);
+  }
+  if (in->self_loops && rows > 0) {
+    KP_LAUNCH(kp::plan_add_loops_kernel, kp::ceil_div(rows, 256), 256, 0, st, rowptr, rowptrT, (int)rows);
+  }
+  size_t temp = workspace_bytes;
+  KP_CUDA(cub::DeviceScan::ExclusiveSum(workspace, temp, rowptr, rowptr, (int)rows + 1, st));
+  temp = workspace_bytes;
+  KP_CUDA(cub::DeviceScan::ExclusiveSum(workspace, temp, rowptrT, rowptrT, (int)rows + 1, st));
+  kp::g_launches.fetch_add(2, std::memory_order_relaxed);
+  KP_LAUNCH(kp::plan_nnz_kernel, 1, 1, 0, st, rowptr, (int)rows, stats);
+  return 0;
+}
+
+int kp_plan_fill(const kp_plan_input* in, const int32_t* rowptr, const int32_t* rowptrT, int32_t* col,
+                 uint16_t* attr16, int32_t* colT, float* dinv, void* workspace, size_t workspace_bytes,
+                 void* stream) {
+  KP_CHECK_ARG(in && rowptr && rowptrT, "kp_plan_fill: null argument");
+  const int N = in->N, E = in->E, K = in->K;
+  size_t need = 0;
+  if (kp_plan_workspace_bytes(N, E, K, &need)) return 1;
+  KP_CHECK_ARG(workspace_bytes >= need && (workspace || need == 0), "kp_plan_fill: workspace too small");
+  KP_CHECK_ARG(!in->self_loops || dinv, "kp_plan_fill: self_loops requires dinv");
+  cudaStream_t st = (cudaStream_t)stream;
+  long long rows = (long long)N * K;
+  if (rows == 0) return 0;
+  char* w = (char*)workspace;
+  size_t cur_b = kp::align_up(sizeof(int) * (size_t)rows, 256);
+  size_t eid_b = kp::align_up(sizeof(int) * ((size_t)E * K + rows), 256);
+  int* cur = (int*)w;
+  int* curT = (int*)(w + cur_b);
+  int* eid = (int*)(w + 2 * cur_b);
+  int* eidT = (int*)(w + 2 * cur_b + eid_b);
+  KP_CUDA(cudaMemsetAsync(cur, 0, 2 * cur_b, st));
+  long long total = (long long)E * K;
+  if (total > 0) {
+    KP_CHECK_ARG(col && attr16 && colT, "kp_plan_fill: null output");
+    KP_LAUNCH(kp::plan_scatter_kernel, kp::ceil_div(total, 256), 256, 0, st, in->src, in->dst, in->attr,
+              in->attr_stride, N, E, K, rowptr, rowptrT, cur, curT, eid, eidT);
+  }
+  KP_LAUNCH(kp::plan_emit_kernel, kp::ceil_div(rows, 128), 128, 0, st, in->src, in->dst, in->attr,
+            in->attr_stride, N, K, in->self_loops, rowptr, rowptrT, eid, eidT, col, attr16, colT, dinv);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,122 @@
+"""GPU parity of the drop-in layers (CUDA kernels through the C ABI) against the torch oracle on the same
+seeded inputs.  Bar (north_star): outputs and gradients within 1e-5 relative, fp32."""
+import pytest
+import torch
+
+from oracle import layers_torch as OL
+from tests.util import RTOL, rel_err, zinc_batch
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_pair(mine, ora, batch, make_x, P_shape, use_pe, gine=False):
+    dev = torch.device("cuda:0")
+    ora.load_state_dict(mine.state_dict())
+    mine = mine.to(dev)
+    mine.train()
+    ora.train()
+    g = torch.Generator().manual_seed(7)
+    x0 = make_x(g)
+    P0 = torch.randn(*P_shape, generator=g) if P_shape is not None else None
+    N = batch["num_nodes"]
+    K = batch["edge_attr"].size(1)
+    pe = None
+    if use_pe and K > 1:
+        pe = torch.randint(0, 5, (N, K - 1), generator=g)
+    elif K > 1 and not gine:
+        pe = batch["pe_attr"]
+    outs = []
+    for where, layer in (("cpu", ora), ("cuda", mine)):
+        d = torch.device("cpu") if where == "cpu" else dev
+        x = x0.clone().to(d).requires_grad_(True)
+        P = P0.clone().to(d).requires_grad_(True) if P0 is not None else None
+        ei, ea = batch["edge_index"].to(d), batch["edge_attr"].to(d)
+        if gine:
+            y = layer(x * 1.0, ei, ea[:, :1])
+        else:
+            y = layer(x * 1.0, ei, ea, pe.to(d) if pe is not None else None, P)
+        gy = torch.randn(y.shape, generator=torch.Generator().manual_seed(11)).to(d)
+        y.backward(gy)
+        grads = {"x": x.grad}
+        if P is not None:
+            grads["P"] = P.grad
+        for n, p in layer.named_parameters():
+            grads[n] = p.grad
+        outs.append((y, grads))
+    (y0, g0), (y1, g1) = outs
+    assert rel_err(y1, y0) < RTOL, ("forward", rel_err(y1, y0))
+    for n in g0:
+        if g0[n] is None:
+            assert g1[n] is None or float(g1[n].abs().max()) == 0.0, n
+            continue
+        assert g1[n] is not None, n
+        assert rel_err(g1[n], g0[n]) < 5 * RTOL, (n, rel_err(g1[n], g0[n]))
+
+
+CASES = [(K, kern, comb, pe) for K in (1, 3, 8) for kern in ("spd", "gd") for comb in ("geometric", "attention")
+         for pe in (False, True) if not (K == 1 and (kern == "gd" or pe))]
+
+
+@pytest.mark.parametrize("K,kern,comb,use_pe", CASES)
+def test_kpginplus(lib, K, kern, comb, use_pe):
+    from kpgnn_b200.layers.KPGINplus import KPGINPlusConv
+    torch.manual_seed(0)
+    H = 104
+    b = zinc_batch(6, K, kern, seed=K)
+    N = b["num_nodes"]
+    _run_pair(KPGINPlusConv(H, H, K, 3, 50, comb), OL.OracleKPGINPlusConv(H, H, K, 3, 50, comb), b,
+              lambda g: torch.randn(N, K, H, generator=g), (N, K, H), use_pe)
+
+
+@pytest.mark.parametrize("K,kern,comb,use_pe", CASES)
+def test_kpgin(lib, K, kern, comb, use_pe):
+    from kpgnn_b200.layers.KPGIN import KPGINConv
+    torch.manual_seed(0)
+    H = 48 if K != 8 else 96
+    b = zinc_batch(6, K, kern, seed=K)
+    N = b["num_nodes"]
+    _run_pair(KPGINConv(H, H, K, 0.1, True, 3, 50, comb), OL.OracleKPGINConv(H, H, K, 0.1, True, 3, 50, comb), b,
+              lambda g: torch.randn(N, H, generator=g), (N, K, H // K), use_pe)
+
+
+@pytest.mark.parametrize("K,kern,comb,use_pe", CASES)
+def test_kpgcn(lib, K, kern, comb, use_pe):
+    from kpgnn_b200.layers.KPGCN import KPGCNConv
+    torch.manual_seed(0)
+    H = 48
+    b = zinc_batch(6, K, kern, seed=K)
+    N = b["num_nodes"]
+    _run_pair(KPGCNConv(H, H, K, 3, 50, comb), OL.OracleKPGCNConv(H, H, K, 3, 50, comb), b,
+              lambda g: torch.randn(N, H, generator=g), (N, K, H // K), use_pe)
+
+
+@pytest.mark.parametrize("aggr", ["add", "mean"])
+@pytest.mark.parametrize("K,kern,comb,use_pe", CASES)
+def test_kpgraphsage(lib, K, kern, comb, use_pe, aggr):
+    from kpgnn_b200.layers.KPGraphSAGE import KPGraphSAGEConv
+    torch.manual_seed(0)
+    H = 48
+    b = zinc_batch(6, K, kern, seed=K)
+    N = b["num_nodes"]
+    _run_pair(KPGraphSAGEConv(H, H, K, aggr, 3, 50, comb), OL.OracleKPGraphSAGEConv(H, H, K, aggr, 3, 50, comb), b,
+              lambda g: torch.randn(N, H, generator=g), (N, K, H // K), use_pe)
+
+
+@pytest.mark.parametrize("K", [1, 8, 16])
+def test_gine(lib, K):
+    from kpgnn_b200.layers.gine import GINEConv
+    torch.manual_seed(0)
+    H = 96
+    b = zinc_batch(6, K, "spd", seed=K)
+    N = b["num_nodes"]
+    _run_pair(GINEConv(H, H, 0.2, 3, True), OL.OracleGINEConv(H, H, 0.2, 3, True), b,
+              lambda g: torch.randn(N, H, generator=g), None, False, gine=True)
+
+
+def test_no_cpu_fallback(lib):
+    from kpgnn_b200 import _lib
+    from kpgnn_b200.layers.KPGINplus import KPGINPlusConv
+    b = zinc_batch(2, 2, "spd")
+    layer = KPGINPlusConv(8, 8, 2, 3, 50, "geometric")
+    with pytest.raises(_lib.KpError):
+        layer(torch.randn(b["num_nodes"], 2, 8), b["edge_index"], b["edge_attr"], None, None)

@@ -1,0 +1,54 @@
+"""Shared helpers for the tests: seeded batches built with the ORACLE extractor (numpy), tolerances."""
+import numpy as np
+import torch
+
+from kpgnn_b200 import synth
+from oracle.extract_np import extract_multi_hop_neighbors_np
+
+# north_star: layer outputs and gradients within 1e-5 relative (fp32)
+RTOL = 1e-5
+
+
+def rel_err(a, b):
+    """max |a-b| / max(|b|_inf, tiny): the '1e-5 relative' bar is on the tensor scale (fp32 sums of ~20 terms
+    cannot be elementwise-relative near zero crossings)."""
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    scale = max(b.abs().max().item(), 1e-30)
+    return (a - b).abs().max().item() / scale
+
+
+def collate(graphs, extract_args):
+    """PyG Batch.from_data_list semantics on oracle-extracted graphs -> dict of CPU tensors."""
+    outs = [extract_multi_hop_neighbors_np(g["num_nodes"], g["edge_index"], g["edge_attr"], *extract_args)
+            for g in graphs]
+    off = 0
+    ei, ea, pe, pea, pca, xs, batch, ys = [], [], [], [], [], [], [], []
+    for i, (g, o) in enumerate(zip(graphs, outs)):
+        ei.append(o["edge_index"] + off)
+        ea.append(o["edge_attr"])
+        if o.get("pe_attr") is not None:
+            pe.append(o["pe_attr"])
+        if o.get("peripheral_edge_attr") is not None:
+            pea.append(o["peripheral_edge_attr"])
+            pca.append(o["peripheral_configuration_attr"])
+        xs.append(g["x"])
+        ys.append(g.get("y", 0.0))
+        batch.append(np.full(g["num_nodes"], i, dtype=np.int64))
+        off += g["num_nodes"]
+    d = {
+        "num_nodes": off,
+        "num_graphs": len(graphs),
+        "x": torch.from_numpy(np.concatenate(xs)),
+        "y": torch.tensor(ys, dtype=torch.float32),
+        "batch": torch.from_numpy(np.concatenate(batch)),
+        "edge_index": torch.from_numpy(np.concatenate(ei, 1)),
+        "edge_attr": torch.from_numpy(np.concatenate(ea, 0)),
+        "pe_attr": torch.from_numpy(np.concatenate(pe, 0)) if pe else None,
+        "peripheral_edge_attr": torch.from_numpy(np.concatenate(pea, 0)) if pea else None,
+        "peripheral_configuration_attr": torch.from_numpy(np.concatenate(pca, 0)) if pca else None,
+    }
+    return d
+
+
+def zinc_batch(num_graphs, K, kernel="spd", seed=0):
+    return collate(synth.zinc_like_graphs(num_graphs, seed=seed), (K, 50, 6, 3, 50, 50, kernel))

@@ -1,0 +1,119 @@
+"""Autograd binding of the fused K-hop aggregation kernels (kp_agg_forward / kp_agg_backward, include/kpgnn.h).
+
+`khop_aggregate` is the single operator all five drop-in layers call in place of PyG's
+`self.propagate(edge_index, x=..., edge_emb=..., mask=edge_attr)` + update + (optionally) GeometricCombine
+(layers/KPGIN.py:100-105, KPGINplus.py:74-78, KPGCN.py:107-116, KPGraphSAGE.py:86-89, gine.py:52-53).
+PyTorch only provides device memory, the current stream and the autograd graph here.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ACT_GELU, ACT_NONE, ACT_RELU  # noqa: F401
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _make_desc(plan, k, x, P, T0, Tk, theta, eps, act, fuse, use_dinv, use_mean):
+    N, kk, d = x.shape
+    assert kk == k and N == plan.N, (x.shape, k, plan.N)
+    desc = _lib.AggDesc()
+    desc.N, desc.Kplan, desc.k, desc.d = N, plan.K, k, d
+    desc.rowptr, desc.col, desc.attr16 = plan.rowptr.data_ptr(), plan.col.data_ptr(), plan.attr16.data_ptr()
+    desc.rowptrT, desc.colT = plan.rowptrT.data_ptr(), plan.colT.data_ptr()
+    desc.dinv = plan.dinv.data_ptr() if use_dinv else None
+    desc.indeg = plan.indeg.data_ptr() if use_mean else None
+    desc.X, desc.x_node_stride, desc.x_hop_stride = x.data_ptr(), x.stride(0), x.stride(1)
+    if P is not None:
+        desc.P, desc.p_node_stride, desc.p_hop_stride = P.data_ptr(), P.stride(0), P.stride(1)
+    else:
+        desc.P, desc.p_node_stride, desc.p_hop_stride = None, 0, 0
+    desc.T0, desc.Tk = _ptr(T0), _ptr(Tk)
+    desc.rows0 = T0.size(0) if T0 is not None else 0
+    desc.rowsk = Tk.size(0) if Tk is not None else 0
+    desc.theta, desc.eps = _ptr(theta), _ptr(eps)
+    desc.act, desc.fuse = act, 1 if fuse else 0
+    return desc
+
+
+def _prep(t, last_contig=True):
+    """fp32 CUDA tensor whose last dim is dense; other strides are passed to the kernel as they are."""
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        raise TypeError("kpgnn_b200 kernels are fp32 (got %s)" % t.dtype)
+    if t.stride(-1) != 1:
+        t = t.contiguous()
+    return t
+
+
+class _KHopAggregate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, P, T0, Tk, theta, eps, plan, k, act, fuse, use_dinv, use_mean):
+        lib = _lib.lib()
+        if not x.is_cuda:
+            raise _lib.KpError("kpgnn_b200 runs on CUDA tensors only (no CPU fallback); got x on %s" % x.device)
+        x = _prep(x.detach())
+        P_ = _prep(P.detach()) if P is not None else None
+        T0_ = T0.detach().contiguous() if T0 is not None else None
+        Tk_ = Tk.detach().contiguous() if Tk is not None else None
+        th_ = theta.detach().contiguous() if theta is not None else None
+        eps_ = eps.detach().contiguous() if eps is not None else None
+        N, _, d = x.shape
+        if T0_ is not None:
+            plan.check_tables(T0_.size(0), Tk_.size(0) if Tk_ is not None else 0, k)
+        desc = _make_desc(plan, k, x, P_, T0_, Tk_, th_, eps_, act, fuse, use_dinv, use_mean)
+        out = torch.empty((N, d) if fuse else (N, k, d), dtype=torch.float32, device=x.device)
+        st = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+        _lib.check(lib.kp_agg_forward(C.byref(desc), out.data_ptr(), st), "kp_agg_forward")
+        ctx.plan, ctx.cfg = plan, (k, act, fuse, use_dinv, use_mean)
+        # saved by hand (not save_for_backward): x may be a slot of a caller-managed ring buffer whose OTHER
+        # slots are written in place later; version-counter checks on the shared base would be false alarms.
+        ctx.saved = (x, P_, T0_, Tk_, th_, eps_)
+        ctx.p_is_none = P is None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = _lib.lib()
+        x, P_, T0_, Tk_, th_, eps_ = ctx.saved
+        plan = ctx.plan
+        k, act, fuse, use_dinv, use_mean = ctx.cfg
+        need = ctx.needs_input_grad
+        N, _, d = x.shape
+        dout = dout.contiguous()
+        desc = _make_desc(plan, k, x, P_, T0_, Tk_, th_, eps_, act, fuse, use_dinv, use_mean)
+        dev = x.device
+        dX = torch.empty((N, k, d), dtype=torch.float32, device=dev) if need[0] else None
+        dP = None
+        if need[1] and P_ is not None:
+            dP = dout if not fuse else torch.empty((N, k, d), dtype=torch.float32, device=dev)
+        dT0 = torch.empty_like(T0_) if (T0_ is not None and need[2]) else None
+        dTk = torch.empty_like(Tk_) if (Tk_ is not None and need[3]) else None
+        if (dT0 is None) != (dTk is None) and Tk_ is not None:
+            # the kernel produces both tables in one pass; allocate the unwanted one too
+            dT0 = dT0 if dT0 is not None else torch.empty_like(T0_)
+            dTk = dTk if dTk is not None else torch.empty_like(Tk_)
+        dth = torch.empty_like(th_) if (th_ is not None and need[4] and fuse) else None
+        deps = torch.empty_like(eps_) if (eps_ is not None and need[5]) else None
+        nbytes = C.c_size_t(0)
+        _lib.check(lib.kp_agg_backward_workspace_bytes(C.byref(desc), C.byref(nbytes)),
+                   "kp_agg_backward_workspace_bytes")
+        ws = torch.empty(max(nbytes.value, 1), dtype=torch.uint8, device=dev)
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(lib.kp_agg_backward(C.byref(desc), dout.data_ptr(), _ptr(dX),
+                                       _ptr(dP) if fuse else None, _ptr(dT0), _ptr(dTk), _ptr(dth), _ptr(deps),
+                                       ws.data_ptr(), ws.numel(), st), "kp_agg_backward")
+        return (dX, dP, dT0 if need[2] else None, dTk if need[3] else None, dth, deps,
+                None, None, None, None, None, None)
+
+
+def khop_aggregate(x, plan, k, P=None, T0=None, Tk=None, theta=None, eps=None, act=ACT_NONE, fuse=False,
+                   use_dinv=False, use_mean=False):
+    """x [N,k,d] fp32 (any node/hop strides, dense last dim) -> [N,d] if fuse else [N,k,d].  See kpgnn.h."""
+    if fuse and theta is None:
+        raise ValueError("fuse=True needs theta [k,d]")
+    return _KHopAggregate.apply(x, P, T0, Tk, theta, eps, plan, k, act, fuse, use_dinv, use_mean)

@@ -36,9 +36,10 @@ def dense_khop_aggregate(x, edge_index, edge_attr, hop1_table, hopk_table, norm=
     if norm is not None:
         msg = norm.unsqueeze(-1) * msg
     msg = msg.masked_fill(edge_attr.unsqueeze(-1) == 0, 0.)
-    out = torch.zeros((x.size(0),) + tuple(msg.shape[1:]), dtype=msg.dtype).index_add_(0, dst, msg)
+    out = torch.zeros((x.size(0),) + tuple(msg.shape[1:]), dtype=msg.dtype, device=msg.device).index_add_(0, dst, msg)
     if aggr == "mean":
-        cnt = torch.zeros(x.size(0), dtype=msg.dtype).index_add_(0, dst, torch.ones(dst.numel(), dtype=msg.dtype))
+        cnt = torch.zeros(x.size(0), dtype=msg.dtype, device=msg.device).index_add_(
+            0, dst, torch.ones(dst.numel(), dtype=msg.dtype, device=msg.device))
         out = out / cnt.clamp_(min=1).view(-1, 1, 1)
     elif aggr not in ("add", "sum"):
         raise NotImplementedError(aggr)
@@ -61,7 +62,7 @@ class OracleGeometricCombine(nn.Module):
 
     def thetas(self):
         a = torch.sigmoid(self.alphas)
-        powers = torch.arange(self.K, dtype=a.dtype).view(-1, 1)
+        powers = torch.arange(self.K, dtype=a.dtype, device=a.device).view(-1, 1)
         return torch.softmax(a.unsqueeze(0) * (1 - a).unsqueeze(0) ** powers, dim=0)      # [K, d]
 
     def forward(self, x):
@@ -202,12 +203,12 @@ class OracleKPGCNConv(_KHopBase):
 
     def forward(self, x, edge_index, edge_attr, pe_attr=None, peripheral_attr=None):
         n = x.size(0)
-        loops = torch.arange(n, dtype=edge_index.dtype).unsqueeze(0).repeat(2, 1)
+        loops = torch.arange(n, dtype=edge_index.dtype, device=edge_index.device).unsqueeze(0).repeat(2, 1)
         edge_index = torch.cat([edge_index, loops], dim=1)                                  # :85
-        edge_attr = torch.cat([edge_attr, torch.ones(n, self.K, dtype=edge_attr.dtype)], 0)  # :87-89
+        edge_attr = torch.cat([edge_attr, torch.ones(n, self.K, dtype=edge_attr.dtype, device=edge_attr.device)], 0)  # :87-89
         x = self._add_path_encoding(self.hop_proj(x).view(-1, self.K, self.output_dk), pe_attr)
         src, dst = edge_index
-        deg = torch.zeros(n, self.K).index_add_(0, dst, (edge_attr > 0).float())             # :11-25
+        deg = torch.zeros(n, self.K, device=x.device).index_add_(0, dst, (edge_attr > 0).float())   # :11-25
         dis = deg.pow(-0.5)
         norm = dis[src] * dis[dst]
         t1, tk = self._tables()

@@ -9,11 +9,11 @@ from oracle.extract_np import extract_multi_hop_neighbors_np
 RTOL = 1e-5
 
 
-def rel_err(a, b):
+def rel_err(a, b, floor=1e-30):
     """max |a-b| / max(|b|_inf, tiny): the '1e-5 relative' bar is on the tensor scale (fp32 sums of ~20 terms
     cannot be elementwise-relative near zero crossings)."""
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
-    scale = max(b.abs().max().item(), 1e-30)
+    scale = max(b.abs().max().item(), floor)
     return (a - b).abs().max().item() / scale
 
 

@@ -1,0 +1,419 @@
+#!/usr/bin/env python
+"""bench.py -- ZINC-shape KP-GIN+ (K=8, 8 layers, hidden 104, residual) TRAINING graphs/s on N B200s, plus the
+K-hop aggregation kernel's achieved HBM bandwidth against the measured roofline, plus the CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one optimisation step (forward + backward + Adam) over one synthetic batch of 128 ZINC-shaped
+graphs per GPU, extraction outputs in the reference's wire layout (int64 edge_index [2,E_K], edge_attr [E_K,K],
+peripheral attrs).  Ours: the whole step is one CUDA graph; the graph plan is rebuilt from the raw int64 batch
+EVERY step (a new batch arrives every step in training) and that is inside every timed region.
+  value : inputs resident in HBM  -> plan rebuild + graph replay
+  e2e   : inputs in pinned host memory -> H2D copy of the batch + plan rebuild + graph replay + D2H loss
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GRAPHS_PER_GPU = 128
+K, LAYERS, HIDDEN = 8, 8, 104
+EXTRACT_ARGS = (K, 50, 6, 3, 50, 50, "spd")          # train_ZINC.py:124-134
+ROOFLINE_GRAPHS = 8192                               # >= 1 GB of algorithmic bytes per forward call
+METRIC = "ZINC-shape KPGINPlus K=8 L=8 H=104 training throughput"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# workload
+# ----------------------------------------------------------------------------------------------------------------
+def host_batch(num_graphs, seed):
+    """Synthetic ZINC-shaped batch in the reference wire layout, on the host (untimed setup)."""
+    from kpgnn_b200 import synth
+    from kpgnn_b200.model import Batch
+    from kpgnn_b200.data_utils import extract_batch_host
+    graphs = synth.zinc_like_graphs(num_graphs, seed=seed)
+    fields = extract_batch_host(graphs, EXTRACT_ARGS)
+    fields["y"] = torch.tensor([g["y"] for g in graphs], dtype=torch.float32)
+    return Batch(**fields)
+
+
+def peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------------------
+class Trainer(object):
+    """Static-buffer training step captured in one CUDA graph (forward + backward + all-reduce + Adam)."""
+
+    def __init__(self, host, device, world):
+        from kpgnn_b200 import plan as kplan
+        from kpgnn_b200.model import zinc_kpginplus
+        self.kplan = kplan
+        self.world, self.device = world, device
+        torch.manual_seed(0)
+        self.model = zinc_kpginplus(K, LAYERS, HIDDEN).to(device).train()
+        self.host = host.pin_memory()
+        self.dev = self.host.to(device)
+        self.params = [p for p in self.model.parameters() if p.requires_grad]
+        self.flat_grad = torch.zeros(sum(p.numel() for p in self.params), device=device)
+        o = 0
+        for p in self.params:
+            p.grad = self.flat_grad[o:o + p.numel()].view_as(p)
+            o += p.numel()
+        self.opt = torch.optim.Adam(self.params, lr=1e-3, capturable=True, fused=True)   # train_ZINC.py:244
+        self.loss = None
+        self.graph = None
+        self.launches_per_step = 0
+        kplan.deferred_checks(True)
+
+    def _step(self):
+        from kpgnn_b200.model import l1_loss
+        self.flat_grad.zero_()
+        loss = l1_loss(self.model(self.dev), self.dev.y)
+        loss.backward()
+        if self.world > 1:
+            torch.distributed.all_reduce(self.flat_grad)       # one NCCL all-reduce per step over NVLink
+            self.flat_grad.div_(self.world)
+        self.opt.step()
+        return loss.detach()
+
+    def capture(self):
+        from kpgnn_b200 import _lib
+        s = torch.cuda.Stream(self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            for _ in range(3):
+                self._step()
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._step()
+        self.launches_per_step = _lib.launch_count() - n0
+        torch.cuda.synchronize(self.device)
+
+    def plan(self):
+        p, _ = self.kplan.get_plan(self.dev.edge_index, self.dev.edge_attr, self.dev.x.size(0))
+        return p
+
+    def refresh_plan(self):
+        from kpgnn_b200 import _lib
+        n0 = _lib.launch_count()
+        base = self.dev.edge_attr
+        ok = self.kplan.refresh_plan(self.plan(), self.dev.edge_index, base, base.size(1))
+        assert ok
+        return _lib.launch_count() - n0
+
+    def upload(self):
+        n = 0
+        for f in self.host.FIELDS:
+            h, d = getattr(self.host, f), getattr(self.dev, f)
+            if torch.is_tensor(h):
+                d.copy_(h, non_blocking=True)
+                n += h.numel() * h.element_size()
+        return n
+
+    def step_resident(self):
+        n = self.refresh_plan()
+        self.graph.replay()
+        return n
+
+    def step_e2e(self):
+        nbytes = self.upload()
+        self.refresh_plan()
+        self.graph.replay()
+        val = self.loss.item()                       # D2H read of the step's loss (train_ZINC.py:45)
+        self.plan().validate()
+        return nbytes, val
+
+
+def flush_l2(buf):
+    buf.add_(1)
+
+
+def timed_steps(fn, steps, device, flush_buf, dist_on):
+    """Per-step CUDA events on the launching stream; L2 flushed between steps (outside the events)."""
+    times = []
+    st = torch.cuda.current_stream(device)
+    for _ in range(steps):
+        flush_l2(flush_buf)
+        if dist_on:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(device)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(st)
+        fn()
+        b.record(st)
+        torch.cuda.synchronize(device)
+        times.append(a.elapsed_time(b))
+    return times
+
+
+def agg_roofline(device, num_graphs, peak, reps=10):
+    """The dominant kernel (fused K-hop aggregation forward, k=8, d=104, GELU + P + geometric combine) timed
+    alone with CUDA events; algorithmic bytes per SURVEY.md 8(d):
+    4*N*k*d [X] + 4*N*k*d [P] + 4*N*d [out] + 4*(N*k+1) [rowptr] + nnz*(4 [col] + 2 [attr16])."""
+    import ctypes as C
+    from kpgnn_b200 import _lib
+    from kpgnn_b200.ops import _make_desc, ACT_GELU
+    from kpgnn_b200.plan import get_plan
+    hb = host_batch(num_graphs, seed=1000 + num_graphs)
+    ei, ea = hb.edge_index.to(device), hb.edge_attr.to(device)
+    N = hb.x.size(0)
+    plan, k = get_plan(ei, ea, N)
+    g = torch.Generator(device=device).manual_seed(0)
+    x = torch.randn(N, K, HIDDEN, device=device, generator=g)
+    P = torch.randn(N, K, HIDDEN, device=device, generator=g)
+    t0 = torch.randn(5, HIDDEN, device=device, generator=g)
+    tk = torch.randn(52, HIDDEN, device=device, generator=g)
+    th = torch.softmax(torch.randn(K, HIDDEN, device=device, generator=g), 0)
+    out = torch.empty(N, HIDDEN, device=device)
+    desc = _make_desc(plan, k, x, P, t0, tk, th, None, ACT_GELU, True, False, False)
+    lib = _lib.lib()
+    st = torch.cuda.current_stream(device)
+    sp = C.c_void_p(st.cuda_stream)
+    alg = 4 * N * K * HIDDEN * 2 + 4 * N * HIDDEN + 4 * (N * K + 1) + plan.nnz * 6
+    flush = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device=device)     # 256 MB > 126 MB L2
+    ts = []
+    for i in range(reps + 3):
+        flush_l2(flush)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(st)
+        _lib.check(lib.kp_agg_forward(C.byref(desc), out.data_ptr(), sp), "kp_agg_forward")
+        b.record(st)
+        torch.cuda.synchronize(device)
+        if i >= 3:
+            ts.append(a.elapsed_time(b))
+    ms = statistics.mean(ts)
+    achieved = alg / (ms * 1e-3) / 1e9
+    del flush
+    return {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+            "frac": round(achieved / peak, 4), "traffic": None, "kernel": "agg_fwd_kernel<4,GELU,fuse>",
+            "graphs_per_launch": num_graphs, "nodes": N, "nnz": plan.nnz, "algorithmic_bytes": alg,
+            "ms_per_launch": round(ms, 5)}
+
+
+def cpu_baseline(steps=4, warmup=1):
+    """The oracle port of the reference training step (dense [E,k,d] messages, torch CPU), all host threads."""
+    from oracle.model_torch import l1_loss, zinc_oracle_model
+    torch.set_num_threads(os.cpu_count())
+    hb = host_batch(GRAPHS_PER_GPU, seed=0)
+    b = {f: getattr(hb, f) for f in hb.FIELDS}
+    b["num_graphs"] = hb.num_graphs
+    torch.manual_seed(0)
+    model = zinc_oracle_model(K, LAYERS, HIDDEN).train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    ts = []
+    for i in range(warmup + steps):
+        t = time.perf_counter()
+        opt.zero_grad()
+        loss = l1_loss(model(b), b["y"])
+        loss.backward()
+        opt.step()
+        loss.item()
+        if i >= warmup:
+            ts.append(time.perf_counter() - t)
+    return ts
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    ts = cpu_baseline(steps=args.steps, warmup=args.warmup)
+    ms = 1e3 * statistics.mean(ts)
+    val = GRAPHS_PER_GPU / (ms * 1e-3)
+    cores = os.cpu_count()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(val, 2), "unit": "graphs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(1),
+        "cpu_baseline": {"value": round(val, 2), "unit": "graphs/s", "cores": cores, "kind": "port",
+                         "sample": "%d optimisation steps of one 128-graph batch (oracle port of the reference "
+                                   "step, torch CPU, %d threads)" % (args.steps, torch.get_num_threads())},
+        "e2e": {"value": round(val, 2), "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(world):
+    return {"workload": "configs[1]: ZINC-shape synthetic molecules, KPGINPlus K=8 8 layers hidden 104 residual, "
+                        "batch 128 per GPU, spd kernel; forward+backward+Adam(lr 1e-3), L1 loss",
+            "graphs_per_gpu": GRAPHS_PER_GPU, "global_batch": GRAPHS_PER_GPU * world,
+            "parallelism": "dp%d" % world, "l2": "flushed between timed steps (256 MB write)",
+            "plan_rebuilt_every_step": True, "cuda_graph": True}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        if args.steps > 10:
+            args.steps = 10
+        run_reference(args, rank, world)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
+    assert args.warmup >= 3, "timing rules: at least 3 warm-up steps"
+    from kpgnn_b200 import build
+    build.build_library()
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    dist_on = world > 1
+    if dist_on:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.distributed.init_process_group("nccl", device_id=device)
+    peak, peak_src = peak_hbm()
+
+    tr = Trainer(host_batch(GRAPHS_PER_GPU, seed=rank), device, world)
+    tr.capture()
+    flush = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device=device)
+    for _ in range(args.warmup):
+        tr.step_resident()
+    torch.cuda.synchronize(device)
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    plan_launches = tr.refresh_plan()
+    t_res = timed_steps(tr.step_resident, args.steps, device, flush, dist_on)
+    for _ in range(3):
+        tr.step_e2e()
+    h2d = [0]
+
+    def e2e():
+        h2d[0], _ = tr.step_e2e()
+    t_e2e = timed_steps(e2e, args.steps, device, flush, dist_on)
+    clocks = sampler.stop() if rank == 0 else None
+
+    def reduce_max(ms):
+        if not dist_on:
+            return ms
+        t = torch.tensor([ms], device=device, dtype=torch.float64)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return float(t.item())
+    ms_res = reduce_max(statistics.mean(t_res))
+    ms_e2e = reduce_max(statistics.mean(t_e2e))
+    total_graphs = GRAPHS_PER_GPU * world
+
+    roof = roof_small = None
+    cpu = None
+    if rank == 0 and not args.no_roofline:
+        roof_small = agg_roofline(device, GRAPHS_PER_GPU, peak)
+        roof = agg_roofline(device, ROOFLINE_GRAPHS, peak)
+        roof["peak_source"] = peak_src
+        roof["note"] = ("fused K-hop aggregation forward timed alone (CUDA events, L2 flushed) at a launch with "
+                        ">= 1 GB algorithmic bytes as SURVEY.md 8(d) requires; roofline_batch128 is the same kernel "
+                        "at the bench batch (21 MB, L2-resident / launch-bound)")
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ts = cpu_baseline()
+        v = GRAPHS_PER_GPU / statistics.mean(ts)
+        cpu = {"value": round(v, 2), "unit": "graphs/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": "4 optimisation steps (after 1 warm-up) of one 128-graph batch, oracle port of the "
+                         "reference step on torch CPU with %d threads" % torch.get_num_threads()}
+    if dist_on:
+        torch.distributed.barrier()
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": round(total_graphs / (ms_res * 1e-3), 1), "unit": "graphs/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_res, 4),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(world),
+            "e2e": {"value": round(total_graphs / (ms_e2e * 1e-3), 1), "unit": "graphs/s",
+                    "h2d_bytes_per_step": int(h2d[0]), "d2h_bytes_per_step": 4 + 16, "ms_per_step": round(ms_e2e, 4)},
+            "gpu_launches": int((tr.launches_per_step + plan_launches) * args.steps),
+            "gpu_launches_per_step": {"in_cuda_graph": int(tr.launches_per_step), "plan_rebuild": int(plan_launches)},
+            "clocks": clocks, "roofline": roof, "roofline_batch128": roof_small, "cpu_baseline": cpu,
+            "loss": float(tr.loss.item()),
+        }
+        print(json.dumps(line), flush=True)
+    if dist_on:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

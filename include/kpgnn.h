@@ -56,10 +56,13 @@ int kp_plan_count(const kp_plan_input* in, int32_t* rowptr, int32_t* rowptrT, in
                   void* workspace, size_t workspace_bytes, void* stream);
 
 /* Pass 2.  Fills col/attr16 (by dst rows), colT (by src rows; holds dst ids) -- nnz entries each -- and, when
- * self_loops, dinv[N*K].  Deterministic: entries of a row are in ascending edge id, loop entry last. */
+ * self_loops, dinv[N*K].  Deterministic: entries of a row are in ascending edge id, loop entry last.
+ * `capacity` = entries allocated in col/attr16/colT; writes beyond it are dropped, so a caller that refreshes
+ * a plan in place without first reading nnz back (CUDA-graph replay loops) cannot overrun its buffers and
+ * detects the overflow later from stats[0] > capacity. */
 int kp_plan_fill(const kp_plan_input* in, const int32_t* rowptr, const int32_t* rowptrT, int32_t* col,
-                 uint16_t* attr16, int32_t* colT, float* dinv, void* workspace, size_t workspace_bytes,
-                 void* stream);
+                 uint16_t* attr16, int32_t* colT, float* dinv, int32_t capacity, void* workspace,
+                 size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Per-hop masked aggregation with fused epilogue (forward) -- the message/aggregate/update of
@@ -104,6 +107,46 @@ int kp_agg_forward(const kp_agg_desc* desc, float* out, void* stream);
 int kp_agg_backward_workspace_bytes(const kp_agg_desc* desc, size_t* bytes);
 int kp_agg_backward(const kp_agg_desc* desc, const float* dOut, float* dX, float* dP, float* dT0, float* dTk,
                     float* dtheta, float* deps, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Batched K-hop neighbourhood + peripheral-subgraph extraction.  Replaces, for a whole batch of graphs,
+ * data_utils.py:20-107 (extract_multi_hop_neighbors), :110-125 (adj_K_order), :128-162 (get_peripheral_attr),
+ * :165-221 (extract_peripheral_attr_v2) and :224-241 (nx_compute_shortest_path_length).
+ *
+ * Input: the batch's ORIGINAL edges as a CSR by source over global node ids, duplicates merged
+ * (emult = multiplicity, etype = summed edge-type value, as the reference's COO->dense conversions do,
+ * data_utils.py:52-53); graphs are the contiguous node ranges gptr[g]..gptr[g+1]; pair_off[g] = sum of n^2 over
+ * the graphs before g.  The dense hop tensor W (uint16, K * total_pairs entries) is the only large scratch:
+ * W[K*pair_off[g] + (k*n + s)*n + v] = min(walk count, cap), masked to dist(s,v)==k+1 for kernel spd.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t G, N, K;
+  int32_t n_max;                  /* largest graph in the batch (<= 65535) */
+  const int32_t* gptr;            /* [G+1] */
+  const int32_t* node_graph;      /* [N] */
+  const int64_t* pair_off;        /* [G+1] */
+  const int32_t* erow;            /* [N+1] */
+  const int32_t* ecol;            /* [E1] global destination ids, ascending inside a row */
+  const int32_t* emult;           /* [E1] */
+  const int32_t* etype;           /* [E1] */
+  int32_t kernel;                 /* 0 = spd, 1 = gd */
+  int32_t cap;                    /* saturation of the walk counts: max(max_edge_attr_num, 1), <= 65535 */
+  int32_t max_edge_attr_num, max_hop_num, max_edge_type, max_edge_count, max_distance_count;
+  int32_t max_type_value;         /* largest etype in the batch (sizes the histogram) */
+} kp_extract_input;
+
+int kp_extract_workspace_bytes(const kp_extract_input* in, int64_t total_pairs, size_t* hop_bytes,
+                               size_t* scratch_bytes);
+/* Fills W and eptr[N+1] = exclusive scan of the K-hop out-degree of every node; E_K = eptr[N]. */
+int kp_extract_hops(const kp_extract_input* in, uint16_t* W, int32_t* eptr, void* scratch, size_t scratch_bytes,
+                    void* stream);
+/* edge_index [2,E_K] (row 0 = src, row 1 = dst) and edge_attr [E_K,K], int64, in the reference's order. */
+int kp_extract_emit(const kp_extract_input* in, const uint16_t* W, const int32_t* eptr, int64_t* edge_index,
+                    int64_t* edge_attr, int64_t EK, void* stream);
+/* peripheral_edge_attr [N,K,max_edge_type,2] and peripheral_configuration_attr [N,K,max_hop_num+1], int64. */
+int kp_extract_peripheral(const kp_extract_input* in, const uint16_t* W, int64_t* peripheral_edge_attr,
+                          int64_t* peripheral_configuration_attr, void* scratch, size_t scratch_bytes,
+                          void* stream);
 
 #ifdef __cplusplus
 }

@@ -31,6 +31,15 @@ class AggDesc(C.Structure):
                 ("theta", C.c_void_p), ("eps", C.c_void_p), ("act", C.c_int32), ("fuse", C.c_int32)]
 
 
+class ExtractInput(C.Structure):
+    _fields_ = [("G", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("n_max", C.c_int32),
+                ("gptr", C.c_void_p), ("node_graph", C.c_void_p), ("pair_off", C.c_void_p),
+                ("erow", C.c_void_p), ("ecol", C.c_void_p), ("emult", C.c_void_p), ("etype", C.c_void_p),
+                ("kernel", C.c_int32), ("cap", C.c_int32),
+                ("max_edge_attr_num", C.c_int32), ("max_hop_num", C.c_int32), ("max_edge_type", C.c_int32),
+                ("max_edge_count", C.c_int32), ("max_distance_count", C.c_int32), ("max_type_value", C.c_int32)]
+
+
 ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
 
 # name -> (restype, argtypes); must list every symbol include/kpgnn.h declares (tests/test_abi.py checks it)
@@ -42,11 +51,19 @@ _SIGNATURES = {
     "kp_plan_count": (C.c_int, [C.POINTER(PlanInput), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_size_t, C.c_void_p]),
     "kp_plan_fill": (C.c_int, [C.POINTER(PlanInput), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                               C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+                               C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]),
     "kp_agg_forward": (C.c_int, [C.POINTER(AggDesc), C.c_void_p, C.c_void_p]),
     "kp_agg_backward_workspace_bytes": (C.c_int, [C.POINTER(AggDesc), C.POINTER(C.c_size_t)]),
     "kp_agg_backward": (C.c_int, [C.POINTER(AggDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "kp_extract_workspace_bytes": (C.c_int, [C.POINTER(ExtractInput), C.c_int64, C.POINTER(C.c_size_t),
+                                             C.POINTER(C.c_size_t)]),
+    "kp_extract_hops": (C.c_int, [C.POINTER(ExtractInput), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                  C.c_void_p]),
+    "kp_extract_emit": (C.c_int, [C.POINTER(ExtractInput), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_int64, C.c_void_p]),
+    "kp_extract_peripheral": (C.c_int, [C.POINTER(ExtractInput), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_size_t, C.c_void_p]),
 }
 
 _lib = None

@@ -67,7 +67,7 @@ __global__ void plan_scatter_kernel(const int64_t* __restrict__ src, const int64
                                     const int64_t* __restrict__ attr, int64_t attr_stride, int N, int E, int K,
                                     const int* __restrict__ rowptr, const int* __restrict__ rowptrT,
                                     int* __restrict__ cur, int* __restrict__ curT, int* __restrict__ eid,
-                                    int* __restrict__ eidT) {
+                                    int* __restrict__ eidT, int cap) {
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)E * K) return;
   int e = (int)(t / K), h = (int)(t - (long long)e * K);
@@ -76,8 +76,10 @@ __global__ void plan_scatter_kernel(const int64_t* __restrict__ src, const int64
   long long a = attr[(long long)e * attr_stride + h];
   if (a <= 0 || a > 65535) return;
   long long r = d * K + h, rT = s * K + h;
-  eid[rowptr[r] + atomicAdd(&cur[r], 1)] = e;
-  eidT[rowptrT[rT] + atomicAdd(&curT[rT], 1)] = e;
+  int p = rowptr[r] + atomicAdd(&cur[r], 1);
+  int pT = rowptrT[rT] + atomicAdd(&curT[rT], 1);
+  if (p < cap) eid[p] = e;
+  if (pT < cap) eidT[pT] = e;
 }
 
 __device__ __forceinline__ void insertion_sort(int* a, int n) {
@@ -97,10 +99,12 @@ __global__ void plan_emit_kernel(const int64_t* __restrict__ src, const int64_t*
                                  int self_loops, const int* __restrict__ rowptr, const int* __restrict__ rowptrT,
                                  int* __restrict__ eid, int* __restrict__ eidT, int* __restrict__ col,
                                  uint16_t* __restrict__ attr16, int* __restrict__ colT,
-                                 float* __restrict__ dinv) {
+                                 float* __restrict__ dinv, int cap) {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= N * K) return;
   int v = r / K, h = r - v * K;
+  if (dinv) dinv[r] = 1.0f / sqrtf((float)(rowptr[r + 1] - rowptr[r]));
+  if (rowptr[r + 1] > cap || rowptrT[r + 1] > cap) return;   // overflow: reported through stats[0] > capacity
   {
     int b = rowptr[r], e = rowptr[r + 1];
     int n = e - b - (self_loops ? 1 : 0);
@@ -114,7 +118,6 @@ __global__ void plan_emit_kernel(const int64_t* __restrict__ src, const int64_t*
       col[e - 1] = v;
       attr16[e - 1] = 1;
     }
-    if (dinv) dinv[r] = 1.0f / sqrtf((float)(e - b));
   }
   {
     int b = rowptrT[r], e = rowptrT[r + 1];
@@ -179,8 +182,8 @@ int kp_plan_count(const kp_plan_input* in, int32_t* rowptr, int32_t* rowptrT, in
 }
 
 int kp_plan_fill(const kp_plan_input* in, const int32_t* rowptr, const int32_t* rowptrT, int32_t* col,
-                 uint16_t* attr16, int32_t* colT, float* dinv, void* workspace, size_t workspace_bytes,
-                 void* stream) {
+                 uint16_t* attr16, int32_t* colT, float* dinv, int32_t capacity, void* workspace,
+                 size_t workspace_bytes, void* stream) {
   KP_CHECK_ARG(in && rowptr && rowptrT, "kp_plan_fill: null argument");
   const int N = in->N, E = in->E, K = in->K;
   size_t need = 0;
@@ -202,10 +205,10 @@ int kp_plan_fill(const kp_plan_input* in, const int32_t* rowptr, const int32_t* 
   if (total > 0) {
     KP_CHECK_ARG(col && attr16 && colT, "kp_plan_fill: null output");
     KP_LAUNCH(kp::plan_scatter_kernel, kp::ceil_div(total, 256), 256, 0, st, in->src, in->dst, in->attr,
-              in->attr_stride, N, E, K, rowptr, rowptrT, cur, curT, eid, eidT);
+              in->attr_stride, N, E, K, rowptr, rowptrT, cur, curT, eid, eidT, (int)capacity);
   }
   KP_LAUNCH(kp::plan_emit_kernel, kp::ceil_div(rows, 128), 128, 0, st, in->src, in->dst, in->attr,
-            in->attr_stride, N, K, in->self_loops, rowptr, rowptrT, eid, eidT, col, attr16, colT, dinv);
+            in->attr_stride, N, K, in->self_loops, rowptr, rowptrT, eid, eidT, col, attr16, colT, dinv, (int)capacity);
   return 0;
 }
 

@@ -1,0 +1,173 @@
+"""Host-side backbone that drives the hot path for the headline workload:
+KP-GIN+ graph regression = the reference's `GraphRegression(GNNPlus(...))` (models/GNNs.py:238-474,
+models/GraphRegression.py:10-51), restated as one module whose parameter names equal the reference's
+state_dict keys, so a reference checkpoint (or the golden state_dict under tests/golden/) loads unchanged.
+
+This is the CALLER of the path, written from scratch so that bench.py / smoke() have a training step on the GPU
+box where the reference tree does not exist; the reference's own `models/GNNs.py` runs on the same drop-in
+layers unchanged.  Dense pieces (Embedding, Linear, BatchNorm) are library GEMMs on purpose.
+"""
+import torch
+import torch.nn as nn
+
+from .layers.KPGINplus import KPGINPlusConv
+from .layers.KPGIN import KPGINConv
+from .layers.gine import GINEConv
+from .layers.feature_encoder import FeatureConcatEncoder
+from .layers.input_encoder import EmbeddingEncoder
+
+
+class Batch(object):
+    """Collated batch in the reference's wire layout (PyG `Batch.from_data_list`): plain attribute bag."""
+    FIELDS = ("x", "edge_index", "edge_attr", "pe_attr", "peripheral_edge_attr", "peripheral_configuration_attr",
+              "batch", "y")
+
+    def __init__(self, **kw):
+        self.num_graphs = kw.pop("num_graphs")
+        self.num_nodes = kw.pop("num_nodes", None)
+        for f in self.FIELDS:
+            setattr(self, f, kw.get(f))
+
+    def __contains__(self, key):
+        return getattr(self, key, None) is not None
+
+    def to(self, device, non_blocking=False):
+        out = Batch(num_graphs=self.num_graphs, num_nodes=self.num_nodes)
+        for f in self.FIELDS:
+            v = getattr(self, f)
+            setattr(out, f, v.to(device, non_blocking=non_blocking) if torch.is_tensor(v) else v)
+        return out
+
+    def pin_memory(self):
+        out = Batch(num_graphs=self.num_graphs, num_nodes=self.num_nodes)
+        for f in self.FIELDS:
+            v = getattr(self, f)
+            setattr(out, f, v.pin_memory() if torch.is_tensor(v) else v)
+        return out
+
+    def nbytes(self):
+        return sum(getattr(self, f).numel() * getattr(self, f).element_size() for f in self.FIELDS
+                   if torch.is_tensor(getattr(self, f)))
+
+
+class _Norm(nn.Module):
+    """state_dict-compatible with torch_geometric.nn.BatchNorm (`module.*` keys), GNNs.py:324-325."""
+
+    def __init__(self, width):
+        super().__init__()
+        self.module = nn.BatchNorm1d(width)
+
+    def reset_parameters(self):
+        self.module.reset_parameters()
+
+    def forward(self, x):
+        return self.module(x)
+
+
+def segment_sum(x, batch, num_graphs):
+    """global_add_pool (GraphRegression.py:26): deterministic on sorted `batch` would need offsets; index_add
+    is what PyG does and is outside the K-hop path."""
+    return torch.zeros((num_graphs, x.size(1)), dtype=x.dtype, device=x.device).index_add_(0, batch, x)
+
+
+class KPGNNPlusBackbone(nn.Module):
+    """GNNPlus (models/GNNs.py:238-474) for norm_type=Batch, virtual_node=False, use_rd=False."""
+
+    def __init__(self, num_layer, hidden_size, K, input_size, num_hop1_edge, max_pe_num, max_edge_count,
+                 max_hop_num, max_distance_count, combine="geometric", JK="concat", residual=True, drop_prob=0.0):
+        super().__init__()
+        assert num_layer >= K
+        self.num_layer, self.hidden_size, self.K = num_layer, hidden_size, K
+        self.JK, self.residual = JK, residual
+        self.dropout = nn.Dropout(drop_prob)
+        width = (num_layer + 1) * hidden_size if JK == "concat" else hidden_size
+        self.output_proj = nn.Sequential(nn.Linear(width, hidden_size), nn.ReLU(), nn.Dropout(drop_prob))
+        self.init_proj = EmbeddingEncoder(input_size, hidden_size)
+        self.peripheral_edge_embedding = FeatureConcatEncoder([num_hop1_edge + 2, max_edge_count + 1], hidden_size,
+                                                              padding=0)
+        self.pew = nn.Parameter(torch.rand(1))
+        self.peripheral_configuration_embedding = FeatureConcatEncoder(
+            [max_distance_count + 1 for _ in range(max_hop_num + 1)], hidden_size, padding=0)
+        self.pcw = nn.Parameter(torch.rand(1))
+        self.gnns = nn.ModuleList(KPGINPlusConv(hidden_size, hidden_size, min(l, K), num_hop1_edge, max_pe_num,
+                                                combine) for l in range(1, num_layer + 1))
+        self.norms = nn.ModuleList(_Norm(hidden_size) for _ in range(num_layer))
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        self.init_proj.reset_parameters()
+        for m in self.output_proj:
+            if hasattr(m, "reset_parameters"):
+                m.reset_parameters()
+        self.peripheral_edge_embedding.reset_parameters()
+        self.peripheral_configuration_embedding.reset_parameters()
+        nn.init.normal_(self.pew)
+        nn.init.normal_(self.pcw)
+        for g in self.gnns:
+            g.reset_parameters()
+        for n in self.norms:
+            n.reset_parameters()
+
+    def peripheral(self, data, num_nodes, like):
+        """GNNs.py:393-400: integer peripheral attributes -> [N,K,H] floats (tanh gates in GNNPlus)."""
+        P = torch.zeros((num_nodes, self.K, self.hidden_size), device=like.device, dtype=like.dtype)
+        if data.peripheral_edge_attr is not None:
+            P = P + torch.tanh(self.pew) * self.peripheral_edge_embedding(data.peripheral_edge_attr).sum(-2)
+        if data.peripheral_configuration_attr is not None:
+            P = P + torch.tanh(self.pcw) * self.peripheral_configuration_embedding(data.peripheral_configuration_attr)
+        return P
+
+    def forward(self, data):
+        x = self.init_proj(data).squeeze()
+        N = x.size(0)
+        P = self.peripheral(data, N, x)
+        h_list = [x]
+        last_h = x
+        for l in range(self.num_layer):
+            k = min(l + 1, self.K)
+            # newest layer first, GNNs.py:413-418
+            xs = torch.stack([h_list[j] for j in range(l, l - k, -1)], dim=1)
+            pe = data.pe_attr[:, :k - 1] if data.pe_attr is not None else None
+            h = self.gnns[l](xs, data.edge_index, data.edge_attr[:, :k], pe, P[:, :k])
+            h = self.norms[l](h)
+            if l != self.num_layer - 1:
+                h = self.dropout(h)
+            if self.residual:
+                h = h + last_h
+                last_h = h
+            h_list.append(h)
+        if self.JK == "concat":
+            rep = torch.cat(h_list, dim=1)
+        elif self.JK == "last":
+            rep = h_list[-1]
+        elif self.JK == "sum":
+            rep = torch.stack(h_list, 0).sum(0)
+        else:
+            raise ValueError("JK=%r not supported by this backbone" % (self.JK,))
+        return self.output_proj(rep)
+
+
+class KPGNNPlusRegressor(nn.Module):
+    """GraphRegression (models/GraphRegression.py:10-51) with sum pooling over KPGNNPlusBackbone."""
+
+    def __init__(self, **kw):
+        super().__init__()
+        self.embedding_model = KPGNNPlusBackbone(**kw)
+        self.regressor = nn.Linear(self.embedding_model.hidden_size, 1)
+
+    def forward(self, data):
+        h = self.embedding_model(data)
+        return self.regressor(segment_sum(h, data.batch, data.num_graphs)).squeeze()
+
+
+def zinc_kpginplus(K=8, num_layer=8, hidden=104, combine="geometric"):
+    """train_ZINC.py defaults: hidden 104, K 8, 8 layers, max_pe_num 50, 3 edge types, max_edge_count 50,
+    max_hop_num 6, max_distance_count 50, JK concat, BatchNorm, sum pooling, residual (README.md:127)."""
+    return KPGNNPlusRegressor(num_layer=num_layer, hidden_size=hidden, K=K, input_size=21, num_hop1_edge=3,
+                              max_pe_num=50, max_edge_count=50, max_hop_num=6, max_distance_count=50,
+                              combine=combine, JK="concat", residual=True, drop_prob=0.0)
+
+
+def l1_loss(score, y):
+    """train_ZINC.py:42"""
+    return (score.squeeze() - y.squeeze()).abs().mean()

@@ -6,6 +6,11 @@ Host-side wrapper over kp_plan_count / kp_plan_fill (include/kpgnn.h).  The refe
 cached ON the `edge_index` tensor object, which `models/GNNs.py` hands unchanged to every layer
 (GNNs.py:190,429,655,679); the column-sliced views `edge_attr[:, :k]` (GNNs.py:429,679) all resolve to the plan
 of their base tensor, which serves every k <= K.
+
+Static-buffer training loops (CUDA graphs) copy each new batch into the SAME device tensors; the cached plan is
+then refreshed IN PLACE (same addresses, so captured graphs stay valid).  With `deferred_checks(True)` the
+refresh does not read nnz back before filling -- the fill kernel drops writes beyond the allocated capacity --
+and `GraphPlan.validate()` raises at the caller's next sync point instead.
 """
 import ctypes as C
 
@@ -13,10 +18,18 @@ import torch
 
 from . import _lib
 
+_DEFERRED = False
+
+
+def deferred_checks(flag):
+    """True: in-place plan refreshes skip the host sync and validate lazily (see module docstring)."""
+    global _DEFERRED
+    _DEFERRED = bool(flag)
+
 
 class GraphPlan(object):
-    __slots__ = ("N", "E", "K", "nnz", "self_loops", "rowptr", "col", "attr16", "rowptrT", "colT", "dinv", "indeg",
-                 "max_attr0", "max_attrk", "device")
+    __slots__ = ("N", "E", "K", "nnz", "capacity", "self_loops", "rowptr", "col", "attr16", "rowptrT", "colT", "dinv",
+                 "indeg", "max_attr0", "max_attrk", "device", "stats", "stats_host", "ws", "pending", "src", "dst")
 
     def check_tables(self, rows0, rowsk, k):
         """nn.Embedding would raise IndexError on an out-of-range attr (KPGIN.py:90,95); so do we."""
@@ -25,53 +38,105 @@ class GraphPlan(object):
         if k > 1 and self.max_attrk >= rowsk:
             raise IndexError("edge_attr[:,1:] has value %d but hopk_edge_emb has %d rows" % (self.max_attrk, rowsk))
 
+    def validate(self):
+        """Completes a deferred refresh: waits for its statistics and raises on overflow / bad indices."""
+        if self.pending is None:
+            return
+        self.pending.synchronize()
+        self.pending = None
+        nnz, m0, mk, bad = self.stats_host.tolist()
+        if bad:
+            raise IndexError("edge_index / edge_attr out of range in %d entries" % bad)
+        if nnz > self.capacity:
+            raise _lib.KpError("in-place plan refresh overflowed: nnz %d > capacity %d" % (nnz, self.capacity))
+        if m0 > self.max_attr0 or mk > self.max_attrk:
+            raise IndexError("refreshed batch has edge attrs (%d,%d) above those the plan was validated for (%d,%d)"
+                             % (m0, mk, self.max_attr0, self.max_attrk))
+        self.nnz = nnz
+
 
 def _stream_ptr(device):
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+def _run_count(p, pin):
+    lib = _lib.lib()
+    _lib.check(lib.kp_plan_count(C.byref(pin), p.rowptr.data_ptr(), p.rowptrT.data_ptr(), p.indeg.data_ptr(),
+                                 p.stats.data_ptr(), p.ws.data_ptr(), p.ws.numel(), _stream_ptr(p.device)),
+               "kp_plan_count")
+
+
+def _run_fill(p, pin):
+    lib = _lib.lib()
+    _lib.check(lib.kp_plan_fill(C.byref(pin), p.rowptr.data_ptr(), p.rowptrT.data_ptr(), p.col.data_ptr(),
+                                p.attr16.data_ptr(), p.colT.data_ptr(),
+                                p.dinv.data_ptr() if p.self_loops else None, p.capacity, p.ws.data_ptr(),
+                                p.ws.numel(), _stream_ptr(p.device)), "kp_plan_fill")
+
+
+def _plan_input(p, edge_index, edge_attr_base, attr_stride):
+    p.src = edge_index[0].contiguous()
+    p.dst = edge_index[1].contiguous()
+    return _lib.PlanInput(p.src.data_ptr(), p.dst.data_ptr(), edge_attr_base.data_ptr(), attr_stride, p.N, p.E, p.K,
+                          1 if p.self_loops else 0)
+
+
 def build_plan(edge_index, edge_attr_base, attr_stride, K, num_nodes, self_loops=False):
     """edge_index [2,E] int64 cuda; edge_attr_base: int64 cuda tensor whose element (e,h) lives at
-    data_ptr + 8*(e*attr_stride + h) for h < K."""
+    data_ptr + 8*(e*attr_stride + h) for h < K.  One host sync (reads nnz to size the compact arrays)."""
     lib = _lib.lib()
     if not edge_index.is_cuda:
         raise _lib.KpError("kpgnn_b200 runs on CUDA tensors only (no CPU fallback); got edge_index on %s"
                            % edge_index.device)
     assert edge_index.dtype == torch.int64 and edge_attr_base.dtype == torch.int64
     dev = edge_index.device
-    E = edge_index.size(1)
-    N = int(num_nodes)
-    src = edge_index[0].contiguous()
-    dst = edge_index[1].contiguous()
-    rows = N * K
-    pin = _lib.PlanInput(src.data_ptr(), dst.data_ptr(), edge_attr_base.data_ptr(), attr_stride, N, E, K,
-                         1 if self_loops else 0)
-    nbytes = C.c_size_t(0)
-    _lib.check(lib.kp_plan_workspace_bytes(N, E, K, C.byref(nbytes)), "kp_plan_workspace_bytes")
-    ws = torch.empty(max(nbytes.value, 1), dtype=torch.uint8, device=dev)
     p = GraphPlan()
-    p.N, p.E, p.K, p.self_loops, p.device = N, E, K, bool(self_loops), dev
+    p.N, p.E, p.K, p.self_loops, p.device = int(num_nodes), edge_index.size(1), K, bool(self_loops), dev
+    p.pending = None
+    rows = p.N * K
+    nbytes = C.c_size_t(0)
+    _lib.check(lib.kp_plan_workspace_bytes(p.N, p.E, K, C.byref(nbytes)), "kp_plan_workspace_bytes")
+    p.ws = torch.empty(max(nbytes.value, 1), dtype=torch.uint8, device=dev)
     p.rowptr = torch.empty(rows + 1, dtype=torch.int32, device=dev)
     p.rowptrT = torch.empty(rows + 1, dtype=torch.int32, device=dev)
-    p.indeg = torch.empty(max(N, 1), dtype=torch.int32, device=dev)
-    stats = torch.empty(4, dtype=torch.int32, device=dev)
-    st = _stream_ptr(dev)
-    _lib.check(lib.kp_plan_count(C.byref(pin), p.rowptr.data_ptr(), p.rowptrT.data_ptr(), p.indeg.data_ptr(),
-                                 stats.data_ptr(), ws.data_ptr(), ws.numel(), st), "kp_plan_count")
-    nnz, p.max_attr0, p.max_attrk, bad = stats.tolist()          # the one host sync per batch
+    p.indeg = torch.empty(max(p.N, 1), dtype=torch.int32, device=dev)
+    p.stats = torch.empty(4, dtype=torch.int32, device=dev)
+    p.stats_host = torch.empty(4, dtype=torch.int32, pin_memory=True)
+    p.dinv = torch.empty(max(rows, 1), dtype=torch.float32, device=dev) if self_loops else None
+    pin = _plan_input(p, edge_index, edge_attr_base, attr_stride)
+    _run_count(p, pin)
+    nnz, p.max_attr0, p.max_attrk, bad = p.stats.tolist()          # the one host sync per batch
     if bad:
         raise IndexError("edge_index / edge_attr out of range in %d entries (node ids must be in [0,%d), "
-                         "attrs in [0,65535])" % (bad, N))
-    p.nnz = nnz
+                         "attrs in [0,65535])" % (bad, p.N))
+    p.nnz = p.capacity = nnz
     p.col = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
     p.colT = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
     p.attr16 = torch.empty(max(nnz, 1), dtype=torch.int16, device=dev)
-    p.dinv = torch.empty(max(rows, 1), dtype=torch.float32, device=dev) if self_loops else None
-    _lib.check(lib.kp_plan_fill(C.byref(pin), p.rowptr.data_ptr(), p.rowptrT.data_ptr(), p.col.data_ptr(),
-                                p.attr16.data_ptr(), p.colT.data_ptr(),
-                                p.dinv.data_ptr() if self_loops else None, ws.data_ptr(), ws.numel(), st),
-               "kp_plan_fill")
+    _run_fill(p, pin)
     return p
+
+
+def refresh_plan(p, edge_index, edge_attr_base, attr_stride):
+    """Rebuild `p` in place for new contents of the same-shaped tensors.  Returns False if the new batch does
+    not fit (caller then builds a fresh plan)."""
+    pin = _plan_input(p, edge_index, edge_attr_base, attr_stride)
+    _run_count(p, pin)
+    if _DEFERRED:
+        _run_fill(p, pin)
+        p.stats_host.copy_(p.stats, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(p.device))
+        p.pending = ev
+        return True
+    nnz, m0, mk, bad = p.stats.tolist()
+    if bad:
+        raise IndexError("edge_index / edge_attr out of range in %d entries" % bad)
+    if nnz > p.capacity:
+        return False
+    p.nnz, p.max_attr0, p.max_attrk = nnz, m0, mk
+    _run_fill(p, pin)
+    return True
 
 
 def _attr_base(edge_attr):
@@ -93,7 +158,8 @@ def get_plan(edge_index, edge_attr, num_nodes, self_loops=False):
     """Cached plan lookup.  Returns (plan, k) where k = edge_attr.size(1) hops of the plan are in use."""
     k = edge_attr.size(1) if edge_attr.dim() == 2 else 1
     base, stride, K = _attr_base(edge_attr)
-    key = (base.data_ptr(), base._version, stride, K, int(num_nodes), bool(self_loops), edge_index._version)
+    key = (base.data_ptr(), stride, K, int(num_nodes), bool(self_loops), edge_index.size(1))
+    versions = (base._version, edge_index._version)
     cache = getattr(edge_index, "_kpgnn_plans", None)
     if cache is None:
         cache = {}
@@ -102,7 +168,14 @@ def get_plan(edge_index, edge_attr, num_nodes, self_loops=False):
         except Exception:      # pragma: no cover - tensors always accept attributes
             pass
     hit = cache.get(key)
+    if hit is not None and hit[2] != versions:
+        # same tensors, new contents (static-buffer loop): refresh in place so captured graphs stay valid
+        if torch.cuda.is_current_stream_capturing() or not refresh_plan(hit[0], edge_index, base, stride):
+            hit = None
+        else:
+            hit = (hit[0], base, versions)
+            cache[key] = hit
     if hit is None:
-        hit = (build_plan(edge_index, base, stride, K, num_nodes, self_loops), base)   # keep base alive
+        hit = (build_plan(edge_index, base, stride, K, num_nodes, self_loops), base, versions)   # keeps base alive
         cache[key] = hit
     return hit[0], k

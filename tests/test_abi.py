@@ -1,0 +1,57 @@
+"""CPU-only: the C-ABI library builds for sm_100a, loads, and exports every symbol include/kpgnn.h declares.
+No compute calls are made (there is no GPU here)."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    names = set()
+    for fn in os.listdir(os.path.join(ROOT, "include")):
+        if fn.endswith(".h"):
+            src = open(os.path.join(ROOT, "include", fn)).read()
+            src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+            names |= set(re.findall(r"\b(kp_[a-z0-9_]+)\s*\(", src))
+    return names
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from kpgnn_b200 import _lib
+    declared = _declared()
+    assert len(declared) >= 8
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(handle, name), "missing export " + name
+    # and the Python binding covers them all
+    assert declared == set(_lib._SIGNATURES.keys())
+
+
+def test_abi_version_and_error_string(lib):
+    assert lib.kp_abi_version() == 1
+    assert isinstance(lib.kp_last_error(), bytes)
+    assert lib.kp_launch_count() >= 0
+
+
+def test_argument_validation_without_gpu(lib):
+    """Entry points reject bad descriptors before touching the device."""
+    import ctypes as C
+    from kpgnn_b200 import _lib
+    n = C.c_size_t(0)
+    assert lib.kp_plan_workspace_bytes(10, 20, 0, C.byref(n)) != 0
+    assert b"bad arguments" in lib.kp_last_error()
+    assert lib.kp_plan_workspace_bytes(10, 20, 3, C.byref(n)) == 0 and n.value > 0
+    d = _lib.AggDesc()
+    assert lib.kp_agg_forward(C.byref(d), None, None) != 0
+
+
+def test_product_never_imports_oracle():
+    bad = []
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "kpgnn_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M):
+                    bad.append(os.path.join(dirpath, f))
+    assert not bad, bad

@@ -1,0 +1,122 @@
+"""GPU parity of the product path against the REFERENCE's own outputs (tests/golden/*.npz, produced by running
+/root/reference unmodified on the CPU in the build container, oracle/make_golden.py).
+Bar: 1e-5 relative, fp32 (north_star); gradients get 5e-5 because GPU GEMM/BatchNorm reductions downstream of
+the kernels run in a different order than the CPU reference's."""
+import numpy as np
+import pytest
+import torch
+
+from tests import golden_util as GU
+from tests.util import rel_err
+
+pytestmark = pytest.mark.gpu
+
+torch.backends.cuda.matmul.allow_tf32 = False
+torch.backends.cudnn.allow_tf32 = False
+NOISE_ONLY = ("mlp.0.bias", "mlp.3.bias")
+
+
+def _product_layers():
+    from kpgnn_b200.layers.KPGIN import KPGINConv
+    from kpgnn_b200.layers.KPGINplus import KPGINPlusConv
+    from kpgnn_b200.layers.KPGCN import KPGCNConv
+    from kpgnn_b200.layers.KPGraphSAGE import KPGraphSAGEConv
+    from kpgnn_b200.layers.gine import GINEConv
+    return {"KPGINConv": KPGINConv, "KPGINPlusConv": KPGINPlusConv, "KPGCNConv": KPGCNConv,
+            "KPGraphSAGEConv": KPGraphSAGEConv, "GINEConv": GINEConv}
+
+
+_Z, _META = GU.load("layers.npz")
+
+
+@pytest.mark.parametrize("idx", range(len(_META)), ids=[m["name"] for m in _META])
+def test_layer_matches_reference_golden(lib, idx):
+    m = _META[idx]
+    c = GU.layer_case(_Z, idx)
+    dev = torch.device("cuda:0")
+    layer = GU.build_layer(m["ctor"], _product_layers())
+    layer.load_state_dict(c["sd"])              # the reference's state_dict loads unchanged
+    layer = layer.to(dev).train()
+    x = c["x"].to(dev).requires_grad_(True)
+    P = c["P"].to(dev).requires_grad_(True) if "P" in c else None
+    ei, ea = c["edge_index"].to(dev), c["edge_attr"].to(dev)
+    if m["gine"]:
+        y = layer(x * 1.0, ei, ea[:, :1])
+    else:
+        pe = c["pe"].to(dev) if "pe" in c else None
+        y = layer(x * 1.0, ei, ea, pe, P)
+    y.backward(c["gy"].to(dev))
+    assert rel_err(y, c["y"]) < 1e-5, ("forward", rel_err(y, c["y"]))
+    assert rel_err(x.grad, c["gx"]) < 5e-5, ("dx", rel_err(x.grad, c["gx"]))
+    if P is not None:
+        assert rel_err(P.grad, c["gP"]) < 5e-5, ("dP", rel_err(P.grad, c["gP"]))
+    gmax = max(float(v.abs().max()) for v in c["gp"].values())
+    for n, p in layer.named_parameters():
+        if n not in c["gp"]:
+            continue
+        ref = c["gp"][n]
+        if p.grad is None:
+            assert float(ref.abs().max()) == 0.0, n
+        elif n in NOISE_ONLY:
+            assert float((p.grad.cpu() - ref).abs().max()) < 1e-4 * gmax, n
+        else:
+            err = rel_err(p.grad, ref, floor=1e-3 * gmax)
+            assert err < 5e-5, (n, err)
+
+
+def test_model_matches_reference_golden(lib):
+    """GraphRegression(GNNPlus(KPGINPlus K=8 L=8 H=104)): the reference's state_dict loads into the product
+    backbone unchanged; score, loss and every parameter gradient match the reference's."""
+    from kpgnn_b200.model import Batch, l1_loss, zinc_kpginplus
+    z, _ = GU.load("model_zinc.npz")
+    dev = torch.device("cuda:0")
+    model = zinc_kpginplus()
+    missing = model.load_state_dict({k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd_")})
+    assert not missing.missing_keys and not missing.unexpected_keys
+    model = model.to(dev).train()
+    fields = {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("b_")}
+    b = Batch(num_graphs=int(fields["batch"].max()) + 1, **fields).to(dev)
+    score = model(b)
+    loss = l1_loss(score, b.y)
+    loss.backward()
+    assert rel_err(score, torch.from_numpy(z["score"])) < 1e-5
+    assert abs(loss.item() - float(z["loss"])) < 1e-5 * abs(float(z["loss"]))
+    gmax = max(float(np.abs(z[k]).max()) for k in z.files if k.startswith("gp_"))
+    worst = 0.0
+    for n, p in model.named_parameters():
+        ref = torch.from_numpy(z["gp_" + n])
+        g = p.grad if p.grad is not None else torch.zeros_like(ref)
+        worst = max(worst, rel_err(g, ref, floor=1e-2 * gmax))
+    assert worst < 5e-5, worst
+
+
+def test_determinism_bitwise(lib):
+    """Two runs of forward+backward on the same inputs give bit-identical outputs and gradients (no float
+    atomics anywhere on the K-hop path)."""
+    from kpgnn_b200.layers.KPGINplus import KPGINPlusConv
+    from tests.util import zinc_batch
+    dev = torch.device("cuda:0")
+    torch.manual_seed(3)
+    b = zinc_batch(16, 8, "spd", seed=9)
+    N = b["num_nodes"]
+    layer = KPGINPlusConv(104, 104, 8, 3, 50, "geometric").to(dev).train()
+    x0 = torch.randn(N, 8, 104, device=dev)
+    P0 = torch.randn(N, 8, 104, device=dev)
+    ei, ea = b["edge_index"].to(dev), b["edge_attr"].to(dev)
+    from kpgnn_b200.ops import khop_aggregate, ACT_GELU
+    from kpgnn_b200.plan import get_plan
+    res = []
+    for _ in range(2):
+        x = x0.clone().requires_grad_(True)
+        P = P0.clone().requires_grad_(True)
+        t0 = layer.hop1_edge_emb.weight.detach().clone().requires_grad_(True)
+        tk = layer.hopk_edge_emb.weight.detach().clone().requires_grad_(True)
+        th = torch.softmax(torch.randn(8, 104, device=dev, generator=torch.Generator(dev).manual_seed(1)), 0)
+        th.requires_grad_(True)
+        ei2 = ei.clone()   # fresh plan each time
+        plan, k = get_plan(ei2, ea, N)
+        y = khop_aggregate(x, plan, k, P=P, T0=t0, Tk=tk, theta=th, act=ACT_GELU, fuse=True)
+        y.backward(torch.ones_like(y))
+        res.append([t.detach().clone() for t in (y, x.grad, P.grad, t0.grad, tk.grad, th.grad)])
+    for a, c in zip(*res):
+        assert torch.equal(a, c)

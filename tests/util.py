@@ -17,10 +17,22 @@ def rel_err(a, b, floor=1e-30):
     return (a - b).abs().max().item() / scale
 
 
+def _extract_or_empty(g, a):
+    """Edgeless graphs cannot be collated by the reference (its E=0 branch sets differently named fields,
+    data_utils.py:37-44); inside a batch they contribute no K-hop edges and all-zero peripheral rows."""
+    if np.asarray(g["edge_index"]).reshape(2, -1).shape[1]:
+        return extract_multi_hop_neighbors_np(g["num_nodes"], g["edge_index"], g["edge_attr"], *a)
+    n, K, H, MET = g["num_nodes"], a[0], a[2], a[3]
+    periph = H > 0 and MET > 0
+    return {"edge_index": np.zeros((2, 0), dtype=np.int64), "edge_attr": np.zeros((0, K), dtype=np.int64),
+            "pe_attr": np.zeros((n, K - 1), dtype=np.int64) if K > 1 else None,
+            "peripheral_edge_attr": np.zeros((n, K, MET, 2), dtype=np.int64) if periph else None,
+            "peripheral_configuration_attr": np.zeros((n, K, H + 1), dtype=np.int64) if periph else None}
+
+
 def collate(graphs, extract_args):
     """PyG Batch.from_data_list semantics on oracle-extracted graphs -> dict of CPU tensors."""
-    outs = [extract_multi_hop_neighbors_np(g["num_nodes"], g["edge_index"], g["edge_attr"], *extract_args)
-            for g in graphs]
+    outs = [_extract_or_empty(g, extract_args) for g in graphs]
     off = 0
     ei, ea, pe, pea, pca, xs, batch, ys = [], [], [], [], [], [], [], []
     for i, (g, o) in enumerate(zip(graphs, outs)):

@@ -325,6 +325,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--roofline-only", type=int, default=0, metavar="GRAPHS",
+                    help="profiling helper: only time the aggregation kernel on GRAPHS graphs and exit")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -348,6 +350,9 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.distributed.init_process_group("nccl", device_id=device)
     peak, peak_src = peak_hbm()
+    if args.roofline_only:
+        print(json.dumps(agg_roofline(device, args.roofline_only, peak, reps=3)), flush=True)
+        return
 
     tr = Trainer(host_batch(GRAPHS_PER_GPU, seed=rank), device, world)
     tr.capture()

@@ -95,6 +95,9 @@ typedef struct {
 } kp_agg_desc;
 
 int kp_agg_forward(const kp_agg_desc* desc, float* out, void* stream);
+/* Test hook: non-zero routes every call through the generic (any width / alignment / stride) kernels instead of
+ * the float4 fast path, so both implementations are parity-tested on the same inputs.  Process-wide. */
+int kp_agg_set_force_generic(int flag);
 
 /* Backward of kp_agg_forward (autograd of the same reference lines).  Deterministic, no float atomics:
  * transposed-CSR gather for dX, owner-computes partial tables for dT0/dTk, per-CTA partials for dtheta/deps.

@@ -13,79 +13,10 @@
 //   B2 (src rows)  dX = wsrc * sum over the transposed CSR of Gs  (+ self term)
 //   B3 (rows)      dT0/dTk by owner-computes partial tables in shared memory, then a fixed-order reduction
 // HBM-bound gather work: no tensor cores on purpose.
-#include "common.cuh"
+#include "agg_common.cuh"
+#include "agg_fast.cuh"
 
 namespace kp {
-
-template <int VEC>
-struct Vf {
-  float v[VEC];
-};
-
-template <int VEC>
-__device__ __forceinline__ Vf<VEC> vload(const float* __restrict__ p);
-template <>
-__device__ __forceinline__ Vf<4> vload<4>(const float* __restrict__ p) {
-  float4 t = __ldg(reinterpret_cast<const float4*>(p));
-  return Vf<4>{{t.x, t.y, t.z, t.w}};
-}
-template <>
-__device__ __forceinline__ Vf<2> vload<2>(const float* __restrict__ p) {
-  float2 t = __ldg(reinterpret_cast<const float2*>(p));
-  return Vf<2>{{t.x, t.y}};
-}
-template <>
-__device__ __forceinline__ Vf<1> vload<1>(const float* __restrict__ p) {
-  return Vf<1>{{__ldg(p)}};
-}
-// streaming variants for data touched exactly once (P, dOut, outputs): keep L1/L2 for the gathered rows
-template <int VEC>
-__device__ __forceinline__ Vf<VEC> vload_stream(const float* __restrict__ p);
-template <>
-__device__ __forceinline__ Vf<4> vload_stream<4>(const float* __restrict__ p) {
-  float4 t = __ldcs(reinterpret_cast<const float4*>(p));
-  return Vf<4>{{t.x, t.y, t.z, t.w}};
-}
-template <>
-__device__ __forceinline__ Vf<2> vload_stream<2>(const float* __restrict__ p) {
-  float2 t = __ldcs(reinterpret_cast<const float2*>(p));
-  return Vf<2>{{t.x, t.y}};
-}
-template <>
-__device__ __forceinline__ Vf<1> vload_stream<1>(const float* __restrict__ p) {
-  return Vf<1>{{__ldcs(p)}};
-}
-template <int VEC>
-__device__ __forceinline__ void vstore(float* __restrict__ p, const Vf<VEC>& x);
-template <>
-__device__ __forceinline__ void vstore<4>(float* __restrict__ p, const Vf<4>& x) {
-  *reinterpret_cast<float4*>(p) = make_float4(x.v[0], x.v[1], x.v[2], x.v[3]);
-}
-template <>
-__device__ __forceinline__ void vstore<2>(float* __restrict__ p, const Vf<2>& x) {
-  *reinterpret_cast<float2*>(p) = make_float2(x.v[0], x.v[1]);
-}
-template <>
-__device__ __forceinline__ void vstore<1>(float* __restrict__ p, const Vf<1>& x) {
-  *p = x.v[0];
-}
-
-template <int ACT>
-__device__ __forceinline__ float act_fwd(float x) {
-  if (ACT == KP_ACT_GELU) return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));  // exact-erf GELU
-  if (ACT == KP_ACT_RELU) return x > 0.f ? x : 0.f;
-  return x;
-}
-template <int ACT>
-__device__ __forceinline__ float act_bwd(float x) {
-  if (ACT == KP_ACT_GELU) {
-    float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
-    float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
-    return cdf + x * pdf;
-  }
-  if (ACT == KP_ACT_RELU) return x > 0.f ? 1.f : 0.f;
-  return 1.f;
-}
 
 struct AggArgs {
   kp_agg_desc d;
@@ -438,7 +369,13 @@ struct Config {
   int cw, rl, grid_b3, rows_per_block;
   size_t smem_b3;
   bool table_atomic;
+  // fast float4 path (agg_fast.cuh)
+  bool fast, tsmem;
+  int fG, fgrid, fgrid_b1, stage_floats;   // stage_floats = tables (+ theta) staged in smem, in floats
+  size_t fsmem_fwd;
 };
+
+static int g_force_generic = 0;   // test hook (kp_agg_set_force_generic): exercise the generic kernels
 
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 static bool aligned8(const void* p) { return ((uintptr_t)p & 7) == 0; }
@@ -476,6 +413,25 @@ static int make_config(const kp_agg_desc& a, Config* c) {
   const int dpad = ((a.d + G * c->vec - 1) / (G * c->vec)) * (G * c->vec);
   c->smem_b1 = sizeof(float) * (size_t)gpb * a.k * dpad;
   c->need_gs = (a.act != KP_ACT_NONE) || a.fuse || a.dinv || a.indeg;
+  // fast path eligibility
+  const long long lim = 0x7fffffffLL;
+  c->fast = !g_force_generic && c->vec == 4 && a.d <= 128 && a.x_node_stride <= lim && a.x_hop_stride <= lim &&
+            (!a.P || (a.p_node_stride <= lim && a.p_hop_stride <= lim)) && (long long)a.k * a.d <= lim;
+  if (c->fast) {
+    int fl = a.d / 4, fG = 4;
+    while (fG < fl) fG <<= 1;
+    c->fG = fG;
+    const int fgpb = 256 / fG;
+    const long long fwant = ((long long)a.N + fgpb - 1) / fgpb;
+    c->fgrid = (int)(fwant < 1 ? 1 : (fwant > kNumSMs * 4 ? kNumSMs * 4 : fwant));
+    c->fgrid_b1 = (int)(fwant < 1 ? 1 : (fwant > kNumSMs * 3 ? kNumSMs * 3 : fwant));
+    const long long tabf = a.T0 ? (long long)(a.rows0 + a.rowsk) * a.d : 0;
+    c->tsmem = a.T0 && tabf * 4 <= 56 * 1024;
+    c->stage_floats = (int)((c->tsmem ? tabf : 0) + (a.fuse ? a.k * a.d : 0));
+    c->fsmem_fwd = sizeof(float) * (size_t)c->stage_floats;
+    c->grid_b1 = c->fgrid_b1;
+    c->smem_b1 = sizeof(float) * ((size_t)c->stage_floats + (size_t)fgpb * a.k * 4 * fG);
+  }
   // table pass
   const int trows = a.T0 ? a.rows0 + (a.k > 1 ? a.rowsk : 0) : 0;
   c->cw = lanes;
@@ -543,6 +499,61 @@ static int launch_b1(const AggArgs& args, const Config& c, const float* dOut, fl
   return 0;
 }
 
+
+// ---- fast-path launchers (agg_fast.cuh) ----
+static FastArgs make_fast_args(const kp_agg_desc& a, const Config& c) {
+  FastArgs fa;
+  fa.d = a;
+  fa.xs = (int)a.x_node_stride;
+  fa.xh = (int)a.x_hop_stride;
+  fa.ps = (int)a.p_node_stride;
+  fa.ph = (int)a.p_hop_stride;
+  fa.tab_floats = c.tsmem ? (a.rows0 + a.rowsk) * a.d : 0;
+  return fa;
+}
+
+template <int G, int ACT, bool FUSE, bool TSMEM>
+static int launch_fwd_fast(const FastArgs& fa, const Config& c, float* out, cudaStream_t st) {
+  if (c.fsmem_fwd > 48 * 1024)
+    KP_CUDA(cudaFuncSetAttribute(agg_fwd_fast_kernel<G, ACT, FUSE, TSMEM>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.fsmem_fwd));
+  KP_LAUNCH((agg_fwd_fast_kernel<G, ACT, FUSE, TSMEM>), c.fgrid, 256, c.fsmem_fwd, st, fa, out);
+  return 0;
+}
+
+template <int G, int ACT, bool FUSE, bool TSMEM>
+static int launch_b1_fast(const FastArgs& fa, const Config& c, const float* dOut, float* Gs, float* dP, float* dth,
+                          float* dep, cudaStream_t st) {
+  const size_t smem = dth ? c.smem_b1 : c.fsmem_fwd;
+  if (smem > 48 * 1024)
+    KP_CUDA(cudaFuncSetAttribute(agg_bwd_dst_fast_kernel<G, ACT, FUSE, TSMEM>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  KP_LAUNCH((agg_bwd_dst_fast_kernel<G, ACT, FUSE, TSMEM>), c.fgrid_b1, 256, smem, st, fa, dOut, Gs, dP, dth, dep,
+            c.stage_floats);
+  return 0;
+}
+
+template <int G>
+static int launch_b2_fast(const FastArgs& fa, const Config& c, const float* Gs, const float* dOut, float* dX,
+                          cudaStream_t st) {
+  if (fa.d.fuse) KP_LAUNCH((agg_bwd_src_fast_kernel<G, true>), c.fgrid, 256, 0, st, fa, Gs, dOut, dX);
+  else           KP_LAUNCH((agg_bwd_src_fast_kernel<G, false>), c.fgrid, 256, 0, st, fa, Gs, dOut, dX);
+  return 0;
+}
+
+#define KP_FAST_T(FN, G, A, F, tsmem, ...) ((tsmem) ? FN<G, A, F, true>(__VA_ARGS__) : FN<G, A, F, false>(__VA_ARGS__))
+#define KP_FAST_F(FN, G, A, fuse, tsmem, ...) \
+  ((fuse) ? KP_FAST_T(FN, G, A, true, tsmem, __VA_ARGS__) : KP_FAST_T(FN, G, A, false, tsmem, __VA_ARGS__))
+#define KP_FAST_A(FN, G, act, fuse, tsmem, ...)                                           \
+  ((act) == KP_ACT_GELU ? KP_FAST_F(FN, G, KP_ACT_GELU, fuse, tsmem, __VA_ARGS__)         \
+   : (act) == KP_ACT_RELU ? KP_FAST_F(FN, G, KP_ACT_RELU, fuse, tsmem, __VA_ARGS__)       \
+                          : KP_FAST_F(FN, G, KP_ACT_NONE, fuse, tsmem, __VA_ARGS__))
+#define KP_FAST_G(FN, g, act, fuse, tsmem, ...)                                           \
+  ((g) == 32 ? KP_FAST_A(FN, 32, act, fuse, tsmem, __VA_ARGS__)                           \
+   : (g) == 16 ? KP_FAST_A(FN, 16, act, fuse, tsmem, __VA_ARGS__)                         \
+   : (g) == 8 ? KP_FAST_A(FN, 8, act, fuse, tsmem, __VA_ARGS__)                           \
+              : KP_FAST_A(FN, 4, act, fuse, tsmem, __VA_ARGS__))
+
 #define KP_DISPATCH_VAF(FN, vec, act, fuse, ...)                                          \
   do {                                                                                    \
     int _rc = 1;                                                                          \
@@ -579,7 +590,16 @@ int kp_agg_forward(const kp_agg_desc* desc, float* out, void* stream) {
                "kp_agg_forward: output not aligned for %d-wide stores", c.vec);
   kp::AggArgs args{*desc, c.G, c.gshift};
   cudaStream_t st = (cudaStream_t)stream;
+  if (c.fast) {
+    const kp::FastArgs fa = kp::make_fast_args(*desc, c);
+    return KP_FAST_G(kp::launch_fwd_fast, c.fG, desc->act, desc->fuse, c.tsmem, fa, c, out, st);
+  }
   KP_DISPATCH_VAF(kp::launch_fwd, c.vec, desc->act, desc->fuse, args, c, out, st);
+  return 0;
+}
+
+int kp_agg_set_force_generic(int flag) {
+  kp::g_force_generic = flag ? 1 : 0;
   return 0;
 }
 
@@ -612,6 +632,9 @@ int kp_agg_backward(const kp_agg_desc* desc, const float* dOut, float* dX, float
     if (deps) KP_CUDA(cudaMemsetAsync(deps, 0, sizeof(float), st));
     return 0;
   }
+  if (c.fast)
+    KP_CHECK_ARG(kp::aligned16(dOut) && kp::aligned16(dX) && kp::aligned16(dP) && kp::aligned16(workspace),
+                 "kp_agg_backward: dOut/dX/dP/workspace must be 16-byte aligned");
   char* ws = (char*)workspace;
   float* Gs = c.need_gs ? (float*)(ws + w.gs) : nullptr;
   float* dth_part = dtheta ? (float*)(ws + w.dtheta) : nullptr;
@@ -622,10 +645,23 @@ int kp_agg_backward(const kp_agg_desc* desc, const float* dOut, float* dX, float
   if (want_b1) {
     float* dPk = dP;
     if (!a.fuse && dP == dOut) dPk = nullptr;
-    KP_DISPATCH_VAF(kp::launch_b1, c.vec, a.act, a.fuse, args, c, dOut, Gs, dPk, dth_part, dep_part, st);
+    if (c.fast) {
+      const kp::FastArgs fa = kp::make_fast_args(a, c);
+      int rc = KP_FAST_G(kp::launch_b1_fast, c.fG, a.act, a.fuse, c.tsmem, fa, c, dOut, Gs, dPk, dth_part, dep_part, st);
+      if (rc) return rc;
+    } else {
+      KP_DISPATCH_VAF(kp::launch_b1, c.vec, a.act, a.fuse, args, c, dOut, Gs, dPk, dth_part, dep_part, st);
+    }
   }
   const float* Gsrc = c.need_gs ? Gs : dOut;
-  if (dX) {
+  if (dX && c.fast) {
+    const kp::FastArgs fa = kp::make_fast_args(a, c);
+    int rc = c.fG == 32 ? kp::launch_b2_fast<32>(fa, c, Gsrc, dOut, dX, st)
+             : c.fG == 16 ? kp::launch_b2_fast<16>(fa, c, Gsrc, dOut, dX, st)
+             : c.fG == 8 ? kp::launch_b2_fast<8>(fa, c, Gsrc, dOut, dX, st)
+                         : kp::launch_b2_fast<4>(fa, c, Gsrc, dOut, dX, st);
+    if (rc) return rc;
+  } else if (dX) {
     if (c.vec == 4) {
       if (a.fuse) KP_LAUNCH((kp::agg_bwd_src_kernel<4, true>), c.grid, 256, 0, st, args, Gsrc, dOut, dX);
       else        KP_LAUNCH((kp::agg_bwd_src_kernel<4, false>), c.grid, 256, 0, st, args, Gsrc, dOut, dX);

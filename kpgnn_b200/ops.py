@@ -85,6 +85,8 @@ class _KHopAggregate(torch.autograd.Function):
         need = ctx.needs_input_grad
         N, _, d = x.shape
         dout = dout.contiguous()
+        if dout.data_ptr() % 16:
+            dout = dout.clone()
         desc = _make_desc(plan, k, x, P_, T0_, Tk_, th_, eps_, act, fuse, use_dinv, use_mean)
         dev = x.device
         dX = torch.empty((N, k, d), dtype=torch.float32, device=dev) if need[0] else None

@@ -18,6 +18,15 @@ torch.backends.cudnn.allow_tf32 = False
 NOISE_ONLY = ("mlp.0.bias", "mlp.3.bias")
 
 
+@pytest.fixture(autouse=True, params=["fast", "generic"])
+def kernel_path(request, lib):
+    """Every case runs through both kernel families: the float4 fast path (agg_fast.cuh) and the generic
+    any-width kernels (agg.cu)."""
+    lib.kp_agg_set_force_generic(1 if request.param == "generic" else 0)
+    yield request.param
+    lib.kp_agg_set_force_generic(0)
+
+
 def _run_pair(mine, ora, batch, make_x, P_shape, use_pe, gine=False):
     dev = torch.device("cuda:0")
     ora.load_state_dict(mine.state_dict())
@@ -128,6 +137,40 @@ def test_gine(lib, K):
     N = b["num_nodes"]
     _run_pair(GINEConv(H, H, 0.2, 3, True), OL.OracleGINEConv(H, H, 0.2, 3, True), b,
               lambda g: torch.randn(N, H, generator=g), None, False, gine=True)
+
+
+@pytest.mark.parametrize("d", [1, 2, 5, 6, 12, 20, 36, 68, 132, 200])
+@pytest.mark.parametrize("fuse", [False, True])
+def test_op_widths_vs_dense_oracle(lib, d, fuse):
+    """Raw operator at widths that exercise every vector width / group size / column-chunk path."""
+    from kpgnn_b200.ops import khop_aggregate, ACT_GELU
+    from kpgnn_b200.plan import get_plan
+    dev = torch.device("cuda:0")
+    K = 3
+    b = zinc_batch(5, K, "gd", seed=d)
+    N = b["num_nodes"]
+    g = torch.Generator().manual_seed(d)
+    ei, ea = b["edge_index"].to(dev), b["edge_attr"].to(dev)
+    t0 = torch.randn(5, d, generator=g).to(dev)
+    tk = torch.randn(52, d, generator=g).to(dev)
+    th0 = torch.softmax(torch.randn(K, d, generator=g), 0).to(dev)
+    x0 = torch.randn(N, K, d, generator=g).to(dev)
+    P0 = torch.randn(N, K, d, generator=g).to(dev)
+    outs = []
+    for mode in ("oracle", "mine"):
+        x, P = x0.clone().requires_grad_(True), P0.clone().requires_grad_(True)
+        T0, Tk, th = (t.clone().requires_grad_(True) for t in (t0, tk, th0))
+        if mode == "oracle":
+            z = torch.nn.functional.gelu(OL.dense_khop_aggregate(x, ei, ea, T0, Tk)) + P
+            y = (z * th).sum(1) if fuse else z
+        else:
+            plan, k = get_plan(ei, ea, N)
+            y = khop_aggregate(x, plan, k, P=P, T0=T0, Tk=Tk, theta=th if fuse else None, act=ACT_GELU, fuse=fuse)
+        gy = torch.randn(y.shape, generator=torch.Generator().manual_seed(3)).to(dev)
+        y.backward(gy)
+        outs.append([y, x.grad, P.grad, T0.grad, Tk.grad] + ([th.grad] if fuse else []))
+    for a, c in zip(outs[1], outs[0]):
+        assert rel_err(a, c) < RTOL, rel_err(a, c)
 
 
 def test_no_cpu_fallback(lib):

@@ -31,18 +31,33 @@ def _stale():
     return any(os.path.getmtime(p) > t for p in deps)
 
 
+def _compile_one(nvcc, src, obj, verbose):
+    cmd = [nvcc] + [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else []) + \
+        ["-c", src, "-o", obj]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    return src, r.returncode, r.stdout
+
+
 def build_library(force=False, verbose=False):
+    """One object per .cu (compiled concurrently), linked into the in-tree shared library."""
     if not force and not _stale():
         return LIB
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()
-    if verbose:
-        print(" ".join(cmd))
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    jobs = [(s, os.path.join(objdir, os.path.basename(s)[:-3] + ".o")) for s in sources()]
+    with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
+        results = list(ex.map(lambda j: _compile_one(nvcc, j[0], j[1], verbose), jobs))
+    for src, rc, out in results:
+        if rc != 0:
+            raise RuntimeError("nvcc failed on %s:\n%s" % (src, out))
+        if verbose:
+            print(out)
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + [o for _, o in jobs]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + r.stdout)
-    if verbose:
-        print(r.stdout)
+        raise RuntimeError("link failed:\n" + r.stdout)
     return LIB
 
 

@@ -14,7 +14,7 @@
 //   B3 (rows)      dT0/dTk by owner-computes partial tables in shared memory, then a fixed-order reduction
 // HBM-bound gather work: no tensor cores on purpose.
 #include "agg_common.cuh"
-#include "agg_fast.cuh"
+#include "agg_fast_host.h"
 
 namespace kp {
 
@@ -370,8 +370,8 @@ struct Config {
   size_t smem_b3;
   bool table_atomic;
   // fast float4 path (agg_fast.cuh)
-  bool fast, tsmem;
-  int fG, fgrid, fgrid_b1, stage_floats;   // stage_floats = tables (+ theta) staged in smem, in floats
+  bool fast, fextra;
+  int ftab, fG, fgrid, fgrid_b1, stage_floats;   // stage_floats = tables (+ theta) staged in smem, in floats
   size_t fsmem_fwd;
 };
 
@@ -413,10 +413,16 @@ static int make_config(const kp_agg_desc& a, Config* c) {
   const int dpad = ((a.d + G * c->vec - 1) / (G * c->vec)) * (G * c->vec);
   c->smem_b1 = sizeof(float) * (size_t)gpb * a.k * dpad;
   c->need_gs = (a.act != KP_ACT_NONE) || a.fuse || a.dinv || a.indeg;
-  // fast path eligibility
-  const long long lim = 0x7fffffffLL;
-  c->fast = !g_force_generic && c->vec == 4 && a.d <= 128 && a.x_node_stride <= lim && a.x_hop_stride <= lim &&
-            (!a.P || (a.p_node_stride <= lim && a.p_hop_stride <= lim)) && (long long)a.k * a.d <= lim;
+  // fast path eligibility: float4 everywhere, one column chunk, every element offset below 2^32
+  const unsigned long long lim = 0xffffffffULL;
+  const unsigned long long n1 = (unsigned long long)(a.N > 0 ? a.N : 1);
+  bool fextra = false;
+  c->fast = !g_force_generic && c->vec == 4 && a.d <= 128 &&
+            fast_combo(a.act, a.fuse != 0, a.dinv || a.indeg || a.eps, &fextra) &&
+            n1 * (unsigned long long)a.x_node_stride + (unsigned long long)a.k * a.x_hop_stride < lim &&
+            (!a.P || n1 * (unsigned long long)a.p_node_stride + (unsigned long long)a.k * a.p_hop_stride < lim) &&
+            n1 * (unsigned long long)a.k * a.d < lim;
+  c->fextra = fextra;
   if (c->fast) {
     int fl = a.d / 4, fG = 4;
     while (fG < fl) fG <<= 1;
@@ -426,8 +432,8 @@ static int make_config(const kp_agg_desc& a, Config* c) {
     c->fgrid = (int)(fwant < 1 ? 1 : (fwant > kNumSMs * 4 ? kNumSMs * 4 : fwant));
     c->fgrid_b1 = (int)(fwant < 1 ? 1 : (fwant > kNumSMs * 3 ? kNumSMs * 3 : fwant));
     const long long tabf = a.T0 ? (long long)(a.rows0 + a.rowsk) * a.d : 0;
-    c->tsmem = a.T0 && tabf * 4 <= 56 * 1024;
-    c->stage_floats = (int)((c->tsmem ? tabf : 0) + (a.fuse ? a.k * a.d : 0));
+    c->ftab = !a.T0 ? TAB_NONE : (tabf * 4 <= 56 * 1024 ? TAB_SMEM : TAB_GLOBAL);
+    c->stage_floats = (int)((c->ftab == TAB_SMEM ? tabf : 0) + (a.fuse ? a.k * a.d : 0));
     c->fsmem_fwd = sizeof(float) * (size_t)c->stage_floats;
     c->grid_b1 = c->fgrid_b1;
     c->smem_b1 = sizeof(float) * ((size_t)c->stage_floats + (size_t)fgpb * a.k * 4 * fG);
@@ -500,59 +506,16 @@ static int launch_b1(const AggArgs& args, const Config& c, const float* dOut, fl
 }
 
 
-// ---- fast-path launchers (agg_fast.cuh) ----
-static FastArgs make_fast_args(const kp_agg_desc& a, const Config& c) {
+// ---- fast-path arguments (kernels live in agg_fast_*.cu) ----
+static FastArgs make_fast_args(const kp_agg_desc& a) {
   FastArgs fa;
   fa.d = a;
-  fa.xs = (int)a.x_node_stride;
-  fa.xh = (int)a.x_hop_stride;
-  fa.ps = (int)a.p_node_stride;
-  fa.ph = (int)a.p_hop_stride;
-  fa.tab_floats = c.tsmem ? (a.rows0 + a.rowsk) * a.d : 0;
+  fa.xs = (unsigned)a.x_node_stride;
+  fa.xh = (unsigned)a.x_hop_stride;
+  fa.ps = (unsigned)a.p_node_stride;
+  fa.ph = (unsigned)a.p_hop_stride;
   return fa;
 }
-
-template <int G, int ACT, bool FUSE, bool TSMEM>
-static int launch_fwd_fast(const FastArgs& fa, const Config& c, float* out, cudaStream_t st) {
-  if (c.fsmem_fwd > 48 * 1024)
-    KP_CUDA(cudaFuncSetAttribute(agg_fwd_fast_kernel<G, ACT, FUSE, TSMEM>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.fsmem_fwd));
-  KP_LAUNCH((agg_fwd_fast_kernel<G, ACT, FUSE, TSMEM>), c.fgrid, 256, c.fsmem_fwd, st, fa, out);
-  return 0;
-}
-
-template <int G, int ACT, bool FUSE, bool TSMEM>
-static int launch_b1_fast(const FastArgs& fa, const Config& c, const float* dOut, float* Gs, float* dP, float* dth,
-                          float* dep, cudaStream_t st) {
-  const size_t smem = dth ? c.smem_b1 : c.fsmem_fwd;
-  if (smem > 48 * 1024)
-    KP_CUDA(cudaFuncSetAttribute(agg_bwd_dst_fast_kernel<G, ACT, FUSE, TSMEM>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  KP_LAUNCH((agg_bwd_dst_fast_kernel<G, ACT, FUSE, TSMEM>), c.fgrid_b1, 256, smem, st, fa, dOut, Gs, dP, dth, dep,
-            c.stage_floats);
-  return 0;
-}
-
-template <int G>
-static int launch_b2_fast(const FastArgs& fa, const Config& c, const float* Gs, const float* dOut, float* dX,
-                          cudaStream_t st) {
-  if (fa.d.fuse) KP_LAUNCH((agg_bwd_src_fast_kernel<G, true>), c.fgrid, 256, 0, st, fa, Gs, dOut, dX);
-  else           KP_LAUNCH((agg_bwd_src_fast_kernel<G, false>), c.fgrid, 256, 0, st, fa, Gs, dOut, dX);
-  return 0;
-}
-
-#define KP_FAST_T(FN, G, A, F, tsmem, ...) ((tsmem) ? FN<G, A, F, true>(__VA_ARGS__) : FN<G, A, F, false>(__VA_ARGS__))
-#define KP_FAST_F(FN, G, A, fuse, tsmem, ...) \
-  ((fuse) ? KP_FAST_T(FN, G, A, true, tsmem, __VA_ARGS__) : KP_FAST_T(FN, G, A, false, tsmem, __VA_ARGS__))
-#define KP_FAST_A(FN, G, act, fuse, tsmem, ...)                                           \
-  ((act) == KP_ACT_GELU ? KP_FAST_F(FN, G, KP_ACT_GELU, fuse, tsmem, __VA_ARGS__)         \
-   : (act) == KP_ACT_RELU ? KP_FAST_F(FN, G, KP_ACT_RELU, fuse, tsmem, __VA_ARGS__)       \
-                          : KP_FAST_F(FN, G, KP_ACT_NONE, fuse, tsmem, __VA_ARGS__))
-#define KP_FAST_G(FN, g, act, fuse, tsmem, ...)                                           \
-  ((g) == 32 ? KP_FAST_A(FN, 32, act, fuse, tsmem, __VA_ARGS__)                           \
-   : (g) == 16 ? KP_FAST_A(FN, 16, act, fuse, tsmem, __VA_ARGS__)                         \
-   : (g) == 8 ? KP_FAST_A(FN, 8, act, fuse, tsmem, __VA_ARGS__)                           \
-              : KP_FAST_A(FN, 4, act, fuse, tsmem, __VA_ARGS__))
 
 #define KP_DISPATCH_VAF(FN, vec, act, fuse, ...)                                          \
   do {                                                                                    \
@@ -590,10 +553,9 @@ int kp_agg_forward(const kp_agg_desc* desc, float* out, void* stream) {
                "kp_agg_forward: output not aligned for %d-wide stores", c.vec);
   kp::AggArgs args{*desc, c.G, c.gshift};
   cudaStream_t st = (cudaStream_t)stream;
-  if (c.fast) {
-    const kp::FastArgs fa = kp::make_fast_args(*desc, c);
-    return KP_FAST_G(kp::launch_fwd_fast, c.fG, desc->act, desc->fuse, c.tsmem, fa, c, out, st);
-  }
+  if (c.fast)
+    return kp::fast_fwd(kp::make_fast_args(*desc), c.fG, desc->act, desc->fuse != 0, c.ftab, c.fextra, c.fgrid,
+                        c.fsmem_fwd, out, st);
   KP_DISPATCH_VAF(kp::launch_fwd, c.vec, desc->act, desc->fuse, args, c, out, st);
   return 0;
 }
@@ -646,8 +608,8 @@ int kp_agg_backward(const kp_agg_desc* desc, const float* dOut, float* dX, float
     float* dPk = dP;
     if (!a.fuse && dP == dOut) dPk = nullptr;
     if (c.fast) {
-      const kp::FastArgs fa = kp::make_fast_args(a, c);
-      int rc = KP_FAST_G(kp::launch_b1_fast, c.fG, a.act, a.fuse, c.tsmem, fa, c, dOut, Gs, dPk, dth_part, dep_part, st);
+      int rc = kp::fast_b1(kp::make_fast_args(a), c.fG, a.act, a.fuse != 0, c.ftab, c.fextra, c.fgrid_b1,
+                           dth_part ? c.smem_b1 : c.fsmem_fwd, dOut, Gs, dPk, dth_part, dep_part, st);
       if (rc) return rc;
     } else {
       KP_DISPATCH_VAF(kp::launch_b1, c.vec, a.act, a.fuse, args, c, dOut, Gs, dPk, dth_part, dep_part, st);
@@ -655,11 +617,7 @@ int kp_agg_backward(const kp_agg_desc* desc, const float* dOut, float* dX, float
   }
   const float* Gsrc = c.need_gs ? Gs : dOut;
   if (dX && c.fast) {
-    const kp::FastArgs fa = kp::make_fast_args(a, c);
-    int rc = c.fG == 32 ? kp::launch_b2_fast<32>(fa, c, Gsrc, dOut, dX, st)
-             : c.fG == 16 ? kp::launch_b2_fast<16>(fa, c, Gsrc, dOut, dX, st)
-             : c.fG == 8 ? kp::launch_b2_fast<8>(fa, c, Gsrc, dOut, dX, st)
-                         : kp::launch_b2_fast<4>(fa, c, Gsrc, dOut, dX, st);
+    int rc = kp::fast_b2(kp::make_fast_args(a), c.fG, a.fuse != 0, c.fextra, c.fgrid, Gsrc, dOut, dX, st);
     if (rc) return rc;
   } else if (dX) {
     if (c.vec == 4) {

@@ -57,25 +57,36 @@ __device__ __forceinline__ void vstore<1>(float* __restrict__ p, const Vf<1>& x)
   *p = x.v[0];
 }
 
-// exact-erf GELU (KPGINplus.py:87-88, F.gelu default) evaluated with the Abramowitz-Stegun 7.1.26 erfc form:
-// |error| < 4.3e-7 absolute over all x in fp32 (torch's own fp32 gelu is 1.2e-6 from the exact value), no
-// cancellation in the negative tail, 2 MUFU + ~12 FP32 ops instead of the ~35-instruction erff.
+// exact-erf GELU (KPGINplus.py:87-88, F.gelu default) evaluated through the Abramowitz-Stegun 7.1.26 erfc form:
+//   0.5*erfc(|x|/sqrt2) = t*(a1/2 + t*(a2/2 + ...)) * exp(-x^2/2),  t = 1/(1 + p*|x|/sqrt2)
+// |error| < 5e-7 absolute over all x in fp32 (torch's own fp32 gelu is 1.2e-6 from the exact value), no
+// cancellation in the negative tail.  Raw MUFU.RCP / MUFU.EX2 (2 ulp) instead of the ~35-instruction erff.
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 __device__ __forceinline__ void gelu_parts(float x, float& half_erfc, float& gauss) {
   const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
-  float p = fmaf(t, 1.061405429f, -1.453152027f);
-  p = fmaf(t, p, 1.421413741f);
-  p = fmaf(t, p, -0.284496736f);
-  p = fmaf(t, p, 0.254829592f);
-  gauss = __expf(-z * z);                 // exp(-x^2/2)
-  half_erfc = 0.5f * p * t * gauss;       // 0.5 * erfc(|x|/sqrt2)
+  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
+  p = fmaf(t, p, 0.5f * 1.421413741f);
+  p = fmaf(t, p, 0.5f * -0.284496736f);
+  p = fmaf(t, p, 0.5f * 0.254829592f);
+  gauss = ex2_approx(z * z * -1.44269504088896340736f);   // exp(-x^2/2)
+  half_erfc = p * t * gauss;
 }
 template <int ACT>
 __device__ __forceinline__ float act_fwd(float x) {
   if (ACT == KP_ACT_GELU) {
     float hc, g;
     gelu_parts(x, hc, g);
-    return x > 0.f ? x - x * hc : x * hc;
+    return fmaf(-fabsf(x), hc, fmaxf(x, 0.f));      // x>0: x - x*hc ; x<=0: x*hc
   }
   if (ACT == KP_ACT_RELU) return x > 0.f ? x : 0.f;
   return x;

@@ -1,0 +1,51 @@
+// agg_fast_host.h -- host entry points of the fast aggregation kernels; each is instantiated in its own
+// translation unit (agg_fast_fwd.cu / agg_fast_b1.cu / agg_fast_b2.cu) so the library builds in parallel.
+#pragma once
+#include "agg_fast.cuh"
+
+namespace kp {
+
+// Template combinations that exist (anything else takes the generic kernels):
+//   (GELU, fuse or not, no extras)  KPGINPlus
+//   (RELU, fuse or not, extras)     KPGCN (norm)
+//   (NONE, unfused, no extras)      KPGraphSAGE add
+//   (NONE, unfused, extras)         KPGIN / GINE / KGIN (self term), KPGraphSAGE mean
+inline bool fast_combo(int act, bool fuse, bool need_extra, bool* extra) {
+  if (act == KP_ACT_GELU) {
+    *extra = false;
+    return !need_extra;
+  }
+  if (act == KP_ACT_RELU) {
+    *extra = true;
+    return true;
+  }
+  *extra = need_extra;
+  return !fuse;
+}
+
+int fast_fwd(const FastArgs& fa, int G, int act, bool fuse, int tab, bool extra, int grid, size_t smem, float* out,
+             cudaStream_t st);
+int fast_b1(const FastArgs& fa, int G, int act, bool fuse, int tab, bool extra, int grid, size_t smem,
+            const float* dOut, float* Gs, float* dP, float* dth, float* dep, cudaStream_t st);
+int fast_b2(const FastArgs& fa, int G, bool fuse, bool extra, int grid, const float* Gs, const float* dOut, float* dX,
+            cudaStream_t st);
+
+// dispatch helper shared by the three translation units
+#define KP_FAST_TAB(FN, G, A, F, X, tab, ...)                                  \
+  ((tab) == TAB_SMEM ? FN<G, A, F, TAB_SMEM, X>(__VA_ARGS__)                   \
+   : (tab) == TAB_GLOBAL ? FN<G, A, F, TAB_GLOBAL, X>(__VA_ARGS__)             \
+                         : FN<G, A, F, TAB_NONE, X>(__VA_ARGS__))
+#define KP_FAST_COMBO(FN, G, act, fuse, extra, tab, ...)                                                          \
+  ((act) == KP_ACT_GELU ? ((fuse) ? KP_FAST_TAB(FN, G, KP_ACT_GELU, true, false, tab, __VA_ARGS__)                \
+                                  : KP_FAST_TAB(FN, G, KP_ACT_GELU, false, false, tab, __VA_ARGS__))              \
+   : (act) == KP_ACT_RELU ? ((fuse) ? KP_FAST_TAB(FN, G, KP_ACT_RELU, true, true, tab, __VA_ARGS__)               \
+                                    : KP_FAST_TAB(FN, G, KP_ACT_RELU, false, true, tab, __VA_ARGS__))             \
+   : (extra) ? KP_FAST_TAB(FN, G, KP_ACT_NONE, false, true, tab, __VA_ARGS__)                                     \
+             : KP_FAST_TAB(FN, G, KP_ACT_NONE, false, false, tab, __VA_ARGS__))
+#define KP_FAST_G(FN, g, act, fuse, extra, tab, ...)                                      \
+  ((g) == 32 ? KP_FAST_COMBO(FN, 32, act, fuse, extra, tab, __VA_ARGS__)                  \
+   : (g) == 16 ? KP_FAST_COMBO(FN, 16, act, fuse, extra, tab, __VA_ARGS__)                \
+   : (g) == 8 ? KP_FAST_COMBO(FN, 8, act, fuse, extra, tab, __VA_ARGS__)                  \
+              : KP_FAST_COMBO(FN, 4, act, fuse, extra, tab, __VA_ARGS__))
+
+}  // namespace kp

@@ -72,14 +72,13 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return r;
 }
 __device__ __forceinline__ void gelu_parts(float x, float& half_erfc, float& gauss) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
+  const float t = rcp_approx(fmaf(0.3275911f * 0.70710678118654752440f, fabsf(x), 1.0f));
   float p = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
   p = fmaf(t, p, 0.5f * 1.421413741f);
   p = fmaf(t, p, 0.5f * -0.284496736f);
   p = fmaf(t, p, 0.5f * 0.254829592f);
-  gauss = ex2_approx(z * z * -1.44269504088896340736f);   // exp(-x^2/2)
-  half_erfc = p * t * gauss;
+  gauss = ex2_approx((x * x) * (-0.5f * 1.44269504088896340736f));   // exp(-x^2/2)
+  half_erfc = (p * t) * gauss;
 }
 template <int ACT>
 __device__ __forceinline__ float act_fwd(float x) {

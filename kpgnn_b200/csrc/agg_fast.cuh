@@ -76,92 +76,99 @@ __device__ __forceinline__ int stage_tables(const kp_agg_desc& a, float* sm) {
   return off;
 }
 
-// One destination (or source) node's hop segments, with the entry prefetch described above.
-template <int G, bool ATTR>
-struct HopCursor {
-  const int* rp;
+// Gathers one node's hop segments.  The node's entry list (all hops, contiguous in the plan) is read through a
+// running window of G entries held one-per-lane in registers (for G = 32 a ZINC-shaped node's ~20 entries are
+// one coalesced load); entries are broadcast with width-G shuffles.  The first two rows of the NEXT segment are
+// requested before the current segment's epilogue runs, so their latency hides behind the activation math.
+template <int G, int TAB, bool NORM>
+struct SegGather {
+  // per kernel
+  const float* Xb;
   const int* col;
   const uint16_t* attr;
-  int b, e, pc, pa;          // current segment and this lane's prefetched entry of its first window
-  int ne, npc, npa;          // next segment (starts at e)
-  int lane;
+  const float* dinv;
+  unsigned xs, gm;
+  int Kp, d, lane;
+  // per node
+  int wb, pc, pa, nend;
+  float4 xa, xb;
+  int npre;
 
-  __device__ __forceinline__ void load_window(int start, int end, int& c, int& a) const {
-    c = 0;
-    a = 0;
-    if (start + lane < end) {
-      c = __ldg(col + start + lane);
-      if (ATTR) a = (int)__ldg(attr + start + lane);
+  __device__ __forceinline__ void load_window() {
+    pc = 0;
+    pa = 0;
+    const unsigned i = (unsigned)(wb + lane);
+    if ((int)i < nend) {
+      pc = __ldg(col + i);
+      if (TAB != TAB_NONE) pa = (int)__ldg(attr + i);
     }
   }
-  __device__ __forceinline__ void begin(const int* rowptr_row, const int* col_, const uint16_t* attr_, int lane_) {
-    rp = rowptr_row;
-    col = col_;
-    attr = attr_;
-    lane = lane_;
-    b = __ldg(rp);
-    e = __ldg(rp + 1);
-    load_window(b, e, pc, pa);
+  __device__ __forceinline__ void open(int start, int node_end) {
+    wb = start;
+    nend = node_end;
+    npre = 0;
+    load_window();
   }
-  __device__ __forceinline__ void prefetch_next(int h, int k) {   // call at the top of hop h
-    ne = e;
-    npc = 0;
-    npa = 0;
-    if (h + 1 < k) {
-      ne = __ldg(rp + h + 2);
-      load_window(e, ne, npc, npa);
+  __device__ __forceinline__ unsigned src(int j) const { return (unsigned)__shfl_sync(gm, pc, j - wb, G); }
+  __device__ __forceinline__ int att(int j) const { return __shfl_sync(gm, pa, j - wb, G); }
+  __device__ __forceinline__ float4 table(int a, const float* Tg, unsigned Tsh) const {
+    if (TAB == TAB_SMEM) return lds4_sh(Tsh + (unsigned)(a * d) * 4u);
+    return ld4(Tg + a * d);
+  }
+  // request the first (up to) two rows of segment [b,e); group-uniform control flow
+  __device__ __forceinline__ void prefetch(int b, int e, unsigned xoff) {
+    npre = 0;
+    if (b < e) {
+      if (b - wb >= G) {
+        wb += G;
+        load_window();
+      }
+      xa = ld4(Xb + (src(b) * xs + xoff));
+      npre = 1;
+      if (b + 1 < e && b + 1 - wb < G) {
+        xb = ld4(Xb + (src(b + 1) * xs + xoff));
+        npre = 2;
+      }
     }
   }
-  __device__ __forceinline__ void advance() {
-    b = e;
-    e = ne;
-    pc = npc;
-    pa = npa;
+  __device__ __forceinline__ void accum(float4& acc, float4 x, int j, int h, const float* Tg, unsigned Tsh) const {
+    if (TAB != TAB_NONE) add4(x, table(att(j), Tg, Tsh));
+    if (NORM && dinv) fma4(acc, __ldg(dinv + (size_t)src(j) * Kp + h), x);
+    else add4(acc, x);
+  }
+  // sum of segment [b,e) (the one last passed to prefetch)
+  __device__ __forceinline__ float4 consume(int b, int e, unsigned xoff, int h, const float* Tg, unsigned Tsh) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int j = b;
+    if (npre >= 1) {
+      accum(acc, xa, j, h, Tg, Tsh);
+      ++j;
+      if (npre == 2) {
+        accum(acc, xb, j, h, Tg, Tsh);
+        ++j;
+      }
+    }
+    while (j < e) {
+      if (j - wb >= G) {
+        wb += G;
+        load_window();
+      }
+      if (j + 1 < e && j + 1 - wb < G) {
+        const float4 x0 = ld4(Xb + (src(j) * xs + xoff));
+        const float4 x1 = ld4(Xb + (src(j + 1) * xs + xoff));
+        accum(acc, x0, j, h, Tg, Tsh);
+        accum(acc, x1, j + 1, h, Tg, Tsh);
+        j += 2;
+      } else {
+        const float4 x0 = ld4(Xb + (src(j) * xs + xoff));
+        accum(acc, x0, j, h, Tg, Tsh);
+        ++j;
+      }
+    }
+    npre = 0;
+    return acc;
   }
 };
-
-// acc = sum over the current segment of w_j * (X[col_j*xs + xoff] + T[attr_j]).  All lanes of the group call.
-// X rows are addressed as  Xb + (col*xs + xoff)  with a 32-bit unsigned element offset.
-template <int G, int TAB, bool NORM>
-__device__ __forceinline__ float4 gather_segment(const HopCursor<G, TAB != TAB_NONE>& cur, unsigned gm, const float* Xb,
-                                                 unsigned xs, unsigned xoff, const float* Tg, unsigned Tsh, int d,
-                                                 const float* dinv_h, int Kp) {
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  int j = cur.b;
-  int pc = cur.pc, pa = cur.pa;
-  const int e = cur.e;
-  while (j < e) {
-    const int cnt = min(G, e - j);
-    for (int q = 0; q < cnt; q += 2) {
-      const bool two = q + 1 < cnt;
-      const int q1 = two ? q + 1 : q;
-      const unsigned u0 = (unsigned)__shfl_sync(gm, pc, q, G), u1 = (unsigned)__shfl_sync(gm, pc, q1, G);
-      float4 x0 = ld4(Xb + (u0 * xs + xoff));
-      float4 x1 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (two) x1 = ld4(Xb + (u1 * xs + xoff));
-      if (TAB != TAB_NONE) {
-        const int a0 = __shfl_sync(gm, pa, q, G), a1 = __shfl_sync(gm, pa, q1, G);
-        if (TAB == TAB_SMEM) {
-          add4(x0, lds4_sh(Tsh + (unsigned)(a0 * d) * 4u));
-          if (two) add4(x1, lds4_sh(Tsh + (unsigned)(a1 * d) * 4u));
-        } else {
-          add4(x0, ld4(Tg + a0 * d));
-          if (two) add4(x1, ld4(Tg + a1 * d));
-        }
-      }
-      if (NORM && dinv_h) {
-        fma4(acc, __ldg(dinv_h + (size_t)u0 * Kp), x0);
-        if (two) fma4(acc, __ldg(dinv_h + (size_t)u1 * Kp), x1);
-      } else {
-        add4(acc, x0);
-        add4(acc, x1);
-      }
-    }
-    j += cnt;
-    if (j < e) cur.load_window(j, e, pc, pa);     // segments longer than G entries
-  }
-  return acc;
-}
 
 template <bool EXTRA>
 __device__ __forceinline__ float fast_row_scale(const kp_agg_desc& a, int v, int h) {
@@ -182,11 +189,10 @@ __global__ void __launch_bounds__(256, 4) agg_fwd_fast_kernel(const FastArgs fa,
   const kp_agg_desc& a = fa.d;
   stage_tables<TAB, FUSE>(a, sm);
   const int d = a.d, k = a.k, Kp = a.Kplan;
-  const unsigned xs = fa.xs, xh = fa.xh;
+  const unsigned xh = fa.xh;
   const int lane = threadIdx.x & (G - 1);
   const bool active = lane * 4 < d;
   const unsigned c = (unsigned)min(lane * 4, d - 4);          // idle lanes shadow the last chunk
-  const unsigned gm = group_mask<G>();
   constexpr int gpb = 256 / G;
   const int gib = threadIdx.x / G;
   const unsigned sm_base = sh_addr(sm);
@@ -194,38 +200,41 @@ __global__ void __launch_bounds__(256, 4) agg_fwd_fast_kernel(const FastArgs fa,
   const unsigned theta_sh = sm_base + ((TAB == TAB_SMEM) ? (unsigned)((a.rows0 + a.rowsk) * d) : 0u) * 4u + c * 4u;
   float self_c = 0.f;
   if (EXTRA && a.eps) self_c = 1.f + __ldg(a.eps);
+  SegGather<G, TAB, EXTRA> sg;
+  sg.Xb = a.X; sg.col = a.col; sg.attr = a.attr16; sg.dinv = EXTRA ? a.dinv : nullptr;
+  sg.xs = fa.xs; sg.gm = group_mask<G>(); sg.Kp = Kp; sg.d = d; sg.lane = lane;
   for (int v = blockIdx.x * gpb + gib; v < a.N; v += gridDim.x * gpb) {
-    HopCursor<G, TAB != TAB_NONE> cur;
-    cur.begin(a.rowptr + (size_t)v * Kp, a.col, a.attr16, lane);
+    const int* rp = a.rowptr + (size_t)v * Kp;
+    int e0 = __ldg(rp), e1 = __ldg(rp + 1), e2 = __ldg(rp + min(2, k));
+    sg.open(e0, __ldg(rp + k));
+    sg.prefetch(e0, e1, c);
     float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
     const float* Pv = a.P ? a.P + ((size_t)v * fa.ps + c) : nullptr;
     float* outv = out + (FUSE ? (size_t)v * d : (size_t)v * k * d) + c;
     for (int h = 0; h < k; ++h) {
-      cur.prefetch_next(h, k);
+      const int e3 = __ldg(rp + min(h + 3, k));                // row pointers run two hops ahead
       float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
       if (Pv) p = ld4s(Pv + h * fa.ph);
       const unsigned xoff = h * xh + c;
       const float* Tg = (TAB == TAB_GLOBAL) ? (h == 0 ? a.T0 : a.Tk) + c : nullptr;
       const unsigned Tsh = sm_base + ((h == 0 ? 0u : n0f) + c) * 4u;
-      const float* dinv_h = (EXTRA && a.dinv) ? a.dinv + h : nullptr;
-      float4 z = gather_segment<G, TAB, EXTRA>(cur, gm, a.X, xs, xoff, Tg, Tsh, d, dinv_h, Kp);
+      float4 z = sg.consume(e0, e1, xoff, h, Tg, Tsh);
+      if (h + 1 < k) sg.prefetch(e1, e2, xoff + xh);          // next segment's rows fly during the epilogue
       if (EXTRA) {
         const float s = fast_row_scale<EXTRA>(a, v, h);
         z.x *= s; z.y *= s; z.z *= s; z.w *= s;
       }
-      z.x = act_fwd<ACT>(z.x) + p.x;
-      z.y = act_fwd<ACT>(z.y) + p.y;
-      z.z = act_fwd<ACT>(z.z) + p.z;
-      z.w = act_fwd<ACT>(z.w) + p.w;
-      if (EXTRA && a.eps) fma4(z, self_c, ld4(a.X + ((unsigned)v * xs + xoff)));
+      z.x = act_fwd<ACT>(z.x); z.y = act_fwd<ACT>(z.y); z.z = act_fwd<ACT>(z.z); z.w = act_fwd<ACT>(z.w);
+      if (EXTRA && a.eps) fma4(z, self_c, ld4(a.X + ((unsigned)v * fa.xs + xoff)));
       if (FUSE) {
         const float4 th = lds4_sh(theta_sh + (unsigned)(h * d) * 4u);
-        o.x = fmaf(th.x, z.x, o.x); o.y = fmaf(th.y, z.y, o.y);
-        o.z = fmaf(th.z, z.z, o.z); o.w = fmaf(th.w, z.w, o.w);
-      } else if (active) {
-        st4s(outv + h * d, z);
+        o.x = fmaf(th.x, z.x, fmaf(th.x, p.x, o.x)); o.y = fmaf(th.y, z.y, fmaf(th.y, p.y, o.y));
+        o.z = fmaf(th.z, z.z, fmaf(th.z, p.z, o.z)); o.w = fmaf(th.w, z.w, fmaf(th.w, p.w, o.w));
+      } else {
+        add4(z, p);
+        if (active) st4s(outv + h * d, z);
       }
-      cur.advance();
+      e0 = e1; e1 = e2; e2 = e3;
     }
     if (FUSE && active) st4s(outv, o);
   }
@@ -242,11 +251,10 @@ agg_bwd_dst_fast_kernel(const FastArgs fa, const float* __restrict__ dOut, float
   const kp_agg_desc& a = fa.d;
   const int staged = stage_tables<TAB, FUSE>(a, sm);
   const int d = a.d, k = a.k, Kp = a.Kplan;
-  const unsigned xs = fa.xs, xh = fa.xh;
+  const unsigned xh = fa.xh;
   const int lane = threadIdx.x & (G - 1);
   const bool active = lane * 4 < d;
   const unsigned c = (unsigned)min(lane * 4, d - 4);
-  const unsigned gm = group_mask<G>();
   constexpr int gpb = 256 / G;
   constexpr int dpad = 4 * G;
   const int gib = threadIdx.x / G;
@@ -265,16 +273,25 @@ agg_bwd_dst_fast_kernel(const FastArgs fa, const float* __restrict__ dOut, float
     for (int i = threadIdx.x; i < gpb * k * dpad; i += blockDim.x) th_all[i] = 0.f;
     __syncthreads();
   }
+  SegGather<G, TAB, EXTRA> sg;
+  sg.Xb = a.X; sg.col = a.col; sg.attr = a.attr16; sg.dinv = EXTRA ? a.dinv : nullptr;
+  sg.xs = fa.xs; sg.gm = group_mask<G>(); sg.Kp = Kp; sg.d = d; sg.lane = lane;
   float eps_acc = 0.f;
   for (int v = blockIdx.x * gpb + gib; v < a.N; v += gridDim.x * gpb) {
-    HopCursor<G, TAB != TAB_NONE> cur;
-    if (recompute) cur.begin(a.rowptr + (size_t)v * Kp, a.col, a.attr16, lane);
+    const int* rp = a.rowptr + (size_t)v * Kp;
+    int e0 = 0, e1 = 0, e2 = 0;
+    if (recompute) {
+      e0 = __ldg(rp); e1 = __ldg(rp + 1); e2 = __ldg(rp + min(2, k));
+      sg.open(e0, __ldg(rp + k));
+      sg.prefetch(e0, e1, c);
+    }
     float4 go = make_float4(0.f, 0.f, 0.f, 0.f);
     if (FUSE) go = ld4s(dOut + ((size_t)v * d + c));
     const float* Pv = (need_z && a.P) ? a.P + ((size_t)v * fa.ps + c) : nullptr;
     const size_t row0 = (size_t)v * k * d + c;
     for (int h = 0; h < k; ++h) {
-      if (recompute) cur.prefetch_next(h, k);
+      int e3 = 0;
+      if (recompute) e3 = __ldg(rp + min(h + 3, k));
       const size_t row = row0 + (size_t)h * d;
       float4 dy;
       if (FUSE) {
@@ -293,15 +310,15 @@ agg_bwd_dst_fast_kernel(const FastArgs fa, const float* __restrict__ dOut, float
         if (Pv) p = ld4s(Pv + h * fa.ph);
         const float* Tg = (TAB == TAB_GLOBAL) ? (h == 0 ? a.T0 : a.Tk) + c : nullptr;
         const unsigned Tsh = sm_base + ((h == 0 ? 0u : n0f) + c) * 4u;
-        const float* dinv_h = (EXTRA && a.dinv) ? a.dinv + h : nullptr;
-        float4 pre = gather_segment<G, TAB, EXTRA>(cur, gm, a.X, xs, xoff, Tg, Tsh, d, dinv_h, Kp);
+        float4 pre = sg.consume(e0, e1, xoff, h, Tg, Tsh);
+        if (h + 1 < k) sg.prefetch(e1, e2, xoff + xh);
         if (EXTRA) {
           pre.x *= s; pre.y *= s; pre.z *= s; pre.w *= s;
         }
         if (need_z) {
           float4 z = make_float4(act_fwd<ACT>(pre.x) + p.x, act_fwd<ACT>(pre.y) + p.y, act_fwd<ACT>(pre.z) + p.z,
                                  act_fwd<ACT>(pre.w) + p.w);
-          if (EXTRA && a.eps) fma4(z, self_c, ld4(a.X + ((unsigned)v * xs + xoff)));
+          if (EXTRA && a.eps) fma4(z, self_c, ld4(a.X + ((unsigned)v * fa.xs + xoff)));
           float4 t = lds4_sh(th_sh + (unsigned)(h * dpad) * 4u);
           t.x = fmaf(go.x, z.x, t.x); t.y = fmaf(go.y, z.y, t.y);
           t.z = fmaf(go.z, z.z, t.z); t.w = fmaf(go.w, z.w, t.w);
@@ -309,10 +326,10 @@ agg_bwd_dst_fast_kernel(const FastArgs fa, const float* __restrict__ dOut, float
         }
         g.x *= act_bwd<ACT>(pre.x); g.y *= act_bwd<ACT>(pre.y);
         g.z *= act_bwd<ACT>(pre.z); g.w *= act_bwd<ACT>(pre.w);
-        cur.advance();
+        e0 = e1; e1 = e2; e2 = e3;
       }
       if (EXTRA && deps_part && active) {
-        const float4 x = ld4(a.X + ((unsigned)v * xs + xoff));
+        const float4 x = ld4(a.X + ((unsigned)v * fa.xs + xoff));
         eps_acc += dy.x * x.x + dy.y * x.y + dy.z * x.z + dy.w * x.w;
       }
       if (Gs && active) {
@@ -357,21 +374,26 @@ agg_bwd_src_fast_kernel(const FastArgs fa, const float* __restrict__ Gs, const f
   const int lane = threadIdx.x & (G - 1);
   const bool active = lane * 4 < d;
   const unsigned c = (unsigned)min(lane * 4, d - 4);
-  const unsigned gm = group_mask<G>();
   constexpr int gpb = 256 / G;
   const int gib = threadIdx.x / G;
   float self_c = 0.f;
   if (EXTRA && a.eps) self_c = 1.f + __ldg(a.eps);
-  const unsigned gs = (unsigned)(k * d);
+  SegGather<G, TAB_NONE, false> sg;
+  sg.Xb = Gs; sg.col = a.colT; sg.attr = nullptr; sg.dinv = nullptr;
+  sg.xs = (unsigned)(k * d); sg.gm = group_mask<G>(); sg.Kp = Kp; sg.d = d; sg.lane = lane;
   for (int u = blockIdx.x * gpb + gib; u < a.N; u += gridDim.x * gpb) {
-    HopCursor<G, false> cur;
-    cur.begin(a.rowptrT + (size_t)u * Kp, a.colT, nullptr, lane);
+    const int* rp = a.rowptrT + (size_t)u * Kp;
+    int e0 = __ldg(rp), e1 = __ldg(rp + 1), e2 = __ldg(rp + min(2, k));
+    sg.open(e0, __ldg(rp + k));
+    sg.prefetch(e0, e1, c);
     float4 go = make_float4(0.f, 0.f, 0.f, 0.f);
     if (EXTRA && FUSE && a.eps) go = ld4(dOut + ((size_t)u * d + c));
     const size_t row0 = (size_t)u * k * d + c;
     for (int h = 0; h < k; ++h) {
-      cur.prefetch_next(h, k);
-      float4 acc = gather_segment<G, TAB_NONE, false>(cur, gm, Gs, gs, (unsigned)(h * d) + c, nullptr, 0u, d, nullptr, Kp);
+      const int e3 = __ldg(rp + min(h + 3, k));
+      const unsigned xoff = (unsigned)(h * d) + c;
+      float4 acc = sg.consume(e0, e1, xoff, h, nullptr, 0u);
+      if (h + 1 < k) sg.prefetch(e1, e2, xoff + d);
       const size_t row = row0 + (size_t)h * d;
       if (EXTRA) {
         if (a.dinv) {
@@ -390,7 +412,7 @@ agg_bwd_src_fast_kernel(const FastArgs fa, const float* __restrict__ Gs, const f
         }
       }
       if (active) st4s(dX + row, acc);
-      cur.advance();
+      e0 = e1; e1 = e2; e2 = e3;
     }
   }
 }

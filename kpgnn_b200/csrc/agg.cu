@@ -429,7 +429,7 @@ static int make_config(const kp_agg_desc& a, Config* c) {
     c->fG = fG;
     const int fgpb = 256 / fG;
     const long long fwant = ((long long)a.N + fgpb - 1) / fgpb;
-    c->fgrid = (int)(fwant < 1 ? 1 : (fwant > kNumSMs * 4 ? kNumSMs * 4 : fwant));
+    c->fgrid = (int)(fwant < 1 ? 1 : (fwant > kNumSMs * KP_FWD_MINB ? kNumSMs * KP_FWD_MINB : fwant));
     c->fgrid_b1 = (int)(fwant < 1 ? 1 : (fwant > kNumSMs * 3 ? kNumSMs * 3 : fwant));
     const long long tabf = a.T0 ? (long long)(a.rows0 + a.rowsk) * a.d : 0;
     c->ftab = !a.T0 ? TAB_NONE : (tabf * 4 <= 56 * 1024 ? TAB_SMEM : TAB_GLOBAL);

@@ -23,6 +23,10 @@
 
 namespace kp {
 
+#ifndef KP_FWD_MINB
+#define KP_FWD_MINB 4
+#endif
+
 enum { TAB_NONE = 0, TAB_SMEM = 1, TAB_GLOBAL = 2 };
 
 struct FastArgs {
@@ -184,7 +188,7 @@ __device__ __forceinline__ float fast_row_scale(const kp_agg_desc& a, int v, int
 // forward
 // ------------------------------------------------------------------------------------------------------------
 template <int G, int ACT, bool FUSE, int TAB, bool EXTRA>
-__global__ void __launch_bounds__(256, 4) agg_fwd_fast_kernel(const FastArgs fa, float* __restrict__ out) {
+__global__ void __launch_bounds__(256, KP_FWD_MINB) agg_fwd_fast_kernel(const FastArgs fa, float* __restrict__ out) {
   extern __shared__ __align__(16) float sm[];
   const kp_agg_desc& a = fa.d;
   stage_tables<TAB, FUSE>(a, sm);
@@ -211,10 +215,12 @@ __global__ void __launch_bounds__(256, 4) agg_fwd_fast_kernel(const FastArgs fa,
     float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
     const float* Pv = a.P ? a.P + ((size_t)v * fa.ps + c) : nullptr;
     float* outv = out + (FUSE ? (size_t)v * d : (size_t)v * k * d) + c;
+    float4 pn = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (Pv) pn = ld4s(Pv);
     for (int h = 0; h < k; ++h) {
       const int e3 = __ldg(rp + min(h + 3, k));                // row pointers run two hops ahead
-      float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (Pv) p = ld4s(Pv + h * fa.ph);
+      const float4 p = pn;                                     // the streamed P row runs one hop ahead
+      if (Pv && h + 1 < k) pn = ld4s(Pv + (h + 1) * fa.ph);
       const unsigned xoff = h * xh + c;
       const float* Tg = (TAB == TAB_GLOBAL) ? (h == 0 ? a.T0 : a.Tk) + c : nullptr;
       const unsigned Tsh = sm_base + ((h == 0 ? 0u : n0f) + c) * 4u;

@@ -321,6 +321,77 @@ agg_bwd_table_kernel(const kp_agg_desc a, const float* __restrict__ Gs, int cw, 
   }
 }
 
+// Fast variant (float4 rows, d <= 128): a group of G lanes owns a private sub-table in shared memory and a
+// contiguous range of (node,hop) rows; it loads RB rows (row pointers + Gs rows) before touching any of them,
+// so RB independent 16-byte loads per lane are in flight, then folds every entry of those rows into its table
+// with LDS.128 / 4 FFMA / STS.128.  Row order inside a group and group order in the final reduction are fixed,
+// so the result is bit-reproducible.
+template <int G>
+__global__ void __launch_bounds__(256)
+agg_bwd_table_fast_kernel(const kp_agg_desc a, const float* __restrict__ Gs, int ngroups_cta, int rows_per_group,
+                          float* __restrict__ part) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int RB = 8;
+  const int trows = a.rows0 + a.rowsk;
+  const int tsz = trows * a.d;
+  for (int i = threadIdx.x * 4; i < tsz * ngroups_cta; i += blockDim.x * 4)
+    *reinterpret_cast<float4*>(smem + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+  const int lane = threadIdx.x & (G - 1);
+  const int gib = threadIdx.x / G;
+  const int c = min(lane * 4, a.d - 4);
+  const bool active = lane * 4 < a.d;
+  const long long R = (long long)a.N * a.k;
+  const long long gid = (long long)blockIdx.x * ngroups_cta + gib;
+  const long long r0 = gid * rows_per_group;
+  const long long r1 = min(R, r0 + rows_per_group);
+  float* tab = smem + (size_t)tsz * gib + c;
+  if (gib < ngroups_cta && active) {
+    for (long long rb = r0; rb < r1; rb += RB) {
+      int b[RB], e[RB], hh[RB];
+      float4 g[RB];
+#pragma unroll
+      for (int u = 0; u < RB; ++u) {
+        const long long row = rb + u;
+        b[u] = e[u] = 0;
+        hh[u] = 0;
+        g[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < r1) {
+          const int v = (int)(row / a.k), h = (int)(row - (long long)v * a.k);
+          const long long pr = (long long)v * a.Kplan + h;
+          b[u] = __ldg(a.rowptr + pr);
+          e[u] = __ldg(a.rowptr + pr + 1);
+          hh[u] = h;
+          g[u] = __ldcs(reinterpret_cast<const float4*>(Gs + row * a.d + c));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < RB; ++u) {
+        const int base = (hh[u] == 0) ? 0 : a.rows0;
+        for (int j = b[u]; j < e[u]; ++j) {
+          const int at = (int)__ldg(a.attr16 + j);
+          float4* dst = reinterpret_cast<float4*>(tab + (size_t)(base + at) * a.d);
+          float4 t = *dst;
+          if (a.dinv) {
+            const float w = __ldg(a.dinv + (long long)__ldg(a.col + j) * a.Kplan + hh[u]);
+            t.x = fmaf(w, g[u].x, t.x); t.y = fmaf(w, g[u].y, t.y);
+            t.z = fmaf(w, g[u].z, t.z); t.w = fmaf(w, g[u].w, t.w);
+          } else {
+            t.x += g[u].x; t.y += g[u].y; t.z += g[u].z; t.w += g[u].w;
+          }
+          *dst = t;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < tsz; i += blockDim.x) {      // fixed-order reduction over the CTA's groups
+    float s = 0.f;
+    for (int q = 0; q < ngroups_cta; ++q) s += smem[(size_t)tsz * q + i];
+    part[(size_t)blockIdx.x * tsz + i] = s;
+  }
+}
+
 // fallback for tables that do not fit in shared memory: global float atomics (NOT bitwise reproducible)
 __global__ void agg_bwd_table_atomic_kernel(const kp_agg_desc a, const float* __restrict__ Gs,
                                             float* __restrict__ dT0, float* __restrict__ dTk) {
@@ -343,13 +414,22 @@ __global__ void agg_bwd_table_atomic_kernel(const kp_agg_desc a, const float* __
   }
 }
 
-// out[i] = sum_b part[b*n + i] in ascending b; optional second destination split at n0 (dT0 | dTk)
+// out[i] = sum_b part[b*n + i] in ascending b (8 loads in flight, adds in order -> bit-reproducible);
+// optional second destination split at n0 (dT0 | dTk)
 __global__ void reduce_partials_kernel(const float* __restrict__ part, int nblocks, int n, int n0,
                                        float* __restrict__ out0, float* __restrict__ out1) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float s = 0.f;
-  for (int b = 0; b < nblocks; ++b) s += part[(size_t)b * n + i];
+  int b = 0;
+  for (; b + 8 <= nblocks; b += 8) {
+    float v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = __ldcs(part + (size_t)(b + q) * n + i);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s += v[q];
+  }
+  for (; b < nblocks; ++b) s += __ldcs(part + (size_t)b * n + i);
   if (i < n0) {
     if (out0) out0[i] = s;
   } else {
@@ -369,6 +449,8 @@ struct Config {
   int cw, rl, grid_b3, rows_per_block;
   size_t smem_b3;
   bool table_atomic;
+  bool b3_fast;
+  int b3_G, b3_groups, b3_threads, b3_rows_per_group;
   // fast float4 path (agg_fast.cuh)
   bool fast, fextra;
   int ftab, fG, fgrid, fgrid_b1, stage_floats;   // stage_floats = tables (+ theta) staged in smem, in floats
@@ -446,22 +528,44 @@ static int make_config(const kp_agg_desc& a, Config* c) {
   c->grid_b3 = 0;
   c->rows_per_block = 0;
   c->smem_b3 = 0;
+  c->b3_fast = false;
   if (trows > 0) {
     size_t tsz = sizeof(float) * (size_t)(a.rows0 + a.rowsk) * a.d;
-    int rl = 256 / lanes;
-    if (rl > 8) rl = 8;
-    while (rl > 1 && tsz * rl > 96 * 1024) rl >>= 1;
-    if (tsz * rl > 200 * 1024 || lanes > 256) {
-      c->table_atomic = true;
-    } else {
-      c->rl = rl;
-      c->smem_b3 = tsz * rl;
-      long long R = (long long)a.N * a.k;
-      long long blocks = (R + 255) / 256;  // at least 256 rows per block keeps the partials small
-      if (blocks > kNumSMs * 2) blocks = kNumSMs * 2;
+    const long long R = (long long)a.N * a.k;
+    if (c->fast && tsz <= 200 * 1024) {
+      // fast table pass: groups of fG lanes, one private sub-table each
+      int groups = 256 / c->fG;
+      while (groups > 1 && tsz * groups > 200 * 1024) groups >>= 1;
+      int threads = groups * c->fG;
+      if (threads < 32) threads = 32;
+      c->b3_fast = true;
+      c->b3_G = c->fG;
+      c->b3_groups = groups;
+      c->b3_threads = threads;
+      c->smem_b3 = tsz * groups;
+      // enough rows per group to amortise zeroing/flushing the sub-table, at most one CTA per SM
+      long long want_groups = (R + 31) / 32;
+      long long blocks = (want_groups + groups - 1) / groups;
+      if (blocks > kNumSMs) blocks = kNumSMs;
       if (blocks < 1) blocks = 1;
       c->grid_b3 = (int)blocks;
-      c->rows_per_block = (int)((R + blocks - 1) / blocks);
+      const long long tg = blocks * groups;
+      c->b3_rows_per_group = (int)((R + tg - 1) / tg);
+    } else {
+      int rl = 256 / lanes;
+      if (rl > 8) rl = 8;
+      while (rl > 1 && tsz * rl > 96 * 1024) rl >>= 1;
+      if (tsz * rl > 200 * 1024 || lanes > 256) {
+        c->table_atomic = true;
+      } else {
+        c->rl = rl;
+        c->smem_b3 = tsz * rl;
+        long long blocks = (R + 255) / 256;  // at least 256 rows per block keeps the partials small
+        if (blocks > kNumSMs * 2) blocks = kNumSMs * 2;
+        if (blocks < 1) blocks = 1;
+        c->grid_b3 = (int)blocks;
+        c->rows_per_block = (int)((R + blocks - 1) / blocks);
+      }
     }
   }
   return 0;
@@ -640,6 +744,21 @@ int kp_agg_backward(const kp_agg_desc* desc, const float* dOut, float* dX, float
     } else {
       float* part = (float*)(ws + w.table);
       const int threads = 256;
+      if (c.b3_fast) {
+#define KP_B3F(GG)                                                                                              \
+  do {                                                                                                          \
+    if (c.smem_b3 > 48 * 1024)                                                                                  \
+      KP_CUDA(cudaFuncSetAttribute(kp::agg_bwd_table_fast_kernel<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                   (int)c.smem_b3));                                                            \
+    KP_LAUNCH((kp::agg_bwd_table_fast_kernel<GG>), c.grid_b3, c.b3_threads, c.smem_b3, st, a, Gsrc, c.b3_groups,  \
+              c.b3_rows_per_group, part);                                                                       \
+  } while (0)
+        if (c.b3_G == 32) KP_B3F(32);
+        else if (c.b3_G == 16) KP_B3F(16);
+        else if (c.b3_G == 8) KP_B3F(8);
+        else KP_B3F(4);
+#undef KP_B3F
+      } else {
 #define KP_B3(V)                                                                                           \
   do {                                                                                                     \
     if (c.smem_b3 > 48 * 1024)                                                                             \
@@ -652,6 +771,7 @@ int kp_agg_backward(const kp_agg_desc* desc, const float* dOut, float* dX, float
       else if (c.vec == 2) KP_B3(2);
       else KP_B3(1);
 #undef KP_B3
+      }
       KP_LAUNCH(kp::reduce_partials_kernel, kp::ceil_div((long long)tn, 256), 256, 0, st, part, c.grid_b3, (int)tn,
                 a.rows0 * a.d, dT0, dTk);
     }

@@ -125,12 +125,9 @@ class Trainer(object):
         self.model = zinc_kpginplus(K, LAYERS, HIDDEN).to(device).train()
         self.host = host.pin_memory()
         self.dev = self.host.to(device)
-        self.params = [p for p in self.model.parameters() if p.requires_grad]
-        self.flat_grad = torch.zeros(sum(p.numel() for p in self.params), device=device)
-        o = 0
-        for p in self.params:
-            p.grad = self.flat_grad[o:o + p.numel()].view_as(p)
-            o += p.numel()
+        from kpgnn_b200.dist import FlatGradients
+        self.grads = FlatGradients(self.model.parameters())
+        self.params = self.grads.params
         self.opt = torch.optim.Adam(self.params, lr=1e-3, capturable=True, fused=True)   # train_ZINC.py:244
         self.loss = None
         self.graph = None
@@ -139,12 +136,10 @@ class Trainer(object):
 
     def _step(self):
         from kpgnn_b200.model import l1_loss
-        self.flat_grad.zero_()
+        self.grads.zero_()
         loss = l1_loss(self.model(self.dev), self.dev.y)
         loss.backward()
-        if self.world > 1:
-            torch.distributed.all_reduce(self.flat_grad)       # one NCCL all-reduce per step over NVLink
-            self.flat_grad.div_(self.world)
+        self.grads.allreduce_mean_(self.world)                 # one NCCL all-reduce per step over NVLink
         self.opt.step()
         return loss.detach()
 

@@ -125,3 +125,18 @@ def test_dropin_layers_construct_inside_unmodified_reference_backbone():
             shapes = {k: tuple(v.shape) for k, v in gnn.state_dict().items()}
         assert keys[0] == keys[1], name
     assert "kpgnn_b200.layers.KPGINplus" in sys.modules
+
+
+def test_install_dropin_aliases_reference_import_names():
+    import subprocess
+    import sys
+    code = ("import kpgnn_b200, sys; kpgnn_b200.install_dropin();"
+            "from layers.gine import GINEConv; from layers.feature_encoder import FeatureConcatEncoder;"
+            "from layers.layer_utils import make_gnn_layer; from layers.combine import *;"
+            "from data_utils import extract_multi_hop_neighbors, resistance_distance, post_transform;"
+            "assert GINEConv.__module__ == 'kpgnn_b200.layers.gine'; assert nn is not None and torch is not None;"
+            "print('ok')")
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr

@@ -143,7 +143,17 @@ class Trainer(object):
         self.opt.step()
         return loss.detach()
 
+    def _fwd_bwd(self):
+        from kpgnn_b200.model import l1_loss
+        self.grads.zero_()
+        loss = l1_loss(self.model(self.dev), self.dev.y)
+        loss.backward()
+        return loss.detach()
+
     def capture(self):
+        """world == 1: the whole step is ONE CUDA graph.  world > 1: forward+backward is one graph, the NCCL
+        all-reduce of the flat gradient is issued eagerly on the same stream, Adam is a second graph (keeps
+        NCCL out of stream capture; the collective is ~2 MB and latency-bound either way)."""
         from kpgnn_b200 import _lib
         s = torch.cuda.Stream(self.device)
         s.wait_stream(torch.cuda.current_stream(self.device))
@@ -154,10 +164,23 @@ class Trainer(object):
         torch.cuda.synchronize(self.device)
         self.graph = torch.cuda.CUDAGraph()
         n0 = _lib.launch_count()
-        with torch.cuda.graph(self.graph):
-            self.loss = self._step()
+        if self.world == 1:
+            with torch.cuda.graph(self.graph):
+                self.loss = self._step()
+        else:
+            with torch.cuda.graph(self.graph):
+                self.loss = self._fwd_bwd()
+            self.graph_opt = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_opt):
+                self.opt.step()
         self.launches_per_step = _lib.launch_count() - n0
         torch.cuda.synchronize(self.device)
+
+    def replay(self):
+        self.graph.replay()
+        if self.world > 1:
+            self.grads.allreduce_mean_(self.world)
+            self.graph_opt.replay()
 
     def plan(self):
         p, _ = self.kplan.get_plan(self.dev.edge_index, self.dev.edge_attr, self.dev.x.size(0))
@@ -182,13 +205,13 @@ class Trainer(object):
 
     def step_resident(self):
         n = self.refresh_plan()
-        self.graph.replay()
+        self.replay()
         return n
 
     def step_e2e(self):
         nbytes = self.upload()
         self.refresh_plan()
-        self.graph.replay()
+        self.replay()
         val = self.loss.item()                       # D2H read of the step's loss (train_ZINC.py:45)
         self.plan().validate()
         return nbytes, val
@@ -313,6 +336,8 @@ def workload_config(world):
 
 
 def main():
+    import faulthandler
+    faulthandler.dump_traceback_later(900, exit=True)      # a hang dumps every thread's stack and exits
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
@@ -349,8 +374,11 @@ def main():
         print(json.dumps(agg_roofline(device, args.roofline_only, peak, reps=3)), flush=True)
         return
 
+    log("[rank %d] building batch" % rank)
     tr = Trainer(host_batch(GRAPHS_PER_GPU, seed=rank), device, world)
+    log("[rank %d] capturing" % rank)
     tr.capture()
+    log("[rank %d] captured, %d of our kernels per step" % (rank, tr.launches_per_step))
     flush = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device=device)
     for _ in range(args.warmup):
         tr.step_resident()
@@ -361,6 +389,7 @@ def main():
         sampler.start()
     plan_launches = tr.refresh_plan()
     t_res = timed_steps(tr.step_resident, args.steps, device, flush, dist_on)
+    log("[rank %d] resident timing done" % rank)
     for _ in range(3):
         tr.step_e2e()
     h2d = [0]
@@ -369,6 +398,7 @@ def main():
         h2d[0], _ = tr.step_e2e()
     t_e2e = timed_steps(e2e, args.steps, device, flush, dist_on)
     clocks = sampler.stop() if rank == 0 else None
+    log("[rank %d] e2e timing done" % rank)
 
     def reduce_max(ms):
         if not dist_on:
@@ -382,7 +412,7 @@ def main():
 
     roof = roof_small = None
     cpu = None
-    if rank == 0 and not args.no_roofline:
+    if rank == 0 and world == 1 and not args.no_roofline:
         roof_small = agg_roofline(device, GRAPHS_PER_GPU, peak)
         roof = agg_roofline(device, ROOFLINE_GRAPHS, peak)
         roof["peak_source"] = peak_src

@@ -276,11 +276,44 @@ def agg_roofline(device, num_graphs, peak, reps=10):
             ts.append(a.elapsed_time(b))
     ms = statistics.mean(ts)
     achieved = alg / (ms * 1e-3) / 1e9
+    # backward of the same call (B1 recompute + B2 transposed gather + B3 table gradients + reductions), timed as
+    # one unit: algorithmic bytes per SURVEY 8(d): dOut + X (recompute) + dX + dP + P (dtheta) + index arrays twice
+    dout = torch.randn(N, HIDDEN, device=device, generator=g)
+    dX = torch.empty(N, K, HIDDEN, device=device)
+    dP = torch.empty(N, K, HIDDEN, device=device)
+    dT0, dTk, dth = torch.empty_like(t0), torch.empty_like(tk), torch.empty_like(th)
+    nb = C.c_size_t(0)
+    _lib.check(lib.kp_agg_backward_workspace_bytes(C.byref(desc), C.byref(nb)), "ws")
+    ws = torch.empty(nb.value, dtype=torch.uint8, device=device)
+    alg_b = 4 * N * HIDDEN + 4 * N * K * HIDDEN * 4 + 2 * (4 * (N * K + 1) + plan.nnz * 6)
+    tb = []
+    for i in range(reps + 3):
+        flush_l2(flush)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(st)
+        _lib.check(lib.kp_agg_backward(C.byref(desc), dout.data_ptr(), dX.data_ptr(), dP.data_ptr(), dT0.data_ptr(),
+                                       dTk.data_ptr(), dth.data_ptr(), None, ws.data_ptr(), ws.numel(), sp),
+                   "kp_agg_backward")
+        b.record(st)
+        torch.cuda.synchronize(device)
+        if i >= 3:
+            tb.append(a.elapsed_time(b))
+    msb = statistics.mean(tb)
     del flush
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "agg_fwd_traffic.json")
+    if os.path.isfile(tp):
+        t = json.load(open(tp))
+        if t.get("graphs_per_launch") == num_graphs:
+            traffic = t["dram_bytes_per_launch"]
     return {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-            "frac": round(achieved / peak, 4), "traffic": None, "kernel": "agg_fwd_kernel<4,GELU,fuse>",
+            "frac": round(achieved / peak, 4), "traffic": traffic, "kernel": "agg_fwd_fast_kernel<32,GELU,fuse,smem>",
             "graphs_per_launch": num_graphs, "nodes": N, "nnz": plan.nnz, "algorithmic_bytes": alg,
-            "ms_per_launch": round(ms, 5)}
+            "ms_per_launch": round(ms, 5),
+            "backward": {"ms": round(msb, 5), "algorithmic_bytes": alg_b,
+                         "achieved": round(alg_b / (msb * 1e-3) / 1e9, 1),
+                         "frac": round(alg_b / (msb * 1e-3) / 1e9 / peak, 4),
+                         "kernels": "agg_bwd_dst_fast + agg_bwd_src_fast + agg_bwd_table_fast + 2x reduce_partials"}}
 
 
 def cpu_baseline(steps=4, warmup=1):

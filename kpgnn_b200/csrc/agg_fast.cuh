@@ -23,6 +23,9 @@
 
 namespace kp {
 
+#ifndef KP_CHUNK_ITERS
+#define KP_CHUNK_ITERS 1
+#endif
 #ifndef KP_FWD_MINB
 #define KP_FWD_MINB 4
 #endif
@@ -207,7 +210,13 @@ __global__ void __launch_bounds__(256, KP_FWD_MINB) agg_fwd_fast_kernel(const Fa
   SegGather<G, TAB, EXTRA> sg;
   sg.Xb = a.X; sg.col = a.col; sg.attr = a.attr16; sg.dinv = EXTRA ? a.dinv : nullptr;
   sg.xs = fa.xs; sg.gm = group_mask<G>(); sg.Kp = Kp; sg.d = d; sg.lane = lane;
-  for (int v = blockIdx.x * gpb + gib; v < a.N; v += gridDim.x * gpb) {
+  // each CTA owns a CONTIGUOUS node range: the nodes of one small graph (whose rows gather each other) stay on
+  // one SM, so re-gathered X rows hit that SM's L1 and the index arrays are read sequentially
+  // CTAs walk the node list in chunks of KP_CHUNK consecutive nodes (about one small graph, whose rows gather
+  // each other -> L1 hits), chunks are dealt round-robin so all SMs sweep HBM in step
+  constexpr int chunk = KP_CHUNK_ITERS * gpb;
+  for (int v0 = blockIdx.x * chunk; v0 < a.N; v0 += gridDim.x * chunk)
+  for (int v = v0 + gib; v < min(a.N, v0 + chunk); v += gpb) {
     const int* rp = a.rowptr + (size_t)v * Kp;
     int e0 = __ldg(rp), e1 = __ldg(rp + 1), e2 = __ldg(rp + min(2, k));
     sg.open(e0, __ldg(rp + k));
@@ -283,7 +292,9 @@ agg_bwd_dst_fast_kernel(const FastArgs fa, const float* __restrict__ dOut, float
   sg.Xb = a.X; sg.col = a.col; sg.attr = a.attr16; sg.dinv = EXTRA ? a.dinv : nullptr;
   sg.xs = fa.xs; sg.gm = group_mask<G>(); sg.Kp = Kp; sg.d = d; sg.lane = lane;
   float eps_acc = 0.f;
-  for (int v = blockIdx.x * gpb + gib; v < a.N; v += gridDim.x * gpb) {
+  constexpr int chunk = KP_CHUNK_ITERS * gpb;
+  for (int v0 = blockIdx.x * chunk; v0 < a.N; v0 += gridDim.x * chunk)
+  for (int v = v0 + gib; v < min(a.N, v0 + chunk); v += gpb) {
     const int* rp = a.rowptr + (size_t)v * Kp;
     int e0 = 0, e1 = 0, e2 = 0;
     if (recompute) {
@@ -387,7 +398,9 @@ agg_bwd_src_fast_kernel(const FastArgs fa, const float* __restrict__ Gs, const f
   SegGather<G, TAB_NONE, false> sg;
   sg.Xb = Gs; sg.col = a.colT; sg.attr = nullptr; sg.dinv = nullptr;
   sg.xs = (unsigned)(k * d); sg.gm = group_mask<G>(); sg.Kp = Kp; sg.d = d; sg.lane = lane;
-  for (int u = blockIdx.x * gpb + gib; u < a.N; u += gridDim.x * gpb) {
+  constexpr int chunk = KP_CHUNK_ITERS * gpb;
+  for (int u0 = blockIdx.x * chunk; u0 < a.N; u0 += gridDim.x * chunk)
+  for (int u = u0 + gib; u < min(a.N, u0 + chunk); u += gpb) {
     const int* rp = a.rowptrT + (size_t)u * Kp;
     int e0 = __ldg(rp), e1 = __ldg(rp + 1), e2 = __ldg(rp + min(2, k));
     sg.open(e0, __ldg(rp + k));

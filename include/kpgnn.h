@@ -112,6 +112,30 @@ int kp_agg_backward(const kp_agg_desc* desc, const float* dOut, float* dX, float
                     float* dtheta, float* deps, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Multi-table gather-sum: the peripheral-attribute embedding stage of the reference's backbones
+ * (models/GNNs.py:172-179 / :393-400 / :637-644 with layers/feature_encoder.py:37-67), after the caller folded
+ * each embedding table through its slice of the encoder's Linear:
+ *     out[r,:]    = sum_{s<S} table[slot_off[s] + idx[r,s], :]
+ *     dTable[t,:] = sum_{(r,s): slot_off[s]+idx[r,s] == t} dOut[r,:]          (deterministic, no float atomics)
+ * idx is [R,S] int64 row-major (table-local indices, the reference's integer peripheral attributes);
+ * slots must be ordered so that their tables are non-decreasing; range_slot/range_row partition the slots and
+ * the table rows into num_ranges (<= 8) consecutive pieces, each small enough for shared memory (<= 200 KB).
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t R, S, d, table_rows;
+  const int64_t* idx;
+  int32_t slot_off[32];
+  int32_t num_ranges;
+  int32_t range_slot[9];
+  int32_t range_row[9];
+} kp_tsum_desc;
+
+int kp_table_sum_forward(const kp_tsum_desc* desc, const float* table, float* out, void* stream);
+int kp_table_sum_backward_workspace_bytes(const kp_tsum_desc* desc, size_t* bytes);
+int kp_table_sum_backward(const kp_tsum_desc* desc, const float* dOut, float* dTable, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Batched K-hop neighbourhood + peripheral-subgraph extraction.  Replaces, for a whole batch of graphs,
  * data_utils.py:20-107 (extract_multi_hop_neighbors), :110-125 (adj_K_order), :128-162 (get_peripheral_attr),
  * :165-221 (extract_peripheral_attr_v2) and :224-241 (nx_compute_shortest_path_length).

@@ -40,6 +40,12 @@ class ExtractInput(C.Structure):
                 ("max_edge_count", C.c_int32), ("max_distance_count", C.c_int32), ("max_type_value", C.c_int32)]
 
 
+class TsumDesc(C.Structure):
+    _fields_ = [("R", C.c_int32), ("S", C.c_int32), ("d", C.c_int32), ("table_rows", C.c_int32),
+                ("idx", C.c_void_p), ("slot_off", C.c_int32 * 32), ("num_ranges", C.c_int32),
+                ("range_slot", C.c_int32 * 9), ("range_row", C.c_int32 * 9)]
+
+
 ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
 
 # name -> (restype, argtypes); must list every symbol include/kpgnn.h declares (tests/test_abi.py checks it)
@@ -57,6 +63,10 @@ _SIGNATURES = {
     "kp_agg_backward_workspace_bytes": (C.c_int, [C.POINTER(AggDesc), C.POINTER(C.c_size_t)]),
     "kp_agg_backward": (C.c_int, [C.POINTER(AggDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "kp_table_sum_forward": (C.c_int, [C.POINTER(TsumDesc), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "kp_table_sum_backward_workspace_bytes": (C.c_int, [C.POINTER(TsumDesc), C.POINTER(C.c_size_t)]),
+    "kp_table_sum_backward": (C.c_int, [C.POINTER(TsumDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                        C.c_void_p]),
     "kp_extract_workspace_bytes": (C.c_int, [C.POINTER(ExtractInput), C.c_int64, C.POINTER(C.c_size_t),
                                              C.POINTER(C.c_size_t)]),
     "kp_extract_hops": (C.c_int, [C.POINTER(ExtractInput), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,

@@ -1,0 +1,221 @@
+// tsum.cu -- multi-table gather-sum and its deterministic gradient (sm_100a).
+//
+//   out[r,:]   = sum_{s<S} table[slot_off[s] + idx[r,s], :]
+//   dTable[t,:] = sum_{(r,s): slot_off[s]+idx[r,s] == t} dOut[r,:]
+//
+// This is the peripheral-attribute embedding stage of the reference's backbones (models/GNNs.py:172-179,
+// 393-400 with layers/feature_encoder.py:37-67) after folding each embedding table through its slice of the
+// encoder's Linear (M_i = E_i W_i^T, done by the caller as tiny GEMMs): the [N,K,c,2H] concatenated embeddings,
+// the [N,K,c,H] projected tensor and the sort-based embedding backward of the reference never exist; P [N,K,H]
+// is written once and its gradient is read once.  HBM-bound row streaming; no float atomics: the gradient uses
+// group-private sub-tables in shared memory and fixed-order reductions.
+#include "agg_common.cuh"
+
+namespace kp {
+
+__device__ __forceinline__ float4 tld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+template <int G>
+__global__ void __launch_bounds__(256) tsum_fwd_kernel(const kp_tsum_desc t, const float* __restrict__ table,
+                                                       float* __restrict__ out) {
+  const int lane = threadIdx.x & (G - 1);
+  const int c = min(lane * 4, t.d - 4);
+  const bool active = lane * 4 < t.d;
+  constexpr int gpb = 256 / G;
+  const unsigned gm = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
+  for (long long r = (long long)blockIdx.x * gpb + threadIdx.x / G; r < t.R; r += (long long)gridDim.x * gpb) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s0 = 0; s0 < t.S; s0 += G) {
+      int row = 0;
+      if (s0 + lane < t.S) row = t.slot_off[s0 + lane] + (int)__ldg(t.idx + r * t.S + s0 + lane);
+      const int n = min(G, t.S - s0);
+      for (int q = 0; q < n; ++q) {
+        const int tr = __shfl_sync(gm, row, q, G);
+        const float4 v = tld4(table + (size_t)tr * t.d + c);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+    }
+    if (active) __stcs(reinterpret_cast<float4*>(out + r * t.d + c), acc);
+  }
+}
+
+// grid (B, Q): CTA (b,q) folds row chunk b into the table rows [t0,t1) that slots [s0,s1) address.
+template <int G>
+__global__ void __launch_bounds__(256)
+tsum_bwd_kernel(const kp_tsum_desc t, const float* __restrict__ dOut, int ngroups, int rows_per_group,
+                float* __restrict__ part) {
+  extern __shared__ __align__(16) float smem[];
+  const int q = blockIdx.y;
+  const int s0 = t.range_slot[q], s1 = t.range_slot[q + 1];
+  const int t0 = t.range_row[q], t1 = t.range_row[q + 1];
+  const int tsz = (t1 - t0) * t.d;
+  for (int i = threadIdx.x * 4; i < tsz * ngroups; i += blockDim.x * 4)
+    *reinterpret_cast<float4*>(smem + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+  const int lane = threadIdx.x & (G - 1);
+  const int gib = threadIdx.x / G;
+  const int c = min(lane * 4, t.d - 4);
+  const bool active = lane * 4 < t.d;
+  const unsigned gm = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
+  const long long gid = (long long)blockIdx.x * ngroups + gib;
+  const long long r0 = gid * rows_per_group, r1 = min((long long)t.R, r0 + rows_per_group);
+  float* tab = smem + (size_t)tsz * gib + c;
+  const int ns = s1 - s0;                      // <= 32 slots, one per lane (host guarantees ns <= G)
+  if (gib < ngroups) {
+    constexpr int RB = 4;
+    for (long long rb = r0; rb < r1; rb += RB) {
+      float4 g[RB];
+      int row[RB];
+#pragma unroll
+      for (int u = 0; u < RB; ++u) {
+        g[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        row[u] = 0;
+        if (rb + u < r1) {
+          g[u] = __ldcs(reinterpret_cast<const float4*>(dOut + (rb + u) * t.d + c));
+          if (lane < ns) row[u] = t.slot_off[s0 + lane] + (int)__ldg(t.idx + (rb + u) * t.S + s0 + lane) - t0;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < RB; ++u) {
+        if (rb + u < r1) {
+          for (int k = 0; k < ns; ++k) {
+            const int tr = __shfl_sync(gm, row[u], k, G);
+            if (active) {
+              float4* dst = reinterpret_cast<float4*>(tab + (size_t)tr * t.d);
+              float4 v = *dst;
+              v.x += g[u].x; v.y += g[u].y; v.z += g[u].z; v.w += g[u].w;
+              *dst = v;
+            }
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  float* dstp = part + (size_t)blockIdx.x * t.table_rows * t.d + (size_t)t0 * t.d;
+  for (int i = threadIdx.x; i < tsz; i += blockDim.x) {
+    float s = 0.f;
+    for (int g = 0; g < ngroups; ++g) s += smem[(size_t)tsz * g + i];
+    dstp[i] = s;
+  }
+}
+
+__global__ void tsum_reduce_kernel(const float* __restrict__ part, int nblocks, int n, float* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  int b = 0;
+  for (; b + 8 <= nblocks; b += 8) {
+    float v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = __ldcs(part + (size_t)(b + q) * n + i);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s += v[q];
+  }
+  for (; b < nblocks; ++b) s += __ldcs(part + (size_t)b * n + i);
+  out[i] = s;
+}
+
+struct TsumCfg {
+  int G, grid_fwd, B, Q, ngroups, threads, rows_per_group;
+  size_t smem;
+};
+
+static int tsum_config(const kp_tsum_desc& t, TsumCfg* c) {
+  KP_CHECK_ARG(t.R >= 0 && t.S >= 1 && t.S <= 32 && t.d >= 4 && t.d <= 128 && t.d % 4 == 0 && t.table_rows >= 1,
+               "kp_table_sum: need 1 <= S <= 32, d %% 4 == 0, 4 <= d <= 128 (got S=%d d=%d)", t.S, t.d);
+  KP_CHECK_ARG(t.idx, "kp_table_sum: null idx");
+  KP_CHECK_ARG(t.num_ranges >= 1 && t.num_ranges <= 8 && t.range_slot[0] == 0 && t.range_slot[t.num_ranges] == t.S &&
+                   t.range_row[0] == 0 && t.range_row[t.num_ranges] == t.table_rows,
+               "kp_table_sum: slot/row ranges must partition the slots and the table");
+  int lanes = t.d / 4, G = 4;
+  while (G < lanes) G <<= 1;
+  c->G = G;
+  const int gpb = 256 / G;
+  long long want = ((long long)t.R + gpb - 1) / gpb;
+  c->grid_fwd = (int)(want < 1 ? 1 : (want > kNumSMs * 8 ? kNumSMs * 8 : want));
+  c->Q = t.num_ranges;
+  size_t maxsub = 0;
+  for (int q = 0; q < t.num_ranges; ++q) {
+    KP_CHECK_ARG(t.range_slot[q + 1] - t.range_slot[q] <= G, "kp_table_sum: a slot range exceeds the group width");
+    size_t sub = sizeof(float) * (size_t)(t.range_row[q + 1] - t.range_row[q]) * t.d;
+    if (sub > maxsub) maxsub = sub;
+  }
+  KP_CHECK_ARG(maxsub <= 200 * 1024, "kp_table_sum: a table range needs %zu bytes of shared memory (> 200 KB)", maxsub);
+  int ng = 256 / G;
+  while (ng > 1 && maxsub * ng > 200 * 1024) ng >>= 1;
+  c->ngroups = ng;
+  c->threads = ng * G < 32 ? 32 : ng * G;
+  c->smem = maxsub * ng;
+  long long wantg = ((long long)t.R + 63) / 64;           // >= 64 rows per group
+  long long B = (wantg + ng - 1) / ng;
+  const long long maxB = (kNumSMs + c->Q - 1) / c->Q;     // about one CTA per SM over the (B,Q) grid
+  if (B > maxB) B = maxB;
+  if (B < 1) B = 1;
+  c->B = (int)B;
+  const long long tg = B * ng;
+  c->rows_per_group = (int)((t.R + tg - 1) / tg);
+  return 0;
+}
+
+}  // namespace kp
+
+extern "C" {
+
+int kp_table_sum_forward(const kp_tsum_desc* desc, const float* table, float* out, void* stream) {
+  KP_CHECK_ARG(desc && table && out, "kp_table_sum_forward: null argument");
+  kp::TsumCfg c;
+  if (kp::tsum_config(*desc, &c)) return 1;
+  if (desc->R == 0) return 0;
+  KP_CHECK_ARG((((uintptr_t)table | (uintptr_t)out) & 15) == 0, "kp_table_sum_forward: table/out must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (c.G) {
+    case 32: KP_LAUNCH(kp::tsum_fwd_kernel<32>, c.grid_fwd, 256, 0, st, *desc, table, out); break;
+    case 16: KP_LAUNCH(kp::tsum_fwd_kernel<16>, c.grid_fwd, 256, 0, st, *desc, table, out); break;
+    case 8:  KP_LAUNCH(kp::tsum_fwd_kernel<8>, c.grid_fwd, 256, 0, st, *desc, table, out); break;
+    default: KP_LAUNCH(kp::tsum_fwd_kernel<4>, c.grid_fwd, 256, 0, st, *desc, table, out); break;
+  }
+  return 0;
+}
+
+int kp_table_sum_backward_workspace_bytes(const kp_tsum_desc* desc, size_t* bytes) {
+  KP_CHECK_ARG(desc && bytes, "kp_table_sum_backward_workspace_bytes: null argument");
+  kp::TsumCfg c;
+  if (kp::tsum_config(*desc, &c)) return 1;
+  *bytes = sizeof(float) * (size_t)c.B * desc->table_rows * desc->d;
+  return 0;
+}
+
+int kp_table_sum_backward(const kp_tsum_desc* desc, const float* dOut, float* dTable, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  KP_CHECK_ARG(desc && dOut && dTable, "kp_table_sum_backward: null argument");
+  kp::TsumCfg c;
+  if (kp::tsum_config(*desc, &c)) return 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n = (size_t)desc->table_rows * desc->d;
+  if (desc->R == 0) {
+    KP_CUDA(cudaMemsetAsync(dTable, 0, sizeof(float) * n, st));
+    return 0;
+  }
+  KP_CHECK_ARG(workspace && workspace_bytes >= sizeof(float) * (size_t)c.B * n, "kp_table_sum_backward: workspace too small");
+  KP_CHECK_ARG((((uintptr_t)dOut | (uintptr_t)workspace) & 15) == 0, "kp_table_sum_backward: dOut/workspace alignment");
+  float* part = (float*)workspace;
+  dim3 grid(c.B, c.Q);
+#define KP_TSB(GG)                                                                                             \
+  do {                                                                                                         \
+    if (c.smem > 48 * 1024)                                                                                    \
+      KP_CUDA(cudaFuncSetAttribute(kp::tsum_bwd_kernel<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem)); \
+    KP_LAUNCH(kp::tsum_bwd_kernel<GG>, grid, c.threads, c.smem, st, *desc, dOut, c.ngroups, c.rows_per_group, part); \
+  } while (0)
+  switch (c.G) {
+    case 32: KP_TSB(32); break;
+    case 16: KP_TSB(16); break;
+    case 8:  KP_TSB(8); break;
+    default: KP_TSB(4); break;
+  }
+#undef KP_TSB
+  KP_LAUNCH(kp::tsum_reduce_kernel, kp::ceil_div((long long)n, 256), 256, 0, st, part, c.B, (int)n, dTable);
+  return 0;
+}
+
+}  // extern "C"

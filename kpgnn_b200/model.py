@@ -109,7 +109,19 @@ class KPGNNPlusBackbone(nn.Module):
             n.reset_parameters()
 
     def peripheral(self, data, num_nodes, like):
-        """GNNs.py:393-400: integer peripheral attributes -> [N,K,H] floats (tanh gates in GNNPlus)."""
+        """GNNs.py:393-400: integer peripheral attributes -> [N,K,H] floats (tanh gates in GNNPlus).
+        Both attribute sets present (the normal case): one fused gather-sum kernel (kpgnn_b200/encoders.py);
+        otherwise the reference's op-by-op form."""
+        if data.peripheral_edge_attr is not None and data.peripheral_configuration_attr is not None:
+            from .encoders import fused_peripheral_attr, peripheral_index
+            idx = getattr(data, "_peripheral_idx", None)
+            ver = (data.peripheral_edge_attr._version, data.peripheral_configuration_attr._version)
+            if idx is None or idx[0] != ver:
+                idx = (ver, peripheral_index(data.peripheral_edge_attr, data.peripheral_configuration_attr))
+                data._peripheral_idx = idx
+            return fused_peripheral_attr(self.peripheral_edge_embedding, self.peripheral_configuration_embedding,
+                                         torch.tanh(self.pew), torch.tanh(self.pcw), idx[1], num_nodes, self.K,
+                                         data.peripheral_edge_attr.size(2))
         P = torch.zeros((num_nodes, self.K, self.hidden_size), device=like.device, dtype=like.dtype)
         if data.peripheral_edge_attr is not None:
             P = P + torch.tanh(self.pew) * self.peripheral_edge_embedding(data.peripheral_edge_attr).sum(-2)

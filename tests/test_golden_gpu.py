@@ -120,3 +120,32 @@ def test_determinism_bitwise(lib):
         res.append([t.detach().clone() for t in (y, x.grad, P.grad, t0.grad, tk.grad, th.grad)])
     for a, c in zip(*res):
         assert torch.equal(a, c)
+
+
+def test_fused_peripheral_encoder_matches_reference_form(lib):
+    """kp_table_sum_* (folded tables + gather-sum) against the reference's lookup -> concat -> Linear -> sum
+    (models/GNNs.py:393-400), forward and every parameter gradient."""
+    from kpgnn_b200.encoders import fused_peripheral_attr, peripheral_index
+    from kpgnn_b200.layers.feature_encoder import FeatureConcatEncoder
+    dev = torch.device("cuda:0")
+    torch.manual_seed(5)
+    N, K, H, c = 333, 8, 104, 3
+    ee = FeatureConcatEncoder([5, 51], H, padding=0).to(dev)
+    ce = FeatureConcatEncoder([51] * 7, H, padding=0).to(dev)
+    pew = torch.randn(1, device=dev, requires_grad=True)
+    pcw = torch.randn(1, device=dev, requires_grad=True)
+    pea = torch.stack([torch.randint(0, 5, (N, K, c)), torch.randint(0, 51, (N, K, c))], -1).to(dev)
+    pca = torch.randint(0, 51, (N, K, 7)).to(dev)
+    gy = torch.randn(N, K, H, device=dev)
+    res = []
+    for fused in (False, True):
+        for p in list(ee.parameters()) + list(ce.parameters()) + [pew, pcw]:
+            p.grad = None
+        if fused:
+            P = fused_peripheral_attr(ee, ce, torch.tanh(pew), torch.tanh(pcw), peripheral_index(pea, pca), N, K, c)
+        else:
+            P = torch.tanh(pew) * ee(pea).sum(-2) + torch.tanh(pcw) * ce(pca)
+        P.backward(gy)
+        res.append([P.detach()] + [p.grad.clone() for p in list(ee.parameters()) + list(ce.parameters()) + [pew, pcw]])
+    for a, b in zip(res[1], res[0]):
+        assert rel_err(a, b) < 2e-5, rel_err(a, b)

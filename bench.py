@@ -394,6 +394,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--blas", default="default", choices=["default", "cublas", "cublaslt"])
     ap.add_argument("--roofline-only", type=int, default=0, metavar="GRAPHS",
                     help="profiling helper: only time the aggregation kernel on GRAPHS graphs and exit")
     args = ap.parse_args()
@@ -414,6 +415,8 @@ def main():
     torch.cuda.set_device(device)
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
+    if args.blas != "default":
+        torch.backends.cuda.preferred_blas_library(args.blas)
     dist_on = world > 1
     if dist_on:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")

@@ -129,8 +129,19 @@ class KPGNNPlusBackbone(nn.Module):
             P = P + torch.tanh(self.pcw) * self.peripheral_configuration_embedding(data.peripheral_configuration_attr)
         return P
 
+    def input_embedding(self, data):
+        """init_proj(data) (GNNs.py:385).  An integer [N] input is a 1-slot gather-sum: same kernel as the
+        peripheral stage, whose deterministic gradient replaces the sort-based embedding backward."""
+        xin = data.x
+        if xin.dim() == 1 and xin.dtype == torch.int64 and xin.is_cuda and self.hidden_size % 4 == 0 \
+                and self.hidden_size <= 128:
+            from .encoders import _TableSum
+            w = self.init_proj.init_proj.weight
+            return _TableSum.apply(w, xin.view(-1, 1), [0], [0, 1], [0, w.size(0)])
+        return self.init_proj(data).squeeze()
+
     def forward(self, data):
-        x = self.init_proj(data).squeeze()
+        x = self.input_embedding(data)
         N = x.size(0)
         P = self.peripheral(data, N, x)
         h_list = [x]

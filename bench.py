@@ -116,7 +116,8 @@ class ClockSampler(object):
 class Trainer(object):
     """Static-buffer training step captured in one CUDA graph (forward + backward + all-reduce + Adam)."""
 
-    def __init__(self, host, device, world):
+    def __init__(self, host, device, world, eager=False):
+        self.eager = eager
         from kpgnn_b200 import plan as kplan
         from kpgnn_b200.model import zinc_kpginplus
         self.kplan = kplan
@@ -126,8 +127,10 @@ class Trainer(object):
         self.host = host.pin_memory()
         self.dev = self.host.to(device)
         from kpgnn_b200.dist import FlatGradients
-        self.grads = FlatGradients(self.model.parameters())
-        self.params = self.grads.params
+        self.params = [p for p in self.model.parameters() if p.requires_grad]
+        # world > 1: gradients live in one flat buffer (a single all-reduce); world == 1: autograd hands each
+        # gradient tensor over without the per-parameter accumulate kernel
+        self.grads = FlatGradients(self.params) if world > 1 else None
         self.opt = torch.optim.Adam(self.params, lr=1e-3, capturable=True, fused=True)   # train_ZINC.py:244
         self.loss = None
         self.graph = None
@@ -150,18 +153,26 @@ class Trainer(object):
         self._tag_idx()
         return n
 
+    def _zero(self):
+        if self.grads is not None:
+            self.grads.zero_()
+        else:
+            for p in self.params:
+                p.grad = None
+
     def _step(self):
         from kpgnn_b200.model import l1_loss
-        self.grads.zero_()
+        self._zero()
         loss = l1_loss(self.model(self.dev), self.dev.y)
         loss.backward()
-        self.grads.allreduce_mean_(self.world)                 # one NCCL all-reduce per step over NVLink
+        if self.grads is not None:
+            self.grads.allreduce_mean_(self.world)             # one NCCL all-reduce per step over NVLink
         self.opt.step()
         return loss.detach()
 
     def _fwd_bwd(self):
         from kpgnn_b200.model import l1_loss
-        self.grads.zero_()
+        self._zero()
         loss = l1_loss(self.model(self.dev), self.dev.y)
         loss.backward()
         return loss.detach()
@@ -171,6 +182,11 @@ class Trainer(object):
         all-reduce of the flat gradient is issued eagerly on the same stream, Adam is a second graph (keeps
         NCCL out of stream capture; the collective is ~2 MB and latency-bound either way)."""
         from kpgnn_b200 import _lib
+        if self.eager:
+            n0 = _lib.launch_count()
+            self.loss = self._step()
+            self.launches_per_step = _lib.launch_count() - n0
+            return
         s = torch.cuda.Stream(self.device)
         s.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(s):
@@ -193,6 +209,9 @@ class Trainer(object):
         torch.cuda.synchronize(self.device)
 
     def replay(self):
+        if self.eager:
+            self.loss = self._step()
+            return
         self.graph.replay()
         if self.world > 1:
             self.grads.allreduce_mean_(self.world)
@@ -395,6 +414,9 @@ def main():
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--blas", default="default", choices=["default", "cublas", "cublaslt"])
+    ap.add_argument("--eager", action="store_true",
+                    help="profiling helper: no CUDA graph (ncu cannot re-launch graph kernel nodes that opted "
+                         "into > 48 KB of dynamic shared memory); numbers from this mode are not bench values")
     ap.add_argument("--roofline-only", type=int, default=0, metavar="GRAPHS",
                     help="profiling helper: only time the aggregation kernel on GRAPHS graphs and exit")
     args = ap.parse_args()
@@ -411,6 +433,9 @@ def main():
     assert args.warmup >= 3, "timing rules: at least 3 warm-up steps"
     from kpgnn_b200 import build
     build.build_library()
+    if os.environ.get("KPGNN_PROFILE_SMEM_CAP"):          # ncu launch lists only (see include/kpgnn.h)
+        from kpgnn_b200 import _lib
+        _lib.lib().kp_table_sum_set_smem_cap(int(os.environ["KPGNN_PROFILE_SMEM_CAP"]))
     device = torch.device("cuda", local)
     torch.cuda.set_device(device)
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -427,7 +452,7 @@ def main():
         return
 
     log("[rank %d] building batch" % rank)
-    tr = Trainer(host_batch(GRAPHS_PER_GPU, seed=rank), device, world)
+    tr = Trainer(host_batch(GRAPHS_PER_GPU, seed=rank), device, world, eager=args.eager)
     log("[rank %d] capturing" % rank)
     tr.capture()
     log("[rank %d] captured, %d of our kernels per step" % (rank, tr.launches_per_step))

@@ -119,18 +119,21 @@ int kp_agg_backward(const kp_agg_desc* desc, const float* dOut, float* dX, float
  *     dTable[t,:] = sum_{(r,s): slot_off[s]+idx[r,s] == t} dOut[r,:]          (deterministic, no float atomics)
  * idx is [R,S] int64 row-major (table-local indices, the reference's integer peripheral attributes);
  * slots must be ordered so that their tables are non-decreasing; range_slot/range_row partition the slots and
- * the table rows into num_ranges (<= 8) consecutive pieces, each small enough for shared memory (<= 200 KB).
+ * the table rows into num_ranges (<= 16) consecutive pieces, each small enough for shared memory (<= 200 KB).
  * ---------------------------------------------------------------------------------------------------------- */
 typedef struct {
   int32_t R, S, d, table_rows;
   const int64_t* idx;
   int32_t slot_off[32];
   int32_t num_ranges;
-  int32_t range_slot[9];
-  int32_t range_row[9];
+  int32_t range_slot[17];
+  int32_t range_row[17];
 } kp_tsum_desc;
 
 int kp_table_sum_forward(const kp_tsum_desc* desc, const float* table, float* out, void* stream);
+/* Profiling hook: caps the shared memory the gradient kernel asks for (ncu cannot re-launch CUDA-graph kernel
+ * nodes that opted into > 48 KB of dynamic shared memory).  Clamped to [16 KB, 200 KB]; default 200 KB. */
+int kp_table_sum_set_smem_cap(size_t bytes);
 int kp_table_sum_backward_workspace_bytes(const kp_tsum_desc* desc, size_t* bytes);
 int kp_table_sum_backward(const kp_tsum_desc* desc, const float* dOut, float* dTable, void* workspace,
                           size_t workspace_bytes, void* stream);

@@ -43,7 +43,7 @@ class ExtractInput(C.Structure):
 class TsumDesc(C.Structure):
     _fields_ = [("R", C.c_int32), ("S", C.c_int32), ("d", C.c_int32), ("table_rows", C.c_int32),
                 ("idx", C.c_void_p), ("slot_off", C.c_int32 * 32), ("num_ranges", C.c_int32),
-                ("range_slot", C.c_int32 * 9), ("range_row", C.c_int32 * 9)]
+                ("range_slot", C.c_int32 * 17), ("range_row", C.c_int32 * 17)]
 
 
 ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
@@ -64,6 +64,7 @@ _SIGNATURES = {
     "kp_agg_backward": (C.c_int, [C.POINTER(AggDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "kp_table_sum_forward": (C.c_int, [C.POINTER(TsumDesc), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "kp_table_sum_set_smem_cap": (C.c_int, [C.c_size_t]),
     "kp_table_sum_backward_workspace_bytes": (C.c_int, [C.POINTER(TsumDesc), C.POINTER(C.c_size_t)]),
     "kp_table_sum_backward": (C.c_int, [C.POINTER(TsumDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                         C.c_void_p]),

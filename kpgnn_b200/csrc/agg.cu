@@ -414,26 +414,23 @@ __global__ void agg_bwd_table_atomic_kernel(const kp_agg_desc a, const float* __
   }
 }
 
-// out[i] = sum_b part[b*n + i] in ascending b (8 loads in flight, adds in order -> bit-reproducible);
-// optional second destination split at n0 (dT0 | dTk)
+// out[i] = sum_b part[b*n + i].  One warp per output element: lane l adds the partials b = l, l+32, ... in order,
+// then a fixed shuffle tree combines the 32 lane sums -> the summation order is a function of (nblocks) only, so
+// the result is bit-reproducible; optional second destination split at n0 (dT0 | dTk).
 __global__ void reduce_partials_kernel(const float* __restrict__ part, int nblocks, int n, int n0,
                                        float* __restrict__ out0, float* __restrict__ out1) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (i >= n) return;
   float s = 0.f;
-  int b = 0;
-  for (; b + 8 <= nblocks; b += 8) {
-    float v[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) v[q] = __ldcs(part + (size_t)(b + q) * n + i);
-#pragma unroll
-    for (int q = 0; q < 8; ++q) s += v[q];
-  }
-  for (; b < nblocks; ++b) s += __ldcs(part + (size_t)b * n + i);
-  if (i < n0) {
-    if (out0) out0[i] = s;
-  } else {
-    if (out1) out1[i - n0] = s;
+  for (int b = lane; b < nblocks; b += 32) s += __ldcs(part + (size_t)b * n + i);
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) {
+    if (i < n0) {
+      if (out0) out0[i] = s;
+    } else {
+      if (out1) out1[i - n0] = s;
+    }
   }
 }
 
@@ -772,14 +769,14 @@ int kp_agg_backward(const kp_agg_desc* desc, const float* dOut, float* dX, float
       else KP_B3(1);
 #undef KP_B3
       }
-      KP_LAUNCH(kp::reduce_partials_kernel, kp::ceil_div((long long)tn, 256), 256, 0, st, part, c.grid_b3, (int)tn,
+      KP_LAUNCH(kp::reduce_partials_kernel, kp::ceil_div((long long)tn * 32, 256), 256, 0, st, part, c.grid_b3, (int)tn,
                 a.rows0 * a.d, dT0, dTk);
     }
   }
   if (dtheta) {
     const int n = a.k * a.d;
-    KP_LAUNCH(kp::reduce_partials_kernel, kp::ceil_div(n, 256), 256, 0, st, dth_part, c.grid_b1, n, n, dtheta,
-              (float*)nullptr);
+    KP_LAUNCH(kp::reduce_partials_kernel, kp::ceil_div((long long)n * 32, 256), 256, 0, st, dth_part, c.grid_b1, n, n,
+              dtheta, (float*)nullptr);
   }
   if (deps) {
     KP_LAUNCH(kp::reduce_partials_kernel, 1, 32, 0, st, dep_part, c.grid_b1, 1, 1, deps, (float*)nullptr);

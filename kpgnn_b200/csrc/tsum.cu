@@ -39,13 +39,14 @@ __global__ void __launch_bounds__(256) tsum_fwd_kernel(const kp_tsum_desc t, con
   }
 }
 
-// grid (B, Q): CTA (b,q) folds row chunk b into the table rows [t0,t1) that slots [s0,s1) address.
+// grid B*Q: CTA (b,q) folds row chunk b into the table rows [t0,t1) that slots [s0,s1) address.  256 threads
+// zero / flush the sub-tables; the first ngroups*G of them walk the rows.
 template <int G>
 __global__ void __launch_bounds__(256)
 tsum_bwd_kernel(const kp_tsum_desc t, const float* __restrict__ dOut, int ngroups, int rows_per_group,
                 float* __restrict__ part) {
   extern __shared__ __align__(16) float smem[];
-  const int q = blockIdx.y;
+  const int q = blockIdx.x % t.num_ranges, bx = blockIdx.x / t.num_ranges;
   const int s0 = t.range_slot[q], s1 = t.range_slot[q + 1];
   const int t0 = t.range_row[q], t1 = t.range_row[q + 1];
   const int tsz = (t1 - t0) * t.d;
@@ -57,9 +58,9 @@ tsum_bwd_kernel(const kp_tsum_desc t, const float* __restrict__ dOut, int ngroup
   const int c = min(lane * 4, t.d - 4);
   const bool active = lane * 4 < t.d;
   const unsigned gm = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
-  const long long gid = (long long)blockIdx.x * ngroups + gib;
+  const long long gid = (long long)bx * ngroups + gib;
   const long long r0 = gid * rows_per_group, r1 = min((long long)t.R, r0 + rows_per_group);
-  float* tab = smem + (size_t)tsz * gib + c;
+  float* tab = smem + (size_t)tsz * (gib < ngroups ? gib : 0) + c;
   const int ns = s1 - s0;                      // <= 32 slots, one per lane (host guarantees ns <= G)
   if (gib < ngroups) {
     constexpr int RB = 4;
@@ -92,7 +93,7 @@ tsum_bwd_kernel(const kp_tsum_desc t, const float* __restrict__ dOut, int ngroup
     }
   }
   __syncthreads();
-  float* dstp = part + (size_t)blockIdx.x * t.table_rows * t.d + (size_t)t0 * t.d;
+  float* dstp = part + (size_t)bx * t.table_rows * t.d + (size_t)t0 * t.d;
   for (int i = threadIdx.x; i < tsz; i += blockDim.x) {
     float s = 0.f;
     for (int g = 0; g < ngroups; ++g) s += smem[(size_t)tsz * g + i];
@@ -101,20 +102,17 @@ tsum_bwd_kernel(const kp_tsum_desc t, const float* __restrict__ dOut, int ngroup
 }
 
 __global__ void tsum_reduce_kernel(const float* __restrict__ part, int nblocks, int n, float* __restrict__ out) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  // one warp per output element, fixed order (see reduce_partials_kernel in agg.cu)
+  const int lane = threadIdx.x & 31;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (i >= n) return;
   float s = 0.f;
-  int b = 0;
-  for (; b + 8 <= nblocks; b += 8) {
-    float v[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) v[q] = __ldcs(part + (size_t)(b + q) * n + i);
-#pragma unroll
-    for (int q = 0; q < 8; ++q) s += v[q];
-  }
-  for (; b < nblocks; ++b) s += __ldcs(part + (size_t)b * n + i);
-  out[i] = s;
+  for (int b = lane; b < nblocks; b += 32) s += __ldcs(part + (size_t)b * n + i);
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[i] = s;
 }
+
+static size_t g_tsum_smem_cap = 200 * 1024;   // profiling hook: kp_table_sum_set_smem_cap
 
 struct TsumCfg {
   int G, grid_fwd, B, Q, ngroups, threads, rows_per_group;
@@ -125,7 +123,7 @@ static int tsum_config(const kp_tsum_desc& t, TsumCfg* c) {
   KP_CHECK_ARG(t.R >= 0 && t.S >= 1 && t.S <= 32 && t.d >= 4 && t.d <= 128 && t.d % 4 == 0 && t.table_rows >= 1,
                "kp_table_sum: need 1 <= S <= 32, d %% 4 == 0, 4 <= d <= 128 (got S=%d d=%d)", t.S, t.d);
   KP_CHECK_ARG(t.idx, "kp_table_sum: null idx");
-  KP_CHECK_ARG(t.num_ranges >= 1 && t.num_ranges <= 8 && t.range_slot[0] == 0 && t.range_slot[t.num_ranges] == t.S &&
+  KP_CHECK_ARG(t.num_ranges >= 1 && t.num_ranges <= 16 && t.range_slot[0] == 0 && t.range_slot[t.num_ranges] == t.S &&
                    t.range_row[0] == 0 && t.range_row[t.num_ranges] == t.table_rows,
                "kp_table_sum: slot/row ranges must partition the slots and the table");
   int lanes = t.d / 4, G = 4;
@@ -143,13 +141,13 @@ static int tsum_config(const kp_tsum_desc& t, TsumCfg* c) {
   }
   KP_CHECK_ARG(maxsub <= 200 * 1024, "kp_table_sum: a table range needs %zu bytes of shared memory (> 200 KB)", maxsub);
   int ng = 256 / G;
-  while (ng > 1 && maxsub * ng > 200 * 1024) ng >>= 1;
+  while (ng > 1 && maxsub * ng > g_tsum_smem_cap) ng >>= 1;
   c->ngroups = ng;
-  c->threads = ng * G < 32 ? 32 : ng * G;
+  c->threads = 256;
   c->smem = maxsub * ng;
   long long wantg = ((long long)t.R + 63) / 64;           // >= 64 rows per group
   long long B = (wantg + ng - 1) / ng;
-  const long long maxB = (kNumSMs + c->Q - 1) / c->Q;     // about one CTA per SM over the (B,Q) grid
+  const long long maxB = (2 * kNumSMs + c->Q - 1) / c->Q; // about two CTAs per SM over the B*Q grid
   if (B > maxB) B = maxB;
   if (B < 1) B = 1;
   c->B = (int)B;
@@ -161,6 +159,11 @@ static int tsum_config(const kp_tsum_desc& t, TsumCfg* c) {
 }  // namespace kp
 
 extern "C" {
+
+int kp_table_sum_set_smem_cap(size_t bytes) {
+  kp::g_tsum_smem_cap = bytes < 16 * 1024 ? 16 * 1024 : (bytes > 200 * 1024 ? 200 * 1024 : bytes);
+  return 0;
+}
 
 int kp_table_sum_forward(const kp_tsum_desc* desc, const float* table, float* out, void* stream) {
   KP_CHECK_ARG(desc && table && out, "kp_table_sum_forward: null argument");
@@ -200,7 +203,7 @@ int kp_table_sum_backward(const kp_tsum_desc* desc, const float* dOut, float* dT
   KP_CHECK_ARG(workspace && workspace_bytes >= sizeof(float) * (size_t)c.B * n, "kp_table_sum_backward: workspace too small");
   KP_CHECK_ARG((((uintptr_t)dOut | (uintptr_t)workspace) & 15) == 0, "kp_table_sum_backward: dOut/workspace alignment");
   float* part = (float*)workspace;
-  dim3 grid(c.B, c.Q);
+  const int grid = c.B * c.Q;
 #define KP_TSB(GG)                                                                                             \
   do {                                                                                                         \
     if (c.smem > 48 * 1024)                                                                                    \
@@ -214,7 +217,7 @@ int kp_table_sum_backward(const kp_tsum_desc* desc, const float* dOut, float* dT
     default: KP_TSB(4); break;
   }
 #undef KP_TSB
-  KP_LAUNCH(kp::tsum_reduce_kernel, kp::ceil_div((long long)n, 256), 256, 0, st, part, c.B, (int)n, dTable);
+  KP_LAUNCH(kp::tsum_reduce_kernel, kp::ceil_div((long long)n * 32, 256), 256, 0, st, part, c.B, (int)n, dTable);
   return 0;
 }
 

@@ -17,7 +17,7 @@ import torch
 from . import _lib
 
 
-def _ranges(table_sizes, slots_per_table, d, max_bytes=96 * 1024, max_ranges=8):
+def _ranges(table_sizes, slots_per_table, d, max_bytes=24 * 1024, max_ranges=16):
     """Partition consecutive tables into ranges whose rows fit a shared-memory sub-table."""
     slot_b, row_b = [0], [0]
     rows = slots = 0

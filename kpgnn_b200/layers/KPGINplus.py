@@ -1,7 +1,7 @@
 """KP-GIN+ layer -- mirror of the reference's layers/KPGINplus.py:10-88 on the fused sm_100a aggregation."""
 import torch.nn.functional as F  # noqa: F401  (star-import surface parity with the reference module)
 
-from ._base import KHopLayer, make_combine, khop_aggregate, get_plan, ACT_GELU
+from ._base import KHopLayer, SplitKLinear, make_combine, khop_aggregate, get_plan, ACT_GELU
 from .combine import *  # noqa: F401,F403
 
 
@@ -20,8 +20,8 @@ class KPGINPlusConv(KHopLayer):
         self.aggr = "add"
         self.K = K
         self.output_size = output_size
-        self.mlp = nn.Sequential(nn.Linear(input_size, output_size), nn.BatchNorm1d(output_size), nn.ReLU(),
-                                 nn.Linear(output_size, output_size), nn.BatchNorm1d(output_size), nn.ReLU())
+        self.mlp = nn.Sequential(SplitKLinear(input_size, output_size), nn.BatchNorm1d(output_size), nn.ReLU(),
+                                 SplitKLinear(output_size, output_size), nn.BatchNorm1d(output_size), nn.ReLU())
         self.hop1_edge_emb = torch.nn.Embedding(num_hop1_edge + 2, input_size, padding_idx=0)
         if self.K > 1:
             self.hopk_edge_emb = torch.nn.Embedding(num_pe + 2, input_size, padding_idx=0)

@@ -30,7 +30,8 @@ def launches(src, dst):
     for row in csv.DictReader(lines):
         rows.append((row["Kernel Name"], float(row["Metric Value"].replace(",", ""))))
     idx = [i for i, r in enumerate(rows) if "plan_count_kernel" in r[0]]
-    a, b = idx[-2], idx[-1]                     # one full step (plan rebuild + CUDA-graph replay)
+    pairs = list(zip(idx[:-1], idx[1:]))
+    a, b = max(pairs, key=lambda p: p[1] - p[0])    # one full step (plan rebuild + forward/backward/Adam)
     seg = rows[a:b]
     tot = sum(v for _, v in seg)
     agg = collections.OrderedDict()

@@ -47,7 +47,11 @@ __device__ __forceinline__ float4 lds4_sh(unsigned addr) {   // explicit LDS.128
 __device__ __forceinline__ void sts4_sh(unsigned addr, const float4& v) {
   asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
 }
-__device__ __forceinline__ unsigned sh_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned sh_addr(const void* p) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(p);
+  asm volatile("" : "+r"(a));        // opaque: keep it in a register instead of re-deriving it (S2R + LEA) per use
+  return a;
+}
 __device__ __forceinline__ void st4s(float* p, const float4& v) { __stcs(reinterpret_cast<float4*>(p), v); }
 __device__ __forceinline__ void st4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ void add4(float4& a, const float4& b) {
@@ -148,7 +152,12 @@ struct SegGather {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     int j = b;
     if (npre >= 1) {
-      accum(acc, xa, j, h, Tg, Tsh);
+      if (NORM && dinv) {
+        accum(acc, xa, j, h, Tg, Tsh);
+      } else {
+        acc = xa;
+        if (TAB != TAB_NONE) add4(acc, table(att(j), Tg, Tsh));
+      }
       ++j;
       if (npre == 2) {
         accum(acc, xb, j, h, Tg, Tsh);

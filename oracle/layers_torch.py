@@ -273,6 +273,33 @@ class OracleGINEConv(nn.Module):
         return self.mlp((out + (1 + self.eps) * x).squeeze())
 
 
+class OracleKGINConv(nn.Module):
+    """run_simulation.py:29-93 (the script itself cannot be imported here: it needs matplotlib; this class is
+    checked against the reference by reading only -- parity UNPINNED for this one module)."""
+
+    def __init__(self, hidden_size, K, eps=0., train_eps=False):
+        super().__init__()
+        self.K, self.hidden_size = K, hidden_size
+        self.proj = nn.Linear(1, K * hidden_size)
+        self.hop_proj1 = nn.Parameter(torch.empty(K, hidden_size, hidden_size))
+        self.hop_bias1 = nn.Parameter(torch.empty(K, hidden_size))
+        self.hop_proj2 = nn.Parameter(torch.empty(K, hidden_size, hidden_size))
+        self.hop_bias2 = nn.Parameter(torch.empty(K, hidden_size))
+        if train_eps:
+            self.eps = nn.Parameter(torch.tensor([float(eps)]))
+        else:
+            self.register_buffer("eps", torch.tensor([float(eps)]))
+        self.combine_proj = nn.Linear(hidden_size * K, hidden_size)
+
+    def forward(self, x, edge_index, edge_attr, batch):
+        x = self.proj(x).view(-1, self.K, self.hidden_size)
+        z = dense_khop_aggregate(x, edge_index, edge_attr, None, None) + (1 + self.eps) * x   # :73-75
+        z = z.permute(1, 0, 2)
+        z = F.relu(torch.matmul(z, self.hop_proj1) + self.hop_bias1.unsqueeze(1))
+        z = F.relu(torch.matmul(z, self.hop_proj2) + self.hop_bias2.unsqueeze(1))
+        return self.combine_proj(z.permute(1, 0, 2).contiguous().view(-1, self.K * self.hidden_size))
+
+
 def make_oracle_layer(model_name, hidden, K, num_layer=None, eps=0., train_eps=False, num_hop1_edge=1, max_pe_num=1,
                       combine="geometric", aggr="add"):
     """layer_utils.py:10-34"""

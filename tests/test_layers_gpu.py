@@ -173,6 +173,24 @@ def test_op_widths_vs_dense_oracle(lib, d, fuse):
         assert rel_err(a, c) < RTOL, rel_err(a, c)
 
 
+@pytest.mark.parametrize("K", [1, 3, 6])
+def test_kgin_simulation_layer(lib, K):
+    """BASELINE config 5 workload: 3-regular graphs, KGINConv(16, K), forward only (run_simulation.py:96-116)."""
+    from kpgnn_b200 import synth
+    from kpgnn_b200.simulation import KGINConv
+    from tests.util import collate
+    torch.manual_seed(0)
+    dev = torch.device("cuda:0")
+    b = collate([synth.regular_graph(80, 3, s) for s in range(2)], (K, 10, 1, 1, 1, 1, "spd"))
+    mine, ora = KGINConv(16, K), OL.OracleKGINConv(16, K)
+    ora.load_state_dict(mine.state_dict())
+    mine, ora = mine.to(dev).eval(), ora.to(dev).eval()
+    x = torch.ones(b["num_nodes"], 1, device=dev)
+    ei, ea, bt = b["edge_index"].to(dev), b["edge_attr"].to(dev), b["batch"].to(dev)
+    with torch.no_grad():
+        assert rel_err(mine(x, ei, ea, bt), ora(x, ei, ea, bt)) < RTOL
+
+
 def test_no_cpu_fallback(lib):
     from kpgnn_b200 import _lib
     from kpgnn_b200.layers.KPGINplus import KPGINPlusConv

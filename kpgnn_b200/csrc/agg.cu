@@ -662,7 +662,9 @@ int kp_agg_forward(const kp_agg_desc* desc, float* out, void* stream) {
 }
 
 int kp_agg_set_force_generic(int flag) {
-  kp::g_force_generic = flag ? 1 : 0;
+  // bit 0: generic kernels instead of the float4 fast path; bit 1: fast path without the cp.async ring
+  kp::g_force_generic = (flag & 1) ? 1 : 0;
+  kp::fast_fwd_set_ring((flag & 2) ? 0 : 1);
   return 0;
 }
 

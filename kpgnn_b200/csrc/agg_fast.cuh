@@ -265,6 +265,126 @@ __global__ void __launch_bounds__(256, KP_FWD_MINB) agg_fwd_fast_kernel(const Fa
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// forward, asynchronous-copy variant (G = 32, i.e. 68 <= d <= 128).  The registers of the plain kernel cap the
+// SM at 32 warps, and with ~1 us loaded-memory latency the two rows + one P row a warp could keep in flight in
+// registers left 37 % of issue slots empty (profiles/r1g_agg_fwd.txt).  Here every warp owns a 9-slot ring in
+// shared memory (3 hops in flight x {row 0, row 1, P row}) filled by cp.async (LDGSTS, no registers held): the
+// P row and the first two gathered rows of hop h+2 are requested while hop h is being reduced.  Each lane copies
+// and later reads back only its own 16 bytes, so cp.async.wait_group is the only synchronisation.
+// ------------------------------------------------------------------------------------------------------------
+#define KP_RING_SLOT_BYTES 416u      /* 26 lanes x 16 B: a 104-float row; rows up to 128 floats use 512 */
+__device__ __forceinline__ void cp_async16_ca(unsigned dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src));
+}
+__device__ __forceinline__ void cp_async16_cg(unsigned dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N));
+}
+
+template <int ACT, bool FUSE, int TAB, bool EXTRA>
+__global__ void __launch_bounds__(256, 4) agg_fwd_ring_kernel(const FastArgs fa, float* __restrict__ out, int stage_floats,
+                                                              unsigned slot_bytes) {
+  constexpr int G = 32;
+  extern __shared__ __align__(16) float sm[];
+  const kp_agg_desc& a = fa.d;
+  stage_tables<TAB, FUSE>(a, sm);
+  const int d = a.d, k = a.k, Kp = a.Kplan;
+  const unsigned xs = fa.xs, xh = fa.xh;
+  const int lane = threadIdx.x & 31;
+  const bool active = lane * 4 < d;
+  const unsigned c = (unsigned)min(lane * 4, d - 4);
+  const int wib = threadIdx.x >> 5;
+  const unsigned sm_base = sh_addr(sm);
+  const unsigned n0f = (TAB == TAB_SMEM) ? (unsigned)(a.rows0 * d) : 0u;
+  const unsigned theta_sh = sm_base + ((TAB == TAB_SMEM) ? (unsigned)((a.rows0 + a.rowsk) * d) : 0u) * 4u + c * 4u;
+  // this lane's byte inside slot s of the warp's ring: ring + (wib*9 + s)*slot_bytes + lane*16
+  const unsigned ring = sm_base + (unsigned)stage_floats * 4u + (unsigned)(wib * 9) * slot_bytes +
+                        min((unsigned)lane * 16u, slot_bytes - 16u);   // idle lanes alias the last chunk (never past the ring)
+  float self_c = 0.f;
+  if (EXTRA && a.eps) self_c = 1.f + __ldg(a.eps);
+  SegGather<G, TAB, EXTRA> sg;
+  sg.Xb = a.X; sg.col = a.col; sg.attr = a.attr16; sg.dinv = EXTRA ? a.dinv : nullptr;
+  sg.xs = xs; sg.gm = 0xffffffffu; sg.Kp = Kp; sg.d = d; sg.lane = lane;
+  for (int v = blockIdx.x * 8 + wib; v < a.N; v += gridDim.x * 8) {
+    const int* rp = a.rowptr + (size_t)v * Kp;
+    const int rpv = (lane <= k) ? __ldg(rp + lane) : 0;             // all k+1 row pointers, one coalesced load
+    const int nbeg = __shfl_sync(0xffffffffu, rpv, 0), nend = __shfl_sync(0xffffffffu, rpv, k);
+    sg.open(nbeg, nend);
+    const bool fits = (nend - nbeg) <= G;                            // whole node inside one entry window
+    const float* Pv = a.P ? a.P + ((size_t)v * fa.ps + c) : nullptr;
+    float* outv = out + (FUSE ? (size_t)v * d : (size_t)v * k * d) + c;
+    auto issue = [&](int h) {                                        // requests for hop h -> ring slots (h%3)*3+{0,1,2}
+      const unsigned slot = ring + (unsigned)((h % 3) * 3) * slot_bytes;
+      if (fits) {
+        const int b = __shfl_sync(0xffffffffu, rpv, h), e = __shfl_sync(0xffffffffu, rpv, h + 1);
+        const unsigned xoff = h * xh + c;
+        if (b < e) {
+          const unsigned u0 = sg.src(b);
+          if (active) cp_async16_ca(slot, a.X + (u0 * xs + xoff));
+          if (b + 1 < e) {
+            const unsigned u1 = sg.src(b + 1);
+            if (active) cp_async16_ca(slot + slot_bytes, a.X + (u1 * xs + xoff));
+          }
+        }
+      }
+      if (Pv && active) cp_async16_cg(slot + 2u * slot_bytes, Pv + h * fa.ph);
+      cp_async_commit();
+    };
+    issue(0);
+    if (k > 1) issue(1); else cp_async_commit();
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int h = 0; h < k; ++h) {
+      if (h + 2 < k) issue(h + 2); else cp_async_commit();
+      cp_async_wait<2>();                                            // hop h's group has landed
+      const int b = __shfl_sync(0xffffffffu, rpv, h), e = __shfl_sync(0xffffffffu, rpv, h + 1);
+      const unsigned slot = ring + (unsigned)((h % 3) * 3) * slot_bytes;
+      const unsigned xoff = h * xh + c;
+      const float* Tg = (TAB == TAB_GLOBAL) ? (h == 0 ? a.T0 : a.Tk) + c : nullptr;
+      const unsigned Tsh = sm_base + ((h == 0 ? 0u : n0f) + c) * 4u;
+      float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      int j = b;
+      if (fits) {
+        if (b < e) {
+          sg.accum(z, lds4_sh(slot), b, h, Tg, Tsh);
+          j = b + 1;
+          if (b + 1 < e) {
+            sg.accum(z, lds4_sh(slot + slot_bytes), b + 1, h, Tg, Tsh);
+            j = b + 2;
+          }
+        }
+      }
+      if (j < e) {
+        sg.npre = 0;
+        float4 rest = sg.consume(j, e, xoff, h, Tg, Tsh);
+        add4(z, rest);
+      }
+      float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (Pv) p = lds4_sh(slot + 2u * slot_bytes);
+      if (EXTRA) {
+        const float s = fast_row_scale<EXTRA>(a, v, h);
+        z.x *= s; z.y *= s; z.z *= s; z.w *= s;
+      }
+      z.x = act_fwd<ACT>(z.x); z.y = act_fwd<ACT>(z.y); z.z = act_fwd<ACT>(z.z); z.w = act_fwd<ACT>(z.w);
+      if (EXTRA && a.eps) fma4(z, self_c, ld4(a.X + ((unsigned)v * xs + xoff)));
+      if (FUSE) {
+        const float4 th = lds4_sh(theta_sh + (unsigned)(h * d) * 4u);
+        o.x = fmaf(th.x, z.x, fmaf(th.x, p.x, o.x)); o.y = fmaf(th.y, z.y, fmaf(th.y, p.y, o.y));
+        o.z = fmaf(th.z, z.z, fmaf(th.z, p.z, o.z)); o.w = fmaf(th.w, z.w, fmaf(th.w, p.w, o.w));
+      } else {
+        add4(z, p);
+        if (active) st4s(outv + h * d, z);
+      }
+    }
+    cp_async_wait<0>();
+    if (FUSE && active) st4s(outv, o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // B1: per destination row -- recompute, Gs, dP, dtheta / deps partials
 // ------------------------------------------------------------------------------------------------------------
 template <int G, int ACT, bool FUSE, int TAB, bool EXTRA>

@@ -18,11 +18,11 @@ torch.backends.cudnn.allow_tf32 = False
 NOISE_ONLY = ("mlp.0.bias", "mlp.3.bias")
 
 
-@pytest.fixture(autouse=True, params=["fast", "generic"])
+@pytest.fixture(autouse=True, params=["fast", "fast-noring", "generic"])
 def kernel_path(request, lib):
-    """Every case runs through both kernel families: the float4 fast path (agg_fast.cuh) and the generic
-    any-width kernels (agg.cu)."""
-    lib.kp_agg_set_force_generic(1 if request.param == "generic" else 0)
+    """Every case runs through all kernel families: the float4 fast path with the cp.async-ring forward kernel,
+    the fast path with the register-prefetch forward kernel, and the generic any-width kernels (agg.cu)."""
+    lib.kp_agg_set_force_generic({"fast": 0, "fast-noring": 2, "generic": 1}[request.param])
     yield request.param
     lib.kp_agg_set_force_generic(0)
 

@@ -138,6 +138,12 @@ int kp_table_sum_backward_workspace_bytes(const kp_tsum_desc* desc, size_t* byte
 int kp_table_sum_backward(const kp_tsum_desc* desc, const float* dOut, float* dTable, void* workspace,
                           size_t workspace_bytes, void* stream);
 
+/* GeometricCombine weights, layers/combine.py:51-58: theta[h,c] = softmax over h of a_c (1-a_c)^h with
+ * a = sigmoid(alphas); theta is [K,d].  Backward returns d(loss)/d(alphas) from d(loss)/d(theta). */
+int kp_geometric_theta_forward(const float* alphas, int32_t K, int32_t d, float* theta, void* stream);
+int kp_geometric_theta_backward(const float* alphas, const float* theta, const float* dtheta, int32_t K, int32_t d,
+                                float* dalphas, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Batched K-hop neighbourhood + peripheral-subgraph extraction.  Replaces, for a whole batch of graphs,
  * data_utils.py:20-107 (extract_multi_hop_neighbors), :110-125 (adj_K_order), :128-162 (get_peripheral_attr),

@@ -222,3 +222,70 @@ int kp_table_sum_backward(const kp_tsum_desc* desc, const float* dOut, float* dT
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------
+// GeometricCombine weights (combine.py:51-58): theta[h,c] = softmax_h( a_c (1-a_c)^h ),  a = sigmoid(alphas).
+// The reference builds them with ~8 elementwise launches per layer (and ~12 more in backward) on a [K,d] tensor;
+// here forward and backward are one single-CTA kernel each.
+// ------------------------------------------------------------------------------------------------------------
+namespace kp {
+
+__global__ void geo_theta_fwd_kernel(const float* __restrict__ alphas, int K, int d, float* __restrict__ theta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d) return;
+  const float a = 1.f / (1.f + expf(-alphas[c]));
+  float m = -INFINITY, pw = 1.f;
+  for (int h = 0; h < K; ++h) {
+    m = fmaxf(m, a * pw);
+    pw *= (1.f - a);
+  }
+  float sum = 0.f;
+  pw = 1.f;
+  for (int h = 0; h < K; ++h) {
+    sum += expf(a * pw - m);
+    pw *= (1.f - a);
+  }
+  pw = 1.f;
+  const float inv = 1.f / sum;
+  for (int h = 0; h < K; ++h) {
+    theta[(size_t)h * d + c] = expf(a * pw - m) * inv;
+    pw *= (1.f - a);
+  }
+}
+
+__global__ void geo_theta_bwd_kernel(const float* __restrict__ alphas, const float* __restrict__ theta,
+                                     const float* __restrict__ dtheta, int K, int d, float* __restrict__ dalphas) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d) return;
+  const float a = 1.f / (1.f + expf(-alphas[c]));
+  float dot = 0.f;
+  for (int h = 0; h < K; ++h) dot += theta[(size_t)h * d + c] * dtheta[(size_t)h * d + c];
+  float da = 0.f, pw = 1.f, pwm1 = 0.f;          // pw = (1-a)^h, pwm1 = (1-a)^(h-1)
+  for (int h = 0; h < K; ++h) {
+    const float dt = theta[(size_t)h * d + c] * (dtheta[(size_t)h * d + c] - dot);
+    da += dt * (pw - a * (float)h * pwm1);
+    pwm1 = pw;
+    pw *= (1.f - a);
+  }
+  dalphas[c] = da * a * (1.f - a);
+}
+
+}  // namespace kp
+
+extern "C" {
+
+int kp_geometric_theta_forward(const float* alphas, int32_t K, int32_t d, float* theta, void* stream) {
+  KP_CHECK_ARG(alphas && theta && K >= 1 && d >= 1, "kp_geometric_theta_forward: bad arguments");
+  KP_LAUNCH(kp::geo_theta_fwd_kernel, kp::ceil_div(d, 128), 128, 0, (cudaStream_t)stream, alphas, K, d, theta);
+  return 0;
+}
+
+int kp_geometric_theta_backward(const float* alphas, const float* theta, const float* dtheta, int32_t K, int32_t d,
+                                float* dalphas, void* stream) {
+  KP_CHECK_ARG(alphas && theta && dtheta && dalphas && K >= 1 && d >= 1, "kp_geometric_theta_backward: bad arguments");
+  KP_LAUNCH(kp::geo_theta_bwd_kernel, kp::ceil_div(d, 128), 128, 0, (cudaStream_t)stream, alphas, theta, dtheta, K, d,
+            dalphas);
+  return 0;
+}
+
+}  // extern "C"

@@ -28,6 +28,35 @@ class AttentionCombine(nn.Module):
         return (x * weight).sum(dim=1)
 
 
+class _GeoTheta(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, alphas, K):
+        import ctypes as C
+        from .. import _lib
+        lib = _lib.lib()
+        alphas = alphas.detach().contiguous()
+        theta = torch.empty((K, alphas.numel()), dtype=torch.float32, device=alphas.device)
+        st = C.c_void_p(torch.cuda.current_stream(alphas.device).cuda_stream)
+        _lib.check(lib.kp_geometric_theta_forward(alphas.data_ptr(), K, alphas.numel(), theta.data_ptr(), st),
+                   "kp_geometric_theta_forward")
+        ctx.save_for_backward(alphas, theta)
+        ctx.K = K
+        return theta
+
+    @staticmethod
+    def backward(ctx, dtheta):
+        import ctypes as C
+        from .. import _lib
+        lib = _lib.lib()
+        alphas, theta = ctx.saved_tensors
+        dtheta = dtheta.contiguous()
+        dal = torch.empty_like(alphas)
+        st = C.c_void_p(torch.cuda.current_stream(alphas.device).cuda_stream)
+        _lib.check(lib.kp_geometric_theta_backward(alphas.data_ptr(), theta.data_ptr(), dtheta.data_ptr(), ctx.K,
+                                                   alphas.numel(), dal.data_ptr(), st), "kp_geometric_theta_backward")
+        return dal, None
+
+
 class GeometricCombine(nn.Module):
     """Geometric combination.  Args: K (hops), hidden_size (per-hop width) -- note the argument order."""
 
@@ -41,7 +70,11 @@ class GeometricCombine(nn.Module):
         nn.init.zeros_(self.alphas)
 
     def thetas(self):
-        """[K, hidden] softmax over hops of alpha*(1-alpha)^k, alpha = sigmoid(alphas) (combine.py:51-58)."""
+        """[K, hidden] softmax over hops of alpha*(1-alpha)^k, alpha = sigmoid(alphas) (combine.py:51-58).
+        On a CUDA device this is one kernel forward and one backward (kp_geometric_theta_*) instead of the
+        reference's ~20 elementwise launches on a [K, hidden] tensor."""
+        if self.alphas.is_cuda:
+            return _GeoTheta.apply(self.alphas, self.K)
         a = torch.sigmoid(self.alphas)
         hops = torch.arange(self.K, device=a.device, dtype=a.dtype).unsqueeze(-1)
         return torch.softmax(a * (1 - a) ** hops, dim=0)

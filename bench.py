@@ -198,9 +198,11 @@ class Trainer(object):
         n0 = _lib.launch_count()
         if self.world == 1:
             with torch.cuda.graph(self.graph):
+                self.refresh_derived()
                 self.loss = self._step()
         else:
             with torch.cuda.graph(self.graph):
+                self.refresh_derived()
                 self.loss = self._fwd_bwd()
             self.graph_opt = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph_opt):
@@ -239,13 +241,14 @@ class Trainer(object):
         return n
 
     def step_resident(self):
-        n = self.refresh_derived()
-        self.replay()
-        return n
+        if self.eager:
+            self.refresh_derived()
+        self.replay()                                # plan + index rebuild are the first nodes of the CUDA graph
 
     def step_e2e(self):
         nbytes = self.upload()
-        self.refresh_derived()
+        if self.eager:
+            self.refresh_derived()
         self.replay()
         val = self.loss.item()                       # D2H read of the step's loss (train_ZINC.py:45)
         self.plan().validate()
@@ -464,7 +467,7 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    plan_launches = tr.refresh_derived()
+    plan_launches = tr.refresh_derived() if args.eager else 0
     t_res = timed_steps(tr.step_resident, args.steps, device, flush, dist_on)
     log("[rank %d] resident timing done" % rank)
     for _ in range(3):
@@ -513,7 +516,7 @@ def main():
             "e2e": {"value": round(total_graphs / (ms_e2e * 1e-3), 1), "unit": "graphs/s",
                     "h2d_bytes_per_step": int(h2d[0]), "d2h_bytes_per_step": 4 + 16, "ms_per_step": round(ms_e2e, 4)},
             "gpu_launches": int((tr.launches_per_step + plan_launches) * args.steps),
-            "gpu_launches_per_step": {"in_cuda_graph": int(tr.launches_per_step), "plan_rebuild": int(plan_launches)},
+            "gpu_launches_per_step": {"ours_in_cuda_graph_incl_plan_rebuild": int(tr.launches_per_step)},
             "clocks": clocks, "roofline": roof, "roofline_batch128": roof_small, "cpu_baseline": cpu,
             "loss": float(tr.loss.item()),
         }

@@ -42,8 +42,11 @@ class GraphPlan(object):
         """Completes a deferred refresh: waits for its statistics and raises on overflow / bad indices."""
         if self.pending is None:
             return
-        self.pending.synchronize()
-        self.pending = None
+        if self.pending == "captured":          # refresh lives inside a CUDA graph: wait for the replay itself
+            torch.cuda.current_stream(self.device).synchronize()
+        else:
+            self.pending.synchronize()
+            self.pending = None
         nnz, m0, mk, bad = self.stats_host.tolist()
         if bad:
             raise IndexError("edge_index / edge_attr out of range in %d entries" % bad)
@@ -125,9 +128,12 @@ def refresh_plan(p, edge_index, edge_attr_base, attr_stride):
     if _DEFERRED:
         _run_fill(p, pin)
         p.stats_host.copy_(p.stats, non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream(p.device))
-        p.pending = ev
+        if torch.cuda.is_current_stream_capturing():
+            p.pending = "captured"              # every replay refreshes stats_host; validate() syncs the stream
+        else:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(p.device))
+            p.pending = ev
         return True
     nnz, m0, mk, bad = p.stats.tolist()
     if bad:

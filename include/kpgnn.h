@@ -138,6 +138,19 @@ int kp_table_sum_backward_workspace_bytes(const kp_tsum_desc* desc, size_t* byte
 int kp_table_sum_backward(const kp_tsum_desc* desc, const float* dOut, float* dTable, void* workspace,
                           size_t workspace_bytes, void* stream);
 
+/* Training-mode BatchNorm1d (+ optional fused ReLU) over [N,C] fp32 rows: the BN / ReLU of the KP-GIN+ MLP
+ * (layers/KPGINplus.py:25-30) and the backbone's norm (models/GNNs.py:430, norm_type "Batch").  Biased variance
+ * for the normalisation, unbiased for running_var, running = (1-momentum)*running + momentum*batch, as
+ * torch.nn.BatchNorm1d.  One kernel each way; N <= kp_bn_max_rows(), C % 4 == 0; callers fall back to the
+ * framework's BatchNorm otherwise (eval mode, larger N). */
+int kp_bn_max_rows(void);
+int kp_bn_forward(const float* x, int32_t N, int32_t C, const float* gamma, const float* beta, float eps,
+                  float momentum, float* running_mean, float* running_var, int64_t* num_batches_tracked, int32_t relu,
+                  float* y, float* save_mean, float* save_invstd, void* stream);
+int kp_bn_backward(const float* x, const float* dy, int32_t N, int32_t C, const float* gamma, const float* beta,
+                   const float* save_mean, const float* save_invstd, int32_t relu, float* dx, float* dgamma,
+                   float* dbeta, void* stream);
+
 /* GeometricCombine weights, layers/combine.py:51-58: theta[h,c] = softmax over h of a_c (1-a_c)^h with
  * a = sigmoid(alphas); theta is [K,d].  Backward returns d(loss)/d(alphas) from d(loss)/d(theta). */
 int kp_geometric_theta_forward(const float* alphas, int32_t K, int32_t d, float* theta, void* stream);

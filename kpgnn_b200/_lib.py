@@ -68,6 +68,12 @@ _SIGNATURES = {
     "kp_table_sum_backward_workspace_bytes": (C.c_int, [C.POINTER(TsumDesc), C.POINTER(C.c_size_t)]),
     "kp_table_sum_backward": (C.c_int, [C.POINTER(TsumDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                         C.c_void_p]),
+    "kp_bn_max_rows": (C.c_int, []),
+    "kp_bn_forward": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
+                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.c_void_p]),
+    "kp_bn_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "kp_geometric_theta_forward": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "kp_geometric_theta_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                               C.c_void_p]),

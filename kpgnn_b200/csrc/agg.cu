@@ -662,9 +662,11 @@ int kp_agg_forward(const kp_agg_desc* desc, float* out, void* stream) {
 }
 
 int kp_agg_set_force_generic(int flag) {
-  // bit 0: generic kernels instead of the float4 fast path; bit 1: fast path without the cp.async ring
+  // bit 0: generic kernels instead of the float4 fast path; bit 1: fast path without the cp.async ring;
+  // bit 2: fast path without the lean (packed-math, L2-prefetch) kernels
   kp::g_force_generic = (flag & 1) ? 1 : 0;
   kp::fast_fwd_set_ring((flag & 2) ? 0 : 1);
+  kp::fast_fwd_set_lean((flag & 4) ? 0 : 1);
   return 0;
 }
 

@@ -23,6 +23,7 @@ inline bool fast_combo(int act, bool fuse, bool need_extra, bool* extra) {
   return !fuse;
 }
 
+void fast_fwd_set_lean(int flag);   // 1 (default): packed-math + L2-prefetch kernels (agg_lean.cuh) where k + 1 <= G
 void fast_fwd_set_ring(int flag);   // 0: plain register-prefetch forward kernel, 1 (default): cp.async ring
 int fast_fwd(const FastArgs& fa, int G, int act, bool fuse, int tab, bool extra, int grid, size_t smem, float* out,
              cudaStream_t st);

@@ -1,0 +1,355 @@
+// agg_lean.cuh -- third generation of the fused K-hop aggregation kernels (sm_100a).
+//
+// Why: ncu on the register-prefetch and cp.async-ring kernels (profiles/r1g, r1i) showed DRAM traffic == the
+// algorithmic bytes but the SMs ISSUE-bound: 63-73 % issue-active at 208-233 warp instructions per (node,hop) row,
+// of which only ~76 were the row's arithmetic; the rest was software-pipelining bookkeeping (ring slots, "rows
+// already requested" state, window checks per entry, 64-bit addressing).  This version spends instructions only on
+// the row itself:
+//   * Blackwell packed fp32 (FADD2 / FMUL2 / FFMA2 on register pairs) for the accumulation, the GELU polynomial
+//     and the theta-combine: 16 bytes of a row are two 64-bit registers from load to store;
+//   * DRAM latency is taken off the instruction stream altogether: one lane per node issues
+//     cp.async.bulk.prefetch.L2 for the X and P rows of the node its group will process `pf` iterations later
+//     (3.3 KB per instruction), so every gather and every P read below is an L1/L2 hit;
+//   * the node's k+1 row pointers are one coalesced load (lane h holds rowptr[v*K+h]) and its entry list one more
+//     (lane i holds entry nbeg+i, already multiplied out to an X element offset and a table byte offset); both are
+//     loaded one node ahead, so the hop loop starts with everything in registers and broadcasts with SHFL;
+//   * the P row runs one hop ahead in registers; gathers are issued two at a time.
+// Requirements beyond the fast path's (d % 4 == 0, d <= 128, 32-bit offsets): k + 1 <= G.
+#pragma once
+#include "agg_fast.cuh"
+
+namespace kp {
+
+typedef unsigned long long u64;
+
+struct P4 {      // four consecutive floats as two packed pairs: lo = (x, y), hi = (z, w)
+  u64 lo, hi;
+};
+
+__device__ __forceinline__ u64 pk2(float a, float b) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpk2(u64 v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+  u64 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+  u64 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+  u64 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ u64 splat2(float a) { return pk2(a, a); }
+__device__ __forceinline__ P4 p4zero() { return P4{0ull, 0ull}; }
+__device__ __forceinline__ P4 add4p(const P4& a, const P4& b) { return P4{add2(a.lo, b.lo), add2(a.hi, b.hi)}; }
+
+// gathered rows: read-only path, L1-allocating (a row is re-gathered by ~2.5 destination rows of the same graph)
+__device__ __forceinline__ P4 ldg4p(const float* p) {
+  P4 v;
+  asm("ld.global.nc.v2.b64 {%0, %1}, [%2];" : "=l"(v.lo), "=l"(v.hi) : "l"(p));
+  return v;
+}
+// rows touched exactly once (P, dOut): no L1 allocation
+__device__ __forceinline__ P4 ldg4p_stream(const float* p) {
+  P4 v;
+  asm("ld.global.nc.L1::no_allocate.v2.b64 {%0, %1}, [%2];" : "=l"(v.lo), "=l"(v.hi) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ P4 lds4p(unsigned addr) {
+  P4 v;
+  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(v.lo), "=l"(v.hi) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts4p(unsigned addr, const P4& v) {
+  asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(addr), "l"(v.lo), "l"(v.hi) : "memory");
+}
+__device__ __forceinline__ void stg4p_stream(float* p, const P4& v) {
+  asm volatile("st.global.cs.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(v.lo), "l"(v.hi) : "memory");
+}
+__device__ __forceinline__ void stg4p(float* p, const P4& v) {
+  asm volatile("st.global.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(v.lo), "l"(v.hi) : "memory");
+}
+// asynchronous L2 prefetch of `bytes` (multiple of 16) starting at a 16-byte aligned global address
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+// exact-erf GELU on a packed pair; same Abramowitz-Stegun 7.1.26 erfc form as agg_common.cuh (|err| < 5e-7), with
+// the polynomial, the exponent argument and the products on the packed pipe.  The polynomial coefficients carry
+// the minus sign, so  gelu(x) = max(x,0) + |x| * (-half_erfc(|x|)).
+#define KP_GELU_C0 (0.3275911f * 0.70710678118654752440f)
+#define KP_GELU_S 0.84932180028801904272f /* sqrt(0.5 * log2(e)):  exp(-x^2/2) = 2^-(S x)^2 */
+__device__ __forceinline__ void gelu_pair_parts(u64 x, u64& neg_half_erfc, u64& gauss) {
+  float x0, x1;
+  unpk2(x, x0, x1);
+  const float t0 = rcp_approx(fmaf(KP_GELU_C0, fabsf(x0), 1.0f));
+  const float t1 = rcp_approx(fmaf(KP_GELU_C0, fabsf(x1), 1.0f));
+  const u64 t = pk2(t0, t1);
+  u64 p = fma2(t, splat2(-0.5f * 1.061405429f), splat2(-0.5f * -1.453152027f));
+  p = fma2(t, p, splat2(-0.5f * 1.421413741f));
+  p = fma2(t, p, splat2(-0.5f * -0.284496736f));
+  p = fma2(t, p, splat2(-0.5f * 0.254829592f));
+  const u64 y = mul2(x, splat2(KP_GELU_S));
+  const u64 q = mul2(y, y);
+  float q0, q1;
+  unpk2(q, q0, q1);
+  gauss = pk2(ex2_approx(-q0), ex2_approx(-q1));
+  neg_half_erfc = mul2(mul2(p, t), gauss);
+}
+template <int ACT>
+__device__ __forceinline__ u64 act_fwd2(u64 x) {
+  if (ACT == KP_ACT_GELU) {
+    u64 nh, g;
+    gelu_pair_parts(x, nh, g);
+    float x0, x1, h0, h1;
+    unpk2(x, x0, x1);
+    unpk2(nh, h0, h1);
+    return pk2(fmaf(fabsf(x0), h0, fmaxf(x0, 0.f)), fmaf(fabsf(x1), h1, fmaxf(x1, 0.f)));
+  }
+  if (ACT == KP_ACT_RELU) {
+    float x0, x1;
+    unpk2(x, x0, x1);
+    return pk2(fmaxf(x0, 0.f), fmaxf(x1, 0.f));
+  }
+  return x;
+}
+// d act / d x on a packed pair
+template <int ACT>
+__device__ __forceinline__ u64 act_bwd2(u64 x) {
+  if (ACT == KP_ACT_GELU) {
+    u64 nh, g;
+    gelu_pair_parts(x, nh, g);
+    float x0, x1, h0, h1;
+    unpk2(x, x0, x1);
+    unpk2(nh, h0, h1);
+    const u64 cdf = pk2(x0 > 0.f ? 1.0f + h0 : -h0, x1 > 0.f ? 1.0f + h1 : -h1);
+    return fma2(mul2(x, splat2(0.39894228040143267794f)), g, cdf);
+  }
+  if (ACT == KP_ACT_RELU) {
+    float x0, x1;
+    unpk2(x, x0, x1);
+    return pk2(x0 > 0.f ? 1.f : 0.f, x1 > 0.f ? 1.f : 0.f);
+  }
+  return splat2(1.f);
+}
+
+__device__ __forceinline__ void l2_prefetch_line(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+__device__ __forceinline__ uint2 lds2_sh(unsigned addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ int lds1_sh(unsigned addr) {
+  int v;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts2_sh(unsigned addr, unsigned x, unsigned y) {
+  asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void sts1_sh(unsigned addr, int x) {
+  asm volatile("st.shared.s32 [%0], %1;" ::"r"(addr), "r"(x) : "memory");
+}
+template <int G>
+__device__ __forceinline__ void group_sync(unsigned gm) {
+  __syncwarp(gm);
+}
+template <typename T>
+__device__ __forceinline__ T* opaque_ptr(T* p) {      // keeps a 64-bit base in registers: address = IMAD.WIDE.U32
+  asm volatile("" : "+l"(p));
+  return p;
+}
+__device__ __forceinline__ const float* at_elem(const float* base, unsigned elem) {
+  return reinterpret_cast<const float*>(reinterpret_cast<const char*>(base) + (size_t)elem * 4u);
+}
+
+#ifndef KP_LEAN_MINB
+#define KP_LEAN_MINB 4
+#endif
+
+// Sum of NE consecutive entries of the group's shared-memory entry window starting at byte address `ent`:
+// the NE gathers are issued back to back, the table rows (shared memory) are added while they fly.
+template <int NE, int TAB>
+__device__ __forceinline__ void lean_gather(P4& z, unsigned ent, const float* Xh) {
+  uint2 en[NE];
+  P4 x[NE];
+#pragma unroll
+  for (int i = 0; i < NE; ++i) en[i] = lds2_sh(ent + 8u * i);
+#pragma unroll
+  for (int i = 0; i < NE; ++i) x[i] = ldg4p(at_elem(Xh, en[i].x));
+  if (TAB == TAB_SMEM) {
+#pragma unroll
+    for (int i = 0; i < NE; ++i) z = add4p(z, lds4p(en[i].y));
+  }
+#pragma unroll
+  for (int i = 0; i < NE; ++i) z = add4p(z, x[i]);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// forward.  Everything except the KP-GCN per-entry norm (dinv) and tables too large for shared memory, which stay
+// on the kernels of agg_fast.cuh.
+// ------------------------------------------------------------------------------------------------------------
+template <int G, int ACT, bool FUSE, int TAB, bool EXTRA>
+__global__ void __launch_bounds__(256, KP_LEAN_MINB)
+agg_fwd_lean_kernel(const FastArgs fa, float* __restrict__ out, unsigned pf_x_lines, unsigned pf_p_lines, int pf_dist) {
+  extern __shared__ __align__(16) float sm[];
+  const kp_agg_desc& a = fa.d;
+  const int staged = stage_tables<TAB, FUSE>(a, sm);
+  const int d = a.d, k = a.k, Kp = a.Kplan, N = a.N;
+  const unsigned xs = fa.xs, d4 = (unsigned)d * 4u;
+  const int lane = threadIdx.x & (G - 1);
+  const bool active = lane * 4 < d;
+  const unsigned c = (unsigned)min(lane * 4, d - 4);            // idle lanes shadow the last chunk
+  constexpr int gpb = 256 / G;
+  const int gib = threadIdx.x / G;
+  const unsigned gm = group_mask<G>();
+  const unsigned sm_base = sh_addr(sm);
+  // table base addresses with this lane's column folded in; hop 0 uses T0, hops >= 1 use Tk
+  const unsigned tab0_sh = sm_base + c * 4u;
+  const unsigned tabk_sh = tab0_sh + ((TAB == TAB_SMEM) ? (unsigned)(a.rows0 * d) * 4u : 0u);
+  const unsigned theta_sh = sm_base + ((TAB == TAB_SMEM) ? (unsigned)((a.rows0 + a.rowsk) * d) : 0u) * 4u + c * 4u;
+  // per-group scratch behind the staged tables: entry window [G] x {X element offset, table byte address} and the
+  // node's row pointers [G]
+  const unsigned win_sh = sm_base + (unsigned)staged * 4u + (unsigned)gib * (12u * G);
+  const unsigned rp_sh = win_sh + 8u * G;
+  const float* Xc = opaque_ptr(a.X + c);
+  const bool hasP = a.P != nullptr;
+  const float* Pc = opaque_ptr(hasP ? a.P + c : a.X + c);
+  float self_c = 0.f;
+  if (EXTRA && a.eps) self_c = 1.f + __ldg(a.eps);
+
+  const int vstride = gridDim.x * gpb;
+  int v = blockIdx.x * gpb + gib;
+  if (v >= N) return;
+  // L2 prefetch: lane l asks for the l-th 128-byte line of a node's X and P rows
+  auto prefetch_node = [&](long long vp) {
+    if (vp < N) {
+      if ((unsigned)lane < pf_x_lines) l2_prefetch_line(reinterpret_cast<const char*>(a.X + (size_t)vp * xs) + lane * 128);
+      if ((unsigned)lane < pf_p_lines) l2_prefetch_line(reinterpret_cast<const char*>(a.P + (size_t)vp * fa.ps) + lane * 128);
+    }
+  };
+  for (int i = 0; i < pf_dist; ++i) prefetch_node((long long)v + (long long)i * vstride);
+
+  // software pipeline over nodes: row pointers two nodes ahead, entries one node ahead (registers), current node in
+  // the group's shared-memory window
+  int rpn = (lane <= k) ? __ldg(a.rowptr + (size_t)v * Kp + lane) : 0;            // "next" = the first node
+  int ncol = 0, nattr = 0;
+  {
+    const int nb = __shfl_sync(gm, rpn, 0, G), ne = __shfl_sync(gm, rpn, k, G);
+    if (nb + lane < ne) {
+      ncol = __ldg(a.col + nb + lane);
+      if (TAB != TAB_NONE) nattr = (int)__ldg(a.attr16 + nb + lane);
+    }
+  }
+  int vn = v;
+  int rpnn = 0;
+  {
+    const int v2 = v + vstride;
+    if (v2 < N && lane <= k) rpnn = __ldg(a.rowptr + (size_t)v2 * Kp + lane);
+  }
+  while (true) {
+    // ---- publish node vn (registers -> the group's window), then request the node after it
+    v = vn;
+    const int nbeg = __shfl_sync(gm, rpn, 0, G), nend = __shfl_sync(gm, rpn, k, G);
+    const int e1 = __shfl_sync(gm, rpn, 1, G);
+    group_sync<G>(gm);                                           // everyone is done reading the previous window
+    sts1_sh(rp_sh + 4u * lane, rpn - nbeg);                      // window-relative row pointers
+    {
+      const unsigned xo = (unsigned)ncol * xs;
+      const unsigned ta = (nbeg + lane < e1 ? tab0_sh : tabk_sh) + (unsigned)nattr * d4;
+      sts2_sh(win_sh + 8u * lane, xo, ta);
+    }
+    group_sync<G>(gm);
+    const bool big = (nend - nbeg) > G;                          // entry list longer than the window: slow path
+    vn = v + vstride;
+    rpn = rpnn;
+    ncol = 0; nattr = 0;
+    if (vn < N) {
+      const int nb = __shfl_sync(gm, rpn, 0, G), ne = __shfl_sync(gm, rpn, k, G);
+      if (nb + lane < ne) {
+        ncol = __ldg(a.col + nb + lane);
+        if (TAB != TAB_NONE) nattr = (int)__ldg(a.attr16 + nb + lane);
+      }
+      const int v2 = vn + vstride;
+      rpnn = (v2 < N && lane <= k) ? __ldg(a.rowptr + (size_t)v2 * Kp + lane) : 0;
+    }
+    prefetch_node((long long)v + (long long)pf_dist * vstride);
+
+    // ---- this node
+    const float* Xh = Xc;                                        // + h * xh per hop
+    const float* Pv = Pc + (size_t)v * fa.ps;
+    float* outv = out + (FUSE ? (size_t)v * d : (size_t)v * k * d) + c;
+    P4 o = p4zero();
+    unsigned ent = win_sh;                                       // byte address of the segment's first entry
+    unsigned th = theta_sh;
+    int b = 0;
+    for (int h = 0; h < k; ++h) {
+      const int e = lds1_sh(rp_sh + 4u * (h + 1));
+      P4 p = p4zero();
+      if (hasP) p = ldg4p_stream(Pv);
+      P4 z = p4zero();
+      if (!big) {
+        int n = e - b;
+        while (n >= 4) {
+          lean_gather<4, TAB>(z, ent, Xh);
+          ent += 32u;
+          n -= 4;
+        }
+        if (n & 2) {
+          lean_gather<2, TAB>(z, ent, Xh);
+          ent += 16u;
+        }
+        if (n & 1) {
+          lean_gather<1, TAB>(z, ent, Xh);
+          ent += 8u;
+        }
+      } else {
+        // rare: more than G entries on one node -- walk the plan arrays directly
+        for (int j = nbeg + b; j < nbeg + e; ++j) {
+          const int cj = __ldg(a.col + j);
+          P4 x = ldg4p(at_elem(Xh, (unsigned)cj * xs));
+          if (TAB == TAB_SMEM) x = add4p(x, lds4p((h == 0 ? tab0_sh : tabk_sh) + (unsigned)__ldg(a.attr16 + j) * d4));
+          z = add4p(z, x);
+        }
+      }
+      b = e;
+      if (EXTRA) {
+        const u64 s = splat2(fast_row_scale<EXTRA>(a, v, h));
+        z.lo = mul2(z.lo, s); z.hi = mul2(z.hi, s);
+      }
+      z.lo = act_fwd2<ACT>(z.lo);
+      z.hi = act_fwd2<ACT>(z.hi);
+      if (EXTRA && a.eps) {
+        const P4 xv = ldg4p(at_elem(Xh, (unsigned)v * xs));
+        const u64 sc = splat2(self_c);
+        z.lo = fma2(sc, xv.lo, z.lo); z.hi = fma2(sc, xv.hi, z.hi);
+      }
+      z = add4p(z, p);
+      if (FUSE) {
+        const P4 t = lds4p(th);
+        o.lo = fma2(t.lo, z.lo, o.lo); o.hi = fma2(t.hi, z.hi, o.hi);
+        th += d4;
+      } else {
+        if (active) stg4p_stream(outv + h * d, z);
+      }
+      Xh += fa.xh;
+      Pv += fa.ph;
+    }
+    if (FUSE && active) stg4p_stream(outv, o);
+    if (vn >= N) break;
+  }
+}
+
+}  // namespace kp

@@ -18,11 +18,12 @@ torch.backends.cudnn.allow_tf32 = False
 NOISE_ONLY = ("mlp.0.bias", "mlp.3.bias")
 
 
-@pytest.fixture(autouse=True, params=["fast", "fast-noring", "generic"])
+@pytest.fixture(autouse=True, params=["lean", "fast-ring", "fast-noring", "generic"])
 def kernel_path(request, lib):
-    """Every case runs through all kernel families: the float4 fast path with the cp.async-ring forward kernel,
-    the fast path with the register-prefetch forward kernel, and the generic any-width kernels (agg.cu)."""
-    lib.kp_agg_set_force_generic({"fast": 0, "fast-noring": 2, "generic": 1}[request.param])
+    """Every case runs through all kernel families: the packed-math / L2-prefetch kernels (agg_lean.cuh, default),
+    the float4 fast path with the cp.async-ring forward kernel, the fast path with the register-prefetch forward
+    kernel, and the generic any-width kernels (agg.cu)."""
+    lib.kp_agg_set_force_generic({"lean": 0, "fast-ring": 4, "fast-noring": 6, "generic": 1}[request.param])
     yield request.param
     lib.kp_agg_set_force_generic(0)
 

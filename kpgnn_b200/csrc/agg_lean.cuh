@@ -182,7 +182,7 @@ __device__ __forceinline__ const float* at_elem(const float* base, unsigned elem
 // Sum of NE consecutive entries of the group's shared-memory entry window starting at byte address `ent`:
 // the NE gathers are issued back to back, the table rows (shared memory) are added while they fly.
 template <int NE, int TAB>
-__device__ __forceinline__ void lean_gather(P4& z, unsigned ent, const float* Xh) {
+__device__ __forceinline__ void lean_gather(P4& z, unsigned ent, const float* Xh, unsigned c4) {
   uint2 en[NE];
   P4 x[NE];
 #pragma unroll
@@ -191,7 +191,7 @@ __device__ __forceinline__ void lean_gather(P4& z, unsigned ent, const float* Xh
   for (int i = 0; i < NE; ++i) x[i] = ldg4p(at_elem(Xh, en[i].x));
   if (TAB == TAB_SMEM) {
 #pragma unroll
-    for (int i = 0; i < NE; ++i) z = add4p(z, lds4p(en[i].y));
+    for (int i = 0; i < NE; ++i) z = add4p(z, lds4p(en[i].y + c4));
   }
 #pragma unroll
   for (int i = 0; i < NE; ++i) z = add4p(z, x[i]);
@@ -216,8 +216,10 @@ agg_fwd_lean_kernel(const FastArgs fa, float* __restrict__ out, unsigned pf_x_li
   const int gib = threadIdx.x / G;
   const unsigned gm = group_mask<G>();
   const unsigned sm_base = sh_addr(sm);
-  // table base addresses with this lane's column folded in; hop 0 uses T0, hops >= 1 use Tk
-  const unsigned tab0_sh = sm_base + c * 4u;
+  // table base addresses (hop 0 uses T0, hops >= 1 use Tk); window entries are shared by the group's lanes, so the
+  // lane's own column offset c4 is added at the lookup
+  const unsigned c4 = c * 4u;
+  const unsigned tab0_sh = sm_base;
   const unsigned tabk_sh = tab0_sh + ((TAB == TAB_SMEM) ? (unsigned)(a.rows0 * d) * 4u : 0u);
   const unsigned theta_sh = sm_base + ((TAB == TAB_SMEM) ? (unsigned)((a.rows0 + a.rowsk) * d) : 0u) * 4u + c * 4u;
   // per-group scratch behind the staged tables: entry window [G] x {X element offset, table byte address} and the
@@ -303,16 +305,16 @@ agg_fwd_lean_kernel(const FastArgs fa, float* __restrict__ out, unsigned pf_x_li
       if (!big) {
         int n = e - b;
         while (n >= 4) {
-          lean_gather<4, TAB>(z, ent, Xh);
+          lean_gather<4, TAB>(z, ent, Xh, c4);
           ent += 32u;
           n -= 4;
         }
         if (n & 2) {
-          lean_gather<2, TAB>(z, ent, Xh);
+          lean_gather<2, TAB>(z, ent, Xh, c4);
           ent += 16u;
         }
         if (n & 1) {
-          lean_gather<1, TAB>(z, ent, Xh);
+          lean_gather<1, TAB>(z, ent, Xh, c4);
           ent += 8u;
         }
       } else {
@@ -320,7 +322,7 @@ agg_fwd_lean_kernel(const FastArgs fa, float* __restrict__ out, unsigned pf_x_li
         for (int j = nbeg + b; j < nbeg + e; ++j) {
           const int cj = __ldg(a.col + j);
           P4 x = ldg4p(at_elem(Xh, (unsigned)cj * xs));
-          if (TAB == TAB_SMEM) x = add4p(x, lds4p((h == 0 ? tab0_sh : tabk_sh) + (unsigned)__ldg(a.attr16 + j) * d4));
+          if (TAB == TAB_SMEM) x = add4p(x, lds4p((h == 0 ? tab0_sh : tabk_sh) + c4 + (unsigned)__ldg(a.attr16 + j) * d4));
           z = add4p(z, x);
         }
       }

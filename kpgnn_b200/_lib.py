@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkpgnn_b200.so")
+# KPGNN_B200_LIB points at an alternative build of the same library (kernel tuning experiments)
+LIB_PATH = os.environ.get("KPGNN_B200_LIB") or os.path.join(_HERE, "libkpgnn_b200.so")
 
 ABI_VERSION = 1
 

@@ -346,10 +346,12 @@ agg_bwd_table_fast_kernel(const kp_agg_desc a, const float* __restrict__ Gs, int
   const long long r0 = gid * rows_per_group;
   const long long r1 = min(R, r0 + rows_per_group);
   float* tab = smem + (size_t)tsz * gib + c;
-  if (gib < ngroups_cta && active) {
+  const unsigned gm = (G == 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
+  if (gib < ngroups_cta) {                 // group-uniform: all G lanes take part in the shuffles below
     for (long long rb = r0; rb < r1; rb += RB) {
       int b[RB], e[RB], hh[RB];
       float4 g[RB];
+      int elast = 0;
 #pragma unroll
       for (int u = 0; u < RB; ++u) {
         const long long row = rb + u;
@@ -361,25 +363,37 @@ agg_bwd_table_fast_kernel(const kp_agg_desc a, const float* __restrict__ Gs, int
           const long long pr = (long long)v * a.Kplan + h;
           b[u] = __ldg(a.rowptr + pr);
           e[u] = __ldg(a.rowptr + pr + 1);
+          elast = e[u];
           hh[u] = h;
           g[u] = __ldcs(reinterpret_cast<const float4*>(Gs + row * a.d + c));
         }
       }
+      // the RB rows' entries are (nearly) contiguous in the plan: one coalesced load puts G of their attribute
+      // values in the group's registers; the per-entry global load that used to sit in the read-modify-write
+      // chain becomes a shuffle
+      int wb = b[0];
+      int wa = (wb + lane < elast) ? (int)__ldg(a.attr16 + wb + lane) : 0;
 #pragma unroll
       for (int u = 0; u < RB; ++u) {
         const int base = (hh[u] == 0) ? 0 : a.rows0;
         for (int j = b[u]; j < e[u]; ++j) {
-          const int at = (int)__ldg(a.attr16 + j);
-          float4* dst = reinterpret_cast<float4*>(tab + (size_t)(base + at) * a.d);
-          float4 t = *dst;
-          if (a.dinv) {
-            const float w = __ldg(a.dinv + (long long)__ldg(a.col + j) * a.Kplan + hh[u]);
-            t.x = fmaf(w, g[u].x, t.x); t.y = fmaf(w, g[u].y, t.y);
-            t.z = fmaf(w, g[u].z, t.z); t.w = fmaf(w, g[u].w, t.w);
-          } else {
-            t.x += g[u].x; t.y += g[u].y; t.z += g[u].z; t.w += g[u].w;
+          if (j - wb >= G) {
+            wb = j;
+            wa = (wb + lane < elast) ? (int)__ldg(a.attr16 + wb + lane) : 0;
           }
-          *dst = t;
+          const int at = __shfl_sync(gm, wa, j - wb, G);
+          if (active) {
+            float4* dst = reinterpret_cast<float4*>(tab + (size_t)(base + at) * a.d);
+            float4 t = *dst;
+            if (a.dinv) {
+              const float w = __ldg(a.dinv + (long long)__ldg(a.col + j) * a.Kplan + hh[u]);
+              t.x = fmaf(w, g[u].x, t.x); t.y = fmaf(w, g[u].y, t.y);
+              t.z = fmaf(w, g[u].z, t.z); t.w = fmaf(w, g[u].w, t.w);
+            } else {
+              t.x += g[u].x; t.y += g[u].y; t.z += g[u].z; t.w += g[u].w;
+            }
+            *dst = t;
+          }
         }
       }
     }

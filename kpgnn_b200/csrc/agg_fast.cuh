@@ -64,7 +64,7 @@ __device__ __forceinline__ void fma4(float4& a, float w, const float4& b) {
 template <int G>
 __device__ __forceinline__ unsigned group_mask() {
   if (G == 32) return 0xffffffffu;
-  return ((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1));
+  return ((1u << (G & 31)) - 1u) << ((threadIdx.x & 31) & ~(G - 1));
 }
 
 // Stages tables (TAB_SMEM) and theta (NEED_THETA) at the start of dynamic shared memory.

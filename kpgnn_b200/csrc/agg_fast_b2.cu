@@ -15,6 +15,8 @@ static int launch(const FastArgs& fa, bool fuse, bool extra, int grid, const flo
 
 int fast_b2(const FastArgs& fa, int G, bool fuse, bool extra, int grid, const float* Gs, const float* dOut, float* dX,
             cudaStream_t st) {
+  int rc = 0;
+  if (!extra && lean_b2(fa, G, Gs, dX, st, &rc)) return rc;
   return G == 32 ? launch<32>(fa, fuse, extra, grid, Gs, dOut, dX, st)
          : G == 16 ? launch<16>(fa, fuse, extra, grid, Gs, dOut, dX, st)
          : G == 8 ? launch<8>(fa, fuse, extra, grid, Gs, dOut, dX, st)

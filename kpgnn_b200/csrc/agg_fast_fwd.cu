@@ -1,6 +1,7 @@
 // agg_fast_fwd.cu -- instantiations of the fast forward aggregation kernel (see agg_fast.cuh).
 #include "agg_fast_host.h"
 #include "agg_lean.cuh"
+#include <stdlib.h>
 
 namespace kp {
 
@@ -33,12 +34,26 @@ static int launch_lean(const FastArgs& fa, int grid, size_t smem, float* out, cu
   const unsigned lines = (unsigned)((a.k * a.d * 4 + 127) / 128);
   const unsigned pfx = (fa.xh == (unsigned)a.d) ? (lines < (unsigned)G ? lines : (unsigned)G) : 0u;
   const unsigned pfp = (a.P && fa.ph == (unsigned)a.d) ? (lines < (unsigned)G ? lines : (unsigned)G) : 0u;
-  const int dist = a.k >= 4 ? 1 : (a.k >= 2 ? 2 : 4);
-  const size_t total = smem + (size_t)(256 / G) * 12 * G;       // + per-group entry window and row pointers
+  int dist = a.k >= 4 ? 1 : (a.k >= 2 ? 2 : 4);
+  unsigned pfx_ = pfx, pfp_ = pfp, bulk = 0;
+  // tuning knobs (profiling only): KP_LEAN_PF_MODE 0 = no L2 prefetch (default: measured fastest), 1 = per-line hints, 2 = bulk prefetch
+  static const int env_mode = getenv("KP_LEAN_PF_MODE") ? atoi(getenv("KP_LEAN_PF_MODE")) : 0;
+  static const int env_dist = getenv("KP_LEAN_PF_DIST") ? atoi(getenv("KP_LEAN_PF_DIST")) : 0;
+  if (env_dist > 0) dist = env_dist;
+  if (env_mode == 0) { pfx_ = 0; pfp_ = 0; }
+  if (env_mode == 2 && pfx) bulk = (unsigned)(a.k * a.d) * 4u;
+  // one 1024-thread CTA per SM when there are enough nodes to give every SM a few blocks (tables staged once per
+  // SM, 32 neighbouring nodes in flight on one L1); 256-thread CTAs for small batches so that all SMs get work
+  static const int env_threads = getenv("KP_LEAN_THREADS") ? atoi(getenv("KP_LEAN_THREADS")) : 0;
+  const int threads = env_threads ? env_threads : ((long long)a.N >= (long long)kNumSMs * (1024 / G) * 2 ? 1024 : 256);
+  const int gpb = threads / G, ctas_per_sm = 1024 / threads;
+  const size_t total = smem + (size_t)gpb * 12 * G;             // + per-group entry window and row pointers
+  const long long want = ((long long)a.N + gpb - 1) / gpb;
+  grid = (int)(want < kNumSMs * ctas_per_sm ? (want < 1 ? 1 : want) : kNumSMs * ctas_per_sm);   // persistent
   if (total > 48 * 1024)
     KP_CUDA(cudaFuncSetAttribute(agg_fwd_lean_kernel<G, ACT, FUSE, TAB, EXTRA>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total));
-  KP_LAUNCH((agg_fwd_lean_kernel<G, ACT, FUSE, TAB, EXTRA>), grid, 256, total, st, fa, out, pfx, pfp, dist);
+  KP_LAUNCH((agg_fwd_lean_kernel<G, ACT, FUSE, TAB, EXTRA>), grid, threads, total, st, fa, out, pfx_, pfp_, dist, bulk);
   return 0;
 }
 
@@ -57,6 +72,34 @@ static int g_use_ring = 1;
 static int g_use_lean = 1;
 void fast_fwd_set_ring(int flag) { g_use_ring = flag; }
 void fast_fwd_set_lean(int flag) { g_use_lean = flag; }
+
+// B2 (dX = gather of Gs through the transposed CSR) without self term / norm is the same computation as the
+// forward with no tables, no activation, no P and an unfused [N,k,d] output: run it on the lean forward kernel.
+bool lean_b2(const FastArgs& fa, int G, const float* Gs, float* dX, cudaStream_t st, int* rc) {
+  const kp_agg_desc& a = fa.d;
+  if (!g_use_lean || !(G == 32 || G == 16) || a.k + 1 > G) return false;
+  FastArgs t = fa;
+  t.d.rowptr = a.rowptrT;
+  t.d.col = a.colT;
+  t.d.attr16 = nullptr;
+  t.d.dinv = nullptr;
+  t.d.indeg = nullptr;
+  t.d.X = Gs;
+  t.d.P = nullptr;
+  t.d.T0 = nullptr;
+  t.d.Tk = nullptr;
+  t.d.rows0 = t.d.rowsk = 0;
+  t.d.theta = nullptr;
+  t.d.eps = nullptr;
+  t.d.act = KP_ACT_NONE;
+  t.d.fuse = 0;
+  t.xs = (unsigned)(a.k * a.d);
+  t.xh = (unsigned)a.d;
+  t.ps = t.ph = 0;
+  *rc = (G == 32) ? launch_lean<32, KP_ACT_NONE, false, TAB_NONE, false>(t, 0, 0, dX, st)
+                  : launch_lean<16, KP_ACT_NONE, false, TAB_NONE, false>(t, 0, 0, dX, st);
+  return true;
+}
 
 int fast_fwd(const FastArgs& fa, int G, int act, bool fuse, int tab, bool extra, int grid, size_t smem, float* out,
              cudaStream_t st) {

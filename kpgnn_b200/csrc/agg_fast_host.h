@@ -27,6 +27,7 @@ void fast_fwd_set_lean(int flag);   // 1 (default): packed-math + L2-prefetch ke
 void fast_fwd_set_ring(int flag);   // 0: plain register-prefetch forward kernel, 1 (default): cp.async ring
 int fast_fwd(const FastArgs& fa, int G, int act, bool fuse, int tab, bool extra, int grid, size_t smem, float* out,
              cudaStream_t st);
+bool lean_b2(const FastArgs& fa, int G, const float* Gs, float* dX, cudaStream_t st, int* rc);
 int fast_b1(const FastArgs& fa, int G, int act, bool fuse, int tab, bool extra, int grid, size_t smem,
             const float* dOut, float* Gs, float* dP, float* dth, float* dep, cudaStream_t st);
 int fast_b2(const FastArgs& fa, int G, bool fuse, bool extra, int grid, const float* Gs, const float* dOut, float* dX,

@@ -178,6 +178,9 @@ __device__ __forceinline__ const float* at_elem(const float* base, unsigned elem
 #ifndef KP_LEAN_MINB
 #define KP_LEAN_MINB 4
 #endif
+#ifndef KP_LEAN_PIPE
+#define KP_LEAN_PIPE 0
+#endif
 
 // Sum of NE consecutive entries of the group's shared-memory entry window starting at byte address `ent`:
 // the NE gathers are issued back to back, the table rows (shared memory) are added while they fly.
@@ -202,8 +205,9 @@ __device__ __forceinline__ void lean_gather(P4& z, unsigned ent, const float* Xh
 // on the kernels of agg_fast.cuh.
 // ------------------------------------------------------------------------------------------------------------
 template <int G, int ACT, bool FUSE, int TAB, bool EXTRA>
-__global__ void __launch_bounds__(256, KP_LEAN_MINB)
-agg_fwd_lean_kernel(const FastArgs fa, float* __restrict__ out, unsigned pf_x_lines, unsigned pf_p_lines, int pf_dist) {
+__global__ void __launch_bounds__(1024, 1)      // <= 64 registers; launched with 256..1024 threads
+agg_fwd_lean_kernel(const FastArgs fa, float* __restrict__ out, unsigned pf_x_lines, unsigned pf_p_lines, int pf_dist,
+                    unsigned pf_bulk_bytes) {
   extern __shared__ __align__(16) float sm[];
   const kp_agg_desc& a = fa.d;
   const int staged = stage_tables<TAB, FUSE>(a, sm);
@@ -212,7 +216,7 @@ agg_fwd_lean_kernel(const FastArgs fa, float* __restrict__ out, unsigned pf_x_li
   const int lane = threadIdx.x & (G - 1);
   const bool active = lane * 4 < d;
   const unsigned c = (unsigned)min(lane * 4, d - 4);            // idle lanes shadow the last chunk
-  constexpr int gpb = 256 / G;
+  const int gpb = blockDim.x / G;
   const int gib = threadIdx.x / G;
   const unsigned gm = group_mask<G>();
   const unsigned sm_base = sh_addr(sm);
@@ -237,6 +241,13 @@ agg_fwd_lean_kernel(const FastArgs fa, float* __restrict__ out, unsigned pf_x_li
   if (v >= N) return;
   // L2 prefetch: lane l asks for the l-th 128-byte line of a node's X and P rows
   auto prefetch_node = [&](long long vp) {
+    if (pf_bulk_bytes) {                     // experiment: one TMA-engine prefetch per node instead of per-line hints
+      if (vp < N && lane == 0) {
+        l2_prefetch_bulk(a.X + (size_t)vp * xs, pf_bulk_bytes);
+        if (hasP) l2_prefetch_bulk(a.P + (size_t)vp * fa.ps, pf_bulk_bytes);
+      }
+      return;
+    }
     if (vp < N) {
       if ((unsigned)lane < pf_x_lines) l2_prefetch_line(reinterpret_cast<const char*>(a.X + (size_t)vp * xs) + lane * 128);
       if ((unsigned)lane < pf_p_lines) l2_prefetch_line(reinterpret_cast<const char*>(a.P + (size_t)vp * fa.ps) + lane * 128);
@@ -296,6 +307,79 @@ agg_fwd_lean_kernel(const FastArgs fa, float* __restrict__ out, unsigned pf_x_li
     P4 o = p4zero();
     unsigned ent = win_sh;                                       // byte address of the segment's first entry
     unsigned th = theta_sh;
+#if KP_LEAN_PIPE
+    // the first two gathered rows of every hop are requested one hop early, so their latency hides behind the
+    // previous hop's activation math; rows 3.. of a segment are gathered on demand
+    P4 xa = p4zero(), xb = p4zero();
+    unsigned ta = 0, tb = 0;
+    int e = lds1_sh(rp_sh + 4u);
+    int n = e;
+    if (!big) {
+      if (n >= 1) {
+        const uint2 en = lds2_sh(ent);
+        xa = ldg4p(at_elem(Xh, en.x));
+        ta = en.y;
+      }
+      if (n >= 2) {
+        const uint2 en = lds2_sh(ent + 8u);
+        xb = ldg4p(at_elem(Xh, en.x));
+        tb = en.y;
+      }
+    }
+    int b = 0;
+    for (int h = 0; h < k; ++h) {
+      const int e2 = (h + 1 < k) ? lds1_sh(rp_sh + 4u * (h + 2)) : e;
+      P4 p = p4zero();
+      if (hasP) p = ldg4p_stream(Pv);
+      P4 z = p4zero();
+      const int nn = e2 - e;
+      if (!big) {
+        if (n >= 1) {
+          z = xa;
+          if (TAB == TAB_SMEM) z = add4p(z, lds4p(ta + c4));
+        }
+        if (n >= 2) {
+          if (TAB == TAB_SMEM) xb = add4p(xb, lds4p(tb + c4));
+          z = add4p(z, xb);
+        }
+        if (n > 2) {
+          int m = n - 2;
+          unsigned er = ent + 16u;
+          while (m >= 4) {
+            lean_gather<4, TAB>(z, er, Xh, c4);
+            er += 32u;
+            m -= 4;
+          }
+          if (m & 2) {
+            lean_gather<2, TAB>(z, er, Xh, c4);
+            er += 16u;
+          }
+          if (m & 1) lean_gather<1, TAB>(z, er, Xh, c4);
+        }
+        ent += 8u * (unsigned)n;
+        const float* Xn = Xh + fa.xh;
+        if (nn >= 1) {
+          const uint2 en = lds2_sh(ent);
+          xa = ldg4p(at_elem(Xn, en.x));
+          ta = en.y;
+        }
+        if (nn >= 2) {
+          const uint2 en = lds2_sh(ent + 8u);
+          xb = ldg4p(at_elem(Xn, en.x));
+          tb = en.y;
+        }
+      } else {
+        for (int j = nbeg + b; j < nbeg + e; ++j) {
+          const int cj = __ldg(a.col + j);
+          P4 x = ldg4p(at_elem(Xh, (unsigned)cj * xs));
+          if (TAB == TAB_SMEM) x = add4p(x, lds4p((h == 0 ? tab0_sh : tabk_sh) + c4 + (unsigned)__ldg(a.attr16 + j) * d4));
+          z = add4p(z, x);
+        }
+      }
+      b = e;
+      e = e2;
+      n = nn;
+#else
     int b = 0;
     for (int h = 0; h < k; ++h) {
       const int e = lds1_sh(rp_sh + 4u * (h + 1));
@@ -327,6 +411,7 @@ agg_fwd_lean_kernel(const FastArgs fa, float* __restrict__ out, unsigned pf_x_li
         }
       }
       b = e;
+#endif
       if (EXTRA) {
         const u64 s = splat2(fast_row_scale<EXTRA>(a, v, h));
         z.lo = mul2(z.lo, s); z.hi = mul2(z.hi, s);

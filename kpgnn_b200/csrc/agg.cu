@@ -346,56 +346,56 @@ agg_bwd_table_fast_kernel(const kp_agg_desc a, const float* __restrict__ Gs, int
   const long long r0 = gid * rows_per_group;
   const long long r1 = min(R, r0 + rows_per_group);
   float* tab = smem + (size_t)tsz * gib + c;
-  const unsigned gm = (G == 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
-  if (gib < ngroups_cta) {                 // group-uniform: all G lanes take part in the shuffles below
-    for (long long rb = r0; rb < r1; rb += RB) {
+  if (gib < ngroups_cta && active) {
+    // Only ~8 warps fit next to the sub-tables, so DRAM latency cannot be hidden by other warps: the loads of
+    // batch i+1 (row pointers + Gs rows) are issued before batch i is folded into the table (two register sets).
+    struct Batch {
       int b[RB], e[RB], hh[RB];
       float4 g[RB];
-      int elast = 0;
+    };
+    auto load = [&](Batch& t, long long rb) {
 #pragma unroll
       for (int u = 0; u < RB; ++u) {
         const long long row = rb + u;
-        b[u] = e[u] = 0;
-        hh[u] = 0;
-        g[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        t.b[u] = t.e[u] = 0;
+        t.hh[u] = 0;
+        t.g[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (row < r1) {
           const int v = (int)(row / a.k), h = (int)(row - (long long)v * a.k);
           const long long pr = (long long)v * a.Kplan + h;
-          b[u] = __ldg(a.rowptr + pr);
-          e[u] = __ldg(a.rowptr + pr + 1);
-          elast = e[u];
-          hh[u] = h;
-          g[u] = __ldcs(reinterpret_cast<const float4*>(Gs + row * a.d + c));
+          t.b[u] = __ldg(a.rowptr + pr);
+          t.e[u] = __ldg(a.rowptr + pr + 1);
+          t.hh[u] = h;
+          t.g[u] = __ldcs(reinterpret_cast<const float4*>(Gs + row * a.d + c));
         }
       }
-      // the RB rows' entries are (nearly) contiguous in the plan: one coalesced load puts G of their attribute
-      // values in the group's registers; the per-entry global load that used to sit in the read-modify-write
-      // chain becomes a shuffle
-      int wb = b[0];
-      int wa = (wb + lane < elast) ? (int)__ldg(a.attr16 + wb + lane) : 0;
+    };
+    auto fold = [&](const Batch& t) {
 #pragma unroll
       for (int u = 0; u < RB; ++u) {
-        const int base = (hh[u] == 0) ? 0 : a.rows0;
-        for (int j = b[u]; j < e[u]; ++j) {
-          if (j - wb >= G) {
-            wb = j;
-            wa = (wb + lane < elast) ? (int)__ldg(a.attr16 + wb + lane) : 0;
+        const int base = (t.hh[u] == 0) ? 0 : a.rows0;
+        for (int j = t.b[u]; j < t.e[u]; ++j) {
+          const int at = (int)__ldg(a.attr16 + j);
+          float4* dst = reinterpret_cast<float4*>(tab + (size_t)(base + at) * a.d);
+          float4 x = *dst;
+          if (a.dinv) {
+            const float w = __ldg(a.dinv + (long long)__ldg(a.col + j) * a.Kplan + t.hh[u]);
+            x.x = fmaf(w, t.g[u].x, x.x); x.y = fmaf(w, t.g[u].y, x.y);
+            x.z = fmaf(w, t.g[u].z, x.z); x.w = fmaf(w, t.g[u].w, x.w);
+          } else {
+            x.x += t.g[u].x; x.y += t.g[u].y; x.z += t.g[u].z; x.w += t.g[u].w;
           }
-          const int at = __shfl_sync(gm, wa, j - wb, G);
-          if (active) {
-            float4* dst = reinterpret_cast<float4*>(tab + (size_t)(base + at) * a.d);
-            float4 t = *dst;
-            if (a.dinv) {
-              const float w = __ldg(a.dinv + (long long)__ldg(a.col + j) * a.Kplan + hh[u]);
-              t.x = fmaf(w, g[u].x, t.x); t.y = fmaf(w, g[u].y, t.y);
-              t.z = fmaf(w, g[u].z, t.z); t.w = fmaf(w, g[u].w, t.w);
-            } else {
-              t.x += g[u].x; t.y += g[u].y; t.z += g[u].z; t.w += g[u].w;
-            }
-            *dst = t;
-          }
+          *dst = x;
         }
       }
+    };
+    Batch A, B;
+    load(A, r0);
+    for (long long rb = r0; rb < r1; rb += 2 * RB) {
+      load(B, rb + RB);
+      fold(A);
+      load(A, rb + 2 * RB);
+      fold(B);
     }
   }
   __syncthreads();
@@ -466,6 +466,10 @@ struct Config {
   bool fast, fextra;
   int ftab, fG, fgrid, fgrid_b1, stage_floats;   // stage_floats = tables (+ theta) staged in smem, in floats
   size_t fsmem_fwd;
+  // lean B1 (agg_lean.cuh): packed-math kernel for the layers without self term / norm / mean
+  bool lean_b1;
+  int lean_b1_threads;
+  size_t lean_b1_smem;
 };
 
 static int g_force_generic = 0;   // test hook (kp_agg_set_force_generic): exercise the generic kernels
@@ -516,6 +520,7 @@ static int make_config(const kp_agg_desc& a, Config* c) {
             (!a.P || n1 * (unsigned long long)a.p_node_stride + (unsigned long long)a.k * a.p_hop_stride < lim) &&
             n1 * (unsigned long long)a.k * a.d < lim;
   c->fextra = fextra;
+  c->lean_b1 = false;
   if (c->fast) {
     int fl = a.d / 4, fG = 4;
     while (fG < fl) fG <<= 1;
@@ -530,6 +535,32 @@ static int make_config(const kp_agg_desc& a, Config* c) {
     c->fsmem_fwd = sizeof(float) * (size_t)c->stage_floats;
     c->grid_b1 = c->fgrid_b1;
     c->smem_b1 = sizeof(float) * ((size_t)c->stage_floats + (size_t)fgpb * a.k * 4 * fG);
+    c->lean_b1 = fast_lean_enabled() && (fG == 32 || fG == 16) && a.k + 1 <= fG && !a.dinv && !a.indeg && !a.eps &&
+                 c->ftab != TAB_GLOBAL && (a.act != KP_ACT_NONE || a.fuse);
+    if (c->lean_b1) {
+      // largest CTA whose dtheta accumulators fit next to the tables; small batches keep 256 threads (more CTAs)
+      int threads = 1024;
+      for (;;) {
+        const int gpb = threads / fG;
+        const size_t sm = sizeof(float) * ((size_t)c->stage_floats + (size_t)gpb * 3 * fG +
+                                           (a.fuse ? (size_t)gpb * a.k * 4 * fG : 0));
+        const bool enough = (long long)a.N >= (long long)kNumSMs * gpb * 2;
+        if ((sm <= 200 * 1024 && enough) || threads == 256) {
+          c->lean_b1_threads = threads;
+          c->lean_b1_smem = sm;
+          break;
+        }
+        threads >>= 1;
+      }
+      if (c->lean_b1_smem > 200 * 1024) {
+        c->lean_b1 = false;
+      } else {
+        const int gpb = c->lean_b1_threads / fG;
+        const long long want = ((long long)a.N + gpb - 1) / gpb;
+        const long long cap = (long long)kNumSMs * (1024 / c->lean_b1_threads);
+        c->grid_b1 = (int)(want < 1 ? 1 : (want > cap ? cap : want));
+      }
+    }
   }
   // table pass
   const int trows = a.T0 ? a.rows0 + (a.k > 1 ? a.rowsk : 0) : 0;
@@ -726,8 +757,12 @@ int kp_agg_backward(const kp_agg_desc* desc, const float* dOut, float* dX, float
   if (want_b1) {
     float* dPk = dP;
     if (!a.fuse && dP == dOut) dPk = nullptr;
-    if (c.fast) {
-      int rc = kp::fast_b1(kp::make_fast_args(a), c.fG, a.act, a.fuse != 0, c.ftab, c.fextra, c.fgrid_b1,
+    if (c.fast && c.lean_b1) {
+      int rc = kp::lean_b1(kp::make_fast_args(a), c.fG, a.act, a.fuse != 0, c.ftab, c.grid_b1, c.lean_b1_threads,
+                           c.lean_b1_smem, dOut, Gs, dPk, dth_part, st);
+      if (rc) return rc;
+    } else if (c.fast) {
+      int rc = kp::fast_b1(kp::make_fast_args(a), c.fG, a.act, a.fuse != 0, c.ftab, c.fextra, c.grid_b1,
                            dth_part ? c.smem_b1 : c.fsmem_fwd, dOut, Gs, dPk, dth_part, dep_part, st);
       if (rc) return rc;
     } else {

@@ -72,6 +72,7 @@ static int g_use_ring = 1;
 static int g_use_lean = 1;
 void fast_fwd_set_ring(int flag) { g_use_ring = flag; }
 void fast_fwd_set_lean(int flag) { g_use_lean = flag; }
+bool fast_lean_enabled() { return g_use_lean != 0; }
 
 // B2 (dX = gather of Gs through the transposed CSR) without self term / norm is the same computation as the
 // forward with no tables, no activation, no P and an unfused [N,k,d] output: run it on the lean forward kernel.

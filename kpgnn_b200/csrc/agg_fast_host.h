@@ -28,6 +28,9 @@ void fast_fwd_set_ring(int flag);   // 0: plain register-prefetch forward kernel
 int fast_fwd(const FastArgs& fa, int G, int act, bool fuse, int tab, bool extra, int grid, size_t smem, float* out,
              cudaStream_t st);
 bool lean_b2(const FastArgs& fa, int G, const float* Gs, float* dX, cudaStream_t st, int* rc);
+bool fast_lean_enabled();
+int lean_b1(const FastArgs& fa, int G, int act, bool fuse, int tab, int grid, int threads, size_t smem,
+            const float* dOut, float* Gs, float* dP, float* dth, cudaStream_t st);
 int fast_b1(const FastArgs& fa, int G, int act, bool fuse, int tab, bool extra, int grid, size_t smem,
             const float* dOut, float* Gs, float* dP, float* dth, float* dep, cudaStream_t st);
 int fast_b2(const FastArgs& fa, int G, bool fuse, bool extra, int grid, const float* Gs, const float* dOut, float* dX,

@@ -439,4 +439,193 @@ agg_fwd_lean_kernel(const FastArgs fa, float* __restrict__ out, unsigned pf_x_li
   }
 }
 
+// gelu(x) and gelu'(x) of a packed pair from one evaluation of the erfc form
+__device__ __forceinline__ void gelu_fwd_bwd2(u64 x, u64& f, u64& df) {
+  u64 nh, g;
+  gelu_pair_parts(x, nh, g);
+  float x0, x1, h0, h1;
+  unpk2(x, x0, x1);
+  unpk2(nh, h0, h1);
+  f = pk2(fmaf(fabsf(x0), h0, fmaxf(x0, 0.f)), fmaf(fabsf(x1), h1, fmaxf(x1, 0.f)));
+  const u64 cdf = pk2(x0 > 0.f ? 1.0f + h0 : -h0, x1 > 0.f ? 1.0f + h1 : -h1);
+  df = fma2(mul2(x, splat2(0.39894228040143267794f)), g, cdf);
+}
+template <int ACT>
+__device__ __forceinline__ void act_fwd_bwd2(u64 x, u64& f, u64& df) {
+  if (ACT == KP_ACT_GELU) {
+    gelu_fwd_bwd2(x, f, df);
+  } else {
+    f = act_fwd2<ACT>(x);
+    df = act_bwd2<ACT>(x);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// B1 (backward by destination row), lean version for the layers without self term / norm / mean:
+//   pre = sum_j (X[col_j,h] + T_h[attr_j])                         (recomputed, never stored by the forward)
+//   dy  = fuse ? theta[h] * dOut[v] : dOut[v,h]       -> dP
+//   Gs  = dy * act'(pre)                               -> workspace, consumed by B2 (dX) and B3 (dT0/dTk)
+//   dtheta[h] += dOut[v] * (act(pre) + P[v,h])         (per-group accumulators in shared memory, fixed-order
+//                                                       reduction per CTA -> dtheta_part[blockIdx.x])
+// Same node pipeline, entry window and packed arithmetic as agg_fwd_lean_kernel.
+// ------------------------------------------------------------------------------------------------------------
+template <int G, int ACT, bool FUSE, int TAB>
+__global__ void __launch_bounds__(1024, 1)
+agg_bwd_dst_lean_kernel(const FastArgs fa, const float* __restrict__ dOut, float* __restrict__ Gs,
+                        float* __restrict__ dP, float* __restrict__ dtheta_part) {
+  extern __shared__ __align__(16) float sm[];
+  const kp_agg_desc& a = fa.d;
+  const int staged = stage_tables<TAB, FUSE>(a, sm);
+  const int d = a.d, k = a.k, Kp = a.Kplan, N = a.N;
+  const unsigned xs = fa.xs, d4 = (unsigned)d * 4u;
+  const int lane = threadIdx.x & (G - 1);
+  const bool active = lane * 4 < d;
+  const unsigned c = (unsigned)min(lane * 4, d - 4);
+  const int gpb = blockDim.x / G;
+  const int gib = threadIdx.x / G;
+  const unsigned gm = group_mask<G>();
+  const unsigned sm_base = sh_addr(sm);
+  const unsigned c4 = c * 4u;
+  const unsigned tab0_sh = sm_base;
+  const unsigned tabk_sh = tab0_sh + ((TAB == TAB_SMEM) ? (unsigned)(a.rows0 * d) * 4u : 0u);
+  const unsigned theta_sh = sm_base + ((TAB == TAB_SMEM) ? (unsigned)((a.rows0 + a.rowsk) * d) : 0u) * 4u + c4;
+  const unsigned win_sh = sm_base + (unsigned)staged * 4u + (unsigned)gib * (12u * G);
+  const unsigned rp_sh = win_sh + 8u * G;
+  // dtheta accumulators: [gpb][k][4G] floats behind the windows; lane l of group g owns columns 4l..4l+3 of copy g
+  constexpr unsigned dpad = 4u * G;
+  const bool need_z = FUSE && dtheta_part != nullptr;
+  float* acc_all = sm + staged + gpb * 3 * G;
+  const unsigned acc_sh = sm_base + (unsigned)(staged + gpb * 3 * G) * 4u + (unsigned)(gib * k) * dpad * 4u + (unsigned)lane * 16u;
+  if (need_z) {
+    for (int i = threadIdx.x; i < gpb * k * (int)dpad; i += blockDim.x) acc_all[i] = 0.f;
+    __syncthreads();
+  }
+  const float* Xc = opaque_ptr(a.X + c);
+  const bool hasP = need_z && a.P != nullptr;
+  const float* Pc = opaque_ptr(hasP ? a.P + c : a.X + c);
+
+  const int vstride = gridDim.x * gpb;
+  int v = blockIdx.x * gpb + gib;
+  if (v < N) {
+    int rpn = (lane <= k) ? __ldg(a.rowptr + (size_t)v * Kp + lane) : 0;
+    int ncol = 0, nattr = 0;
+    {
+      const int nb = __shfl_sync(gm, rpn, 0, G), ne = __shfl_sync(gm, rpn, k, G);
+      if (nb + lane < ne) {
+        ncol = __ldg(a.col + nb + lane);
+        if (TAB != TAB_NONE) nattr = (int)__ldg(a.attr16 + nb + lane);
+      }
+    }
+    int vn = v;
+    int rpnn = 0;
+    {
+      const int v2 = v + vstride;
+      if (v2 < N && lane <= k) rpnn = __ldg(a.rowptr + (size_t)v2 * Kp + lane);
+    }
+    while (true) {
+      v = vn;
+      const int nbeg = __shfl_sync(gm, rpn, 0, G), nend = __shfl_sync(gm, rpn, k, G);
+      const int e1 = __shfl_sync(gm, rpn, 1, G);
+      group_sync<G>(gm);
+      sts1_sh(rp_sh + 4u * lane, rpn - nbeg);
+      {
+        const unsigned xo = (unsigned)ncol * xs;
+        const unsigned ta = (nbeg + lane < e1 ? tab0_sh : tabk_sh) + (unsigned)nattr * d4;
+        sts2_sh(win_sh + 8u * lane, xo, ta);
+      }
+      group_sync<G>(gm);
+      const bool big = (nend - nbeg) > G;
+      vn = v + vstride;
+      rpn = rpnn;
+      ncol = 0; nattr = 0;
+      if (vn < N) {
+        const int nb = __shfl_sync(gm, rpn, 0, G), ne = __shfl_sync(gm, rpn, k, G);
+        if (nb + lane < ne) {
+          ncol = __ldg(a.col + nb + lane);
+          if (TAB != TAB_NONE) nattr = (int)__ldg(a.attr16 + nb + lane);
+        }
+        const int v2 = vn + vstride;
+        rpnn = (v2 < N && lane <= k) ? __ldg(a.rowptr + (size_t)v2 * Kp + lane) : 0;
+      }
+
+      const float* Xh = Xc;
+      const float* Pv = Pc + (size_t)v * fa.ps;
+      const size_t row0 = (size_t)v * k * d + c;
+      P4 go = p4zero();
+      if (FUSE) go = ldg4p_stream(dOut + ((size_t)v * d + c));
+      unsigned ent = win_sh;
+      unsigned th = theta_sh;
+      unsigned ac = acc_sh;
+      int b = 0;
+      for (int h = 0; h < k; ++h) {
+        const int e = lds1_sh(rp_sh + 4u * (h + 1));
+        const size_t row = row0 + (size_t)h * d;
+        P4 p = p4zero();
+        if (hasP) p = ldg4p_stream(Pv);
+        P4 dy;
+        if (FUSE) {
+          const P4 t = lds4p(th);
+          dy.lo = mul2(t.lo, go.lo); dy.hi = mul2(t.hi, go.hi);
+          th += d4;
+        } else {
+          dy = ldg4p_stream(dOut + row);
+        }
+        if (dP && active) stg4p_stream(dP + row, dy);
+        P4 z = p4zero();
+        if (!big) {
+          int n = e - b;
+          while (n >= 4) {
+            lean_gather<4, TAB>(z, ent, Xh, c4);
+            ent += 32u;
+            n -= 4;
+          }
+          if (n & 2) {
+            lean_gather<2, TAB>(z, ent, Xh, c4);
+            ent += 16u;
+          }
+          if (n & 1) {
+            lean_gather<1, TAB>(z, ent, Xh, c4);
+            ent += 8u;
+          }
+        } else {
+          for (int j = nbeg + b; j < nbeg + e; ++j) {
+            const int cj = __ldg(a.col + j);
+            P4 x = ldg4p(at_elem(Xh, (unsigned)cj * xs));
+            if (TAB == TAB_SMEM) x = add4p(x, lds4p((h == 0 ? tab0_sh : tabk_sh) + c4 + (unsigned)__ldg(a.attr16 + j) * d4));
+            z = add4p(z, x);
+          }
+        }
+        b = e;
+        P4 f, df;
+        act_fwd_bwd2<ACT>(z.lo, f.lo, df.lo);
+        act_fwd_bwd2<ACT>(z.hi, f.hi, df.hi);
+        if (need_z) {
+          f = add4p(f, p);
+          P4 t = lds4p(ac);
+          t.lo = fma2(go.lo, f.lo, t.lo); t.hi = fma2(go.hi, f.hi, t.hi);
+          sts4p(ac, t);
+          ac += dpad * 4u;
+        }
+        if (Gs && active) {
+          P4 g;
+          g.lo = mul2(dy.lo, df.lo); g.hi = mul2(dy.hi, df.hi);
+          stg4p(Gs + row, g);
+        }
+        Xh += fa.xh;
+        Pv += fa.ph;
+      }
+      if (vn >= N) break;
+    }
+  }
+  if (dtheta_part) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < k * d; i += blockDim.x) {   // fixed-order reduction over the CTA's groups
+      const int h = i / d, cc = i - h * d;
+      float s = 0.f;
+      for (int g = 0; g < gpb; ++g) s += acc_all[((size_t)g * k + h) * dpad + cc];
+      dtheta_part[(size_t)blockIdx.x * k * d + i] = s;
+    }
+  }
+}
+
 }  // namespace kp

@@ -2,6 +2,7 @@
 import torch.nn.functional as F  # noqa: F401  (star-import surface parity with the reference module)
 
 from ._base import KHopLayer, SplitKLinear, make_combine, khop_aggregate, get_plan, ACT_GELU
+from .norm import FusedBatchNorm1d
 from .combine import *  # noqa: F401,F403
 
 
@@ -20,8 +21,9 @@ class KPGINPlusConv(KHopLayer):
         self.aggr = "add"
         self.K = K
         self.output_size = output_size
-        self.mlp = nn.Sequential(SplitKLinear(input_size, output_size), nn.BatchNorm1d(output_size), nn.ReLU(),
-                                 SplitKLinear(output_size, output_size), nn.BatchNorm1d(output_size), nn.ReLU())
+        self.mlp = nn.Sequential(   # Linear-BN-ReLU x2 (KPGINplus.py:25-30); ReLUs folded into the BN kernels
+            SplitKLinear(input_size, output_size), FusedBatchNorm1d(output_size, relu=True), nn.Identity(),
+            SplitKLinear(output_size, output_size), FusedBatchNorm1d(output_size, relu=True), nn.Identity())
         self.hop1_edge_emb = torch.nn.Embedding(num_hop1_edge + 2, input_size, padding_idx=0)
         if self.K > 1:
             self.hopk_edge_emb = torch.nn.Embedding(num_pe + 2, input_size, padding_idx=0)

@@ -10,6 +10,7 @@ import torch.nn as nn
 from ..ops import khop_aggregate, ACT_NONE
 from ..plan import get_plan
 from ._base import SplitKLinear
+from .norm import FusedBatchNorm1d
 
 
 class GINEConv(nn.Module):
@@ -24,8 +25,9 @@ class GINEConv(nn.Module):
             self.eps = torch.nn.Parameter(torch.Tensor([eps]))
         else:
             self.register_buffer('eps', torch.Tensor([eps]))
-        self.mlp = nn.Sequential(SplitKLinear(input_size, output_size), nn.BatchNorm1d(output_size), nn.ReLU(),
-                                 SplitKLinear(output_size, output_size), nn.BatchNorm1d(output_size), nn.ReLU())
+        self.mlp = nn.Sequential(   # Linear-BN-ReLU x2; the ReLUs are folded into the BatchNorm kernels
+            SplitKLinear(input_size, output_size), FusedBatchNorm1d(output_size, relu=True), nn.Identity(),
+            SplitKLinear(output_size, output_size), FusedBatchNorm1d(output_size, relu=True), nn.Identity())
         self.hop1_edge_emb = torch.nn.Embedding(num_hop1_edge + 2, self.input_size, padding_idx=0)
         self.reset_parameters()
 

@@ -15,6 +15,7 @@ from .layers.KPGIN import KPGINConv
 from .layers.gine import GINEConv
 from .layers.feature_encoder import FeatureConcatEncoder
 from .layers.input_encoder import EmbeddingEncoder
+from .layers.norm import FusedBatchNorm1d
 
 
 class Batch(object):
@@ -55,7 +56,7 @@ class _Norm(nn.Module):
 
     def __init__(self, width):
         super().__init__()
-        self.module = nn.BatchNorm1d(width)
+        self.module = FusedBatchNorm1d(width)
 
     def reset_parameters(self):
         self.module.reset_parameters()

@@ -13,10 +13,15 @@
 //   B2 (src rows)  dX = wsrc * sum over the transposed CSR of Gs  (+ self term)
 //   B3 (rows)      dT0/dTk by owner-computes partial tables in shared memory, then a fixed-order reduction
 // HBM-bound gather work: no tensor cores on purpose.
+#include <stdlib.h>
+
 #include "agg_common.cuh"
 #include "agg_fast_host.h"
 
 namespace kp {
+bool b3_match_ok(const kp_agg_desc& a, const float* Gs);
+int b3_match_grid(const kp_agg_desc& a);
+int b3_match(const kp_agg_desc& a, const float* Gs, float* part, int grid, cudaStream_t st);
 
 struct AggArgs {
   kp_agg_desc d;
@@ -322,11 +327,13 @@ agg_bwd_table_kernel(const kp_agg_desc a, const float* __restrict__ Gs, int cw, 
 }
 
 // Fast variant (float4 rows, d <= 128): a group of G lanes owns a private sub-table in shared memory and a
-// contiguous range of (node,hop) rows; it loads RB rows (row pointers + Gs rows) before touching any of them,
-// so RB independent 16-byte loads per lane are in flight, then folds every entry of those rows into its table
-// with LDS.128 / 4 FFMA / STS.128.  Row order inside a group and group order in the final reduction are fixed,
-// so the result is bit-reproducible.
-template <int G>
+// contiguous range of (node,hop) rows.  Only ~8 warps fit next to the sub-tables, so nothing hides latency but
+// the warp itself: the loads of batch i+1 (row pointers + Gs rows, RB rows) are issued before batch i is folded
+// into the table (two register sets), and the fold is instruction-lean -- the first version spent 64 warp
+// instructions per entry on 64-bit index arithmetic (profiles/r1q_b3.txt): (node,hop) advance incrementally,
+// table addresses are 32-bit shared addresses, the read-modify-write is LDS.128 / 2 FADD2 / STS.128.
+// Row order inside a group and group order in the final reduction are fixed -> bit-reproducible.
+template <int G, bool NORM>
 __global__ void __launch_bounds__(256)
 agg_bwd_table_fast_kernel(const kp_agg_desc a, const float* __restrict__ Gs, int ngroups_cta, int rows_per_group,
                           float* __restrict__ part) {
@@ -345,56 +352,77 @@ agg_bwd_table_fast_kernel(const kp_agg_desc a, const float* __restrict__ Gs, int
   const long long gid = (long long)blockIdx.x * ngroups_cta + gib;
   const long long r0 = gid * rows_per_group;
   const long long r1 = min(R, r0 + rows_per_group);
-  float* tab = smem + (size_t)tsz * gib + c;
-  if (gib < ngroups_cta && active) {
-    // Only ~8 warps fit next to the sub-tables, so DRAM latency cannot be hidden by other warps: the loads of
-    // batch i+1 (row pointers + Gs rows) are issued before batch i is folded into the table (two register sets).
+  const unsigned d4 = (unsigned)a.d * 4u;
+  const unsigned tab0 = (unsigned)__cvta_generic_to_shared(smem + (size_t)tsz * gib + c);
+  const unsigned tabk = tab0 + (unsigned)a.rows0 * d4;
+  if (gib < ngroups_cta && active && r0 < r1) {
     struct Batch {
-      int b[RB], e[RB], hh[RB];
+      int b[RB], e[RB];
+      unsigned tb[RB];           // table base of the row's hop (0 = no row)
+      int hh[RB];
       float4 g[RB];
     };
-    auto load = [&](Batch& t, long long rb) {
+    // running (node, hop) of the next row to load
+    int lv = (int)(r0 / a.k), lh = (int)(r0 - (long long)lv * a.k);
+    const int* rp = a.rowptr + (size_t)lv * a.Kplan + lh;
+    const float* gp = Gs + (size_t)r0 * a.d + c;
+    long long lrow = r0;
+    auto load = [&](Batch& t) {
 #pragma unroll
       for (int u = 0; u < RB; ++u) {
-        const long long row = rb + u;
         t.b[u] = t.e[u] = 0;
+        t.tb[u] = tab0;
         t.hh[u] = 0;
         t.g[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row < r1) {
-          const int v = (int)(row / a.k), h = (int)(row - (long long)v * a.k);
-          const long long pr = (long long)v * a.Kplan + h;
-          t.b[u] = __ldg(a.rowptr + pr);
-          t.e[u] = __ldg(a.rowptr + pr + 1);
-          t.hh[u] = h;
-          t.g[u] = __ldcs(reinterpret_cast<const float4*>(Gs + row * a.d + c));
+        if (lrow < r1) {
+          t.b[u] = __ldg(rp);
+          t.e[u] = __ldg(rp + 1);
+          t.tb[u] = lh == 0 ? tab0 : tabk;
+          t.hh[u] = lh;
+          t.g[u] = __ldcs(reinterpret_cast<const float4*>(gp));
+          ++lrow;
+          gp += a.d;
+          ++rp;
+          if (++lh == a.k) {
+            lh = 0;
+            rp += a.Kplan - a.k;
+          }
         }
       }
     };
     auto fold = [&](const Batch& t) {
 #pragma unroll
       for (int u = 0; u < RB; ++u) {
-        const int base = (t.hh[u] == 0) ? 0 : a.rows0;
-        for (int j = t.b[u]; j < t.e[u]; ++j) {
-          const int at = (int)__ldg(a.attr16 + j);
-          float4* dst = reinterpret_cast<float4*>(tab + (size_t)(base + at) * a.d);
-          float4 x = *dst;
-          if (a.dinv) {
-            const float w = __ldg(a.dinv + (long long)__ldg(a.col + j) * a.Kplan + t.hh[u]);
-            x.x = fmaf(w, t.g[u].x, x.x); x.y = fmaf(w, t.g[u].y, x.y);
-            x.z = fmaf(w, t.g[u].z, x.z); x.w = fmaf(w, t.g[u].w, x.w);
+        const unsigned long long glo = (unsigned long long)__float_as_uint(t.g[u].x) |
+                                       ((unsigned long long)__float_as_uint(t.g[u].y) << 32);
+        const unsigned long long ghi = (unsigned long long)__float_as_uint(t.g[u].z) |
+                                       ((unsigned long long)__float_as_uint(t.g[u].w) << 32);
+        const uint16_t* ap = a.attr16 + t.b[u];
+        const int n = t.e[u] - t.b[u];
+        for (int j = 0; j < n; ++j) {
+          const unsigned addr = t.tb[u] + (unsigned)__ldg(ap + j) * d4;
+          unsigned long long xlo, xhi;
+          asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(xlo), "=l"(xhi) : "r"(addr));
+          if (NORM) {
+            const float w = __ldg(a.dinv + (long long)__ldg(a.col + t.b[u] + j) * a.Kplan + t.hh[u]);
+            unsigned long long ww;
+            asm("mov.b64 %0, {%1, %1};" : "=l"(ww) : "f"(w));
+            asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(xlo) : "l"(ww), "l"(glo));
+            asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(xhi) : "l"(ww), "l"(ghi));
           } else {
-            x.x += t.g[u].x; x.y += t.g[u].y; x.z += t.g[u].z; x.w += t.g[u].w;
+            asm("add.rn.f32x2 %0, %0, %1;" : "+l"(xlo) : "l"(glo));
+            asm("add.rn.f32x2 %0, %0, %1;" : "+l"(xhi) : "l"(ghi));
           }
-          *dst = x;
+          asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(addr), "l"(xlo), "l"(xhi) : "memory");
         }
       }
     };
     Batch A, B;
-    load(A, r0);
+    load(A);
     for (long long rb = r0; rb < r1; rb += 2 * RB) {
-      load(B, rb + RB);
+      load(B);
       fold(A);
-      load(A, rb + 2 * RB);
+      load(A);
       fold(B);
     }
   }
@@ -461,6 +489,7 @@ struct Config {
   size_t smem_b3;
   bool table_atomic;
   bool b3_fast;
+  bool b3_match;    // register-accumulator kernel (agg_b3_match.cu)
   int b3_G, b3_groups, b3_threads, b3_rows_per_group;
   // fast float4 path (agg_fast.cuh)
   bool fast, fextra;
@@ -571,7 +600,15 @@ static int make_config(const kp_agg_desc& a, Config* c) {
   c->rows_per_block = 0;
   c->smem_b3 = 0;
   c->b3_fast = false;
-  if (trows > 0) {
+  c->b3_match = false;
+  // The register-accumulator kernel (agg_b3_match.cu) is correct and deterministic but, measured at 8 192 graphs,
+  // slower (1 056 us) than the sub-table kernel (624 us): its hot table row serialises one warp per tile.  It stays
+  // opt-in (KP_B3_MATCH=1) until the per-tile work is balanced.
+  static const bool use_match = getenv("KP_B3_MATCH") && atoi(getenv("KP_B3_MATCH")) != 0;
+  if (use_match && trows > 0 && c->fast && fast_lean_enabled() && b3_match_ok(a, nullptr)) {
+    c->b3_match = true;
+    c->grid_b3 = b3_match_grid(a);
+  } else if (trows > 0) {
     size_t tsz = sizeof(float) * (size_t)(a.rows0 + a.rowsk) * a.d;
     const long long R = (long long)a.N * a.k;
     if (c->fast && tsz <= 200 * 1024) {
@@ -794,14 +831,24 @@ int kp_agg_backward(const kp_agg_desc* desc, const float* dOut, float* dX, float
     } else {
       float* part = (float*)(ws + w.table);
       const int threads = 256;
-      if (c.b3_fast) {
+      if (c.b3_match) {
+        int rc = kp::b3_match(a, Gsrc, part, c.grid_b3, st);
+        if (rc) return rc;
+      } else if (c.b3_fast) {
 #define KP_B3F(GG)                                                                                              \
   do {                                                                                                          \
-    if (c.smem_b3 > 48 * 1024)                                                                                  \
-      KP_CUDA(cudaFuncSetAttribute(kp::agg_bwd_table_fast_kernel<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                   (int)c.smem_b3));                                                            \
-    KP_LAUNCH((kp::agg_bwd_table_fast_kernel<GG>), c.grid_b3, c.b3_threads, c.smem_b3, st, a, Gsrc, c.b3_groups,  \
-              c.b3_rows_per_group, part);                                                                       \
+    if (c.smem_b3 > 48 * 1024) {                                                                                \
+      KP_CUDA(cudaFuncSetAttribute(kp::agg_bwd_table_fast_kernel<GG, false>,                                    \
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem_b3));               \
+      KP_CUDA(cudaFuncSetAttribute(kp::agg_bwd_table_fast_kernel<GG, true>,                                     \
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem_b3));               \
+    }                                                                                                           \
+    if (a.dinv)                                                                                                 \
+      KP_LAUNCH((kp::agg_bwd_table_fast_kernel<GG, true>), c.grid_b3, c.b3_threads, c.smem_b3, st, a, Gsrc,     \
+                c.b3_groups, c.b3_rows_per_group, part);                                                        \
+    else                                                                                                        \
+      KP_LAUNCH((kp::agg_bwd_table_fast_kernel<GG, false>), c.grid_b3, c.b3_threads, c.smem_b3, st, a, Gsrc,    \
+                c.b3_groups, c.b3_rows_per_group, part);                                                        \
   } while (0)
         if (c.b3_G == 32) KP_B3F(32);
         else if (c.b3_G == 16) KP_B3F(16);

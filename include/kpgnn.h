@@ -95,8 +95,11 @@ typedef struct {
 } kp_agg_desc;
 
 int kp_agg_forward(const kp_agg_desc* desc, float* out, void* stream);
-/* Test hook: non-zero routes every call through the generic (any width / alignment / stride) kernels instead of
- * the float4 fast path, so both implementations are parity-tested on the same inputs.  Process-wide. */
+/* Test hook, process-wide; a bit set of kernel-family selectors so every implementation is parity-tested on the
+ * same inputs.  bit 0: generic (any width / alignment / stride) kernels instead of the float4 fast path;
+ * bit 1: register-prefetch instead of cp.async-ring forward kernel; bit 2: no packed-math ("lean") kernels;
+ * bit 4: TMA-staged forward kernel for every eligible call; bit 5: TMA-staged forward kernel for large batches.
+ * 0 = production default (lean kernels, no TMA staging). */
 int kp_agg_set_force_generic(int flag);
 
 /* Backward of kp_agg_forward (autograd of the same reference lines).  Deterministic, no float atomics:

@@ -749,6 +749,9 @@ int kp_agg_set_force_generic(int flag) {
   kp::g_force_generic = (flag & 1) ? 1 : 0;
   kp::fast_fwd_set_ring((flag & 2) ? 0 : 1);
   kp::fast_fwd_set_lean((flag & 4) ? 0 : 1);
+  // TMA-staged forward kernel (agg_tma.cuh): off by default (measured slightly slower than the lean kernel);
+  // bit 4: use it for every eligible call, however small (tests); bit 5: use it for large batches only
+  kp::fast_fwd_set_tma((flag & 16) ? 2 : ((flag & 32) ? 1 : 0));
   return 0;
 }
 

@@ -104,6 +104,10 @@ bool lean_b2(const FastArgs& fa, int G, const float* Gs, float* dX, cudaStream_t
 
 int fast_fwd(const FastArgs& fa, int G, int act, bool fuse, int tab, bool extra, int grid, size_t smem, float* out,
              cudaStream_t st) {
+  if (g_use_lean) {
+    int rc = 0;
+    if (tma_fwd(fa, G, act, fuse, tab, extra, smem, out, st, &rc)) return rc;
+  }
   if (g_use_lean && (G == 32 || G == 16) && fa.d.k + 1 <= G && !fa.d.dinv && tab != TAB_GLOBAL) {
     if (G == 32) return KP_LEAN_COMBO(32, act, fuse, extra, tab, fa, grid, smem, out, st);
     return KP_LEAN_COMBO(16, act, fuse, extra, tab, fa, grid, smem, out, st);

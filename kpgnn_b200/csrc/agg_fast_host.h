@@ -29,6 +29,9 @@ int fast_fwd(const FastArgs& fa, int G, int act, bool fuse, int tab, bool extra,
              cudaStream_t st);
 bool lean_b2(const FastArgs& fa, int G, const float* Gs, float* dX, cudaStream_t st, int* rc);
 bool fast_lean_enabled();
+void fast_fwd_set_tma(int mode);   // 0 = never, 1 = large batches (default), 2 = always
+bool tma_fwd(const FastArgs& fa, int G, int act, bool fuse, int tab, bool extra, size_t staged_bytes, float* out,
+             cudaStream_t st, int* rc);
 int lean_b1(const FastArgs& fa, int G, int act, bool fuse, int tab, int grid, int threads, size_t smem,
             const float* dOut, float* Gs, float* dP, float* dth, cudaStream_t st);
 int fast_b1(const FastArgs& fa, int G, int act, bool fuse, int tab, bool extra, int grid, size_t smem,

@@ -23,7 +23,7 @@ for K, H, ng in ((1, 104, 6), (3, 104, 6), (8, 104, 6), (8, 104, 300), (4, 64, 5
                 continue
             for useP in (True, False):
                 outs = []
-                for flag in (0, 4, 1):
+                for flag in (16, 4, 1):
                     lib.kp_agg_set_force_generic(flag)
                     y = khop_aggregate(x, plan, k, P=P if useP else None, T0=t0, Tk=tk, theta=th if fuse else None,
                                        act=act, fuse=fuse)

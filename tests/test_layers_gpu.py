@@ -18,12 +18,13 @@ torch.backends.cudnn.allow_tf32 = False
 NOISE_ONLY = ("mlp.0.bias", "mlp.3.bias")
 
 
-@pytest.fixture(autouse=True, params=["lean", "fast-ring", "fast-noring", "generic"])
+@pytest.fixture(autouse=True, params=["tma", "lean", "fast-ring", "fast-noring", "generic"])
 def kernel_path(request, lib):
-    """Every case runs through all kernel families: the packed-math / L2-prefetch kernels (agg_lean.cuh, default),
+    """Every case runs through all kernel families: the TMA-staged forward kernel (agg_tma.cuh; forced on, it is
+    only chosen by itself for large batches), the packed-math kernels (agg_lean.cuh, default),
     the float4 fast path with the cp.async-ring forward kernel, the fast path with the register-prefetch forward
     kernel, and the generic any-width kernels (agg.cu)."""
-    lib.kp_agg_set_force_generic({"lean": 0, "fast-ring": 4, "fast-noring": 6, "generic": 1}[request.param])
+    lib.kp_agg_set_force_generic({"tma": 16, "lean": 8, "fast-ring": 12, "fast-noring": 14, "generic": 1}[request.param])
     yield request.param
     lib.kp_agg_set_force_generic(0)
 

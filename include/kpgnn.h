@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define KPGNN_ABI_VERSION 1
+#define KPGNN_ABI_VERSION 2
 
 const char* kp_last_error(void);
 int kp_abi_version(void);
@@ -92,6 +92,9 @@ typedef struct {
   const float* theta;              /* [k,d], required when fuse */
   const float* eps;                /* device scalar or NULL */
   int32_t act, fuse;
+  int32_t amax0, amaxk;            /* largest attr16 value present in hop 0 / in hops >= 1 of the plan
+                                      (kp_plan_count stats[1], stats[2]); -1 = not supplied.  Backward only: selects
+                                      the register-accumulator table-gradient kernel when both are <= 31 */
 } kp_agg_desc;
 
 int kp_agg_forward(const kp_agg_desc* desc, float* out, void* stream);

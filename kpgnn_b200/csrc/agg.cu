@@ -19,9 +19,10 @@
 #include "agg_fast_host.h"
 
 namespace kp {
-bool b3_match_ok(const kp_agg_desc& a, const float* Gs);
-int b3_match_grid(const kp_agg_desc& a);
-int b3_match(const kp_agg_desc& a, const float* Gs, float* part, int grid, cudaStream_t st);
+// count-matrix table-gradient pass (agg_b3_count.cu)
+bool b3_count_ok(const kp_agg_desc& a, int G);
+size_t b3_count_part_floats(const kp_agg_desc& a);
+int b3_count(const kp_agg_desc& a, int G, const float* Gs, float* part, float* dT0, float* dTk, cudaStream_t st);
 
 struct AggArgs {
   kp_agg_desc d;
@@ -489,7 +490,8 @@ struct Config {
   size_t smem_b3;
   bool table_atomic;
   bool b3_fast;
-  bool b3_match;    // register-accumulator kernel (agg_b3_match.cu)
+  bool b3_count;    // count-matrix kernel with register accumulators (agg_b3_count.cu)
+  size_t b3_part_floats;
   int b3_G, b3_groups, b3_threads, b3_rows_per_group;
   // fast float4 path (agg_fast.cuh)
   bool fast, fextra;
@@ -600,14 +602,15 @@ static int make_config(const kp_agg_desc& a, Config* c) {
   c->rows_per_block = 0;
   c->smem_b3 = 0;
   c->b3_fast = false;
-  c->b3_match = false;
-  // The register-accumulator kernel (agg_b3_match.cu) is correct and deterministic but, measured at 8 192 graphs,
-  // slower (1 056 us) than the sub-table kernel (624 us): its hot table row serialises one warp per tile.  It stays
-  // opt-in (KP_B3_MATCH=1) until the per-tile work is balanced.
-  static const bool use_match = getenv("KP_B3_MATCH") && atoi(getenv("KP_B3_MATCH")) != 0;
-  if (use_match && trows > 0 && c->fast && fast_lean_enabled() && b3_match_ok(a, nullptr)) {
-    c->b3_match = true;
-    c->grid_b3 = b3_match_grid(a);
+  c->b3_count = false;
+  c->b3_part_floats = 0;
+  // count-matrix kernel: needs the plan's largest-embedding-row statistics (desc.amax0 / amaxk) to be <= 31;
+  // KP_B3_COUNT=0 keeps the sub-table kernel (A/B measurements)
+  static const bool use_count = !(getenv("KP_B3_COUNT") && atoi(getenv("KP_B3_COUNT")) == 0);
+  if (use_count && trows > 0 && c->fast && fast_lean_enabled() && b3_count_ok(a, c->fG)) {
+    c->b3_count = true;
+    c->grid_b3 = 1;
+    c->b3_part_floats = b3_count_part_floats(a);
   } else if (trows > 0) {
     size_t tsz = sizeof(float) * (size_t)(a.rows0 + a.rowsk) * a.d;
     const long long R = (long long)a.N * a.k;
@@ -665,7 +668,8 @@ static WsLayout ws_layout(const kp_agg_desc& a, const Config& c) {
   w.gs = take(c.need_gs ? sizeof(float) * (size_t)a.N * a.k * a.d : 0);
   w.dtheta = take(sizeof(float) * (size_t)c.grid_b1 * a.k * a.d);
   w.deps = take(sizeof(float) * (size_t)c.grid_b1);
-  w.table = take(c.grid_b3 ? sizeof(float) * (size_t)c.grid_b3 * (a.rows0 + a.rowsk) * a.d : 0);
+  w.table = take(c.b3_count ? sizeof(float) * c.b3_part_floats
+                            : (c.grid_b3 ? sizeof(float) * (size_t)c.grid_b3 * (a.rows0 + a.rowsk) * a.d : 0));
   w.total = off;
   return w;
 }
@@ -834,8 +838,8 @@ int kp_agg_backward(const kp_agg_desc* desc, const float* dOut, float* dX, float
     } else {
       float* part = (float*)(ws + w.table);
       const int threads = 256;
-      if (c.b3_match) {
-        int rc = kp::b3_match(a, Gsrc, part, c.grid_b3, st);
+      if (c.b3_count) {
+        int rc = kp::b3_count(a, c.fG, Gsrc, part, dT0, dTk, st);
         if (rc) return rc;
       } else if (c.b3_fast) {
 #define KP_B3F(GG)                                                                                              \
@@ -872,8 +876,9 @@ int kp_agg_backward(const kp_agg_desc* desc, const float* dOut, float* dX, float
       else KP_B3(1);
 #undef KP_B3
       }
-      KP_LAUNCH(kp::reduce_partials_kernel, kp::ceil_div((long long)tn * 32, 256), 256, 0, st, part, c.grid_b3, (int)tn,
-                a.rows0 * a.d, dT0, dTk);
+      if (!c.b3_count)
+        KP_LAUNCH(kp::reduce_partials_kernel, kp::ceil_div((long long)tn * 32, 256), 256, 0, st, part, c.grid_b3,
+                  (int)tn, a.rows0 * a.d, dT0, dTk);
     }
   }
   if (dtheta) {

@@ -36,6 +36,7 @@ def _make_desc(plan, k, x, P, T0, Tk, theta, eps, act, fuse, use_dinv, use_mean)
     desc.rowsk = Tk.size(0) if Tk is not None else 0
     desc.theta, desc.eps = _ptr(theta), _ptr(eps)
     desc.act, desc.fuse = act, 1 if fuse else 0
+    desc.amax0, desc.amaxk = plan.max_attr0, plan.max_attrk
     return desc
 
 

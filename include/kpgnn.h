@@ -157,6 +157,42 @@ int kp_bn_backward(const float* x, const float* dy, int32_t N, int32_t C, const 
                    const float* save_mean, const float* save_invstd, int32_t relu, float* dx, float* dgamma,
                    float* dbeta, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Fused dense block of a KP-GIN+ layer, training mode: everything between the aggregation and the next layer,
+ *     y1 = X W1^T + b1;  z1 = relu(BN1(y1));  y2 = z1 W2^T + b2;  z2 = relu(BN2(y2))     (layers/KPGINplus.py:25-30,78)
+ *     out = BN3(z2) + R                                                                    (models/GNNs.py:430-438)
+ * as ONE persistent kernel per direction (BN3 and R optional).  Each CTA owns a slab of rows and both weight
+ * matrices in shared memory; the three batch statistics are merged across CTAs (Chan's parallel variance, fixed
+ * order -> bit-reproducible) behind a grid-wide barrier.  fp32 FMA throughout (no TF32).  The backward is the
+ * autograd of the same lines: dX, dW1, db1, dW2, db2 and the BN affine gradients, per-CTA partial weight
+ * gradients summed in a fixed order.  Replaces 2 GEMMs + 3 BatchNorm kernels + bias/residual elementwise kernels
+ * forward and 4 GEMMs + 3 BatchNorm backward kernels + 4 column sums backward.
+ * N <= kp_dense_block_max_rows(Cin, Cout); Cin, Cout multiples of 4, <= 128; running statistics required.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t N, Cin, Cout;
+  const float* X;                                   /* [N,Cin] */
+  const float *W1, *b1, *g1, *be1;                  /* Linear1 [Cout,Cin],[Cout]; BN1 weight/bias */
+  const float *W2, *b2, *g2, *be2;                  /* Linear2 [Cout,Cout],[Cout]; BN2 weight/bias */
+  const float *g3, *be3;                            /* outer BatchNorm weight/bias, NULL = no BN3 */
+  const float* R;                                   /* residual [N,Cout] added to the result, or NULL */
+  float eps1, eps2, eps3, mom1, mom2, mom3;
+  float *rm1, *rv1, *rm2, *rv2, *rm3, *rv3;         /* running mean / var (updated in place) or NULL */
+  int64_t *nbt1, *nbt2, *nbt3;                      /* num_batches_tracked (incremented) or NULL */
+  float *Y1, *Y2, *Z2;                              /* saved for backward: y1, y2 [N,Cout]; z2 (only with BN3) */
+  float* stats;                                     /* [6,Cout]: mean1, invstd1, mean2, invstd2, mean3, invstd3 */
+} kp_dense_desc;
+
+int kp_dense_block_max_rows(int32_t Cin, int32_t Cout);
+int kp_dense_block_workspace_bytes(const kp_dense_desc* desc, size_t* fwd_bytes, size_t* bwd_bytes);
+int kp_dense_block_forward(const kp_dense_desc* desc, float* out, void* workspace, size_t workspace_bytes,
+                           void* stream);
+/* dOut [N,Cout]; dX [N,Cin]; dbn = [6,Cout]: dg1, dbe1, dg2, dbe2, dg3, dbe3 (last two untouched without BN3).
+ * The residual's gradient is dOut itself (the caller aliases it). */
+int kp_dense_block_backward(const kp_dense_desc* desc, const float* dOut, float* dX, float* dW1, float* db1,
+                            float* dW2, float* db2, float* dbn, void* workspace, size_t workspace_bytes,
+                            void* stream);
+
 /* GeometricCombine weights, layers/combine.py:51-58: theta[h,c] = softmax over h of a_c (1-a_c)^h with
  * a = sigmoid(alphas); theta is [K,d].  Backward returns d(loss)/d(alphas) from d(loss)/d(theta). */
 int kp_geometric_theta_forward(const float* alphas, int32_t K, int32_t d, float* theta, void* stream);

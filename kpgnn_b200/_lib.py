@@ -48,6 +48,20 @@ class TsumDesc(C.Structure):
                 ("range_slot", C.c_int32 * 17), ("range_row", C.c_int32 * 17)]
 
 
+class DenseDesc(C.Structure):
+    _fields_ = [("N", C.c_int32), ("Cin", C.c_int32), ("Cout", C.c_int32),
+                ("X", C.c_void_p),
+                ("W1", C.c_void_p), ("b1", C.c_void_p), ("g1", C.c_void_p), ("be1", C.c_void_p),
+                ("W2", C.c_void_p), ("b2", C.c_void_p), ("g2", C.c_void_p), ("be2", C.c_void_p),
+                ("g3", C.c_void_p), ("be3", C.c_void_p), ("R", C.c_void_p),
+                ("eps1", C.c_float), ("eps2", C.c_float), ("eps3", C.c_float),
+                ("mom1", C.c_float), ("mom2", C.c_float), ("mom3", C.c_float),
+                ("rm1", C.c_void_p), ("rv1", C.c_void_p), ("rm2", C.c_void_p), ("rv2", C.c_void_p),
+                ("rm3", C.c_void_p), ("rv3", C.c_void_p),
+                ("nbt1", C.c_void_p), ("nbt2", C.c_void_p), ("nbt3", C.c_void_p),
+                ("Y1", C.c_void_p), ("Y2", C.c_void_p), ("Z2", C.c_void_p), ("stats", C.c_void_p)]
+
+
 ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
 
 # name -> (restype, argtypes); must list every symbol include/kpgnn.h declares (tests/test_abi.py checks it)
@@ -76,6 +90,12 @@ _SIGNATURES = {
                                 C.c_void_p]),
     "kp_bn_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "kp_dense_block_max_rows": (C.c_int, [C.c_int32, C.c_int32]),
+    "kp_dense_block_workspace_bytes": (C.c_int, [C.POINTER(DenseDesc), C.POINTER(C.c_size_t),
+                                                 C.POINTER(C.c_size_t)]),
+    "kp_dense_block_forward": (C.c_int, [C.POINTER(DenseDesc), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "kp_dense_block_backward": (C.c_int, [C.POINTER(DenseDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "kp_geometric_theta_forward": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "kp_geometric_theta_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                               C.c_void_p]),

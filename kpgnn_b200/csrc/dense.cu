@@ -1,0 +1,707 @@
+// dense.cu -- the dense block of a KP-GIN+ layer as ONE persistent kernel per direction (sm_100a):
+//     y1 = X W1^T + b1;  z1 = relu(BN1(y1));  y2 = z1 W2^T + b2;  z2 = relu(BN2(y2));  out = BN3(z2) + R
+// (layers/KPGINplus.py:25-30,78 and models/GNNs.py:430-438; BN3 and R optional).
+//
+// Why: at molecule-batch sizes (N ~ 3 000 rows, 104 channels) the step was a chain of ~45 kernels of 2-11 us each
+// per layer around the aggregation (2 + 4 SIMT GEMMs, 3 + 3 BatchNorm kernels, 4 column sums, bias / residual
+// adds; profiles/r1v_step_kineto.txt) -- all latency, no bandwidth.  Here each CTA keeps a slab of <= 40 rows and
+// BOTH weight matrices in shared memory for the whole block; the only cross-CTA dependencies are the three batch
+// statistics (and, backward, the weight-gradient sums), exchanged through small per-CTA partials in L2 behind a
+// grid-wide barrier.  Statistics use Chan's parallel variance (per-slab mean / M2 merged in a fixed order), the
+// weight gradients are per-CTA [Cout x Cin] partials summed in a fixed order: bit-reproducible, no float atomics.
+// All arithmetic is fp32 FMA (the 1e-5 parity bar rules out TF32); the GEMMs are ~64 MFLOP -- latency, not
+// throughput, is what this kernel removes.
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace kp {
+
+constexpr int DB_THREADS = 256;
+constexpr int DB_WARPS = DB_THREADS / 32;
+constexpr int DB_ROWS = 36;          // target rows per CTA: 9 row tiles x 26 column tiles <= 256 threads at 104 channels
+constexpr int DB_MAX_GRID = kNumSMs; // every CTA must be resident: one per SM
+
+__device__ __forceinline__ unsigned db_ld_acquire(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// All CTAs are co-resident (grid <= #SMs, one CTA per SM by shared-memory footprint), so spinning is safe.
+__device__ __forceinline__ void db_grid_barrier(unsigned* ctr, unsigned target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(ctr, 1u);
+    while (db_ld_acquire(ctr) < target) {
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// out[r][n] = bias[n] + sum_k A[r][k] * B[k][n]   for r < nrp (multiple of 4), n < Nn; all in shared memory
+__device__ __forceinline__ void db_gemm_AB(const float* __restrict__ A, int lda, int Kd, const float* __restrict__ B,
+                                           int Nn, const float* __restrict__ bias, int nrp, float* __restrict__ out,
+                                           int ldo) {
+  const int ctn = Nn >> 2, ntiles = ctn * (nrp >> 2);
+  for (int t = threadIdx.x; t < ntiles; t += DB_THREADS) {
+    const int rt = t / ctn, ct = t - rt * ctn;
+    const int r = rt * 4, n = ct * 4;
+    float4 acc[4];
+    const float4 bv = bias ? __ldg(reinterpret_cast<const float4*>(bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j] = bv;
+    const float* a = A + r * lda;
+    const float* b = B + n;
+#pragma unroll 2
+    for (int k = 0; k < Kd; k += 4) {
+      float4 x[4], w[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) x[j] = *reinterpret_cast<const float4*>(a + j * lda + k);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) w[j] = *reinterpret_cast<const float4*>(b + (k + j) * Nn);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc[j].x = fmaf(x[j].x, w[0].x, acc[j].x); acc[j].y = fmaf(x[j].x, w[0].y, acc[j].y);
+        acc[j].z = fmaf(x[j].x, w[0].z, acc[j].z); acc[j].w = fmaf(x[j].x, w[0].w, acc[j].w);
+        acc[j].x = fmaf(x[j].y, w[1].x, acc[j].x); acc[j].y = fmaf(x[j].y, w[1].y, acc[j].y);
+        acc[j].z = fmaf(x[j].y, w[1].z, acc[j].z); acc[j].w = fmaf(x[j].y, w[1].w, acc[j].w);
+        acc[j].x = fmaf(x[j].z, w[2].x, acc[j].x); acc[j].y = fmaf(x[j].z, w[2].y, acc[j].y);
+        acc[j].z = fmaf(x[j].z, w[2].z, acc[j].z); acc[j].w = fmaf(x[j].z, w[2].w, acc[j].w);
+        acc[j].x = fmaf(x[j].w, w[3].x, acc[j].x); acc[j].y = fmaf(x[j].w, w[3].y, acc[j].y);
+        acc[j].z = fmaf(x[j].w, w[3].z, acc[j].z); acc[j].w = fmaf(x[j].w, w[3].w, acc[j].w);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(out + (r + j) * ldo + n) = acc[j];
+  }
+}
+
+// outg[m][n] = sum_{r<nr} A[r][m] * B[r][n]  (A, B in shared memory; outg in global memory, [M][Nn])
+__device__ __forceinline__ void db_gemm_AtB(const float* __restrict__ A, int lda, int M, const float* __restrict__ B,
+                                            int ldb, int Nn, int nr, float* __restrict__ outg) {
+  const int ctn = Nn >> 2, ntiles = ctn * (M >> 2);
+  for (int t = threadIdx.x; t < ntiles; t += DB_THREADS) {
+    const int mt = t / ctn, ct = t - mt * ctn;
+    const int m = mt * 4, n = ct * 4;
+    float4 acc[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int r = 0; r < nr; ++r) {
+      const float4 a = *reinterpret_cast<const float4*>(A + r * lda + m);
+      const float4 b = *reinterpret_cast<const float4*>(B + r * ldb + n);
+      acc[0].x = fmaf(a.x, b.x, acc[0].x); acc[0].y = fmaf(a.x, b.y, acc[0].y);
+      acc[0].z = fmaf(a.x, b.z, acc[0].z); acc[0].w = fmaf(a.x, b.w, acc[0].w);
+      acc[1].x = fmaf(a.y, b.x, acc[1].x); acc[1].y = fmaf(a.y, b.y, acc[1].y);
+      acc[1].z = fmaf(a.y, b.z, acc[1].z); acc[1].w = fmaf(a.y, b.w, acc[1].w);
+      acc[2].x = fmaf(a.z, b.x, acc[2].x); acc[2].y = fmaf(a.z, b.y, acc[2].y);
+      acc[2].z = fmaf(a.z, b.z, acc[2].z); acc[2].w = fmaf(a.z, b.w, acc[2].w);
+      acc[3].x = fmaf(a.w, b.x, acc[3].x); acc[3].y = fmaf(a.w, b.y, acc[3].y);
+      acc[3].z = fmaf(a.w, b.z, acc[3].z); acc[3].w = fmaf(a.w, b.w, acc[3].w);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) __stcg(reinterpret_cast<float4*>(outg + (size_t)(m + j) * Nn + n), acc[j]);
+  }
+}
+
+// global [nr][C] rows r0.. -> shared slab [nrp][C] (rows >= nr zero-filled)
+__device__ __forceinline__ void db_load_slab(const float* __restrict__ g, int r0, int nr, int nrp, int C,
+                                             float* __restrict__ s) {
+  const int c4n = C >> 2;
+  for (int i = threadIdx.x; i < nrp * c4n; i += DB_THREADS) {
+    const int r = i / c4n, c = (i - r * c4n) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < nr) v = __ldg(reinterpret_cast<const float4*>(g + (size_t)(r0 + r) * C + c));
+    *reinterpret_cast<float4*>(s + r * C + c) = v;
+  }
+}
+__device__ __forceinline__ void db_store_slab(const float* __restrict__ s, int r0, int nr, int C, float* __restrict__ g) {
+  const int c4n = C >> 2;
+  for (int i = threadIdx.x; i < nr * c4n; i += DB_THREADS) {
+    const int r = i / c4n, c = (i - r * c4n) * 4;
+    *reinterpret_cast<float4*>(g + (size_t)(r0 + r) * C + c) = *reinterpret_cast<const float4*>(s + r * C + c);
+  }
+}
+
+// per-slab column statistics: psum[c] = sum_r S[r][c],  pm2[c] = sum_r (S[r][c] - slab mean)^2   (global partials)
+__device__ __forceinline__ void db_slab_stats(const float* __restrict__ S, int C, int nr, float* __restrict__ psum,
+                                              float* __restrict__ pm2) {
+  for (int c = threadIdx.x; c < C; c += DB_THREADS) {
+    float s = 0.f;
+    for (int r = 0; r < nr; ++r) s += S[r * C + c];
+    const float mean = nr > 0 ? s / (float)nr : 0.f;
+    float q = 0.f;
+    for (int r = 0; r < nr; ++r) {
+      const float dx = S[r * C + c] - mean;
+      q = fmaf(dx, dx, q);
+    }
+    __stcg(psum + c, s);
+    __stcg(pm2 + c, q);
+  }
+}
+
+// Merge the per-CTA partials [grid][2][C] into batch mean / inverse std (Chan et al.), identically in every CTA.
+// red: shared [DB_WARPS][C]; mean_s / istd_s: shared [C].  var_out (optional, shared [C]) receives the biased variance.
+__device__ __forceinline__ void db_merge_stats(const float* __restrict__ part, int grid, int Rc, int N, int C,
+                                               float eps, float* __restrict__ red, float* __restrict__ mean_s,
+                                               float* __restrict__ istd_s, float* __restrict__ var_s) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = lane * 4;
+  const bool on = c < C;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (on) {
+#pragma unroll 4
+    for (int b = warp; b < grid; b += DB_WARPS) {
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(part + (size_t)b * 2 * C + c));
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    *reinterpret_cast<float4*>(red + warp * C + c) = s;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += DB_THREADS) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < DB_WARPS; ++w) t += red[w * C + i];
+    mean_s[i] = t / (float)N;
+  }
+  __syncthreads();
+  float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (on) {
+    const float4 mu = *reinterpret_cast<const float4*>(mean_s + c);
+#pragma unroll 4
+    for (int b = warp; b < grid; b += DB_WARPS) {
+      const int nb = min(Rc, N - b * Rc);
+      if (nb <= 0) continue;
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(part + (size_t)b * 2 * C + c));
+      const float4 m2 = __ldcg(reinterpret_cast<const float4*>(part + (size_t)b * 2 * C + C + c));
+      const float fn = (float)nb, inv = 1.f / fn;
+      const float dx = v.x * inv - mu.x, dy = v.y * inv - mu.y, dz = v.z * inv - mu.z, dw = v.w * inv - mu.w;
+      q.x += fmaf(fn * dx, dx, m2.x); q.y += fmaf(fn * dy, dy, m2.y);
+      q.z += fmaf(fn * dz, dz, m2.z); q.w += fmaf(fn * dw, dw, m2.w);
+    }
+    *reinterpret_cast<float4*>(red + warp * C + c) = q;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += DB_THREADS) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < DB_WARPS; ++w) t += red[w * C + i];
+    const float var = t / (float)N;
+    var_s[i] = var;
+    istd_s[i] = rsqrtf(var + eps);
+  }
+  __syncthreads();
+}
+
+// running statistics + saved statistics, by CTA 0 only (torch.nn.BatchNorm1d: unbiased variance into running_var)
+__device__ __forceinline__ void db_publish_stats(const float* mean_s, const float* istd_s, const float* var_s, int N,
+                                                 int C, float mom, float* rm, float* rv, long long* nbt,
+                                                 float* save_mean, float* save_istd) {
+  const float unb = N > 1 ? (float)N / (float)(N - 1) : 1.f;
+  for (int i = threadIdx.x; i < C; i += DB_THREADS) {
+    save_mean[i] = mean_s[i];
+    save_istd[i] = istd_s[i];
+    if (rm) rm[i] = fmaf(mom, mean_s[i] - rm[i], rm[i]);
+    if (rv) rv[i] = fmaf(mom, var_s[i] * unb - rv[i], rv[i]);
+  }
+  if (nbt && threadIdx.x == 0) *nbt += 1;
+}
+
+// S[r][c] <- relu?( g[c] * (S[r][c] - mean[c]) * istd[c] + be[c] ) for r < nr (rows >= nr stay zero)
+template <bool RELU>
+__device__ __forceinline__ void db_bn_apply(const float* __restrict__ S, int C, int nr, const float* __restrict__ g,
+                                            const float* __restrict__ be, const float* __restrict__ mean_s,
+                                            const float* __restrict__ istd_s, float* __restrict__ D) {
+  const int c4n = C >> 2;
+  for (int i = threadIdx.x; i < nr * c4n; i += DB_THREADS) {
+    const int r = i / c4n, c = (i - r * c4n) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(S + r * C + c);
+    const float4 mu = *reinterpret_cast<const float4*>(mean_s + c);
+    const float4 is = *reinterpret_cast<const float4*>(istd_s + c);
+    const float4 gg = __ldg(reinterpret_cast<const float4*>(g + c));
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(be + c));
+    float4 o = make_float4(fmaf((v.x - mu.x) * is.x, gg.x, bb.x), fmaf((v.y - mu.y) * is.y, gg.y, bb.y),
+                           fmaf((v.z - mu.z) * is.z, gg.z, bb.z), fmaf((v.w - mu.w) * is.w, gg.w, bb.w));
+    if (RELU) {
+      o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+    }
+    *reinterpret_cast<float4*>(D + r * C + c) = o;
+  }
+}
+
+struct DbShared {
+  float *W1, *W2, *A, *Y, *Z, *red, *mean, *istd, *var;
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(DB_THREADS, 1)
+dense_block_fwd_kernel(const kp_dense_desc m, float* __restrict__ out, float* __restrict__ part, unsigned* bar, int Rc) {
+  extern __shared__ __align__(16) float smem[];
+  const int Ci = m.Cin, Co = m.Cout, N = m.N;
+  const int grid = gridDim.x;
+  const int r0 = blockIdx.x * Rc;
+  const int nr = max(0, min(Rc, N - r0));
+  const int Rp = (Rc + 3) & ~3;
+  float* W1t = smem;                    // [Ci][Co]
+  float* W2t = W1t + Ci * Co;           // [Co][Co]
+  float* A = W2t + Co * Co;             // [Rp][Ci]
+  float* Y = A + Rp * Ci;               // [Rp][Co]
+  float* Z = Y + Rp * Co;               // [Rp][Co]
+  float* red = Z + Rp * Co;             // [DB_WARPS][Co]
+  float* mean_s = red + DB_WARPS * Co;  // [Co]
+  float* istd_s = mean_s + Co;
+  float* var_s = istd_s + Co;
+  // weights, transposed so that a thread's 4 output channels are one float4
+  for (int i = threadIdx.x; i < Co * Ci; i += DB_THREADS) {
+    const int o = i / Ci, k = i - o * Ci;
+    W1t[k * Co + o] = __ldg(m.W1 + i);
+  }
+  for (int i = threadIdx.x; i < Co * Co; i += DB_THREADS) {
+    const int o = i / Co, k = i - o * Co;
+    W2t[k * Co + o] = __ldg(m.W2 + i);
+  }
+  db_load_slab(m.X, r0, nr, Rp, Ci, A);
+  for (int i = threadIdx.x; i < Rp * Co; i += DB_THREADS) Z[i] = 0.f;
+  __syncthreads();
+  float* part0 = part;
+  float* part1 = part + (size_t)grid * 2 * Co;
+  float* part2 = part1 + (size_t)grid * 2 * Co;
+
+  // ---- Linear1 + BN1 + ReLU ----
+  db_gemm_AB(A, Ci, Ci, W1t, Co, m.b1, Rp, Y, Co);
+  __syncthreads();
+  db_store_slab(Y, r0, nr, Co, m.Y1);
+  db_slab_stats(Y, Co, nr, part0 + (size_t)blockIdx.x * 2 * Co, part0 + (size_t)blockIdx.x * 2 * Co + Co);
+  db_grid_barrier(bar, 1u * grid);
+  db_merge_stats(part0, grid, Rc, N, Co, m.eps1, red, mean_s, istd_s, var_s);
+  if (blockIdx.x == 0)
+    db_publish_stats(mean_s, istd_s, var_s, N, Co, m.mom1, m.rm1, m.rv1, (long long*)m.nbt1, m.stats, m.stats + Co);
+  db_bn_apply<true>(Y, Co, nr, m.g1, m.be1, mean_s, istd_s, Z);
+  __syncthreads();
+
+  // ---- Linear2 + BN2 + ReLU ----
+  db_gemm_AB(Z, Co, Co, W2t, Co, m.b2, Rp, Y, Co);
+  __syncthreads();
+  db_store_slab(Y, r0, nr, Co, m.Y2);
+  db_slab_stats(Y, Co, nr, part1 + (size_t)blockIdx.x * 2 * Co, part1 + (size_t)blockIdx.x * 2 * Co + Co);
+  db_grid_barrier(bar, 2u * grid);
+  db_merge_stats(part1, grid, Rc, N, Co, m.eps2, red, mean_s, istd_s, var_s);
+  if (blockIdx.x == 0)
+    db_publish_stats(mean_s, istd_s, var_s, N, Co, m.mom2, m.rm2, m.rv2, (long long*)m.nbt2, m.stats + 2 * Co,
+                     m.stats + 3 * Co);
+  db_bn_apply<true>(Y, Co, nr, m.g2, m.be2, mean_s, istd_s, Z);
+  __syncthreads();
+
+  // ---- outer BatchNorm + residual ----
+  if (m.g3) {
+    db_store_slab(Z, r0, nr, Co, m.Z2);
+    db_slab_stats(Z, Co, nr, part2 + (size_t)blockIdx.x * 2 * Co, part2 + (size_t)blockIdx.x * 2 * Co + Co);
+    db_grid_barrier(bar, 3u * grid);
+    db_merge_stats(part2, grid, Rc, N, Co, m.eps3, red, mean_s, istd_s, var_s);
+    if (blockIdx.x == 0)
+      db_publish_stats(mean_s, istd_s, var_s, N, Co, m.mom3, m.rm3, m.rv3, (long long*)m.nbt3, m.stats + 4 * Co,
+                       m.stats + 5 * Co);
+    db_bn_apply<false>(Z, Co, nr, m.g3, m.be3, mean_s, istd_s, Y);
+    __syncthreads();
+  }
+  const float* res = m.g3 ? Y : Z;
+  const int c4n = Co >> 2;
+  for (int i = threadIdx.x; i < nr * c4n; i += DB_THREADS) {
+    const int r = i / c4n, c = (i - r * c4n) * 4;
+    float4 v = *reinterpret_cast<const float4*>(res + r * Co + c);
+    if (m.R) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(m.R + (size_t)(r0 + r) * Co + c));
+      v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+    }
+    *reinterpret_cast<float4*>(out + (size_t)(r0 + r) * Co + c) = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------------------
+// slab partial sums p1[c] = sum_r D[r][c], p2[c] = sum_r D[r][c] * XH[r][c]  -> global partial [2][C]
+__device__ __forceinline__ void db_slab_dots(const float* __restrict__ D, const float* __restrict__ XH, int C, int nr,
+                                             float* __restrict__ p) {
+  for (int c = threadIdx.x; c < C; c += DB_THREADS) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int r = 0; r < nr; ++r) {
+      const float dv = D[r * C + c];
+      s1 += dv;
+      s2 = fmaf(dv, XH[r * C + c], s2);
+    }
+    __stcg(p + c, s1);
+    __stcg(p + C + c, s2);
+  }
+}
+// plain fixed-order sums of the [grid][2][C] partials into shared s1[C], s2[C]
+__device__ __forceinline__ void db_merge_sums(const float* __restrict__ part, int grid, int C, float* __restrict__ red,
+                                              float* __restrict__ s1, float* __restrict__ s2) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // 2*C floats per partial = up to 64 float4: lanes take float4 lane and lane + 32
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+  const int n4 = (2 * C) >> 2;
+#pragma unroll 4
+  for (int q = warp; q < grid; q += DB_WARPS) {
+    const float4* p = reinterpret_cast<const float4*>(part + (size_t)q * 2 * C);
+    if (lane < n4) {
+      const float4 v = __ldcg(p + lane);
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    if (lane + 32 < n4) {
+      const float4 v = __ldcg(p + lane + 32);
+      b.x += v.x; b.y += v.y; b.z += v.z; b.w += v.w;
+    }
+  }
+  if (lane < n4) *reinterpret_cast<float4*>(red + warp * 2 * C + lane * 4) = a;
+  if (lane + 32 < n4) *reinterpret_cast<float4*>(red + warp * 2 * C + (lane + 32) * 4) = b;
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += DB_THREADS) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < DB_WARPS; ++w) t += red[w * 2 * C + i];
+    if (i < C) s1[i] = t;
+    else s2[i - C] = t;
+  }
+  __syncthreads();
+}
+// XH <- (S - mean) * istd   (normalised activations of the slab)
+__device__ __forceinline__ void db_xhat(const float* __restrict__ S, int C, int nrp, const float* __restrict__ mean,
+                                        const float* __restrict__ istd, float* __restrict__ XH) {
+  const int c4n = C >> 2;
+  for (int i = threadIdx.x; i < nrp * c4n; i += DB_THREADS) {
+    const int c = (i % c4n) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(S + i * 4);
+    const float4 mu = __ldg(reinterpret_cast<const float4*>(mean + c));
+    const float4 is = __ldg(reinterpret_cast<const float4*>(istd + c));
+    *reinterpret_cast<float4*>(XH + i * 4) =
+        make_float4((v.x - mu.x) * is.x, (v.y - mu.y) * is.y, (v.z - mu.z) * is.z, (v.w - mu.w) * is.w);
+  }
+}
+// D <- g * istd * (D - s1/N - XH * s2/N)   for r < nr
+__device__ __forceinline__ void db_bn_bwd_apply(float* __restrict__ D, const float* __restrict__ XH, int C, int nr, int N,
+                                                const float* __restrict__ g, const float* __restrict__ istd,
+                                                const float* __restrict__ s1, const float* __restrict__ s2) {
+  const int c4n = C >> 2;
+  const float invn = 1.f / (float)N;
+  for (int i = threadIdx.x; i < nr * c4n; i += DB_THREADS) {
+    const int c = (i % c4n) * 4;
+    const float4 dv = *reinterpret_cast<const float4*>(D + i * 4);
+    const float4 xh = *reinterpret_cast<const float4*>(XH + i * 4);
+    const float4 gg = __ldg(reinterpret_cast<const float4*>(g + c));
+    const float4 is = __ldg(reinterpret_cast<const float4*>(istd + c));
+    const float4 a = *reinterpret_cast<const float4*>(s1 + c);
+    const float4 b = *reinterpret_cast<const float4*>(s2 + c);
+    *reinterpret_cast<float4*>(D + i * 4) =
+        make_float4(gg.x * is.x * (dv.x - a.x * invn - xh.x * (b.x * invn)),
+                    gg.y * is.y * (dv.y - a.y * invn - xh.y * (b.y * invn)),
+                    gg.z * is.z * (dv.z - a.z * invn - xh.z * (b.z * invn)),
+                    gg.w * is.w * (dv.w - a.w * invn - xh.w * (b.w * invn)));
+  }
+}
+// D[r][c] <- 0 where g*XH + be <= 0 (the ReLU after the BatchNorm was inactive)
+__device__ __forceinline__ void db_relu_mask(float* __restrict__ D, const float* __restrict__ XH, int C, int nr,
+                                             const float* __restrict__ g, const float* __restrict__ be) {
+  const int c4n = C >> 2;
+  for (int i = threadIdx.x; i < nr * c4n; i += DB_THREADS) {
+    const int c = (i % c4n) * 4;
+    float4 dv = *reinterpret_cast<const float4*>(D + i * 4);
+    const float4 xh = *reinterpret_cast<const float4*>(XH + i * 4);
+    const float4 gg = __ldg(reinterpret_cast<const float4*>(g + c));
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(be + c));
+    if (fmaf(gg.x, xh.x, bb.x) <= 0.f) dv.x = 0.f;
+    if (fmaf(gg.y, xh.y, bb.y) <= 0.f) dv.y = 0.f;
+    if (fmaf(gg.z, xh.z, bb.z) <= 0.f) dv.z = 0.f;
+    if (fmaf(gg.w, xh.w, bb.w) <= 0.f) dv.w = 0.f;
+    *reinterpret_cast<float4*>(D + i * 4) = dv;
+  }
+}
+// column sums of a slab -> global partial [C]
+__device__ __forceinline__ void db_slab_colsum(const float* __restrict__ D, int C, int nr, float* __restrict__ p) {
+  for (int c = threadIdx.x; c < C; c += DB_THREADS) {
+    float s = 0.f;
+    for (int r = 0; r < nr; ++r) s += D[r * C + c];
+    __stcg(p + c, s);
+  }
+}
+
+// workspace layout (floats): pa, pb, pc [grid][2][Co] | pW1 [grid][Co*Ci] | pW2 [grid][Co*Co] | pb1, pb2 [grid][Co]
+__global__ void __launch_bounds__(DB_THREADS, 1)
+dense_block_bwd_kernel(const kp_dense_desc m, const float* __restrict__ dOut, float* __restrict__ dX,
+                       float* __restrict__ dW1, float* __restrict__ db1, float* __restrict__ dW2,
+                       float* __restrict__ db2, float* __restrict__ dbn, float* __restrict__ ws, unsigned* bar, int Rc) {
+  extern __shared__ __align__(16) float smem[];
+  const int Ci = m.Cin, Co = m.Cout, N = m.N;
+  const int grid = gridDim.x;
+  const int r0 = blockIdx.x * Rc;
+  const int nr = max(0, min(Rc, N - r0));
+  const int Rp = (Rc + 3) & ~3;
+  const int Cm = max(Ci, Co);
+  float* W1 = smem;                   // [Co][Ci] row-major (dX = dy1 W1)
+  float* W2 = W1 + Co * Ci;           // [Co][Co] row-major (dz1 = dy2 W2)
+  float* D = W2 + Co * Co;            // [Rp][Co]  running gradient of the current stage
+  float* XH = D + Rp * Co;            // [Rp][Cm]  x-hat of BN3 / BN2, later the X slab
+  float* XH1 = XH + Rp * Cm;          // [Rp][Co]  x-hat of BN1
+  float* Z1 = XH1 + Rp * Co;          // [Rp][Co]  z1 = relu(BN1(y1))
+  float* E = Z1 + Rp * Co;            // [Rp][Cm]  dz1 / dy1, later dX
+  float* red = E + Rp * Cm;           // [DB_WARPS][2*Co]
+  float* s1 = red + DB_WARPS * 2 * Co;
+  float* s2 = s1 + Co;
+  float* pa = ws;
+  float* pb = pa + (size_t)grid * 2 * Co;
+  float* pc = pb + (size_t)grid * 2 * Co;
+  float* pW1 = pc + (size_t)grid * 2 * Co;
+  float* pW2 = pW1 + (size_t)grid * Co * Ci;
+  float* pb1 = pW2 + (size_t)grid * Co * Co;
+  float* pb2 = pb1 + (size_t)grid * Co;
+  const float* mean1 = m.stats, *istd1 = m.stats + Co, *mean2 = m.stats + 2 * Co, *istd2 = m.stats + 3 * Co;
+  const float* mean3 = m.stats + 4 * Co, *istd3 = m.stats + 5 * Co;
+
+  for (int i = threadIdx.x * 4; i < Co * Ci; i += DB_THREADS * 4)
+    *reinterpret_cast<float4*>(W1 + i) = __ldg(reinterpret_cast<const float4*>(m.W1 + i));
+  for (int i = threadIdx.x * 4; i < Co * Co; i += DB_THREADS * 4)
+    *reinterpret_cast<float4*>(W2 + i) = __ldg(reinterpret_cast<const float4*>(m.W2 + i));
+  db_load_slab(dOut, r0, nr, Rp, Co, D);
+  unsigned phase = 0;
+  if (m.g3) {
+    // ---- outer BatchNorm ----
+    db_load_slab(m.Z2, r0, nr, Rp, Co, XH);
+    __syncthreads();
+    db_xhat(XH, Co, Rp, mean3, istd3, XH);
+    __syncthreads();
+    db_slab_dots(D, XH, Co, nr, pa + (size_t)blockIdx.x * 2 * Co);
+    db_grid_barrier(bar, ++phase * grid);
+    db_merge_sums(pa, grid, Co, red, s1, s2);
+    if (blockIdx.x == 0)
+      for (int i = threadIdx.x; i < Co; i += DB_THREADS) {
+        dbn[4 * Co + i] = s2[i];
+        dbn[5 * Co + i] = s1[i];
+      }
+    db_bn_bwd_apply(D, XH, Co, nr, N, m.g3, istd3, s1, s2);
+  }
+  __syncthreads();
+  // ---- ReLU2 + BN2 ----
+  db_load_slab(m.Y2, r0, nr, Rp, Co, XH);
+  __syncthreads();
+  db_xhat(XH, Co, Rp, mean2, istd2, XH);
+  __syncthreads();
+  db_relu_mask(D, XH, Co, nr, m.g2, m.be2);
+  __syncthreads();
+  db_slab_dots(D, XH, Co, nr, pb + (size_t)blockIdx.x * 2 * Co);
+  // meanwhile: z1 and x-hat1 of the slab (needed after the barrier)
+  db_load_slab(m.Y1, r0, nr, Rp, Co, XH1);
+  __syncthreads();
+  db_xhat(XH1, Co, Rp, mean1, istd1, XH1);
+  for (int i = threadIdx.x; i < Rp * Co; i += DB_THREADS) Z1[i] = 0.f;
+  __syncthreads();
+  {
+    const int c4n = Co >> 2;
+    for (int i = threadIdx.x; i < nr * c4n; i += DB_THREADS) {
+      const int c = (i % c4n) * 4;
+      const float4 xh = *reinterpret_cast<const float4*>(XH1 + i * 4);
+      const float4 gg = __ldg(reinterpret_cast<const float4*>(m.g1 + c));
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(m.be1 + c));
+      *reinterpret_cast<float4*>(Z1 + i * 4) =
+          make_float4(fmaxf(fmaf(gg.x, xh.x, bb.x), 0.f), fmaxf(fmaf(gg.y, xh.y, bb.y), 0.f),
+                      fmaxf(fmaf(gg.z, xh.z, bb.z), 0.f), fmaxf(fmaf(gg.w, xh.w, bb.w), 0.f));
+    }
+  }
+  db_grid_barrier(bar, ++phase * grid);
+  db_merge_sums(pb, grid, Co, red, s1, s2);
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < Co; i += DB_THREADS) {
+      dbn[2 * Co + i] = s2[i];
+      dbn[3 * Co + i] = s1[i];
+    }
+  db_bn_bwd_apply(D, XH, Co, nr, N, m.g2, istd2, s1, s2);      // D = dy2
+  __syncthreads();
+  // ---- Linear2: dW2 partial, db2 partial, dz1 = dy2 W2 ----
+  db_gemm_AtB(D, Co, Co, Z1, Co, Co, nr, pW2 + (size_t)blockIdx.x * Co * Co);
+  db_slab_colsum(D, Co, nr, pb2 + (size_t)blockIdx.x * Co);
+  db_gemm_AB(D, Co, Co, W2, Co, nullptr, Rp, E, Co);
+  __syncthreads();
+  // ---- ReLU1 + BN1 ----
+  db_relu_mask(E, XH1, Co, nr, m.g1, m.be1);
+  __syncthreads();
+  db_slab_dots(E, XH1, Co, nr, pc + (size_t)blockIdx.x * 2 * Co);
+  db_load_slab(m.X, r0, nr, Rp, Ci, XH);                       // X slab for dW1 (x-hat2 is no longer needed)
+  db_grid_barrier(bar, ++phase * grid);
+  db_merge_sums(pc, grid, Co, red, s1, s2);
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < Co; i += DB_THREADS) {
+      dbn[0 * Co + i] = s2[i];
+      dbn[1 * Co + i] = s1[i];
+    }
+  db_bn_bwd_apply(E, XH1, Co, nr, N, m.g1, istd1, s1, s2);     // E = dy1
+  __syncthreads();
+  // ---- Linear1: dW1 partial, db1 partial, dX = dy1 W1 ----
+  db_gemm_AtB(E, Co, Co, XH, Ci, Ci, nr, pW1 + (size_t)blockIdx.x * Co * Ci);
+  db_slab_colsum(E, Co, nr, pb1 + (size_t)blockIdx.x * Co);
+  db_gemm_AB(E, Co, Co, W1, Ci, nullptr, Rp, D, Ci);           // D reused as [Rp][Ci] (Ci <= Co checked on host)
+  __syncthreads();
+  db_store_slab(D, r0, nr, Ci, dX);
+  db_grid_barrier(bar, ++phase * grid);
+  // ---- fixed-order sums of the per-CTA weight-gradient partials: 8 lanes per output float4 ----
+  {
+    const int nW1 = (Co * Ci) >> 2, nW2 = (Co * Co) >> 2, nb = Co >> 2;
+    const int total = nW1 + nW2 + 2 * nb;
+    const int sub = threadIdx.x & 7;
+    const int wg = (blockIdx.x * DB_THREADS + threadIdx.x) >> 5, nwg = (grid * DB_THREADS) >> 5;
+    for (int e0 = wg * 4; e0 < total; e0 += nwg * 4) {          // warp-uniform trip count (full-mask shuffles)
+      const int e = e0 + ((threadIdx.x & 31) >> 3);
+      const bool ok = e < total;
+      const float* src = pW1;
+      float* dst = dW1;
+      size_t stride = 0;
+      if (e < nW1) {
+        src = pW1 + (size_t)e * 4; dst = dW1 + (size_t)e * 4; stride = (size_t)Co * Ci;
+      } else if (e < nW1 + nW2) {
+        src = pW2 + (size_t)(e - nW1) * 4; dst = dW2 + (size_t)(e - nW1) * 4; stride = (size_t)Co * Co;
+      } else if (e < nW1 + nW2 + nb) {
+        src = pb1 + (size_t)(e - nW1 - nW2) * 4; dst = db1 + (size_t)(e - nW1 - nW2) * 4; stride = Co;
+      } else if (ok) {
+        src = pb2 + (size_t)(e - nW1 - nW2 - nb) * 4; dst = db2 + (size_t)(e - nW1 - nW2 - nb) * 4; stride = Co;
+      }
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ok) {
+#pragma unroll 4
+        for (int q = sub; q < grid; q += 8) {
+          const float4 v = __ldcg(reinterpret_cast<const float4*>(src + (size_t)q * stride));
+          s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+      }
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
+        s.x += __shfl_xor_sync(0xffffffffu, s.x, o);
+        s.y += __shfl_xor_sync(0xffffffffu, s.y, o);
+        s.z += __shfl_xor_sync(0xffffffffu, s.z, o);
+        s.w += __shfl_xor_sync(0xffffffffu, s.w, o);
+      }
+      if (ok && sub == 0) *reinterpret_cast<float4*>(dst) = s;
+    }
+  }
+}
+
+struct DbCfg {
+  int grid, Rc;
+  size_t smem_fwd, smem_bwd, ws_fwd, ws_bwd;
+};
+
+static size_t db_smem_fwd(int Ci, int Co, int Rc) {
+  const int Rp = (Rc + 3) & ~3;
+  return sizeof(float) * ((size_t)Ci * Co + (size_t)Co * Co + (size_t)Rp * Ci + 2 * (size_t)Rp * Co +
+                          (size_t)DB_WARPS * Co + 3 * (size_t)Co);
+}
+static size_t db_smem_bwd(int Ci, int Co, int Rc) {
+  const int Rp = (Rc + 3) & ~3;
+  const int Cm = Ci > Co ? Ci : Co;
+  return sizeof(float) * ((size_t)Ci * Co + (size_t)Co * Co + 3 * (size_t)Rp * Co + 2 * (size_t)Rp * Cm +
+                          (size_t)DB_WARPS * 2 * Co + 2 * (size_t)Co);
+}
+static const size_t kDbSmemBudget = 220 * 1024;
+
+static int db_max_rc(int Ci, int Co) {
+  int rc = 0;
+  for (int r = 4; r <= 256; r += 4)
+    if (db_smem_fwd(Ci, Co, r) <= kDbSmemBudget && db_smem_bwd(Ci, Co, r) <= kDbSmemBudget) rc = r;
+  return rc;
+}
+
+static int db_config(const kp_dense_desc& m, DbCfg* c) {
+  KP_CHECK_ARG(m.N >= 2 && m.Cin >= 4 && m.Cout >= 4 && m.Cin % 4 == 0 && m.Cout % 4 == 0 && m.Cin <= 128 &&
+                   m.Cout <= 128 && m.Cin <= m.Cout,
+               "kp_dense_block: need N >= 2, channels multiples of 4, Cin <= Cout <= 128 (got N=%d Cin=%d Cout=%d)",
+               m.N, m.Cin, m.Cout);
+  const int rcmax = db_max_rc(m.Cin, m.Cout);
+  KP_CHECK_ARG(rcmax > 0 && (long long)m.N <= (long long)rcmax * DB_MAX_GRID,
+               "kp_dense_block: N=%d exceeds kp_dense_block_max_rows", m.N);
+  static const int env_rows = getenv("KP_DENSE_ROWS") ? atoi(getenv("KP_DENSE_ROWS")) : 0;
+  int Rc = env_rows > 0 ? env_rows : DB_ROWS;
+  if ((long long)Rc * DB_MAX_GRID < m.N) Rc = (m.N + DB_MAX_GRID - 1) / DB_MAX_GRID;
+  Rc = (Rc + 3) & ~3;
+  if (Rc > rcmax) Rc = rcmax;
+  c->Rc = Rc;
+  c->grid = (m.N + Rc - 1) / Rc;
+  c->smem_fwd = db_smem_fwd(m.Cin, m.Cout, Rc);
+  c->smem_bwd = db_smem_bwd(m.Cin, m.Cout, Rc);
+  c->ws_fwd = 256 + sizeof(float) * (size_t)c->grid * 2 * m.Cout * 3;
+  c->ws_bwd = 256 + sizeof(float) * (size_t)c->grid *
+                        (6 * (size_t)m.Cout + (size_t)m.Cout * m.Cin + (size_t)m.Cout * m.Cout + 2 * (size_t)m.Cout);
+  return 0;
+}
+
+}  // namespace kp
+
+extern "C" {
+
+int kp_dense_block_max_rows(int32_t Cin, int32_t Cout) {
+  if (Cin < 4 || Cout < 4 || Cin % 4 || Cout % 4 || Cin > 128 || Cout > 128 || Cin > Cout) return 0;
+  return kp::db_max_rc(Cin, Cout) * kp::DB_MAX_GRID;
+}
+
+int kp_dense_block_workspace_bytes(const kp_dense_desc* desc, size_t* fwd_bytes, size_t* bwd_bytes) {
+  KP_CHECK_ARG(desc && fwd_bytes && bwd_bytes, "kp_dense_block_workspace_bytes: null argument");
+  kp::DbCfg c;
+  if (kp::db_config(*desc, &c)) return 1;
+  *fwd_bytes = c.ws_fwd;
+  *bwd_bytes = c.ws_bwd;
+  return 0;
+}
+
+static int kp_dense_check(const kp_dense_desc& m) {
+  KP_CHECK_ARG(m.X && m.W1 && m.b1 && m.g1 && m.be1 && m.W2 && m.b2 && m.g2 && m.be2 && m.Y1 && m.Y2 && m.stats,
+               "kp_dense_block: null argument");
+  KP_CHECK_ARG(!m.g3 || (m.be3 && m.Z2), "kp_dense_block: BN3 needs be3 and Z2");
+  KP_CHECK_ARG((((uintptr_t)m.X | (uintptr_t)m.W1 | (uintptr_t)m.b1 | (uintptr_t)m.g1 | (uintptr_t)m.be1 |
+                 (uintptr_t)m.W2 | (uintptr_t)m.b2 | (uintptr_t)m.g2 | (uintptr_t)m.be2 | (uintptr_t)m.g3 |
+                 (uintptr_t)m.be3 | (uintptr_t)m.R | (uintptr_t)m.Y1 | (uintptr_t)m.Y2 | (uintptr_t)m.Z2 |
+                 (uintptr_t)m.stats) & 15) == 0,
+               "kp_dense_block: pointers must be 16-byte aligned");
+  return 0;
+}
+
+int kp_dense_block_forward(const kp_dense_desc* desc, float* out, void* workspace, size_t workspace_bytes,
+                           void* stream) {
+  KP_CHECK_ARG(desc && out && workspace, "kp_dense_block_forward: null argument");
+  const kp_dense_desc& m = *desc;
+  kp::DbCfg c;
+  if (kp::db_config(m, &c)) return 1;
+  if (kp_dense_check(m)) return 1;
+  KP_CHECK_ARG(workspace_bytes >= c.ws_fwd && (((uintptr_t)workspace | (uintptr_t)out) & 15) == 0,
+               "kp_dense_block_forward: workspace too small or misaligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  KP_CUDA(cudaMemsetAsync(workspace, 0, 256, st));
+  KP_CUDA(cudaFuncSetAttribute(kp::dense_block_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)c.smem_fwd));
+  KP_LAUNCH(kp::dense_block_fwd_kernel, c.grid, kp::DB_THREADS, c.smem_fwd, st, m, out,
+            (float*)((char*)workspace + 256), (unsigned*)workspace, c.Rc);
+  return 0;
+}
+
+int kp_dense_block_backward(const kp_dense_desc* desc, const float* dOut, float* dX, float* dW1, float* db1,
+                            float* dW2, float* db2, float* dbn, void* workspace, size_t workspace_bytes,
+                            void* stream) {
+  KP_CHECK_ARG(desc && dOut && dX && dW1 && db1 && dW2 && db2 && dbn && workspace,
+               "kp_dense_block_backward: null argument");
+  const kp_dense_desc& m = *desc;
+  kp::DbCfg c;
+  if (kp::db_config(m, &c)) return 1;
+  if (kp_dense_check(m)) return 1;
+  KP_CHECK_ARG(workspace_bytes >= c.ws_bwd &&
+                   (((uintptr_t)workspace | (uintptr_t)dOut | (uintptr_t)dX | (uintptr_t)dW1 | (uintptr_t)db1 |
+                     (uintptr_t)dW2 | (uintptr_t)db2 | (uintptr_t)dbn) & 15) == 0,
+               "kp_dense_block_backward: workspace too small or pointers misaligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  KP_CUDA(cudaMemsetAsync(workspace, 0, 256, st));
+  KP_CUDA(cudaFuncSetAttribute(kp::dense_block_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)c.smem_bwd));
+  KP_LAUNCH(kp::dense_block_bwd_kernel, c.grid, kp::DB_THREADS, c.smem_bwd, st, m, dOut, dX, dW1, db1, dW2, db2, dbn,
+            (float*)((char*)workspace + 256), (unsigned*)workspace, c.Rc);
+  return 0;
+}
+
+}  // extern "C"

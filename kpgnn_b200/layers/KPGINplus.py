@@ -3,6 +3,7 @@ import torch.nn.functional as F  # noqa: F401  (star-import surface parity with 
 
 from ._base import KHopLayer, SplitKLinear, make_combine, khop_aggregate, get_plan, ACT_GELU
 from .norm import FusedBatchNorm1d
+from .dense_block import fused_dense_block
 from .combine import *  # noqa: F401,F403
 
 
@@ -46,7 +47,10 @@ class KPGINPlusConv(KHopLayer):
         if hasattr(m, "reset_parameters"):
             m.reset_parameters()
 
-    def forward(self, x, edge_index, edge_attr, pe_attr=None, peripheral_attr=None):
+    def forward(self, x, edge_index, edge_attr, pe_attr=None, peripheral_attr=None, post_norm=None, residual=None):
+        """Reference signature (KPGINplus.py:61) plus two optional keywords used by this repo's backbone:
+        `post_norm` (the BatchNorm GNNs.py:430 applies to the layer output) and `residual` (GNNs.py:436) are folded
+        into the layer's dense-block kernel; returns post_norm(mlp(.)) + residual."""
         self._check_hops(edge_attr)
         plan, k = get_plan(edge_index, edge_attr, x.size(0))
         x = self._add_path_encoding(x, pe_attr)
@@ -56,4 +60,13 @@ class KPGINPlusConv(KHopLayer):
                                act=ACT_GELU, fuse=True)
         else:
             h = self.combine(khop_aggregate(x, plan, k, P=peripheral_attr, T0=t0, Tk=tk, act=ACT_GELU))
-        return self.mlp(h)
+        bn3 = getattr(post_norm, "module", post_norm)          # backbone wraps its norms (state_dict key `module.*`)
+        out = fused_dense_block(h, self.mlp[0], self.mlp[1], self.mlp[3], self.mlp[4], bn3, residual)
+        if out is not None:
+            return out
+        out = self.mlp(h)
+        if post_norm is not None:
+            out = post_norm(out)
+        if residual is not None:
+            out = out + residual
+        return out

@@ -152,13 +152,21 @@ class KPGNNPlusBackbone(nn.Module):
             # newest layer first, GNNs.py:413-418
             xs = torch.stack([h_list[j] for j in range(l, l - k, -1)], dim=1)
             pe = data.pe_attr[:, :k - 1] if data.pe_attr is not None else None
-            h = self.gnns[l](xs, data.edge_index, data.edge_attr[:, :k], pe, P[:, :k])
-            h = self.norms[l](h)
-            if l != self.num_layer - 1:
-                h = self.dropout(h)
-            if self.residual:
-                h = h + last_h
-                last_h = h
+            last = l == self.num_layer - 1
+            if self.training and (last or self.dropout.p == 0.0):
+                # norm + (identity dropout) + residual ride in the layer's dense-block kernel (GNNs.py:430-438)
+                h = self.gnns[l](xs, data.edge_index, data.edge_attr[:, :k], pe, P[:, :k], post_norm=self.norms[l],
+                                 residual=last_h if self.residual else None)
+                if self.residual:
+                    last_h = h
+            else:
+                h = self.gnns[l](xs, data.edge_index, data.edge_attr[:, :k], pe, P[:, :k])
+                h = self.norms[l](h)
+                if not last:
+                    h = self.dropout(h)
+                if self.residual:
+                    h = h + last_h
+                    last_h = h
             h_list.append(h)
         if self.JK == "concat":
             rep = torch.cat(h_list, dim=1)

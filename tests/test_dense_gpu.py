@@ -1,0 +1,140 @@
+"""Fused dense block (csrc/dense.cu) against the same modules run one by one in plain torch fp32:
+Linear-BN-ReLU-Linear-BN-ReLU (layers/KPGINplus.py:25-30) + the backbone's BatchNorm and residual
+(models/GNNs.py:430-438).  Forward, every gradient, running statistics, determinism, fallbacks."""
+import pytest
+import torch
+import torch.nn as nn
+
+pytestmark = pytest.mark.gpu
+torch.backends.cuda.matmul.allow_tf32 = False
+torch.backends.cudnn.allow_tf32 = False
+
+
+def _modules(Cin, Cout, seed, dev):
+    torch.manual_seed(seed)
+    mods = [nn.Linear(Cin, Cout), nn.BatchNorm1d(Cout), nn.Linear(Cout, Cout), nn.BatchNorm1d(Cout),
+            nn.BatchNorm1d(Cout)]
+    with torch.no_grad():
+        for m in mods:
+            if isinstance(m, nn.BatchNorm1d):
+                m.weight.copy_(torch.randn(Cout) * 0.5 + 1.0)
+                m.bias.copy_(torch.randn(Cout) * 0.3)
+    return [m.to(dev).train() for m in mods]
+
+
+def _run(mods, x0, r0, gy, fused, use_bn3, use_res, steps=2):
+    from kpgnn_b200.layers.dense_block import fused_dense_block
+    lin1, bn1, lin2, bn2, bn3 = mods
+    x = x0.clone().requires_grad_(True)
+    r = r0.clone().requires_grad_(True) if use_res else None
+    for _ in range(steps):                                   # two steps: running statistics accumulate
+        if fused:
+            y = fused_dense_block(x, lin1, bn1, lin2, bn2, bn3 if use_bn3 else None, r)
+            assert y is not None
+        else:
+            y = torch.relu(bn2(lin2(torch.relu(bn1(lin1(x))))))
+            if use_bn3:
+                y = bn3(y)
+            if use_res:
+                y = y + r
+    y.backward(gy)
+    out = {"y": y.detach(), "dx": x.grad}
+    if use_res:
+        out["dr"] = r.grad
+    for name, m in zip(("lin1", "bn1", "lin2", "bn2", "bn3"), mods):
+        if name == "bn3" and not use_bn3:
+            continue
+        out[name + ".dw"] = m.weight.grad
+        out[name + ".db"] = m.bias.grad
+        if isinstance(m, nn.BatchNorm1d):
+            out[name + ".rm"], out[name + ".rv"] = m.running_mean.clone(), m.running_var.clone()
+            out[name + ".nbt"] = m.num_batches_tracked.clone().float()
+    return out
+
+
+@pytest.mark.parametrize("N", [3, 37, 300, 2952, 5000])
+@pytest.mark.parametrize("C", [(104, 104), (32, 64), (128, 128)])
+@pytest.mark.parametrize("tail", ["bn3+res", "bn3", "res", "none"])
+def test_dense_block_matches_torch(lib, N, C, tail):
+    dev = torch.device("cuda:0")
+    Cin, Cout = C
+    if N > lib.kp_dense_block_max_rows(Cin, Cout):
+        pytest.skip("more rows than one slab per SM")
+    use_bn3, use_res = "bn3" in tail, "res" in tail
+    g = torch.Generator().manual_seed(N + Cin)
+    x0 = (torch.randn(N, Cin, generator=g) * 2 + 0.5).to(dev)
+    r0 = torch.randn(N, Cout, generator=g).to(dev)
+    gy = torch.randn(N, Cout, generator=g).to(dev)
+    ref = _run(_modules(Cin, Cout, 1, dev), x0, r0, gy, False, use_bn3, use_res)
+    got = _run(_modules(Cin, Cout, 1, dev), x0, r0, gy, True, use_bn3, use_res)
+    wscale = max(float(ref["lin1.dw"].abs().max()), float(ref["lin2.dw"].abs().max()))
+    for k, a in ref.items():
+        b = got[k]
+        # Linear biases in front of a BatchNorm have an analytically zero gradient: both sides are rounding noise
+        scale = wscale if k in ("lin1.db", "lin2.db") else max(float(a.abs().max()), 1e-6)
+        tol = 1e-4 if N <= 5 else 2e-5           # N=3: the BN input gradients are themselves near-cancelling
+        assert float((a - b).abs().max()) / scale < tol, (k, float((a - b).abs().max()), scale)
+
+
+def test_dense_block_deterministic(lib):
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(5)
+    x0 = torch.randn(2952, 104, generator=g).to(dev)
+    r0 = torch.randn(2952, 104, generator=g).to(dev)
+    gy = torch.randn(2952, 104, generator=g).to(dev)
+    a = _run(_modules(104, 104, 2, dev), x0, r0, gy, True, True, True)
+    b = _run(_modules(104, 104, 2, dev), x0, r0, gy, True, True, True)
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+
+
+def test_dense_block_fallbacks(lib):
+    from kpgnn_b200.layers.dense_block import fused_dense_block
+    dev = torch.device("cuda:0")
+    lin1, bn1, lin2, bn2, bn3 = _modules(104, 104, 3, dev)
+    x = torch.randn(64, 104, device=dev)
+    assert fused_dense_block(x, lin1, bn1, lin2, bn2) is not None
+    bn1.eval()
+    assert fused_dense_block(x, lin1, bn1, lin2, bn2) is None            # eval mode -> caller runs the modules
+    bn1.train()
+    big = torch.randn(lib.kp_dense_block_max_rows(104, 104) + 1, 104, device=dev)
+    assert fused_dense_block(big, lin1, bn1, lin2, bn2) is None
+    assert fused_dense_block(x.cpu(), lin1, bn1, lin2, bn2) is None
+
+
+def test_layer_with_post_norm_matches_unfused(lib):
+    """KPGINPlusConv(..., post_norm=, residual=) == norm(layer(.)) + residual with the modules run one by one."""
+    import copy
+    from kpgnn_b200.layers.KPGINplus import KPGINPlusConv
+    from kpgnn_b200.layers import dense_block
+    from tests.util import zinc_batch
+    dev = torch.device("cuda:0")
+    b = zinc_batch(32, 4, "spd", seed=3)
+    N = b["num_nodes"]
+    ei, ea = b["edge_index"].to(dev), b["edge_attr"].to(dev)
+    torch.manual_seed(0)
+    layer = KPGINPlusConv(104, 104, 4, 3, 50, "geometric").to(dev).train()
+    norm = nn.BatchNorm1d(104).to(dev).train()
+    layer2, norm2 = copy.deepcopy(layer), copy.deepcopy(norm)
+    x0, P0, r0 = torch.randn(N, 4, 104, device=dev), torch.randn(N, 4, 104, device=dev), torch.randn(N, 104, device=dev)
+    outs = []
+    for lay, nm, fused in ((layer, norm, True), (layer2, norm2, False)):
+        x, P, r = (t.clone().requires_grad_(True) for t in (x0, P0, r0))
+        if fused:
+            y = lay(x * 1.0, ei, ea, None, P, post_norm=nm, residual=r)
+        else:
+            saved = dense_block.fused_dense_block
+            dense_block.fused_dense_block = lambda *a, **k: None
+            import kpgnn_b200.layers.KPGINplus as mod
+            mod.fused_dense_block = lambda *a, **k: None
+            try:
+                y = lay(x * 1.0, ei, ea, None, P, post_norm=nm, residual=r)
+            finally:
+                dense_block.fused_dense_block = saved
+                mod.fused_dense_block = saved
+        y.square().sum().backward()
+        outs.append([y.detach(), x.grad, P.grad, r.grad, lay.mlp[0].weight.grad, lay.mlp[3].weight.grad,
+                     lay.hopk_edge_emb.weight.grad, nm.weight.grad, nm.bias.grad, nm.running_var.clone()])
+    for a, c in zip(*outs):
+        scale = max(float(c.abs().max()), 1e-6)
+        assert float((a - c).abs().max()) / scale < 2e-5

@@ -4,7 +4,7 @@
 //
 // Why: at molecule-batch sizes (N ~ 3 000 rows, 104 channels) the step was a chain of ~45 kernels of 2-11 us each
 // per layer around the aggregation (2 + 4 SIMT GEMMs, 3 + 3 BatchNorm kernels, 4 column sums, bias / residual
-// adds; profiles/r1v_step_kineto.txt) -- all latency, no bandwidth.  Here each CTA keeps a slab of <= 40 rows and
+// adds; profiles/r1v_step_kineto.txt) -- all latency, no bandwidth.  Here each CTA keeps a slab of ~36 rows and
 // BOTH weight matrices in shared memory for the whole block; the only cross-CTA dependencies are the three batch
 // statistics (and, backward, the weight-gradient sums), exchanged through small per-CTA partials in L2 behind a
 // grid-wide barrier.  Statistics use Chan's parallel variance (per-slab mean / M2 merged in a fixed order), the
@@ -38,6 +38,81 @@ __device__ __forceinline__ void db_grid_barrier(unsigned* ctr, unsigned target) 
     __threadfence();
   }
   __syncthreads();
+}
+
+constexpr int DB_MAXI = (DB_MAX_GRID + DB_WARPS - 1) / DB_WARPS;   // partials per warp in a merge (held in registers)
+
+__device__ __forceinline__ void db_cp16(float* dst, const float* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src)
+               : "memory");
+}
+__device__ __forceinline__ void db_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void db_cp_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Forward weight layout: row o of W [Co][Kd] keeps its 16-byte chunks, chunk kc stored at position kc ^ ((o>>2)&7)
+// of a row padded to a multiple of 8 chunks.  A thread that owns output channels 4ct..4ct+3 then reads float4s
+// whose bank group depends on ct only through the XOR: 8 consecutive threads hit 8 different bank groups
+// (conflict-free) although the rows are 4*stride apart -- and the copy from global memory is a pure 16-byte
+// permutation, so cp.async does it without a transposition pass through registers.
+__host__ __device__ __forceinline__ int db_wstride(int Kd) { return (((Kd >> 2) + 7) & ~7) << 2; }
+
+__device__ __forceinline__ void db_cp_weight_swizzled(const float* __restrict__ W, int Co, int Kd, float* __restrict__ Ws) {
+  const int ck = Kd >> 2, ws = db_wstride(Kd);
+  for (int i = threadIdx.x; i < Co * ck; i += DB_THREADS) {
+    const int o = i / ck, kc = i - o * ck;
+    db_cp16(Ws + o * ws + ((kc ^ ((o >> 2) & 7)) << 2), W + (size_t)i * 4);
+  }
+}
+__device__ __forceinline__ void db_cp_rows(const float* __restrict__ g, int nfloats, float* __restrict__ sdst) {
+  for (int i = threadIdx.x * 4; i < nfloats; i += DB_THREADS * 4) db_cp16(sdst + i, g + i);
+}
+// global rows r0..r0+nr of a [N][C] matrix -> shared slab (rows >= nr are zero-filled by plain stores)
+__device__ __forceinline__ void db_cp_slab(const float* __restrict__ g, int r0, int nr, int nrp, int C,
+                                           float* __restrict__ sdst) {
+  const int n = nr * C;
+  const float* src = g + (size_t)r0 * C;
+  for (int i = threadIdx.x * 4; i < nrp * C; i += DB_THREADS * 4) {
+    if (i < n) db_cp16(sdst + i, src + i);
+    else *reinterpret_cast<float4*>(sdst + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+// out[r][o] = bias[o] + sum_k A[r][k] * W[o][k]   (W in the swizzled layout above), r < nrp, o < Co
+__device__ __forceinline__ void db_gemm_AWt(const float* __restrict__ A, int lda, int Kd, const float* __restrict__ Ws,
+                                            int Co, const float* __restrict__ bias, int nrp, float* __restrict__ out,
+                                            int ldo) {
+  const int ctn = Co >> 2, ntiles = ctn * (nrp >> 2), ws = db_wstride(Kd);
+  for (int t = threadIdx.x; t < ntiles; t += DB_THREADS) {
+    const int rt = t / ctn, ct = t - rt * ctn;
+    const int r = rt * 4, o = ct * 4, sw = ct & 7;
+    float4 acc[4];
+    const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + o));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j] = bv;
+    const float* a = A + r * lda;
+    const float* w0 = Ws + o * ws;
+#pragma unroll 2
+    for (int kc = 0; kc < (Kd >> 2); ++kc) {
+      float4 x[4], w[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) x[j] = *reinterpret_cast<const float4*>(a + j * lda + (kc << 2));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) w[j] = *reinterpret_cast<const float4*>(w0 + j * ws + ((kc ^ sw) << 2));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc[j].x = fmaf(x[j].x, w[0].x, acc[j].x); acc[j].x = fmaf(x[j].y, w[0].y, acc[j].x);
+        acc[j].x = fmaf(x[j].z, w[0].z, acc[j].x); acc[j].x = fmaf(x[j].w, w[0].w, acc[j].x);
+        acc[j].y = fmaf(x[j].x, w[1].x, acc[j].y); acc[j].y = fmaf(x[j].y, w[1].y, acc[j].y);
+        acc[j].y = fmaf(x[j].z, w[1].z, acc[j].y); acc[j].y = fmaf(x[j].w, w[1].w, acc[j].y);
+        acc[j].z = fmaf(x[j].x, w[2].x, acc[j].z); acc[j].z = fmaf(x[j].y, w[2].y, acc[j].z);
+        acc[j].z = fmaf(x[j].z, w[2].z, acc[j].z); acc[j].z = fmaf(x[j].w, w[2].w, acc[j].z);
+        acc[j].w = fmaf(x[j].x, w[3].x, acc[j].w); acc[j].w = fmaf(x[j].y, w[3].y, acc[j].w);
+        acc[j].w = fmaf(x[j].z, w[3].z, acc[j].w); acc[j].w = fmaf(x[j].w, w[3].w, acc[j].w);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(out + (r + j) * ldo + o) = acc[j];
+  }
 }
 
 // out[r][n] = bias[n] + sum_k A[r][k] * B[k][n]   for r < nrp (multiple of 4), n < Nn; all in shared memory
@@ -106,17 +181,6 @@ __device__ __forceinline__ void db_gemm_AtB(const float* __restrict__ A, int lda
   }
 }
 
-// global [nr][C] rows r0.. -> shared slab [nrp][C] (rows >= nr zero-filled)
-__device__ __forceinline__ void db_load_slab(const float* __restrict__ g, int r0, int nr, int nrp, int C,
-                                             float* __restrict__ s) {
-  const int c4n = C >> 2;
-  for (int i = threadIdx.x; i < nrp * c4n; i += DB_THREADS) {
-    const int r = i / c4n, c = (i - r * c4n) * 4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r < nr) v = __ldg(reinterpret_cast<const float4*>(g + (size_t)(r0 + r) * C + c));
-    *reinterpret_cast<float4*>(s + r * C + c) = v;
-  }
-}
 __device__ __forceinline__ void db_store_slab(const float* __restrict__ s, int r0, int nr, int C, float* __restrict__ g) {
   const int c4n = C >> 2;
   for (int i = threadIdx.x; i < nr * c4n; i += DB_THREADS) {
@@ -126,19 +190,30 @@ __device__ __forceinline__ void db_store_slab(const float* __restrict__ s, int r
 }
 
 // per-slab column statistics: psum[c] = sum_r S[r][c],  pm2[c] = sum_r (S[r][c] - slab mean)^2   (global partials)
+// S has nrp = multiple-of-4 rows; rows >= nr are excluded (they may hold anything).
 __device__ __forceinline__ void db_slab_stats(const float* __restrict__ S, int C, int nr, float* __restrict__ psum,
                                               float* __restrict__ pm2) {
   for (int c = threadIdx.x; c < C; c += DB_THREADS) {
-    float s = 0.f;
-    for (int r = 0; r < nr; ++r) s += S[r * C + c];
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int r = 0;
+    for (; r + 4 <= nr; r += 4) {
+      s0 += S[r * C + c]; s1 += S[(r + 1) * C + c]; s2 += S[(r + 2) * C + c]; s3 += S[(r + 3) * C + c];
+    }
+    for (; r < nr; ++r) s0 += S[r * C + c];
+    const float s = (s0 + s1) + (s2 + s3);
     const float mean = nr > 0 ? s / (float)nr : 0.f;
-    float q = 0.f;
-    for (int r = 0; r < nr; ++r) {
-      const float dx = S[r * C + c] - mean;
-      q = fmaf(dx, dx, q);
+    float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+    for (r = 0; r + 4 <= nr; r += 4) {
+      const float d0 = S[r * C + c] - mean, d1 = S[(r + 1) * C + c] - mean, d2 = S[(r + 2) * C + c] - mean,
+                  d3 = S[(r + 3) * C + c] - mean;
+      q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1); q2 = fmaf(d2, d2, q2); q3 = fmaf(d3, d3, q3);
+    }
+    for (; r < nr; ++r) {
+      const float d0 = S[r * C + c] - mean;
+      q0 = fmaf(d0, d0, q0);
     }
     __stcg(psum + c, s);
-    __stcg(pm2 + c, q);
+    __stcg(pm2 + c, (q0 + q1) + (q2 + q3));
   }
 }
 
@@ -150,15 +225,24 @@ __device__ __forceinline__ void db_merge_stats(const float* __restrict__ part, i
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = lane * 4;
   const bool on = c < C;
-  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (on) {
-#pragma unroll 4
-    for (int b = warp; b < grid; b += DB_WARPS) {
-      const float4 v = __ldcg(reinterpret_cast<const float4*>(part + (size_t)b * 2 * C + c));
-      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  // every partial this thread needs is requested before the first one is used: one L2 round trip per merge
+  float4 ps[DB_MAXI], pm[DB_MAXI];
+#pragma unroll
+  for (int i = 0; i < DB_MAXI; ++i) {
+    const int b = warp + i * DB_WARPS;
+    ps[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    pm[i] = ps[i];
+    if (on && b < grid) {
+      ps[i] = __ldcg(reinterpret_cast<const float4*>(part + (size_t)b * 2 * C + c));
+      pm[i] = __ldcg(reinterpret_cast<const float4*>(part + (size_t)b * 2 * C + C + c));
     }
-    *reinterpret_cast<float4*>(red + warp * C + c) = s;
   }
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < DB_MAXI; ++i) {
+    s.x += ps[i].x; s.y += ps[i].y; s.z += ps[i].z; s.w += ps[i].w;
+  }
+  if (on) *reinterpret_cast<float4*>(red + warp * C + c) = s;
   __syncthreads();
   for (int i = threadIdx.x; i < C; i += DB_THREADS) {
     float t = 0.f;
@@ -168,21 +252,20 @@ __device__ __forceinline__ void db_merge_stats(const float* __restrict__ part, i
   }
   __syncthreads();
   float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (on) {
-    const float4 mu = *reinterpret_cast<const float4*>(mean_s + c);
-#pragma unroll 4
-    for (int b = warp; b < grid; b += DB_WARPS) {
-      const int nb = min(Rc, N - b * Rc);
-      if (nb <= 0) continue;
-      const float4 v = __ldcg(reinterpret_cast<const float4*>(part + (size_t)b * 2 * C + c));
-      const float4 m2 = __ldcg(reinterpret_cast<const float4*>(part + (size_t)b * 2 * C + C + c));
+  const float4 mu = on ? *reinterpret_cast<const float4*>(mean_s + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < DB_MAXI; ++i) {
+    const int b = warp + i * DB_WARPS;
+    const int nb = min(Rc, N - b * Rc);
+    if (b < grid && nb > 0) {
       const float fn = (float)nb, inv = 1.f / fn;
-      const float dx = v.x * inv - mu.x, dy = v.y * inv - mu.y, dz = v.z * inv - mu.z, dw = v.w * inv - mu.w;
-      q.x += fmaf(fn * dx, dx, m2.x); q.y += fmaf(fn * dy, dy, m2.y);
-      q.z += fmaf(fn * dz, dz, m2.z); q.w += fmaf(fn * dw, dw, m2.w);
+      const float dx = ps[i].x * inv - mu.x, dy = ps[i].y * inv - mu.y, dz = ps[i].z * inv - mu.z,
+                  dw = ps[i].w * inv - mu.w;
+      q.x += fmaf(fn * dx, dx, pm[i].x); q.y += fmaf(fn * dy, dy, pm[i].y);
+      q.z += fmaf(fn * dz, dz, pm[i].z); q.w += fmaf(fn * dw, dw, pm[i].w);
     }
-    *reinterpret_cast<float4*>(red + warp * C + c) = q;
   }
+  if (on) *reinterpret_cast<float4*>(red + warp * C + c) = q;
   __syncthreads();
   for (int i = threadIdx.x; i < C; i += DB_THREADS) {
     float t = 0.f;
@@ -246,66 +329,53 @@ dense_block_fwd_kernel(const kp_dense_desc m, float* __restrict__ out, float* __
   const int r0 = blockIdx.x * Rc;
   const int nr = max(0, min(Rc, N - r0));
   const int Rp = (Rc + 3) & ~3;
-  float* W1t = smem;                    // [Ci][Co]
-  float* W2t = W1t + Ci * Co;           // [Co][Co]
-  float* A = W2t + Co * Co;             // [Rp][Ci]
-  float* Y = A + Rp * Ci;               // [Rp][Co]
-  float* Z = Y + Rp * Co;               // [Rp][Co]
-  float* red = Z + Rp * Co;             // [DB_WARPS][Co]
-  float* mean_s = red + DB_WARPS * Co;  // [Co]
-  float* istd_s = mean_s + Co;
-  float* var_s = istd_s + Co;
-  // weights, transposed so that a thread's 4 output channels are one float4
-  for (int i = threadIdx.x; i < Co * Ci; i += DB_THREADS) {
-    const int o = i / Ci, k = i - o * Ci;
-    W1t[k * Co + o] = __ldg(m.W1 + i);
-  }
-  for (int i = threadIdx.x; i < Co * Co; i += DB_THREADS) {
-    const int o = i / Co, k = i - o * Co;
-    W2t[k * Co + o] = __ldg(m.W2 + i);
-  }
-  db_load_slab(m.X, r0, nr, Rp, Ci, A);
-  for (int i = threadIdx.x; i < Rp * Co; i += DB_THREADS) Z[i] = 0.f;
+  float* W1s = smem;                         // [Co][wstride(Ci)] swizzled
+  float* W2s = W1s + Co * db_wstride(Ci);    // [Co][wstride(Co)] swizzled
+  float* A = W2s + Co * db_wstride(Co);      // [Rp][Ci]
+  float* Y = A + Rp * Ci;                    // [Rp][Co]
+  float* Z = Y + Rp * Co;                    // [Rp][Co]
+  float* red = Z + Rp * Co;                  // [DB_WARPS][Co]
+  float* st = red + DB_WARPS * Co;           // [3][3][Co]: (mean, istd, var) of BN1, BN2, BN3
+  // everything this CTA will read from global memory except the partials is requested now, asynchronously
+  db_cp_slab(m.X, r0, nr, Rp, Ci, A);
+  db_cp_weight_swizzled(m.W1, Co, Ci, W1s);
+  db_cp_weight_swizzled(m.W2, Co, Co, W2s);
+  db_cp_commit();
+  for (int i = threadIdx.x * 4; i < Rp * Co; i += DB_THREADS * 4)
+    *reinterpret_cast<float4*>(Z + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+  db_cp_wait_all();
   __syncthreads();
   float* part0 = part;
   float* part1 = part + (size_t)grid * 2 * Co;
   float* part2 = part1 + (size_t)grid * 2 * Co;
 
   // ---- Linear1 + BN1 + ReLU ----
-  db_gemm_AB(A, Ci, Ci, W1t, Co, m.b1, Rp, Y, Co);
+  db_gemm_AWt(A, Ci, Ci, W1s, Co, m.b1, Rp, Y, Co);
   __syncthreads();
-  db_store_slab(Y, r0, nr, Co, m.Y1);
   db_slab_stats(Y, Co, nr, part0 + (size_t)blockIdx.x * 2 * Co, part0 + (size_t)blockIdx.x * 2 * Co + Co);
+  db_store_slab(Y, r0, nr, Co, m.Y1);
   db_grid_barrier(bar, 1u * grid);
-  db_merge_stats(part0, grid, Rc, N, Co, m.eps1, red, mean_s, istd_s, var_s);
-  if (blockIdx.x == 0)
-    db_publish_stats(mean_s, istd_s, var_s, N, Co, m.mom1, m.rm1, m.rv1, (long long*)m.nbt1, m.stats, m.stats + Co);
-  db_bn_apply<true>(Y, Co, nr, m.g1, m.be1, mean_s, istd_s, Z);
+  db_merge_stats(part0, grid, Rc, N, Co, m.eps1, red, st, st + Co, st + 2 * Co);
+  db_bn_apply<true>(Y, Co, nr, m.g1, m.be1, st, st + Co, Z);
   __syncthreads();
 
   // ---- Linear2 + BN2 + ReLU ----
-  db_gemm_AB(Z, Co, Co, W2t, Co, m.b2, Rp, Y, Co);
+  db_gemm_AWt(Z, Co, Co, W2s, Co, m.b2, Rp, Y, Co);
   __syncthreads();
-  db_store_slab(Y, r0, nr, Co, m.Y2);
   db_slab_stats(Y, Co, nr, part1 + (size_t)blockIdx.x * 2 * Co, part1 + (size_t)blockIdx.x * 2 * Co + Co);
+  db_store_slab(Y, r0, nr, Co, m.Y2);
   db_grid_barrier(bar, 2u * grid);
-  db_merge_stats(part1, grid, Rc, N, Co, m.eps2, red, mean_s, istd_s, var_s);
-  if (blockIdx.x == 0)
-    db_publish_stats(mean_s, istd_s, var_s, N, Co, m.mom2, m.rm2, m.rv2, (long long*)m.nbt2, m.stats + 2 * Co,
-                     m.stats + 3 * Co);
-  db_bn_apply<true>(Y, Co, nr, m.g2, m.be2, mean_s, istd_s, Z);
+  db_merge_stats(part1, grid, Rc, N, Co, m.eps2, red, st + 3 * Co, st + 4 * Co, st + 5 * Co);
+  db_bn_apply<true>(Y, Co, nr, m.g2, m.be2, st + 3 * Co, st + 4 * Co, Z);
   __syncthreads();
 
   // ---- outer BatchNorm + residual ----
   if (m.g3) {
-    db_store_slab(Z, r0, nr, Co, m.Z2);
     db_slab_stats(Z, Co, nr, part2 + (size_t)blockIdx.x * 2 * Co, part2 + (size_t)blockIdx.x * 2 * Co + Co);
+    db_store_slab(Z, r0, nr, Co, m.Z2);
     db_grid_barrier(bar, 3u * grid);
-    db_merge_stats(part2, grid, Rc, N, Co, m.eps3, red, mean_s, istd_s, var_s);
-    if (blockIdx.x == 0)
-      db_publish_stats(mean_s, istd_s, var_s, N, Co, m.mom3, m.rm3, m.rv3, (long long*)m.nbt3, m.stats + 4 * Co,
-                       m.stats + 5 * Co);
-    db_bn_apply<false>(Z, Co, nr, m.g3, m.be3, mean_s, istd_s, Y);
+    db_merge_stats(part2, grid, Rc, N, Co, m.eps3, red, st + 6 * Co, st + 7 * Co, st + 8 * Co);
+    db_bn_apply<false>(Z, Co, nr, m.g3, m.be3, st + 6 * Co, st + 7 * Co, Y);
     __syncthreads();
   }
   const float* res = m.g3 ? Y : Z;
@@ -319,46 +389,63 @@ dense_block_fwd_kernel(const kp_dense_desc m, float* __restrict__ out, float* __
     }
     *reinterpret_cast<float4*>(out + (size_t)(r0 + r) * Co + c) = v;
   }
+  // saved + running statistics: by the last CTA (the shortest slab), off everybody's critical path
+  if (blockIdx.x == grid - 1) {
+    db_publish_stats(st, st + Co, st + 2 * Co, N, Co, m.mom1, m.rm1, m.rv1, (long long*)m.nbt1, m.stats, m.stats + Co);
+    db_publish_stats(st + 3 * Co, st + 4 * Co, st + 5 * Co, N, Co, m.mom2, m.rm2, m.rv2, (long long*)m.nbt2,
+                     m.stats + 2 * Co, m.stats + 3 * Co);
+    if (m.g3)
+      db_publish_stats(st + 6 * Co, st + 7 * Co, st + 8 * Co, N, Co, m.mom3, m.rm3, m.rv3, (long long*)m.nbt3,
+                       m.stats + 4 * Co, m.stats + 5 * Co);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------------------
 // slab partial sums p1[c] = sum_r D[r][c], p2[c] = sum_r D[r][c] * XH[r][c]  -> global partial [2][C]
-__device__ __forceinline__ void db_slab_dots(const float* __restrict__ D, const float* __restrict__ XH, int C, int nr,
+__device__ __forceinline__ void db_slab_dots(const float* __restrict__ D, const float* __restrict__ XH, int C, int nrp,
                                              float* __restrict__ p) {
+  // rows >= nr of D are zero, so the padded row count can be used (4 independent chains)
   for (int c = threadIdx.x; c < C; c += DB_THREADS) {
-    float s1 = 0.f, s2 = 0.f;
-    for (int r = 0; r < nr; ++r) {
-      const float dv = D[r * C + c];
-      s1 += dv;
-      s2 = fmaf(dv, XH[r * C + c], s2);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+    for (int r = 0; r < nrp; r += 4) {
+      const float d0 = D[r * C + c], d1 = D[(r + 1) * C + c], d2 = D[(r + 2) * C + c], d3 = D[(r + 3) * C + c];
+      a0 += d0; a1 += d1; a2 += d2; a3 += d3;
+      b0 = fmaf(d0, XH[r * C + c], b0); b1 = fmaf(d1, XH[(r + 1) * C + c], b1);
+      b2 = fmaf(d2, XH[(r + 2) * C + c], b2); b3 = fmaf(d3, XH[(r + 3) * C + c], b3);
     }
-    __stcg(p + c, s1);
-    __stcg(p + C + c, s2);
+    __stcg(p + c, (a0 + a1) + (a2 + a3));
+    __stcg(p + C + c, (b0 + b1) + (b2 + b3));
   }
 }
 // plain fixed-order sums of the [grid][2][C] partials into shared s1[C], s2[C]
 __device__ __forceinline__ void db_merge_sums(const float* __restrict__ part, int grid, int C, float* __restrict__ red,
                                               float* __restrict__ s1, float* __restrict__ s2) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // 2*C floats per partial = up to 64 float4: lanes take float4 lane and lane + 32
-  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-  const int n4 = (2 * C) >> 2;
-#pragma unroll 4
-  for (int q = warp; q < grid; q += DB_WARPS) {
-    const float4* p = reinterpret_cast<const float4*>(part + (size_t)q * 2 * C);
-    if (lane < n4) {
-      const float4 v = __ldcg(p + lane);
-      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
-    }
-    if (lane + 32 < n4) {
-      const float4 v = __ldcg(p + lane + 32);
-      b.x += v.x; b.y += v.y; b.z += v.z; b.w += v.w;
+  const int c = lane * 4;
+  const bool on = c < C;
+  float4 pa[DB_MAXI], pb[DB_MAXI];                       // all requested up front: one L2 round trip
+#pragma unroll
+  for (int i = 0; i < DB_MAXI; ++i) {
+    const int b = warp + i * DB_WARPS;
+    pa[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    pb[i] = pa[i];
+    if (on && b < grid) {
+      pa[i] = __ldcg(reinterpret_cast<const float4*>(part + (size_t)b * 2 * C + c));
+      pb[i] = __ldcg(reinterpret_cast<const float4*>(part + (size_t)b * 2 * C + C + c));
     }
   }
-  if (lane < n4) *reinterpret_cast<float4*>(red + warp * 2 * C + lane * 4) = a;
-  if (lane + 32 < n4) *reinterpret_cast<float4*>(red + warp * 2 * C + (lane + 32) * 4) = b;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b4 = a;
+#pragma unroll
+  for (int i = 0; i < DB_MAXI; ++i) {
+    a.x += pa[i].x; a.y += pa[i].y; a.z += pa[i].z; a.w += pa[i].w;
+    b4.x += pb[i].x; b4.y += pb[i].y; b4.z += pb[i].z; b4.w += pb[i].w;
+  }
+  if (on) {
+    *reinterpret_cast<float4*>(red + warp * 2 * C + c) = a;
+    *reinterpret_cast<float4*>(red + warp * 2 * C + C + c) = b4;
+  }
   __syncthreads();
   for (int i = threadIdx.x; i < 2 * C; i += DB_THREADS) {
     float t = 0.f;
@@ -420,12 +507,14 @@ __device__ __forceinline__ void db_relu_mask(float* __restrict__ D, const float*
     *reinterpret_cast<float4*>(D + i * 4) = dv;
   }
 }
-// column sums of a slab -> global partial [C]
-__device__ __forceinline__ void db_slab_colsum(const float* __restrict__ D, int C, int nr, float* __restrict__ p) {
+// column sums of a slab (rows >= nr are zero) -> global partial [C]
+__device__ __forceinline__ void db_slab_colsum(const float* __restrict__ D, int C, int nrp, float* __restrict__ p) {
   for (int c = threadIdx.x; c < C; c += DB_THREADS) {
-    float s = 0.f;
-    for (int r = 0; r < nr; ++r) s += D[r * C + c];
-    __stcg(p + c, s);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int r = 0; r < nrp; r += 4) {
+      a0 += D[r * C + c]; a1 += D[(r + 1) * C + c]; a2 += D[(r + 2) * C + c]; a3 += D[(r + 3) * C + c];
+    }
+    __stcg(p + c, (a0 + a1) + (a2 + a3));
   }
 }
 
@@ -440,15 +529,16 @@ dense_block_bwd_kernel(const kp_dense_desc m, const float* __restrict__ dOut, fl
   const int r0 = blockIdx.x * Rc;
   const int nr = max(0, min(Rc, N - r0));
   const int Rp = (Rc + 3) & ~3;
-  const int Cm = max(Ci, Co);
   float* W1 = smem;                   // [Co][Ci] row-major (dX = dy1 W1)
   float* W2 = W1 + Co * Ci;           // [Co][Co] row-major (dz1 = dy2 W2)
-  float* D = W2 + Co * Co;            // [Rp][Co]  running gradient of the current stage
-  float* XH = D + Rp * Co;            // [Rp][Cm]  x-hat of BN3 / BN2, later the X slab
-  float* XH1 = XH + Rp * Cm;          // [Rp][Co]  x-hat of BN1
-  float* Z1 = XH1 + Rp * Co;          // [Rp][Co]  z1 = relu(BN1(y1))
-  float* E = Z1 + Rp * Co;            // [Rp][Cm]  dz1 / dy1, later dX
-  float* red = E + Rp * Cm;           // [DB_WARPS][2*Co]
+  float* D = W2 + Co * Co;            // [Rp][Co]  dOut -> dz2 -> dy2, finally dX ([Rp][Ci], Ci <= Co)
+  float* X3 = D + Rp * Co;            // [Rp][Co]  z2 -> x-hat3
+  float* X2 = X3 + Rp * Co;           // [Rp][Co]  y2 -> x-hat2
+  float* X1 = X2 + Rp * Co;           // [Rp][Co]  y1 -> x-hat1
+  float* Z1 = X1 + Rp * Co;           // [Rp][Co]  z1 = relu(BN1(y1))
+  float* E = Z1 + Rp * Co;            // [Rp][Co]  dz1 -> dy1
+  float* XS = E + Rp * Co;            // [Rp][Ci]  X slab
+  float* red = XS + Rp * Ci;          // [DB_WARPS][2*Co]
   float* s1 = red + DB_WARPS * 2 * Co;
   float* s2 = s1 + Co;
   float* pa = ws;
@@ -461,87 +551,97 @@ dense_block_bwd_kernel(const kp_dense_desc m, const float* __restrict__ dOut, fl
   const float* mean1 = m.stats, *istd1 = m.stats + Co, *mean2 = m.stats + 2 * Co, *istd2 = m.stats + 3 * Co;
   const float* mean3 = m.stats + 4 * Co, *istd3 = m.stats + 5 * Co;
 
-  for (int i = threadIdx.x * 4; i < Co * Ci; i += DB_THREADS * 4)
-    *reinterpret_cast<float4*>(W1 + i) = __ldg(reinterpret_cast<const float4*>(m.W1 + i));
-  for (int i = threadIdx.x * 4; i < Co * Co; i += DB_THREADS * 4)
-    *reinterpret_cast<float4*>(W2 + i) = __ldg(reinterpret_cast<const float4*>(m.W2 + i));
-  db_load_slab(dOut, r0, nr, Rp, Co, D);
+  // every slab and both weight matrices are requested now, asynchronously: one round trip to L2 / HBM
+  db_cp_slab(dOut, r0, nr, Rp, Co, D);
+  if (m.g3) db_cp_slab(m.Z2, r0, nr, Rp, Co, X3);
+  db_cp_slab(m.Y2, r0, nr, Rp, Co, X2);
+  db_cp_slab(m.Y1, r0, nr, Rp, Co, X1);
+  db_cp_slab(m.X, r0, nr, Rp, Ci, XS);
+  db_cp_rows(m.W2, Co * Co, W2);
+  db_cp_rows(m.W1, Co * Ci, W1);
+  db_cp_commit();
+  db_cp_wait_all();
+  __syncthreads();
   unsigned phase = 0;
+  // x-hats of the three BatchNorms and z1, while nothing else can proceed anyway
+  if (m.g3) db_xhat(X3, Co, Rp, mean3, istd3, X3);
+  db_xhat(X2, Co, Rp, mean2, istd2, X2);
+  db_xhat(X1, Co, Rp, mean1, istd1, X1);
+  {
+    const int c4n = Co >> 2;
+    for (int i = threadIdx.x; i < Rp * c4n; i += DB_THREADS) {
+      const int r = i / c4n, c = (i - r * c4n) * 4;
+      float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < nr) {
+        // recomputed from the x-hat this same thread just stored
+        const float4 xh = *reinterpret_cast<const float4*>(X1 + i * 4);
+        const float4 gg = __ldg(reinterpret_cast<const float4*>(m.g1 + c));
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(m.be1 + c));
+        z = make_float4(fmaxf(fmaf(gg.x, xh.x, bb.x), 0.f), fmaxf(fmaf(gg.y, xh.y, bb.y), 0.f),
+                        fmaxf(fmaf(gg.z, xh.z, bb.z), 0.f), fmaxf(fmaf(gg.w, xh.w, bb.w), 0.f));
+      }
+      *reinterpret_cast<float4*>(Z1 + i * 4) = z;
+    }
+  }
+  __syncthreads();
   if (m.g3) {
     // ---- outer BatchNorm ----
-    db_load_slab(m.Z2, r0, nr, Rp, Co, XH);
-    __syncthreads();
-    db_xhat(XH, Co, Rp, mean3, istd3, XH);
-    __syncthreads();
-    db_slab_dots(D, XH, Co, nr, pa + (size_t)blockIdx.x * 2 * Co);
+    db_slab_dots(D, X3, Co, Rp, pa + (size_t)blockIdx.x * 2 * Co);
     db_grid_barrier(bar, ++phase * grid);
     db_merge_sums(pa, grid, Co, red, s1, s2);
-    if (blockIdx.x == 0)
+    if (blockIdx.x == grid - 1)
       for (int i = threadIdx.x; i < Co; i += DB_THREADS) {
         dbn[4 * Co + i] = s2[i];
         dbn[5 * Co + i] = s1[i];
       }
-    db_bn_bwd_apply(D, XH, Co, nr, N, m.g3, istd3, s1, s2);
+    db_bn_bwd_apply(D, X3, Co, nr, N, m.g3, istd3, s1, s2);
+    __syncthreads();
   }
-  __syncthreads();
   // ---- ReLU2 + BN2 ----
-  db_load_slab(m.Y2, r0, nr, Rp, Co, XH);
+  db_relu_mask(D, X2, Co, nr, m.g2, m.be2);
   __syncthreads();
-  db_xhat(XH, Co, Rp, mean2, istd2, XH);
-  __syncthreads();
-  db_relu_mask(D, XH, Co, nr, m.g2, m.be2);
-  __syncthreads();
-  db_slab_dots(D, XH, Co, nr, pb + (size_t)blockIdx.x * 2 * Co);
-  // meanwhile: z1 and x-hat1 of the slab (needed after the barrier)
-  db_load_slab(m.Y1, r0, nr, Rp, Co, XH1);
-  __syncthreads();
-  db_xhat(XH1, Co, Rp, mean1, istd1, XH1);
-  for (int i = threadIdx.x; i < Rp * Co; i += DB_THREADS) Z1[i] = 0.f;
-  __syncthreads();
-  {
-    const int c4n = Co >> 2;
-    for (int i = threadIdx.x; i < nr * c4n; i += DB_THREADS) {
-      const int c = (i % c4n) * 4;
-      const float4 xh = *reinterpret_cast<const float4*>(XH1 + i * 4);
-      const float4 gg = __ldg(reinterpret_cast<const float4*>(m.g1 + c));
-      const float4 bb = __ldg(reinterpret_cast<const float4*>(m.be1 + c));
-      *reinterpret_cast<float4*>(Z1 + i * 4) =
-          make_float4(fmaxf(fmaf(gg.x, xh.x, bb.x), 0.f), fmaxf(fmaf(gg.y, xh.y, bb.y), 0.f),
-                      fmaxf(fmaf(gg.z, xh.z, bb.z), 0.f), fmaxf(fmaf(gg.w, xh.w, bb.w), 0.f));
-    }
-  }
+  db_slab_dots(D, X2, Co, Rp, pb + (size_t)blockIdx.x * 2 * Co);
   db_grid_barrier(bar, ++phase * grid);
   db_merge_sums(pb, grid, Co, red, s1, s2);
-  if (blockIdx.x == 0)
+  if (blockIdx.x == grid - 1)
     for (int i = threadIdx.x; i < Co; i += DB_THREADS) {
       dbn[2 * Co + i] = s2[i];
       dbn[3 * Co + i] = s1[i];
     }
-  db_bn_bwd_apply(D, XH, Co, nr, N, m.g2, istd2, s1, s2);      // D = dy2
+  db_bn_bwd_apply(D, X2, Co, nr, N, m.g2, istd2, s1, s2);      // D = dy2
   __syncthreads();
-  // ---- Linear2: dW2 partial, db2 partial, dz1 = dy2 W2 ----
-  db_gemm_AtB(D, Co, Co, Z1, Co, Co, nr, pW2 + (size_t)blockIdx.x * Co * Co);
-  db_slab_colsum(D, Co, nr, pb2 + (size_t)blockIdx.x * Co);
+  // ---- Linear2: dz1 = dy2 W2 first (critical path), then the dW2 / db2 partials ----
   db_gemm_AB(D, Co, Co, W2, Co, nullptr, Rp, E, Co);
   __syncthreads();
-  // ---- ReLU1 + BN1 ----
-  db_relu_mask(E, XH1, Co, nr, m.g1, m.be1);
+  db_relu_mask(E, X1, Co, nr, m.g1, m.be1);
   __syncthreads();
-  db_slab_dots(E, XH1, Co, nr, pc + (size_t)blockIdx.x * 2 * Co);
-  db_load_slab(m.X, r0, nr, Rp, Ci, XH);                       // X slab for dW1 (x-hat2 is no longer needed)
-  db_grid_barrier(bar, ++phase * grid);
+  db_slab_dots(E, X1, Co, Rp, pc + (size_t)blockIdx.x * 2 * Co);
+  __syncthreads();
+  if (threadIdx.x == 0) {                                       // arrive early, wait after the off-path work
+    __threadfence();
+    atomicAdd(bar, 1u);
+  }
+  ++phase;
+  db_gemm_AtB(D, Co, Co, Z1, Co, Co, nr, pW2 + (size_t)blockIdx.x * Co * Co);
+  db_slab_colsum(D, Co, Rp, pb2 + (size_t)blockIdx.x * Co);
+  if (threadIdx.x == 0) {
+    while (db_ld_acquire(bar) < phase * grid) {
+    }
+    __threadfence();
+  }
+  __syncthreads();
   db_merge_sums(pc, grid, Co, red, s1, s2);
-  if (blockIdx.x == 0)
+  if (blockIdx.x == grid - 1)
     for (int i = threadIdx.x; i < Co; i += DB_THREADS) {
       dbn[0 * Co + i] = s2[i];
       dbn[1 * Co + i] = s1[i];
     }
-  db_bn_bwd_apply(E, XH1, Co, nr, N, m.g1, istd1, s1, s2);     // E = dy1
+  db_bn_bwd_apply(E, X1, Co, nr, N, m.g1, istd1, s1, s2);      // E = dy1
   __syncthreads();
-  // ---- Linear1: dW1 partial, db1 partial, dX = dy1 W1 ----
-  db_gemm_AtB(E, Co, Co, XH, Ci, Ci, nr, pW1 + (size_t)blockIdx.x * Co * Ci);
-  db_slab_colsum(E, Co, nr, pb1 + (size_t)blockIdx.x * Co);
-  db_gemm_AB(E, Co, Co, W1, Ci, nullptr, Rp, D, Ci);           // D reused as [Rp][Ci] (Ci <= Co checked on host)
+  // ---- Linear1: dX = dy1 W1, dW1 / db1 partials ----
+  db_gemm_AB(E, Co, Co, W1, Ci, nullptr, Rp, D, Ci);
+  db_gemm_AtB(E, Co, Co, XS, Ci, Ci, nr, pW1 + (size_t)blockIdx.x * Co * Ci);
+  db_slab_colsum(E, Co, Rp, pb1 + (size_t)blockIdx.x * Co);
   __syncthreads();
   db_store_slab(D, r0, nr, Ci, dX);
   db_grid_barrier(bar, ++phase * grid);
@@ -566,13 +666,17 @@ dense_block_bwd_kernel(const kp_dense_desc m, const float* __restrict__ dOut, fl
       } else if (ok) {
         src = pb2 + (size_t)(e - nW1 - nW2 - nb) * 4; dst = db2 + (size_t)(e - nW1 - nW2 - nb) * 4; stride = Co;
       }
+      float4 pv[DB_MAXI];
+#pragma unroll
+      for (int i = 0; i < DB_MAXI; ++i) {
+        const int q = sub + i * 8;
+        pv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok && q < grid) pv[i] = __ldcg(reinterpret_cast<const float4*>(src + (size_t)q * stride));
+      }
       float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (ok) {
-#pragma unroll 4
-        for (int q = sub; q < grid; q += 8) {
-          const float4 v = __ldcg(reinterpret_cast<const float4*>(src + (size_t)q * stride));
-          s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-        }
+#pragma unroll
+      for (int i = 0; i < DB_MAXI; ++i) {
+        s.x += pv[i].x; s.y += pv[i].y; s.z += pv[i].z; s.w += pv[i].w;
       }
 #pragma unroll
       for (int o = 1; o < 8; o <<= 1) {
@@ -593,13 +697,12 @@ struct DbCfg {
 
 static size_t db_smem_fwd(int Ci, int Co, int Rc) {
   const int Rp = (Rc + 3) & ~3;
-  return sizeof(float) * ((size_t)Ci * Co + (size_t)Co * Co + (size_t)Rp * Ci + 2 * (size_t)Rp * Co +
-                          (size_t)DB_WARPS * Co + 3 * (size_t)Co);
+  return sizeof(float) * ((size_t)Co * db_wstride(Ci) + (size_t)Co * db_wstride(Co) + (size_t)Rp * Ci +
+                          2 * (size_t)Rp * Co + (size_t)DB_WARPS * Co + 9 * (size_t)Co);
 }
 static size_t db_smem_bwd(int Ci, int Co, int Rc) {
   const int Rp = (Rc + 3) & ~3;
-  const int Cm = Ci > Co ? Ci : Co;
-  return sizeof(float) * ((size_t)Ci * Co + (size_t)Co * Co + 3 * (size_t)Rp * Co + 2 * (size_t)Rp * Cm +
+  return sizeof(float) * ((size_t)Ci * Co + (size_t)Co * Co + 6 * (size_t)Rp * Co + (size_t)Rp * Ci +
                           (size_t)DB_WARPS * 2 * Co + 2 * (size_t)Co);
 }
 static const size_t kDbSmemBudget = 220 * 1024;

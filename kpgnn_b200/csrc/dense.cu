@@ -17,9 +17,9 @@
 
 namespace kp {
 
-constexpr int DB_THREADS = 256;
+constexpr int DB_THREADS = 512;   // 16 warps: the block is a chain of short phases, warps are the only latency hiding
 constexpr int DB_WARPS = DB_THREADS / 32;
-constexpr int DB_ROWS = 36;          // target rows per CTA: 9 row tiles x 26 column tiles <= 256 threads at 104 channels
+constexpr int DB_ROWS = 36;          // target rows per CTA: 18 row pairs x 26 channel quads <= 512 threads at 104 channels
 constexpr int DB_MAX_GRID = kNumSMs; // every CTA must be resident: one per SM
 
 __device__ __forceinline__ unsigned db_ld_acquire(const unsigned* p) {
@@ -40,6 +40,31 @@ __device__ __forceinline__ void db_grid_barrier(unsigned* ctr, unsigned target) 
   __syncthreads();
 }
 
+// -DKP_DENSE_TIMING: CTA 0 prints the nanosecond timestamps of its phase boundaries (tuning builds only)
+#ifdef KP_DENSE_TIMING
+#define DB_T(i)                                                              \
+  do {                                                                       \
+    if (blockIdx.x == 0 && threadIdx.x == 0) {                               \
+      unsigned long long _t;                                                 \
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(_t));                  \
+      tstamp[i] = _t;                                                        \
+    }                                                                        \
+  } while (0)
+#define DB_T_DECL __shared__ unsigned long long tstamp[24];
+#define DB_T_PRINT(n, name)                                                  \
+  do {                                                                       \
+    if (blockIdx.x == 0 && threadIdx.x == 0) {                               \
+      printf(name ":");                                                      \
+      for (int _i = 1; _i < n; ++_i) printf(" %d", (int)(tstamp[_i] - tstamp[_i - 1])); \
+      printf("  total %d ns\n", (int)(tstamp[n - 1] - tstamp[0]));           \
+    }                                                                        \
+  } while (0)
+#else
+#define DB_T(i)
+#define DB_T_DECL
+#define DB_T_PRINT(n, name)
+#endif
+
 constexpr int DB_MAXI = (DB_MAX_GRID + DB_WARPS - 1) / DB_WARPS;   // partials per warp in a merge (held in registers)
 
 __device__ __forceinline__ void db_cp16(float* dst, const float* src) {
@@ -58,10 +83,10 @@ __host__ __device__ __forceinline__ int db_wstride(int Kd) { return (((Kd >> 2) 
 
 __device__ __forceinline__ void db_cp_weight_swizzled(const float* __restrict__ W, int Co, int Kd, float* __restrict__ Ws) {
   const int ck = Kd >> 2, ws = db_wstride(Kd);
-  for (int i = threadIdx.x; i < Co * ck; i += DB_THREADS) {
-    const int o = i / ck, kc = i - o * ck;
-    db_cp16(Ws + o * ws + ((kc ^ ((o >> 2) & 7)) << 2), W + (size_t)i * 4);
-  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int o = warp; o < Co; o += DB_WARPS)
+    for (int kc = lane; kc < ck; kc += 32)
+      db_cp16(Ws + o * ws + ((kc ^ ((o >> 2) & 7)) << 2), W + (size_t)o * Kd + (kc << 2));
 }
 __device__ __forceinline__ void db_cp_rows(const float* __restrict__ g, int nfloats, float* __restrict__ sdst) {
   for (int i = threadIdx.x * 4; i < nfloats; i += DB_THREADS * 4) db_cp16(sdst + i, g + i);
@@ -77,7 +102,9 @@ __device__ __forceinline__ void db_cp_slab(const float* __restrict__ g, int r0, 
   }
 }
 
-// out[r][o] = bias[o] + sum_k A[r][k] * W[o][k]   (W in the swizzled layout above), r < nrp, o < Co
+// out[r][o] = bias[o] + sum_k A[r][k] * W[o][k]   (W in the swizzled layout above), r < nrp (multiple of 4), o < Co.
+// Thread tile 4 rows x 4 channels: the phase is bound by shared-memory bandwidth (every row tile re-reads W), measured
+// 5.1 us with 2x4 tiles on 16 warps vs ~3 us with 4x4 tiles on 8 of them.
 __device__ __forceinline__ void db_gemm_AWt(const float* __restrict__ A, int lda, int Kd, const float* __restrict__ Ws,
                                             int Co, const float* __restrict__ bias, int nrp, float* __restrict__ out,
                                             int ldo) {
@@ -115,18 +142,16 @@ __device__ __forceinline__ void db_gemm_AWt(const float* __restrict__ A, int lda
   }
 }
 
-// out[r][n] = bias[n] + sum_k A[r][k] * B[k][n]   for r < nrp (multiple of 4), n < Nn; all in shared memory
+// out[r][n] = sum_k A[r][k] * B[k][n]   for r < nrp (multiple of 4), n < Nn; all in shared memory; thread tile 4 x 4
 __device__ __forceinline__ void db_gemm_AB(const float* __restrict__ A, int lda, int Kd, const float* __restrict__ B,
-                                           int Nn, const float* __restrict__ bias, int nrp, float* __restrict__ out,
-                                           int ldo) {
+                                           int Nn, int nrp, float* __restrict__ out, int ldo) {
   const int ctn = Nn >> 2, ntiles = ctn * (nrp >> 2);
   for (int t = threadIdx.x; t < ntiles; t += DB_THREADS) {
     const int rt = t / ctn, ct = t - rt * ctn;
     const int r = rt * 4, n = ct * 4;
     float4 acc[4];
-    const float4 bv = bias ? __ldg(reinterpret_cast<const float4*>(bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[j] = bv;
+    for (int j = 0; j < 4; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     const float* a = A + r * lda;
     const float* b = B + n;
 #pragma unroll 2
@@ -182,51 +207,69 @@ __device__ __forceinline__ void db_gemm_AtB(const float* __restrict__ A, int lda
 }
 
 __device__ __forceinline__ void db_store_slab(const float* __restrict__ s, int r0, int nr, int C, float* __restrict__ g) {
-  const int c4n = C >> 2;
-  for (int i = threadIdx.x; i < nr * c4n; i += DB_THREADS) {
-    const int r = i / c4n, c = (i - r * c4n) * 4;
-    *reinterpret_cast<float4*>(g + (size_t)(r0 + r) * C + c) = *reinterpret_cast<const float4*>(s + r * C + c);
+  float* dst = g + (size_t)r0 * C;                      // the slab's rows are contiguous in the [N][C] matrix
+  for (int i = threadIdx.x * 4; i < nr * C; i += DB_THREADS * 4)
+    *reinterpret_cast<float4*>(dst + i) = *reinterpret_cast<const float4*>(s + i);
+}
+
+// Two column sums over the slab's rows, row-parallel: warp w takes rows w, w+16, ...; lane l the channels 4l..4l+3.
+// F(r, c) -> (float4 u, float4 v) contributions; per-warp partials go through `red` [DB_WARPS][2][C]; thread c < C
+// then adds the DB_WARPS partials in order and hands (sum_u, sum_v) to FIN(c, su, sv).  One __syncthreads inside.
+template <typename F, typename FIN>
+__device__ __forceinline__ void db_col_reduce2(int C, int nrows, float* __restrict__ red, F f, FIN fin) {
+  const int warp = threadIdx.x >> 5, c = (threadIdx.x & 31) * 4;
+  if (c < C) {
+    float4 u = make_float4(0.f, 0.f, 0.f, 0.f), v = u;
+    for (int r = warp; r < nrows; r += DB_WARPS) f(r, c, u, v);
+    *reinterpret_cast<float4*>(red + (warp * 2) * C + c) = u;
+    *reinterpret_cast<float4*>(red + (warp * 2 + 1) * C + c) = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += DB_THREADS) {
+    float su = 0.f, sv = 0.f;
+#pragma unroll
+    for (int w = 0; w < DB_WARPS; ++w) {
+      su += red[(w * 2) * C + i];
+      sv += red[(w * 2 + 1) * C + i];
+    }
+    fin(i, su, sv);
   }
 }
 
-// per-slab column statistics: psum[c] = sum_r S[r][c],  pm2[c] = sum_r (S[r][c] - slab mean)^2   (global partials)
-// S has nrp = multiple-of-4 rows; rows >= nr are excluded (they may hold anything).
-__device__ __forceinline__ void db_slab_stats(const float* __restrict__ S, int C, int nr, float* __restrict__ psum,
-                                              float* __restrict__ pm2) {
-  for (int c = threadIdx.x; c < C; c += DB_THREADS) {
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int r = 0;
-    for (; r + 4 <= nr; r += 4) {
-      s0 += S[r * C + c]; s1 += S[(r + 1) * C + c]; s2 += S[(r + 2) * C + c]; s3 += S[(r + 3) * C + c];
-    }
-    for (; r < nr; ++r) s0 += S[r * C + c];
-    const float s = (s0 + s1) + (s2 + s3);
-    const float mean = nr > 0 ? s / (float)nr : 0.f;
-    float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
-    for (r = 0; r + 4 <= nr; r += 4) {
-      const float d0 = S[r * C + c] - mean, d1 = S[(r + 1) * C + c] - mean, d2 = S[(r + 2) * C + c] - mean,
-                  d3 = S[(r + 3) * C + c] - mean;
-      q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1); q2 = fmaf(d2, d2, q2); q3 = fmaf(d3, d3, q3);
-    }
-    for (; r < nr; ++r) {
-      const float d0 = S[r * C + c] - mean;
-      q0 = fmaf(d0, d0, q0);
-    }
-    __stcg(psum + c, s);
-    __stcg(pm2 + c, (q0 + q1) + (q2 + q3));
-  }
+// per-slab column statistics: psum[c] = sum_r S[r][c],  pm2[c] = sum_r (S[r][c] - slab mean)^2   (global partials).
+// Single pass over data shifted by the slab's first row (a sample of the column, so no catastrophic cancellation):
+// with d = x - K:  sum = sum(d) + n K,  M2 = sum(d^2) - sum(d)^2 / n.
+__device__ __forceinline__ void db_slab_stats(const float* __restrict__ S, int C, int nr, float* __restrict__ red,
+                                              float* __restrict__ psum, float* __restrict__ pm2) {
+  db_col_reduce2(
+      C, nr, red,
+      [&](int r, int c, float4& u, float4& v) {
+        const float4 k = *reinterpret_cast<const float4*>(S + c);
+        const float4 x = *reinterpret_cast<const float4*>(S + r * C + c);
+        const float dx = x.x - k.x, dy = x.y - k.y, dz = x.z - k.z, dw = x.w - k.w;
+        u.x += dx; u.y += dy; u.z += dz; u.w += dw;
+        v.x = fmaf(dx, dx, v.x); v.y = fmaf(dy, dy, v.y); v.z = fmaf(dz, dz, v.z); v.w = fmaf(dw, dw, v.w);
+      },
+      [&](int c, float su, float sv) {
+        const float fn = (float)nr;
+        __stcg(psum + c, nr > 0 ? fmaf(fn, S[c], su) : 0.f);
+        __stcg(pm2 + c, nr > 0 ? fmaxf(sv - su * su / fn, 0.f) : 0.f);
+      });
 }
 
-// Merge the per-CTA partials [grid][2][C] into batch mean / inverse std (Chan et al.), identically in every CTA.
-// red: shared [DB_WARPS][C]; mean_s / istd_s: shared [C].  var_out (optional, shared [C]) receives the biased variance.
+// Merge the per-CTA partials [grid][2][C] into batch mean / inverse std (Chan et al.), identically in every CTA:
+//   mean = K + sum_b n_b d_b / N,   M2 = sum_b M2_b + sum_b n_b d_b^2 - (sum_b n_b d_b)^2 / N,   d_b = mean_b - K
+// with the pivot K = mean of slab 0 (shifted data: single pass, no catastrophic cancellation).  Every partial this
+// thread needs is requested before the first one is used: one L2 round trip.  red: shared [DB_WARPS][3][C].
 __device__ __forceinline__ void db_merge_stats(const float* __restrict__ part, int grid, int Rc, int N, int C,
                                                float eps, float* __restrict__ red, float* __restrict__ mean_s,
                                                float* __restrict__ istd_s, float* __restrict__ var_s) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = lane * 4;
   const bool on = c < C;
-  // every partial this thread needs is requested before the first one is used: one L2 round trip per merge
   float4 ps[DB_MAXI], pm[DB_MAXI];
+  float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (on) p0 = __ldcg(reinterpret_cast<const float4*>(part + c));
 #pragma unroll
   for (int i = 0; i < DB_MAXI; ++i) {
     const int b = warp + i * DB_WARPS;
@@ -237,41 +280,42 @@ __device__ __forceinline__ void db_merge_stats(const float* __restrict__ part, i
       pm[i] = __ldcg(reinterpret_cast<const float4*>(part + (size_t)b * 2 * C + C + c));
     }
   }
-  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-  for (int i = 0; i < DB_MAXI; ++i) {
-    s.x += ps[i].x; s.y += ps[i].y; s.z += ps[i].z; s.w += ps[i].w;
-  }
-  if (on) *reinterpret_cast<float4*>(red + warp * C + c) = s;
-  __syncthreads();
-  for (int i = threadIdx.x; i < C; i += DB_THREADS) {
-    float t = 0.f;
-#pragma unroll
-    for (int w = 0; w < DB_WARPS; ++w) t += red[w * C + i];
-    mean_s[i] = t / (float)N;
-  }
-  __syncthreads();
-  float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-  const float4 mu = on ? *reinterpret_cast<const float4*>(mean_s + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float fn_full = (float)min(Rc, N), inv_full = 1.f / fn_full;    // every slab is full except the last
+  const float fn_last = (float)(N - (grid - 1) * Rc), inv_last = 1.f / fn_last;
+  const float inv0 = grid == 1 ? inv_last : inv_full;
+  const float4 K = make_float4(p0.x * inv0, p0.y * inv0, p0.z * inv0, p0.w * inv0);
+  float4 sa = make_float4(0.f, 0.f, 0.f, 0.f), sb = sa, sm = sa;
 #pragma unroll
   for (int i = 0; i < DB_MAXI; ++i) {
     const int b = warp + i * DB_WARPS;
-    const int nb = min(Rc, N - b * Rc);
-    if (b < grid && nb > 0) {
-      const float fn = (float)nb, inv = 1.f / fn;
-      const float dx = ps[i].x * inv - mu.x, dy = ps[i].y * inv - mu.y, dz = ps[i].z * inv - mu.z,
-                  dw = ps[i].w * inv - mu.w;
-      q.x += fmaf(fn * dx, dx, pm[i].x); q.y += fmaf(fn * dy, dy, pm[i].y);
-      q.z += fmaf(fn * dz, dz, pm[i].z); q.w += fmaf(fn * dw, dw, pm[i].w);
+    if (b < grid) {
+      const float fn = b == grid - 1 ? fn_last : fn_full, inv = b == grid - 1 ? inv_last : inv_full;
+      const float dx = fmaf(ps[i].x, inv, -K.x), dy = fmaf(ps[i].y, inv, -K.y), dz = fmaf(ps[i].z, inv, -K.z),
+                  dw = fmaf(ps[i].w, inv, -K.w);
+      sa.x = fmaf(fn, dx, sa.x); sa.y = fmaf(fn, dy, sa.y); sa.z = fmaf(fn, dz, sa.z); sa.w = fmaf(fn, dw, sa.w);
+      sb.x = fmaf(fn * dx, dx, sb.x); sb.y = fmaf(fn * dy, dy, sb.y);
+      sb.z = fmaf(fn * dz, dz, sb.z); sb.w = fmaf(fn * dw, dw, sb.w);
+      sm.x += pm[i].x; sm.y += pm[i].y; sm.z += pm[i].z; sm.w += pm[i].w;
     }
   }
-  if (on) *reinterpret_cast<float4*>(red + warp * C + c) = q;
+  if (on) {
+    *reinterpret_cast<float4*>(red + (warp * 3) * C + c) = sa;
+    *reinterpret_cast<float4*>(red + (warp * 3 + 1) * C + c) = sb;
+    *reinterpret_cast<float4*>(red + (warp * 3 + 2) * C + c) = sm;
+    if (warp == 0) *reinterpret_cast<float4*>(mean_s + c) = K;          // pivot, replaced by the mean below
+  }
   __syncthreads();
   for (int i = threadIdx.x; i < C; i += DB_THREADS) {
-    float t = 0.f;
+    float a = 0.f, b2 = 0.f, m2 = 0.f;
 #pragma unroll
-    for (int w = 0; w < DB_WARPS; ++w) t += red[w * C + i];
-    const float var = t / (float)N;
+    for (int w = 0; w < DB_WARPS; ++w) {
+      a += red[(w * 3) * C + i];
+      b2 += red[(w * 3 + 1) * C + i];
+      m2 += red[(w * 3 + 2) * C + i];
+    }
+    const float invn = 1.f / (float)N;
+    const float var = fmaxf((m2 + (b2 - a * a * invn)) * invn, 0.f);
+    mean_s[i] = fmaf(a, invn, mean_s[i]);
     var_s[i] = var;
     istd_s[i] = rsqrtf(var + eps);
   }
@@ -297,14 +341,15 @@ template <bool RELU>
 __device__ __forceinline__ void db_bn_apply(const float* __restrict__ S, int C, int nr, const float* __restrict__ g,
                                             const float* __restrict__ be, const float* __restrict__ mean_s,
                                             const float* __restrict__ istd_s, float* __restrict__ D) {
-  const int c4n = C >> 2;
-  for (int i = threadIdx.x; i < nr * c4n; i += DB_THREADS) {
-    const int r = i / c4n, c = (i - r * c4n) * 4;
+  const int warp = threadIdx.x >> 5, c = (threadIdx.x & 31) * 4;
+  if (c >= C) return;
+  const float4 mu = *reinterpret_cast<const float4*>(mean_s + c);
+  const float4 is = *reinterpret_cast<const float4*>(istd_s + c);
+  const float4 gg = __ldg(reinterpret_cast<const float4*>(g + c));
+  const float4 bb = __ldg(reinterpret_cast<const float4*>(be + c));
+  for (int r = warp; r < nr; r += DB_WARPS) {
     const float4 v = *reinterpret_cast<const float4*>(S + r * C + c);
-    const float4 mu = *reinterpret_cast<const float4*>(mean_s + c);
-    const float4 is = *reinterpret_cast<const float4*>(istd_s + c);
-    const float4 gg = __ldg(reinterpret_cast<const float4*>(g + c));
-    const float4 bb = __ldg(reinterpret_cast<const float4*>(be + c));
+    // ((v - mean) * invstd) * gamma + beta, in this order: the backward recomputes x-hat = (v - mean) * invstd
     float4 o = make_float4(fmaf((v.x - mu.x) * is.x, gg.x, bb.x), fmaf((v.y - mu.y) * is.y, gg.y, bb.y),
                            fmaf((v.z - mu.z) * is.z, gg.z, bb.z), fmaf((v.w - mu.w) * is.w, gg.w, bb.w));
     if (RELU) {
@@ -314,16 +359,14 @@ __device__ __forceinline__ void db_bn_apply(const float* __restrict__ S, int C, 
   }
 }
 
-struct DbShared {
-  float *W1, *W2, *A, *Y, *Z, *red, *mean, *istd, *var;
-};
-
 // ------------------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(DB_THREADS, 1)
 dense_block_fwd_kernel(const kp_dense_desc m, float* __restrict__ out, float* __restrict__ part, unsigned* bar, int Rc) {
   extern __shared__ __align__(16) float smem[];
+  DB_T_DECL
+  DB_T(0);
   const int Ci = m.Cin, Co = m.Cout, N = m.N;
   const int grid = gridDim.x;
   const int r0 = blockIdx.x * Rc;
@@ -334,17 +377,19 @@ dense_block_fwd_kernel(const kp_dense_desc m, float* __restrict__ out, float* __
   float* A = W2s + Co * db_wstride(Co);      // [Rp][Ci]
   float* Y = A + Rp * Ci;                    // [Rp][Co]
   float* Z = Y + Rp * Co;                    // [Rp][Co]
-  float* red = Z + Rp * Co;                  // [DB_WARPS][Co]
-  float* st = red + DB_WARPS * Co;           // [3][3][Co]: (mean, istd, var) of BN1, BN2, BN3
+  float* red = Z + Rp * Co;                  // [DB_WARPS][3][Co]
+  float* st = red + DB_WARPS * 3 * Co;       // [3][3][Co]: (mean, istd, var) of BN1, BN2, BN3
   // everything this CTA will read from global memory except the partials is requested now, asynchronously
   db_cp_slab(m.X, r0, nr, Rp, Ci, A);
   db_cp_weight_swizzled(m.W1, Co, Ci, W1s);
-  db_cp_weight_swizzled(m.W2, Co, Co, W2s);
+  db_cp_commit();
+  db_cp_weight_swizzled(m.W2, Co, Co, W2s);              // second group: lands behind the first GEMM
   db_cp_commit();
   for (int i = threadIdx.x * 4; i < Rp * Co; i += DB_THREADS * 4)
     *reinterpret_cast<float4*>(Z + i) = make_float4(0.f, 0.f, 0.f, 0.f);
-  db_cp_wait_all();
+  asm volatile("cp.async.wait_group 1;" ::: "memory");
   __syncthreads();
+  DB_T(1);
   float* part0 = part;
   float* part1 = part + (size_t)grid * 2 * Co;
   float* part2 = part1 + (size_t)grid * 2 * Co;
@@ -352,43 +397,62 @@ dense_block_fwd_kernel(const kp_dense_desc m, float* __restrict__ out, float* __
   // ---- Linear1 + BN1 + ReLU ----
   db_gemm_AWt(A, Ci, Ci, W1s, Co, m.b1, Rp, Y, Co);
   __syncthreads();
-  db_slab_stats(Y, Co, nr, part0 + (size_t)blockIdx.x * 2 * Co, part0 + (size_t)blockIdx.x * 2 * Co + Co);
+  DB_T(2);
+  db_slab_stats(Y, Co, nr, red, part0 + (size_t)blockIdx.x * 2 * Co, part0 + (size_t)blockIdx.x * 2 * Co + Co);
   db_store_slab(Y, r0, nr, Co, m.Y1);
+  DB_T(3);
   db_grid_barrier(bar, 1u * grid);
+  DB_T(4);
   db_merge_stats(part0, grid, Rc, N, Co, m.eps1, red, st, st + Co, st + 2 * Co);
+  DB_T(5);
   db_bn_apply<true>(Y, Co, nr, m.g1, m.be1, st, st + Co, Z);
+  db_cp_wait_all();
   __syncthreads();
+  DB_T(6);
 
   // ---- Linear2 + BN2 + ReLU ----
   db_gemm_AWt(Z, Co, Co, W2s, Co, m.b2, Rp, Y, Co);
   __syncthreads();
-  db_slab_stats(Y, Co, nr, part1 + (size_t)blockIdx.x * 2 * Co, part1 + (size_t)blockIdx.x * 2 * Co + Co);
+  DB_T(7);
+  db_slab_stats(Y, Co, nr, red, part1 + (size_t)blockIdx.x * 2 * Co, part1 + (size_t)blockIdx.x * 2 * Co + Co);
   db_store_slab(Y, r0, nr, Co, m.Y2);
+  DB_T(8);
   db_grid_barrier(bar, 2u * grid);
+  DB_T(9);
   db_merge_stats(part1, grid, Rc, N, Co, m.eps2, red, st + 3 * Co, st + 4 * Co, st + 5 * Co);
+  DB_T(10);
   db_bn_apply<true>(Y, Co, nr, m.g2, m.be2, st + 3 * Co, st + 4 * Co, Z);
   __syncthreads();
+  DB_T(11);
 
   // ---- outer BatchNorm + residual ----
   if (m.g3) {
-    db_slab_stats(Z, Co, nr, part2 + (size_t)blockIdx.x * 2 * Co, part2 + (size_t)blockIdx.x * 2 * Co + Co);
+    db_slab_stats(Z, Co, nr, red, part2 + (size_t)blockIdx.x * 2 * Co, part2 + (size_t)blockIdx.x * 2 * Co + Co);
     db_store_slab(Z, r0, nr, Co, m.Z2);
+    DB_T(12);
     db_grid_barrier(bar, 3u * grid);
+    DB_T(13);
     db_merge_stats(part2, grid, Rc, N, Co, m.eps3, red, st + 6 * Co, st + 7 * Co, st + 8 * Co);
+    DB_T(14);
     db_bn_apply<false>(Z, Co, nr, m.g3, m.be3, st + 6 * Co, st + 7 * Co, Y);
     __syncthreads();
+    DB_T(15);
   }
   const float* res = m.g3 ? Y : Z;
-  const int c4n = Co >> 2;
-  for (int i = threadIdx.x; i < nr * c4n; i += DB_THREADS) {
-    const int r = i / c4n, c = (i - r * c4n) * 4;
-    float4 v = *reinterpret_cast<const float4*>(res + r * Co + c);
-    if (m.R) {
-      const float4 q = __ldg(reinterpret_cast<const float4*>(m.R + (size_t)(r0 + r) * Co + c));
-      v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+  {
+    float* dst = out + (size_t)r0 * Co;
+    const float* rsd = m.R ? m.R + (size_t)r0 * Co : nullptr;
+    for (int i = threadIdx.x * 4; i < nr * Co; i += DB_THREADS * 4) {
+      float4 v = *reinterpret_cast<const float4*>(res + i);
+      if (rsd) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(rsd + i));
+        v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+      }
+      *reinterpret_cast<float4*>(dst + i) = v;
     }
-    *reinterpret_cast<float4*>(out + (size_t)(r0 + r) * Co + c) = v;
   }
+  DB_T(16);
+  DB_T_PRINT(17, "fwd load gemm1 stats1 bar1 merge1 apply1 gemm2 stats2 bar2 merge2 apply2 stats3 bar3 merge3 apply3 out");
   // saved + running statistics: by the last CTA (the shortest slab), off everybody's critical path
   if (blockIdx.x == grid - 1) {
     db_publish_stats(st, st + Co, st + 2 * Co, N, Co, m.mom1, m.rm1, m.rv1, (long long*)m.nbt1, m.stats, m.stats + Co);
@@ -404,20 +468,20 @@ dense_block_fwd_kernel(const kp_dense_desc m, float* __restrict__ out, float* __
 // backward
 // ------------------------------------------------------------------------------------------------------------
 // slab partial sums p1[c] = sum_r D[r][c], p2[c] = sum_r D[r][c] * XH[r][c]  -> global partial [2][C]
-__device__ __forceinline__ void db_slab_dots(const float* __restrict__ D, const float* __restrict__ XH, int C, int nrp,
-                                             float* __restrict__ p) {
-  // rows >= nr of D are zero, so the padded row count can be used (4 independent chains)
-  for (int c = threadIdx.x; c < C; c += DB_THREADS) {
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
-    for (int r = 0; r < nrp; r += 4) {
-      const float d0 = D[r * C + c], d1 = D[(r + 1) * C + c], d2 = D[(r + 2) * C + c], d3 = D[(r + 3) * C + c];
-      a0 += d0; a1 += d1; a2 += d2; a3 += d3;
-      b0 = fmaf(d0, XH[r * C + c], b0); b1 = fmaf(d1, XH[(r + 1) * C + c], b1);
-      b2 = fmaf(d2, XH[(r + 2) * C + c], b2); b3 = fmaf(d3, XH[(r + 3) * C + c], b3);
-    }
-    __stcg(p + c, (a0 + a1) + (a2 + a3));
-    __stcg(p + C + c, (b0 + b1) + (b2 + b3));
-  }
+__device__ __forceinline__ void db_slab_dots(const float* __restrict__ D, const float* __restrict__ XH, int C, int nr,
+                                             float* __restrict__ red, float* __restrict__ p) {
+  db_col_reduce2(
+      C, nr, red,
+      [&](int r, int c, float4& u, float4& v) {
+        const float4 d = *reinterpret_cast<const float4*>(D + r * C + c);
+        const float4 x = *reinterpret_cast<const float4*>(XH + r * C + c);
+        u.x += d.x; u.y += d.y; u.z += d.z; u.w += d.w;
+        v.x = fmaf(d.x, x.x, v.x); v.y = fmaf(d.y, x.y, v.y); v.z = fmaf(d.z, x.z, v.z); v.w = fmaf(d.w, x.w, v.w);
+      },
+      [&](int c, float su, float sv) {
+        __stcg(p + c, su);
+        __stcg(p + C + c, sv);
+      });
 }
 // plain fixed-order sums of the [grid][2][C] partials into shared s1[C], s2[C]
 __device__ __forceinline__ void db_merge_sums(const float* __restrict__ part, int grid, int C, float* __restrict__ red,
@@ -456,16 +520,16 @@ __device__ __forceinline__ void db_merge_sums(const float* __restrict__ part, in
   }
   __syncthreads();
 }
-// XH <- (S - mean) * istd   (normalised activations of the slab)
+// XH <- (S - mean) * istd   (normalised activations of the slab), all nrp rows
 __device__ __forceinline__ void db_xhat(const float* __restrict__ S, int C, int nrp, const float* __restrict__ mean,
                                         const float* __restrict__ istd, float* __restrict__ XH) {
-  const int c4n = C >> 2;
-  for (int i = threadIdx.x; i < nrp * c4n; i += DB_THREADS) {
-    const int c = (i % c4n) * 4;
-    const float4 v = *reinterpret_cast<const float4*>(S + i * 4);
-    const float4 mu = __ldg(reinterpret_cast<const float4*>(mean + c));
-    const float4 is = __ldg(reinterpret_cast<const float4*>(istd + c));
-    *reinterpret_cast<float4*>(XH + i * 4) =
+  const int warp = threadIdx.x >> 5, c = (threadIdx.x & 31) * 4;
+  if (c >= C) return;
+  const float4 mu = __ldg(reinterpret_cast<const float4*>(mean + c));
+  const float4 is = __ldg(reinterpret_cast<const float4*>(istd + c));
+  for (int r = warp; r < nrp; r += DB_WARPS) {
+    const float4 v = *reinterpret_cast<const float4*>(S + r * C + c);
+    *reinterpret_cast<float4*>(XH + r * C + c) =
         make_float4((v.x - mu.x) * is.x, (v.y - mu.y) * is.y, (v.z - mu.z) * is.z, (v.w - mu.w) * is.w);
   }
 }
@@ -473,49 +537,51 @@ __device__ __forceinline__ void db_xhat(const float* __restrict__ S, int C, int 
 __device__ __forceinline__ void db_bn_bwd_apply(float* __restrict__ D, const float* __restrict__ XH, int C, int nr, int N,
                                                 const float* __restrict__ g, const float* __restrict__ istd,
                                                 const float* __restrict__ s1, const float* __restrict__ s2) {
-  const int c4n = C >> 2;
+  const int warp = threadIdx.x >> 5, c = (threadIdx.x & 31) * 4;
+  if (c >= C) return;
   const float invn = 1.f / (float)N;
-  for (int i = threadIdx.x; i < nr * c4n; i += DB_THREADS) {
-    const int c = (i % c4n) * 4;
-    const float4 dv = *reinterpret_cast<const float4*>(D + i * 4);
-    const float4 xh = *reinterpret_cast<const float4*>(XH + i * 4);
-    const float4 gg = __ldg(reinterpret_cast<const float4*>(g + c));
-    const float4 is = __ldg(reinterpret_cast<const float4*>(istd + c));
-    const float4 a = *reinterpret_cast<const float4*>(s1 + c);
-    const float4 b = *reinterpret_cast<const float4*>(s2 + c);
-    *reinterpret_cast<float4*>(D + i * 4) =
-        make_float4(gg.x * is.x * (dv.x - a.x * invn - xh.x * (b.x * invn)),
-                    gg.y * is.y * (dv.y - a.y * invn - xh.y * (b.y * invn)),
-                    gg.z * is.z * (dv.z - a.z * invn - xh.z * (b.z * invn)),
-                    gg.w * is.w * (dv.w - a.w * invn - xh.w * (b.w * invn)));
+  const float4 gg = __ldg(reinterpret_cast<const float4*>(g + c));
+  const float4 is = __ldg(reinterpret_cast<const float4*>(istd + c));
+  const float4 a = *reinterpret_cast<const float4*>(s1 + c);
+  const float4 b = *reinterpret_cast<const float4*>(s2 + c);
+  const float4 k = make_float4(gg.x * is.x, gg.y * is.y, gg.z * is.z, gg.w * is.w);
+  const float4 m1 = make_float4(a.x * invn, a.y * invn, a.z * invn, a.w * invn);
+  const float4 m2 = make_float4(b.x * invn, b.y * invn, b.z * invn, b.w * invn);
+  for (int r = warp; r < nr; r += DB_WARPS) {
+    const float4 dv = *reinterpret_cast<const float4*>(D + r * C + c);
+    const float4 xh = *reinterpret_cast<const float4*>(XH + r * C + c);
+    *reinterpret_cast<float4*>(D + r * C + c) =
+        make_float4(k.x * (dv.x - m1.x - xh.x * m2.x), k.y * (dv.y - m1.y - xh.y * m2.y),
+                    k.z * (dv.z - m1.z - xh.z * m2.z), k.w * (dv.w - m1.w - xh.w * m2.w));
   }
 }
 // D[r][c] <- 0 where g*XH + be <= 0 (the ReLU after the BatchNorm was inactive)
 __device__ __forceinline__ void db_relu_mask(float* __restrict__ D, const float* __restrict__ XH, int C, int nr,
                                              const float* __restrict__ g, const float* __restrict__ be) {
-  const int c4n = C >> 2;
-  for (int i = threadIdx.x; i < nr * c4n; i += DB_THREADS) {
-    const int c = (i % c4n) * 4;
-    float4 dv = *reinterpret_cast<const float4*>(D + i * 4);
-    const float4 xh = *reinterpret_cast<const float4*>(XH + i * 4);
-    const float4 gg = __ldg(reinterpret_cast<const float4*>(g + c));
-    const float4 bb = __ldg(reinterpret_cast<const float4*>(be + c));
+  const int warp = threadIdx.x >> 5, c = (threadIdx.x & 31) * 4;
+  if (c >= C) return;
+  const float4 gg = __ldg(reinterpret_cast<const float4*>(g + c));
+  const float4 bb = __ldg(reinterpret_cast<const float4*>(be + c));
+  for (int r = warp; r < nr; r += DB_WARPS) {
+    float4 dv = *reinterpret_cast<const float4*>(D + r * C + c);
+    const float4 xh = *reinterpret_cast<const float4*>(XH + r * C + c);
     if (fmaf(gg.x, xh.x, bb.x) <= 0.f) dv.x = 0.f;
     if (fmaf(gg.y, xh.y, bb.y) <= 0.f) dv.y = 0.f;
     if (fmaf(gg.z, xh.z, bb.z) <= 0.f) dv.z = 0.f;
     if (fmaf(gg.w, xh.w, bb.w) <= 0.f) dv.w = 0.f;
-    *reinterpret_cast<float4*>(D + i * 4) = dv;
+    *reinterpret_cast<float4*>(D + r * C + c) = dv;
   }
 }
-// column sums of a slab (rows >= nr are zero) -> global partial [C]
-__device__ __forceinline__ void db_slab_colsum(const float* __restrict__ D, int C, int nrp, float* __restrict__ p) {
-  for (int c = threadIdx.x; c < C; c += DB_THREADS) {
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    for (int r = 0; r < nrp; r += 4) {
-      a0 += D[r * C + c]; a1 += D[(r + 1) * C + c]; a2 += D[(r + 2) * C + c]; a3 += D[(r + 3) * C + c];
-    }
-    __stcg(p + c, (a0 + a1) + (a2 + a3));
-  }
+// column sums of a slab -> global partial [C]
+__device__ __forceinline__ void db_slab_colsum(const float* __restrict__ A, int C, int nr, float* __restrict__ red,
+                                               float* __restrict__ pA) {
+  db_col_reduce2(
+      C, nr, red,
+      [&](int r, int c, float4& u, float4& v) {
+        const float4 a = *reinterpret_cast<const float4*>(A + r * C + c);
+        u.x += a.x; u.y += a.y; u.z += a.z; u.w += a.w;
+      },
+      [&](int c, float su, float sv) { __stcg(pA + c, su); });
 }
 
 // workspace layout (floats): pa, pb, pc [grid][2][Co] | pW1 [grid][Co*Ci] | pW2 [grid][Co*Co] | pb1, pb2 [grid][Co]
@@ -524,6 +590,8 @@ dense_block_bwd_kernel(const kp_dense_desc m, const float* __restrict__ dOut, fl
                        float* __restrict__ dW1, float* __restrict__ db1, float* __restrict__ dW2,
                        float* __restrict__ db2, float* __restrict__ dbn, float* __restrict__ ws, unsigned* bar, int Rc) {
   extern __shared__ __align__(16) float smem[];
+  DB_T_DECL
+  DB_T(0);
   const int Ci = m.Cin, Co = m.Cout, N = m.N;
   const int grid = gridDim.x;
   const int r0 = blockIdx.x * Rc;
@@ -562,31 +630,33 @@ dense_block_bwd_kernel(const kp_dense_desc m, const float* __restrict__ dOut, fl
   db_cp_commit();
   db_cp_wait_all();
   __syncthreads();
+  DB_T(1);
   unsigned phase = 0;
   // x-hats of the three BatchNorms and z1, while nothing else can proceed anyway
   if (m.g3) db_xhat(X3, Co, Rp, mean3, istd3, X3);
   db_xhat(X2, Co, Rp, mean2, istd2, X2);
   db_xhat(X1, Co, Rp, mean1, istd1, X1);
   {
-    const int c4n = Co >> 2;
-    for (int i = threadIdx.x; i < Rp * c4n; i += DB_THREADS) {
-      const int r = i / c4n, c = (i - r * c4n) * 4;
-      float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r < nr) {
-        // recomputed from the x-hat this same thread just stored
-        const float4 xh = *reinterpret_cast<const float4*>(X1 + i * 4);
-        const float4 gg = __ldg(reinterpret_cast<const float4*>(m.g1 + c));
-        const float4 bb = __ldg(reinterpret_cast<const float4*>(m.be1 + c));
-        z = make_float4(fmaxf(fmaf(gg.x, xh.x, bb.x), 0.f), fmaxf(fmaf(gg.y, xh.y, bb.y), 0.f),
-                        fmaxf(fmaf(gg.z, xh.z, bb.z), 0.f), fmaxf(fmaf(gg.w, xh.w, bb.w), 0.f));
+    const int warp = threadIdx.x >> 5, c = (threadIdx.x & 31) * 4;
+    if (c < Co) {
+      const float4 gg = __ldg(reinterpret_cast<const float4*>(m.g1 + c));
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(m.be1 + c));
+      for (int r = warp; r < Rp; r += DB_WARPS) {             // same (warp, lane) -> element mapping as db_xhat
+        float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < nr) {
+          const float4 xh = *reinterpret_cast<const float4*>(X1 + r * Co + c);
+          z = make_float4(fmaxf(fmaf(gg.x, xh.x, bb.x), 0.f), fmaxf(fmaf(gg.y, xh.y, bb.y), 0.f),
+                          fmaxf(fmaf(gg.z, xh.z, bb.z), 0.f), fmaxf(fmaf(gg.w, xh.w, bb.w), 0.f));
+        }
+        *reinterpret_cast<float4*>(Z1 + r * Co + c) = z;
       }
-      *reinterpret_cast<float4*>(Z1 + i * 4) = z;
     }
   }
   __syncthreads();
+  DB_T(2);
   if (m.g3) {
     // ---- outer BatchNorm ----
-    db_slab_dots(D, X3, Co, Rp, pa + (size_t)blockIdx.x * 2 * Co);
+    db_slab_dots(D, X3, Co, nr, red, pa + (size_t)blockIdx.x * 2 * Co);
     db_grid_barrier(bar, ++phase * grid);
     db_merge_sums(pa, grid, Co, red, s1, s2);
     if (blockIdx.x == grid - 1)
@@ -597,11 +667,13 @@ dense_block_bwd_kernel(const kp_dense_desc m, const float* __restrict__ dOut, fl
     db_bn_bwd_apply(D, X3, Co, nr, N, m.g3, istd3, s1, s2);
     __syncthreads();
   }
+  DB_T(3);
   // ---- ReLU2 + BN2 ----
   db_relu_mask(D, X2, Co, nr, m.g2, m.be2);
   __syncthreads();
-  db_slab_dots(D, X2, Co, Rp, pb + (size_t)blockIdx.x * 2 * Co);
+  db_slab_dots(D, X2, Co, nr, red, pb + (size_t)blockIdx.x * 2 * Co);
   db_grid_barrier(bar, ++phase * grid);
+  DB_T(4);
   db_merge_sums(pb, grid, Co, red, s1, s2);
   if (blockIdx.x == grid - 1)
     for (int i = threadIdx.x; i < Co; i += DB_THREADS) {
@@ -610,26 +682,31 @@ dense_block_bwd_kernel(const kp_dense_desc m, const float* __restrict__ dOut, fl
     }
   db_bn_bwd_apply(D, X2, Co, nr, N, m.g2, istd2, s1, s2);      // D = dy2
   __syncthreads();
+  DB_T(5);
   // ---- Linear2: dz1 = dy2 W2 first (critical path), then the dW2 / db2 partials ----
-  db_gemm_AB(D, Co, Co, W2, Co, nullptr, Rp, E, Co);
+  db_gemm_AB(D, Co, Co, W2, Co, Rp, E, Co);
   __syncthreads();
+  DB_T(6);
   db_relu_mask(E, X1, Co, nr, m.g1, m.be1);
   __syncthreads();
-  db_slab_dots(E, X1, Co, Rp, pc + (size_t)blockIdx.x * 2 * Co);
+  db_slab_dots(E, X1, Co, nr, red, pc + (size_t)blockIdx.x * 2 * Co);
   __syncthreads();
   if (threadIdx.x == 0) {                                       // arrive early, wait after the off-path work
     __threadfence();
     atomicAdd(bar, 1u);
   }
   ++phase;
+  DB_T(7);
   db_gemm_AtB(D, Co, Co, Z1, Co, Co, nr, pW2 + (size_t)blockIdx.x * Co * Co);
-  db_slab_colsum(D, Co, Rp, pb2 + (size_t)blockIdx.x * Co);
+  db_slab_colsum(D, Co, nr, red, pb2 + (size_t)blockIdx.x * Co);
+  DB_T(8);
   if (threadIdx.x == 0) {
     while (db_ld_acquire(bar) < phase * grid) {
     }
     __threadfence();
   }
   __syncthreads();
+  DB_T(9);
   db_merge_sums(pc, grid, Co, red, s1, s2);
   if (blockIdx.x == grid - 1)
     for (int i = threadIdx.x; i < Co; i += DB_THREADS) {
@@ -638,21 +715,25 @@ dense_block_bwd_kernel(const kp_dense_desc m, const float* __restrict__ dOut, fl
     }
   db_bn_bwd_apply(E, X1, Co, nr, N, m.g1, istd1, s1, s2);      // E = dy1
   __syncthreads();
+  DB_T(10);
   // ---- Linear1: dX = dy1 W1, dW1 / db1 partials ----
-  db_gemm_AB(E, Co, Co, W1, Ci, nullptr, Rp, D, Ci);
+  db_gemm_AB(E, Co, Co, W1, Ci, Rp, D, Ci);
+  DB_T(11);
   db_gemm_AtB(E, Co, Co, XS, Ci, Ci, nr, pW1 + (size_t)blockIdx.x * Co * Ci);
-  db_slab_colsum(E, Co, Rp, pb1 + (size_t)blockIdx.x * Co);
+  db_slab_colsum(E, Co, nr, red, pb1 + (size_t)blockIdx.x * Co);
   __syncthreads();
+  DB_T(12);
   db_store_slab(D, r0, nr, Ci, dX);
   db_grid_barrier(bar, ++phase * grid);
+  DB_T(13);
   // ---- fixed-order sums of the per-CTA weight-gradient partials: 8 lanes per output float4 ----
   {
     const int nW1 = (Co * Ci) >> 2, nW2 = (Co * Co) >> 2, nb = Co >> 2;
     const int total = nW1 + nW2 + 2 * nb;
-    const int sub = threadIdx.x & 7;
+    const int sub = threadIdx.x & 15;
     const int wg = (blockIdx.x * DB_THREADS + threadIdx.x) >> 5, nwg = (grid * DB_THREADS) >> 5;
-    for (int e0 = wg * 4; e0 < total; e0 += nwg * 4) {          // warp-uniform trip count (full-mask shuffles)
-      const int e = e0 + ((threadIdx.x & 31) >> 3);
+    for (int e0 = wg * 2; e0 < total; e0 += nwg * 2) {          // warp-uniform trip count (full-mask shuffles)
+      const int e = e0 + ((threadIdx.x & 31) >> 4);
       const bool ok = e < total;
       const float* src = pW1;
       float* dst = dW1;
@@ -666,10 +747,10 @@ dense_block_bwd_kernel(const kp_dense_desc m, const float* __restrict__ dOut, fl
       } else if (ok) {
         src = pb2 + (size_t)(e - nW1 - nW2 - nb) * 4; dst = db2 + (size_t)(e - nW1 - nW2 - nb) * 4; stride = Co;
       }
-      float4 pv[DB_MAXI];
+      float4 pv[DB_MAXI];                                        // DB_MAXI * 16 >= the largest grid
 #pragma unroll
       for (int i = 0; i < DB_MAXI; ++i) {
-        const int q = sub + i * 8;
+        const int q = sub + i * 16;
         pv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (ok && q < grid) pv[i] = __ldcg(reinterpret_cast<const float4*>(src + (size_t)q * stride));
       }
@@ -679,7 +760,7 @@ dense_block_bwd_kernel(const kp_dense_desc m, const float* __restrict__ dOut, fl
         s.x += pv[i].x; s.y += pv[i].y; s.z += pv[i].z; s.w += pv[i].w;
       }
 #pragma unroll
-      for (int o = 1; o < 8; o <<= 1) {
+      for (int o = 1; o < 16; o <<= 1) {
         s.x += __shfl_xor_sync(0xffffffffu, s.x, o);
         s.y += __shfl_xor_sync(0xffffffffu, s.y, o);
         s.z += __shfl_xor_sync(0xffffffffu, s.z, o);
@@ -688,6 +769,8 @@ dense_block_bwd_kernel(const kp_dense_desc m, const float* __restrict__ dOut, fl
       if (ok && sub == 0) *reinterpret_cast<float4*>(dst) = s;
     }
   }
+  DB_T(14);
+  DB_T_PRINT(15, "bwd load xhat bn3 mask2+dots2+bar merge2+apply2 gemm_dz1 mask1+dots1 dW2+colsum wait merge1+apply1 gemm_dX dW1+colsum store+bar... reduce");
 }
 
 struct DbCfg {
@@ -698,7 +781,7 @@ struct DbCfg {
 static size_t db_smem_fwd(int Ci, int Co, int Rc) {
   const int Rp = (Rc + 3) & ~3;
   return sizeof(float) * ((size_t)Co * db_wstride(Ci) + (size_t)Co * db_wstride(Co) + (size_t)Rp * Ci +
-                          2 * (size_t)Rp * Co + (size_t)DB_WARPS * Co + 9 * (size_t)Co);
+                          2 * (size_t)Rp * Co + (size_t)DB_WARPS * 3 * Co + 9 * (size_t)Co);
 }
 static size_t db_smem_bwd(int Ci, int Co, int Rc) {
   const int Rp = (Rc + 3) & ~3;

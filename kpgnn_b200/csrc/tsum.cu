@@ -63,7 +63,7 @@ tsum_bwd_kernel(const kp_tsum_desc t, const float* __restrict__ dOut, int ngroup
   float* tab = smem + (size_t)tsz * (gib < ngroups ? gib : 0) + c;
   const int ns = s1 - s0;                      // <= 32 slots, one per lane (host guarantees ns <= G)
   if (gib < ngroups) {
-    constexpr int RB = 4;
+    constexpr int RB = 8;                    // rows in flight per group
     for (long long rb = r0; rb < r1; rb += RB) {
       float4 g[RB];
       int row[RB];
@@ -147,7 +147,9 @@ static int tsum_config(const kp_tsum_desc& t, TsumCfg* c) {
   c->smem = maxsub * ng;
   long long wantg = ((long long)t.R + 63) / 64;           // >= 64 rows per group
   long long B = (wantg + ng - 1) / ng;
-  const long long maxB = (2 * kNumSMs + c->Q - 1) / c->Q; // about two CTAs per SM over the B*Q grid
+  // one CTA per SM over the B*Q grid (the sub-tables fill an SM's shared memory: a second wave would only
+  // repeat the zero / flush of ~190 KB and double the partial tables)
+  const long long maxB = kNumSMs / c->Q > 0 ? kNumSMs / c->Q : 1;
   if (B > maxB) B = maxB;
   if (B < 1) B = 1;
   c->B = (int)B;

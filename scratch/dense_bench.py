@@ -15,22 +15,15 @@ def fwd():
 for _ in range(5):
     y = fwd(); y.backward(gy)
 torch.cuda.synchronize()
-def timeit(fn, n=50):
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    g = torch.cuda.CUDAGraph()
-    s = torch.cuda.Stream()
-    with torch.cuda.stream(s):
-        fn()
-        torch.cuda.synchronize()
-        with torch.cuda.graph(g, stream=s):
-            for _ in range(n):
-                fn()
+from torch.profiler import ProfilerActivity, profile
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    for _ in range(10):
+        y = fwd(); y.backward(gy)
     torch.cuda.synchronize()
-    g.replay(); torch.cuda.synchronize()
-    a.record(); g.replay(); b.record(); torch.cuda.synchronize()
-    return a.elapsed_time(b) / n * 1e3
-tf = timeit(lambda: fwd())
-def fb():
-    y = fwd(); y.backward(gy)
-tfb = timeit(fb)
-print("rows/CTA env=%s  N=%d: fwd %.1f us, fwd+bwd %.1f us (bwd %.1f us)" % (os.environ.get("KP_DENSE_ROWS", "default"), N, tf, tfb, tfb - tf))
+import collections
+agg = collections.defaultdict(list)
+for e in prof.events():
+    if e.device_type == torch.autograd.DeviceType.CUDA:
+        agg[e.name[:60]].append(e.time_range.end - e.time_range.start)
+for k, v in agg.items():
+    print("%-62s n=%3d  min %.1f  med %.1f us" % (k, len(v), min(v), sorted(v)[len(v) // 2]))

@@ -112,6 +112,11 @@ __global__ void tsum_reduce_kernel(const float* __restrict__ part, int nblocks, 
   if (lane == 0) out[i] = s;
 }
 
+// tile-sorted register-accumulation gradient (tsum_sorted.cu)
+size_t ts_sorted_workspace_bytes(const kp_tsum_desc& t);
+int ts_sorted_backward(const kp_tsum_desc& t, const float* dOut, float* dTable, void* workspace, size_t workspace_bytes,
+                       cudaStream_t st);
+
 static size_t g_tsum_smem_cap = 200 * 1024;   // profiling hook: kp_table_sum_set_smem_cap
 
 struct TsumCfg {
@@ -188,6 +193,8 @@ int kp_table_sum_backward_workspace_bytes(const kp_tsum_desc* desc, size_t* byte
   kp::TsumCfg c;
   if (kp::tsum_config(*desc, &c)) return 1;
   *bytes = sizeof(float) * (size_t)c.B * desc->table_rows * desc->d;
+  const size_t sorted = kp::ts_sorted_workspace_bytes(*desc);
+  if (sorted > *bytes) *bytes = sorted;
   return 0;
 }
 
@@ -201,6 +208,10 @@ int kp_table_sum_backward(const kp_tsum_desc* desc, const float* dOut, float* dT
   if (desc->R == 0) {
     KP_CUDA(cudaMemsetAsync(dTable, 0, sizeof(float) * n, st));
     return 0;
+  }
+  {
+    const int rc = kp::ts_sorted_backward(*desc, dOut, dTable, workspace, workspace_bytes, st);
+    if (rc >= 0) return rc;
   }
   KP_CHECK_ARG(workspace && workspace_bytes >= sizeof(float) * (size_t)c.B * n, "kp_table_sum_backward: workspace too small");
   KP_CHECK_ARG((((uintptr_t)dOut | (uintptr_t)workspace) & 15) == 0, "kp_table_sum_backward: dOut/workspace alignment");

@@ -16,6 +16,7 @@ from .layers.gine import GINEConv
 from .layers.feature_encoder import FeatureConcatEncoder
 from .layers.input_encoder import EmbeddingEncoder
 from .layers.norm import FusedBatchNorm1d
+from .layers._base import SplitKLinear
 
 
 class Batch(object):
@@ -82,7 +83,7 @@ class KPGNNPlusBackbone(nn.Module):
         self.JK, self.residual = JK, residual
         self.dropout = nn.Dropout(drop_prob)
         width = (num_layer + 1) * hidden_size if JK == "concat" else hidden_size
-        self.output_proj = nn.Sequential(nn.Linear(width, hidden_size), nn.ReLU(), nn.Dropout(drop_prob))
+        self.output_proj = nn.Sequential(SplitKLinear(width, hidden_size), nn.ReLU(), nn.Dropout(drop_prob))
         self.init_proj = EmbeddingEncoder(input_size, hidden_size)
         self.peripheral_edge_embedding = FeatureConcatEncoder([num_hop1_edge + 2, max_edge_count + 1], hidden_size,
                                                               padding=0)

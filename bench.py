@@ -345,13 +345,13 @@ def agg_roofline(device, num_graphs, peak, reps=10):
         if t.get("graphs_per_launch") == num_graphs:
             traffic = t["dram_bytes_per_launch"]
     return {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-            "frac": round(achieved / peak, 4), "traffic": traffic, "kernel": "agg_fwd_fast_kernel<32,GELU,fuse,smem>",
+            "frac": round(achieved / peak, 4), "traffic": traffic, "kernel": "agg_fwd_lean_kernel<32,GELU,fuse,smem-tables>",
             "graphs_per_launch": num_graphs, "nodes": N, "nnz": plan.nnz, "algorithmic_bytes": alg,
             "ms_per_launch": round(ms, 5),
             "backward": {"ms": round(msb, 5), "algorithmic_bytes": alg_b,
                          "achieved": round(alg_b / (msb * 1e-3) / 1e9, 1),
                          "frac": round(alg_b / (msb * 1e-3) / 1e9 / peak, 4),
-                         "kernels": "agg_bwd_dst_fast + agg_bwd_src_fast + agg_bwd_table_fast + 2x reduce_partials"}}
+                         "kernels": "agg_bwd_dst_lean (B1) + agg_fwd_lean<gather> (B2) + agg_bwd_table_count (B3) + reductions"}}
 
 
 def cpu_baseline(steps=4, warmup=1):

@@ -129,34 +129,44 @@ tsum_bwd_sorted_kernel(const kp_tsum_desc t, const TsTables tb, const float* __r
   }
 }
 
-// dTable[t, :] = sum over the CTAs that have row t (flag), in CTA order.  One warp per table row; lane l first
-// collects the flags of CTAs l, l+32, ... and the warp walks the set bits in ascending CTA order.
-__global__ void tsum_sorted_reduce_kernel(const float* __restrict__ part, const unsigned char* __restrict__ flags,
-                                          int nctas, int table_rows, int d, float* __restrict__ dTable) {
-  const int lane = threadIdx.x & 31;
-  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (row >= table_rows) return;
+// dTable[t, :] = sum over the CTAs that have row t (flag), in CTA order.  One 256-thread CTA per table row: warp w
+// takes the w-th eighth of the producer CTAs, 8 independent loads in flight per lane (rows without the flag are not
+// read and count as zero); the 8 warp sums are then added in warp order.  A warp-per-row loop over ~120 producers
+// was one dependent L2 round trip per pair of partials: 60 us.
+__global__ void __launch_bounds__(256)
+tsum_sorted_reduce_kernel(const float* __restrict__ part, const unsigned char* __restrict__ flags, int nctas,
+                          int table_rows, int d, float* __restrict__ dTable) {
+  __shared__ float4 red[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row = blockIdx.x;
   const int c = min(lane * 4, d - 4);
-  float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
-  for (int b0 = 0; b0 < nctas; b0 += 32) {
-    const int b = b0 + lane;
-    const unsigned m = __ballot_sync(0xffffffffu, b < nctas && flags[(size_t)b * table_rows + row] != 0);
-    unsigned mm = m;
-    while (mm) {
-      const int q0 = __ffs(mm) - 1;
-      mm &= mm - 1u;
-      const float4 x0 = __ldcg(reinterpret_cast<const float4*>(part + ((size_t)(b0 + q0) * table_rows + row) * d + c));
-      a0.x += x0.x; a0.y += x0.y; a0.z += x0.z; a0.w += x0.w;
-      if (mm) {
-        const int q1 = __ffs(mm) - 1;
-        mm &= mm - 1u;
-        const float4 x1 = __ldcg(reinterpret_cast<const float4*>(part + ((size_t)(b0 + q1) * table_rows + row) * d + c));
-        a1.x += x1.x; a1.y += x1.y; a1.z += x1.z; a1.w += x1.w;
-      }
+  const int chunk = (nctas + 7) >> 3;
+  const int q0 = warp * chunk, q1 = min(nctas, q0 + chunk);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int qb = q0; qb < q1; qb += 8) {
+    float4 x[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int q = qb + u;
+      if (q < q1 && flags[(size_t)q * table_rows + row] != 0)
+        x[u] = __ldcg(reinterpret_cast<const float4*>(part + ((size_t)q * table_rows + row) * d + c));
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      acc.x += x[u].x; acc.y += x[u].y; acc.z += x[u].z; acc.w += x[u].w;
     }
   }
-  a0.x += a1.x; a0.y += a1.y; a0.z += a1.z; a0.w += a1.w;
-  if (lane * 4 < d) *reinterpret_cast<float4*>(dTable + (size_t)row * d + c) = a0;
+  red[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0 && lane * 4 < d) {
+    float4 s = red[0][lane];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) {
+      s.x += red[w][lane].x; s.y += red[w][lane].y; s.z += red[w][lane].z; s.w += red[w][lane].w;
+    }
+    *reinterpret_cast<float4*>(dTable + (size_t)row * d + c) = s;
+  }
 }
 
 struct TsSortedCfg {
@@ -224,8 +234,7 @@ int ts_sorted_backward(const kp_tsum_desc& t, const float* dOut, float* dTable, 
   unsigned char* flags = (unsigned char*)workspace + c.part_bytes;
   KP_CUDA(cudaFuncSetAttribute(tsum_bwd_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
   KP_LAUNCH(tsum_bwd_sorted_kernel, c.grid, TS_THREADS, c.smem, st, t, c.tb, dOut, c.TR, c.max_ns, part, flags);
-  KP_LAUNCH(tsum_sorted_reduce_kernel, ceil_div((long long)t.table_rows * 32, 256), 256, 0, st, part, flags, c.grid,
-            t.table_rows, t.d, dTable);
+  KP_LAUNCH(tsum_sorted_reduce_kernel, t.table_rows, 256, 0, st, part, flags, c.grid, t.table_rows, t.d, dTable);
   return 0;
 }
 

@@ -31,7 +31,11 @@ def launches(src, dst):
         rows.append((row["Kernel Name"], float(row["Metric Value"].replace(",", ""))))
     idx = [i for i, r in enumerate(rows) if "plan_count_kernel" in r[0]]
     pairs = list(zip(idx[:-1], idx[1:]))
-    a, b = max(pairs, key=lambda p: p[1] - p[0])    # one full step (plan rebuild + forward/backward/Adam)
+    # one full steady-state step (plan rebuild + forward/backward/Adam): the most common segment length, which skips
+    # the first step (lazy optimizer-state initialisation) and the short plan-only segments of the e2e phase
+    lens = collections.Counter(p[1] - p[0] for p in pairs if p[1] - p[0] > 50)
+    common = lens.most_common(1)[0][0]
+    a, b = [p for p in pairs if p[1] - p[0] == common][0]
     seg = rows[a:b]
     tot = sum(v for _, v in seg)
     agg = collections.OrderedDict()

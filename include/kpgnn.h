@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define KPGNN_ABI_VERSION 2
+#define KPGNN_ABI_VERSION 3
 
 const char* kp_last_error(void);
 int kp_abi_version(void);
@@ -181,6 +181,11 @@ typedef struct {
   int64_t *nbt1, *nbt2, *nbt3;                      /* num_batches_tracked (incremented) or NULL */
   float *Y1, *Y2, *Z2;                              /* saved for backward: y1, y2 [N,Cout]; z2 (only with BN3) */
   float* stats;                                     /* [6,Cout]: mean1, invstd1, mean2, invstd2, mean3, invstd3 */
+  /* Row strides in elements (0 = Cout): `out` and R may be column blocks of a wider matrix -- the layer-history
+   * buffer [N, L+1, H] of kpgnn_b200/stack.py -- and so may dOut in the backward.  dR (backward only, may be NULL):
+   * the residual's gradient is ACCUMULATED there, dR[row] += dOut[row], instead of being returned to the caller. */
+  int64_t out_stride, r_stride, dout_stride, dr_stride;
+  float* dR;
 } kp_dense_desc;
 
 int kp_dense_block_max_rows(int32_t Cin, int32_t Cout);
@@ -192,6 +197,19 @@ int kp_dense_block_forward(const kp_dense_desc* desc, float* out, void* workspac
 int kp_dense_block_backward(const kp_dense_desc* desc, const float* dOut, float* dX, float* dW1, float* db1,
                             float* dW2, float* db2, float* dbn, void* workspace, size_t workspace_bytes,
                             void* stream);
+
+/* Gradient of the peripheral term shared by the L layers of a KP-GIN+ stack (models/GNNs.py:393-400,429): layer l
+ * adds P[:, :k_l] after its activation and combines hops with theta_l (combine.py:43-47), so
+ *     dP[v,h,:] = sum over layers l with k_l > h of theta_l[h,:] * dAgg_l[v,:]        (theta_l == NULL: weight 1)
+ * where dAgg_l [N,d] is the gradient w.r.t. layer l's aggregation output.  One kernel instead of L zero-padded
+ * slices and L-1 accumulations of [N,K,d] tensors. */
+typedef struct {
+  int32_t N, K, d, L;
+  const float* dagg[32];
+  const float* theta[32];           /* [k_l, d] or NULL */
+  int32_t k[32];
+} kp_pgrad_desc;
+int kp_peripheral_grad(const kp_pgrad_desc* desc, float* dP, void* stream);
 
 /* GeometricCombine weights, layers/combine.py:51-58: theta[h,c] = softmax over h of a_c (1-a_c)^h with
  * a = sigmoid(alphas); theta is [K,d].  Backward returns d(loss)/d(alphas) from d(loss)/d(theta). */

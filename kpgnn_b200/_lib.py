@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # KPGNN_B200_LIB points at an alternative build of the same library (kernel tuning experiments)
 LIB_PATH = os.environ.get("KPGNN_B200_LIB") or os.path.join(_HERE, "libkpgnn_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class KpError(RuntimeError):
@@ -59,7 +59,14 @@ class DenseDesc(C.Structure):
                 ("rm1", C.c_void_p), ("rv1", C.c_void_p), ("rm2", C.c_void_p), ("rv2", C.c_void_p),
                 ("rm3", C.c_void_p), ("rv3", C.c_void_p),
                 ("nbt1", C.c_void_p), ("nbt2", C.c_void_p), ("nbt3", C.c_void_p),
-                ("Y1", C.c_void_p), ("Y2", C.c_void_p), ("Z2", C.c_void_p), ("stats", C.c_void_p)]
+                ("Y1", C.c_void_p), ("Y2", C.c_void_p), ("Z2", C.c_void_p), ("stats", C.c_void_p),
+                ("out_stride", C.c_int64), ("r_stride", C.c_int64), ("dout_stride", C.c_int64),
+                ("dr_stride", C.c_int64), ("dR", C.c_void_p)]
+
+
+class PgradDesc(C.Structure):
+    _fields_ = [("N", C.c_int32), ("K", C.c_int32), ("d", C.c_int32), ("L", C.c_int32),
+                ("dagg", C.c_void_p * 32), ("theta", C.c_void_p * 32), ("k", C.c_int32 * 32)]
 
 
 ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
@@ -96,6 +103,7 @@ _SIGNATURES = {
     "kp_dense_block_forward": (C.c_int, [C.POINTER(DenseDesc), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "kp_dense_block_backward": (C.c_int, [C.POINTER(DenseDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "kp_peripheral_grad": (C.c_int, [C.POINTER(PgradDesc), C.c_void_p, C.c_void_p]),
     "kp_geometric_theta_forward": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "kp_geometric_theta_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                               C.c_void_p]),

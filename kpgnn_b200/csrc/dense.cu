@@ -440,16 +440,17 @@ dense_block_fwd_kernel(const kp_dense_desc m, float* __restrict__ out, float* __
   }
   const float* res = m.g3 ? Y : Z;
   {
-    float* dst = out + (size_t)r0 * Co;
-    const float* rsd = m.R ? m.R + (size_t)r0 * Co : nullptr;
-    for (int i = threadIdx.x * 4; i < nr * Co; i += DB_THREADS * 4) {
-      float4 v = *reinterpret_cast<const float4*>(res + i);
-      if (rsd) {
-        const float4 q = __ldg(reinterpret_cast<const float4*>(rsd + i));
-        v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+    const size_t so = m.out_stride ? (size_t)m.out_stride : (size_t)Co, sr = m.r_stride ? (size_t)m.r_stride : (size_t)Co;
+    const int warp = threadIdx.x >> 5, c = (threadIdx.x & 31) * 4;
+    if (c < Co)
+      for (int r = warp; r < nr; r += DB_WARPS) {
+        float4 v = *reinterpret_cast<const float4*>(res + r * Co + c);
+        if (m.R) {
+          const float4 q = __ldg(reinterpret_cast<const float4*>(m.R + (size_t)(r0 + r) * sr + c));
+          v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+        }
+        *reinterpret_cast<float4*>(out + (size_t)(r0 + r) * so + c) = v;
       }
-      *reinterpret_cast<float4*>(dst + i) = v;
-    }
   }
   DB_T(16);
   DB_T_PRINT(17, "fwd load gemm1 stats1 bar1 merge1 apply1 gemm2 stats2 bar2 merge2 apply2 stats3 bar3 merge3 apply3 out");
@@ -620,7 +621,15 @@ dense_block_bwd_kernel(const kp_dense_desc m, const float* __restrict__ dOut, fl
   const float* mean3 = m.stats + 4 * Co, *istd3 = m.stats + 5 * Co;
 
   // every slab and both weight matrices are requested now, asynchronously: one round trip to L2 / HBM
-  db_cp_slab(dOut, r0, nr, Rp, Co, D);
+  {
+    const size_t sd = m.dout_stride ? (size_t)m.dout_stride : (size_t)Co;
+    const int warp = threadIdx.x >> 5, c = (threadIdx.x & 31) * 4;
+    if (c < Co)
+      for (int r = warp; r < Rp; r += DB_WARPS) {
+        if (r < nr) db_cp16(D + r * Co + c, dOut + (size_t)(r0 + r) * sd + c);
+        else *reinterpret_cast<float4*>(D + r * Co + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+  }
   if (m.g3) db_cp_slab(m.Z2, r0, nr, Rp, Co, X3);
   db_cp_slab(m.Y2, r0, nr, Rp, Co, X2);
   db_cp_slab(m.Y1, r0, nr, Rp, Co, X1);
@@ -631,6 +640,18 @@ dense_block_bwd_kernel(const kp_dense_desc m, const float* __restrict__ dOut, fl
   db_cp_wait_all();
   __syncthreads();
   DB_T(1);
+  if (m.dR) {                                   // residual: dR[row] += dOut[row] (rows are owned by exactly one CTA)
+    const size_t sr = m.dr_stride ? (size_t)m.dr_stride : (size_t)Co;
+    const int warp = threadIdx.x >> 5, c = (threadIdx.x & 31) * 4;
+    if (c < Co)
+      for (int r = warp; r < nr; r += DB_WARPS) {
+        float4* p = reinterpret_cast<float4*>(m.dR + (size_t)(r0 + r) * sr + c);
+        float4 a = *p;
+        const float4 g = *reinterpret_cast<const float4*>(D + r * Co + c);
+        a.x += g.x; a.y += g.y; a.z += g.z; a.w += g.w;
+        *p = a;
+      }
+  }
   unsigned phase = 0;
   // x-hats of the three BatchNorms and z1, while nothing else can proceed anyway
   if (m.g3) db_xhat(X3, Co, Rp, mean3, istd3, X3);
@@ -802,6 +823,10 @@ static int db_config(const kp_dense_desc& m, DbCfg* c) {
                    m.Cout <= 128 && m.Cin <= m.Cout,
                "kp_dense_block: need N >= 2, channels multiples of 4, Cin <= Cout <= 128 (got N=%d Cin=%d Cout=%d)",
                m.N, m.Cin, m.Cout);
+  KP_CHECK_ARG(m.out_stride % 4 == 0 && m.r_stride % 4 == 0 && m.dout_stride % 4 == 0 && m.dr_stride % 4 == 0 &&
+                   m.out_stride >= 0 && m.r_stride >= 0 && m.dout_stride >= 0 && m.dr_stride >= 0 &&
+                   (((uintptr_t)m.dR) & 15) == 0,
+               "kp_dense_block: row strides must be non-negative multiples of 4 elements");
   const int rcmax = db_max_rc(m.Cin, m.Cout);
   KP_CHECK_ARG(rcmax > 0 && (long long)m.N <= (long long)rcmax * DB_MAX_GRID,
                "kp_dense_block: N=%d exceeds kp_dense_block_max_rows", m.N);

@@ -302,3 +302,56 @@ int kp_geometric_theta_backward(const float* alphas, const float* theta, const f
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------
+// kp_peripheral_grad: dP[v,h,:] = sum_{l: k_l > h} theta_l[h,:] * dAgg_l[v,:]   (see include/kpgnn.h)
+// thread per (node, 4 channels): the L gradients are read once into registers, the K hop rows written once.
+// ------------------------------------------------------------------------------------------------------------
+namespace kp {
+
+template <int LMAX>
+__global__ void __launch_bounds__(256) pgrad_kernel(const kp_pgrad_desc p, float* __restrict__ dP) {
+  const int c4n = p.d >> 2;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)p.N * c4n) return;
+  const int v = (int)(i / c4n), c = (int)(i - (long long)v * c4n) * 4;
+  float4 g[LMAX];
+#pragma unroll
+  for (int l = 0; l < LMAX; ++l) {
+    g[l] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (l < p.L) g[l] = __ldg(reinterpret_cast<const float4*>(p.dagg[l] + (size_t)v * p.d + c));
+  }
+  for (int h = 0; h < p.K; ++h) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int l = 0; l < LMAX; ++l) {
+      if (l < p.L && p.k[l] > h) {
+        float4 t = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (p.theta[l]) t = __ldg(reinterpret_cast<const float4*>(p.theta[l] + (size_t)h * p.d + c));
+        s.x = fmaf(t.x, g[l].x, s.x); s.y = fmaf(t.y, g[l].y, s.y);
+        s.z = fmaf(t.z, g[l].z, s.z); s.w = fmaf(t.w, g[l].w, s.w);
+      }
+    }
+    *reinterpret_cast<float4*>(dP + ((size_t)v * p.K + h) * p.d + c) = s;
+  }
+}
+
+}  // namespace kp
+
+extern "C" int kp_peripheral_grad(const kp_pgrad_desc* desc, float* dP, void* stream) {
+  KP_CHECK_ARG(desc && dP, "kp_peripheral_grad: null argument");
+  const kp_pgrad_desc& p = *desc;
+  KP_CHECK_ARG(p.N >= 0 && p.K >= 1 && p.d >= 4 && p.d % 4 == 0 && p.L >= 1 && p.L <= 32,
+               "kp_peripheral_grad: need d %% 4 == 0, 1 <= L <= 32 (got d=%d L=%d)", p.d, p.L);
+  for (int l = 0; l < p.L; ++l)
+    KP_CHECK_ARG(p.dagg[l] && p.k[l] >= 1 && p.k[l] <= p.K && (((uintptr_t)p.dagg[l] | (uintptr_t)p.theta[l]) & 15) == 0,
+                 "kp_peripheral_grad: layer %d: null / misaligned gradient or bad hop count", l);
+  KP_CHECK_ARG(((uintptr_t)dP & 15) == 0, "kp_peripheral_grad: dP must be 16-byte aligned");
+  if (p.N == 0) return 0;
+  const long long n = (long long)p.N * (p.d >> 2);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p.L <= 8) KP_LAUNCH(kp::pgrad_kernel<8>, kp::ceil_div(n, 256), 256, 0, st, p, dP);
+  else if (p.L <= 16) KP_LAUNCH(kp::pgrad_kernel<16>, kp::ceil_div(n, 256), 256, 0, st, p, dP);
+  else KP_LAUNCH(kp::pgrad_kernel<32>, kp::ceil_div(n, 256), 256, 0, st, p, dP);
+  return 0;
+}

@@ -146,6 +146,9 @@ class KPGNNPlusBackbone(nn.Module):
         x = self.input_embedding(data)
         N = x.size(0)
         P = self.peripheral(data, N, x)
+        fused = self._forward_stack(data, x, P)
+        if fused is not None:
+            return fused
         h_list = [x]
         last_h = x
         for l in range(self.num_layer):
@@ -178,6 +181,36 @@ class KPGNNPlusBackbone(nn.Module):
         else:
             raise ValueError("JK=%r not supported by this backbone" % (self.JK,))
         return self.output_proj(rep)
+
+    use_stack = True          # tests switch this off to compare against the layer-by-layer path
+
+    def _forward_stack(self, data, x, P):
+        """All layers as one autograd node over a layer-history buffer (kpgnn_b200/stack.py); None if not applicable."""
+        from .stack import kpginplus_stack, stack_applicable
+        from .layers._base import _all_zero, SplitKLinear  # noqa: F401
+        from .layers._base import _SplitKLinearFn
+        from .plan import get_plan
+        if not (self.use_stack and self.training and self.JK in ("concat", "last") and P is not None and x.is_cuda):
+            return None
+        pe_zero = data.pe_attr is None or data.pe_attr.numel() == 0 or _all_zero(data.pe_attr)
+        norms = [n.module for n in self.norms]
+        if data.edge_attr.dim() != 2 or data.edge_attr.size(1) != self.K:
+            return None
+        plan, _ = get_plan(data.edge_index, data.edge_attr, x.size(0))
+        if not stack_applicable(self.gnns, norms, x, P, plan, pe_zero, self.dropout.p):
+            return None
+        Hn = kpginplus_stack(self.gnns, norms, x, P, plan, self.residual)      # [N, L+1, H], slot L-j = h_j
+        lin = self.output_proj[0]
+        if self.JK == "last":
+            return self.output_proj(Hn[:, 0])
+        H, L1 = self.hidden_size, self.num_layer + 1
+        # JK concat (GNNs.py:455): Hn viewed [N, (L+1)H] holds the layer outputs newest first, so the projection's
+        # column blocks are flipped instead of the activations
+        Wf = lin.weight.view(lin.out_features, L1, H).flip(1).reshape(lin.out_features, L1 * H)
+        rep = _SplitKLinearFn.apply(Hn.view(x.size(0), L1 * H), Wf, lin.bias)
+        for m in list(self.output_proj)[1:]:
+            rep = m(rep)
+        return rep
 
 
 class KPGNNPlusRegressor(nn.Module):

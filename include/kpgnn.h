@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define KPGNN_ABI_VERSION 3
+#define KPGNN_ABI_VERSION 4
 
 const char* kp_last_error(void);
 int kp_abi_version(void);
@@ -186,6 +186,10 @@ typedef struct {
    * the residual's gradient is ACCUMULATED there, dR[row] += dOut[row], instead of being returned to the caller. */
   int64_t out_stride, r_stride, dout_stride, dr_stride;
   float* dR;
+  /* Optional persistent grid-barrier state: 256 bytes of device memory, zeroed ONCE by the caller and used by one
+   * stream at a time; every launch leaves it zero again, so no memset node precedes the kernel.  NULL: the first
+   * 256 bytes of the workspace are used and cleared by a cudaMemsetAsync before each launch. */
+  uint32_t* barrier;
 } kp_dense_desc;
 
 int kp_dense_block_max_rows(int32_t Cin, int32_t Cout);
@@ -210,6 +214,20 @@ typedef struct {
   int32_t k[32];
 } kp_pgrad_desc;
 int kp_peripheral_grad(const kp_pgrad_desc* desc, float* dP, void* stream);
+
+/* Adam over a list of tensors in ONE launch (torch.optim.Adam semantics, no amsgrad / weight decay; the reference
+ * trains with torch.optim.Adam(lr), train_ZINC.py:244).  `tensors_dev` is a device array describing every tensor,
+ * `chunks_dev` a device array of (tensor index, element offset) pairs, one per 1024-element chunk; `state_dev` two
+ * device ints {steps taken, scratch}, zero-initialised by the caller, advanced by the kernel (graph-replay safe). */
+typedef struct {
+  float* p;
+  const float* g;
+  float* m;
+  float* v;
+  int32_t n, pad;
+} kp_adam_tensor;
+int kp_adam_step(const kp_adam_tensor* tensors_dev, const int32_t* chunks_dev, int32_t nchunks, float lr, double beta1,
+                 double beta2, float eps, int32_t* state_dev, void* stream);   /* betas in double: 1-beta is formed exactly */
 
 /* GeometricCombine weights, layers/combine.py:51-58: theta[h,c] = softmax over h of a_c (1-a_c)^h with
  * a = sigmoid(alphas); theta is [K,d].  Backward returns d(loss)/d(alphas) from d(loss)/d(theta). */

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # KPGNN_B200_LIB points at an alternative build of the same library (kernel tuning experiments)
 LIB_PATH = os.environ.get("KPGNN_B200_LIB") or os.path.join(_HERE, "libkpgnn_b200.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class KpError(RuntimeError):
@@ -61,7 +61,7 @@ class DenseDesc(C.Structure):
                 ("nbt1", C.c_void_p), ("nbt2", C.c_void_p), ("nbt3", C.c_void_p),
                 ("Y1", C.c_void_p), ("Y2", C.c_void_p), ("Z2", C.c_void_p), ("stats", C.c_void_p),
                 ("out_stride", C.c_int64), ("r_stride", C.c_int64), ("dout_stride", C.c_int64),
-                ("dr_stride", C.c_int64), ("dR", C.c_void_p)]
+                ("dr_stride", C.c_int64), ("dR", C.c_void_p), ("barrier", C.c_void_p)]
 
 
 class PgradDesc(C.Structure):
@@ -103,6 +103,8 @@ _SIGNATURES = {
     "kp_dense_block_forward": (C.c_int, [C.POINTER(DenseDesc), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "kp_dense_block_backward": (C.c_int, [C.POINTER(DenseDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "kp_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_double, C.c_double, C.c_float,
+                               C.c_void_p, C.c_void_p]),
     "kp_peripheral_grad": (C.c_int, [C.POINTER(PgradDesc), C.c_void_p, C.c_void_p]),
     "kp_geometric_theta_forward": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "kp_geometric_theta_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
@@ -135,6 +137,22 @@ def lib():
             raise KpError("libkpgnn_b200.so ABI %d != expected %d; rebuild" % (handle.kp_abi_version(), ABI_VERSION))
         _lib = handle
     return _lib
+
+
+_BARRIERS = {}
+
+
+def barrier_state(device):
+    """Persistent zero-initialised grid-barrier state for kp_dense_block_* on `device` (one per stream in use)."""
+    import torch
+    key = (device.index if device.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream(device).cuda_stream if not torch.cuda.is_current_stream_capturing() else -1)
+    key = key[0]
+    t = _BARRIERS.get(key)
+    if t is None:
+        t = torch.zeros(64, dtype=torch.int32, device=device)
+        _BARRIERS[key] = t
+    return t
 
 
 def check(rc, what):

@@ -454,6 +454,10 @@ dense_block_fwd_kernel(const kp_dense_desc m, float* __restrict__ out, float* __
   }
   DB_T(16);
   DB_T_PRINT(17, "fwd load gemm1 stats1 bar1 merge1 apply1 gemm2 stats2 bar2 merge2 apply2 stats3 bar3 merge3 apply3 out");
+  if (threadIdx.x == 0 && atomicAdd(bar + 1, 1u) == gridDim.x - 1) {   // every CTA is past its last barrier: leave zeros
+    bar[0] = 0u;
+    bar[1] = 0u;
+  }
   // saved + running statistics: by the last CTA (the shortest slab), off everybody's critical path
   if (blockIdx.x == grid - 1) {
     db_publish_stats(st, st + Co, st + 2 * Co, N, Co, m.mom1, m.rm1, m.rv1, (long long*)m.nbt1, m.stats, m.stats + Co);
@@ -790,6 +794,10 @@ dense_block_bwd_kernel(const kp_dense_desc m, const float* __restrict__ dOut, fl
       if (ok && sub == 0) *reinterpret_cast<float4*>(dst) = s;
     }
   }
+  if (threadIdx.x == 0 && atomicAdd(bar + 1, 1u) == gridDim.x - 1) {
+    bar[0] = 0u;
+    bar[1] = 0u;
+  }
   DB_T(14);
   DB_T_PRINT(15, "bwd load xhat bn3 mask2+dots2+bar merge2+apply2 gemm_dz1 mask1+dots1 dW2+colsum wait merge1+apply1 gemm_dX dW1+colsum store+bar... reduce");
 }
@@ -885,11 +893,12 @@ int kp_dense_block_forward(const kp_dense_desc* desc, float* out, void* workspac
   KP_CHECK_ARG(workspace_bytes >= c.ws_fwd && (((uintptr_t)workspace | (uintptr_t)out) & 15) == 0,
                "kp_dense_block_forward: workspace too small or misaligned");
   cudaStream_t st = (cudaStream_t)stream;
-  KP_CUDA(cudaMemsetAsync(workspace, 0, 256, st));
+  unsigned* bar = m.barrier ? (unsigned*)m.barrier : (unsigned*)workspace;
+  if (!m.barrier) KP_CUDA(cudaMemsetAsync(workspace, 0, 256, st));
   KP_CUDA(cudaFuncSetAttribute(kp::dense_block_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)c.smem_fwd));
   KP_LAUNCH(kp::dense_block_fwd_kernel, c.grid, kp::DB_THREADS, c.smem_fwd, st, m, out,
-            (float*)((char*)workspace + 256), (unsigned*)workspace, c.Rc);
+            (float*)((char*)workspace + 256), bar, c.Rc);
   return 0;
 }
 
@@ -907,11 +916,12 @@ int kp_dense_block_backward(const kp_dense_desc* desc, const float* dOut, float*
                      (uintptr_t)dW2 | (uintptr_t)db2 | (uintptr_t)dbn) & 15) == 0,
                "kp_dense_block_backward: workspace too small or pointers misaligned");
   cudaStream_t st = (cudaStream_t)stream;
-  KP_CUDA(cudaMemsetAsync(workspace, 0, 256, st));
+  unsigned* bar = m.barrier ? (unsigned*)m.barrier : (unsigned*)workspace;
+  if (!m.barrier) KP_CUDA(cudaMemsetAsync(workspace, 0, 256, st));
   KP_CUDA(cudaFuncSetAttribute(kp::dense_block_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)c.smem_bwd));
   KP_LAUNCH(kp::dense_block_bwd_kernel, c.grid, kp::DB_THREADS, c.smem_bwd, st, m, dOut, dX, dW1, db1, dW2, db2, dbn,
-            (float*)((char*)workspace + 256), (unsigned*)workspace, c.Rc);
+            (float*)((char*)workspace + 256), bar, c.Rc);
   return 0;
 }
 

@@ -48,6 +48,7 @@ class _DenseBlock(torch.autograd.Function):
         d.Z2 = saved[2].data_ptr() if g3 is not None else None
         d.stats = stats.data_ptr()
         out = torch.empty((N, Cout), dtype=torch.float32, device=dev)
+        d.barrier = _lib.barrier_state(dev).data_ptr()
         fb, bb = C.c_size_t(0), C.c_size_t(0)
         _lib.check(lib.kp_dense_block_workspace_bytes(C.byref(d), C.byref(fb), C.byref(bb)), "kp_dense_block ws")
         ws = torch.empty(fb.value, dtype=torch.uint8, device=dev)

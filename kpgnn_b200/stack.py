@@ -91,6 +91,7 @@ class _KPGINPlusStack(torch.autograd.Function):
             stats = torch.empty((6, H), dtype=torch.float32, device=dev)
             d.Y1, d.Y2, d.Z2, d.stats = keep[0].data_ptr(), keep[1].data_ptr(), keep[2].data_ptr(), stats.data_ptr()
             out = Hn[:, L - l - 1]
+            d.barrier = _lib.barrier_state(dev).data_ptr()
             d.out_stride = hs
             if residual:
                 d.R, d.r_stride = Hn[:, L - l].data_ptr(), hs

@@ -161,11 +161,10 @@ class Trainer(object):
         return n
 
     def _zero(self):
-        if self.grads is not None:
-            self.grads.zero_()
-        else:
-            for p in self.params:
-                p.grad = None
+        # autograd hands every gradient tensor over (no per-parameter accumulate kernels); with world > 1 they are
+        # packed into the flat all-reduce buffer by one concatenation after backward
+        for p in self.params:
+            p.grad = None
 
     def _step(self):
         from kpgnn_b200.model import l1_loss
@@ -173,6 +172,7 @@ class Trainer(object):
         loss = l1_loss(self.model(self.dev), self.dev.y)
         loss.backward()
         if self.grads is not None:
+            self.grads.gather_()
             self.grads.allreduce_mean_(self.world)             # one NCCL all-reduce per step over NVLink
         self.opt.step()
         return loss.detach()
@@ -182,6 +182,8 @@ class Trainer(object):
         self._zero()
         loss = l1_loss(self.model(self.dev), self.dev.y)
         loss.backward()
+        if self.grads is not None:
+            self.grads.gather_()
         return loss.detach()
 
     def capture(self):

@@ -38,6 +38,27 @@ class FlatGradients(object):
     def zero_(self):
         self.flat.zero_()
 
+    def release(self):
+        """Gather mode: let autograd hand over fresh gradient tensors (no per-parameter accumulate kernel) ..."""
+        for p in self.params:
+            p.grad = None
+
+    def gather_(self):
+        """... and pack them into the flat buffer with ONE concatenation after backward; parameters without a gradient
+        contribute zeros.  Leaves every p.grad as a view of the flat buffer again (what the optimizer reads)."""
+        pieces = []
+        o = 0
+        for p in self.params:
+            g = p.grad
+            pieces.append(g.reshape(-1) if g is not None else self.flat.new_zeros(p.numel()))
+            o += p.numel()
+        torch.cat(pieces, out=self.flat)
+        o = 0
+        for p in self.params:
+            p.grad = self.flat[o:o + p.numel()].view_as(p)
+            o += p.numel()
+        return self.flat
+
     def allreduce_mean_(self, world=None):
         """Sum over ranks, divide by the world size (loss = per-rank mean => global mean for equal shards)."""
         if world is None:

@@ -53,6 +53,20 @@ def test_two_rank_flat_allreduce_matches_single_process(tmp_path):
     assert torch.allclose(got, fg.flat, atol=1e-6)
 
 
+def test_gather_mode_equals_view_mode():
+    g = torch.Generator().manual_seed(2)
+    X, y = torch.randn(8, 6, generator=g), torch.randn(8, generator=g)
+    a, b = _model(), _model()
+    fa, fb = FlatGradients(a.parameters()), FlatGradients(b.parameters())
+    fa.zero_()
+    (a(X).squeeze() - y).abs().mean().backward()
+    fb.release()
+    (b(X).squeeze() - y).abs().mean().backward()
+    fb.gather_()
+    assert torch.equal(fa.flat, fb.flat)
+    assert all(p.grad.data_ptr() >= fb.flat.data_ptr() for p in b.parameters())
+
+
 def test_shards_are_contiguous_and_cover():
     items = list(range(11))
     parts = [shard_graphs(items, r, 4) for r in range(4)]

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define KPGNN_ABI_VERSION 4
+#define KPGNN_ABI_VERSION 5
 
 const char* kp_last_error(void);
 int kp_abi_version(void);
@@ -95,6 +95,12 @@ typedef struct {
   int32_t amax0, amaxk;            /* largest attr16 value present in hop 0 / in hops >= 1 of the plan
                                       (kp_plan_count stats[1], stats[2]); -1 = not supplied.  Backward only: selects
                                       the register-accumulator table-gradient kernel when both are <= 31 */
+  /* Backward only: dX row (v,h) lives at dX + v*dx_node_stride + h*dx_hop_stride (elements, multiples of 4; 0 = the
+   * contiguous [N,k,d] layout) and, with dx_accumulate, is ADDED to instead of written -- the layer-history gradient
+   * buffer of kpgnn_b200/stack.py.  Served by the lean gather kernel only: kp_agg_backward returns 3 (and touches
+   * nothing) when another kernel family would have to run, and the caller falls back to a temporary. */
+  int64_t dx_node_stride, dx_hop_stride;
+  int32_t dx_accumulate, pad0;
 } kp_agg_desc;
 
 int kp_agg_forward(const kp_agg_desc* desc, float* out, void* stream);

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # KPGNN_B200_LIB points at an alternative build of the same library (kernel tuning experiments)
 LIB_PATH = os.environ.get("KPGNN_B200_LIB") or os.path.join(_HERE, "libkpgnn_b200.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class KpError(RuntimeError):
@@ -30,7 +30,9 @@ class AggDesc(C.Structure):
                 ("P", C.c_void_p), ("p_node_stride", C.c_int64), ("p_hop_stride", C.c_int64),
                 ("T0", C.c_void_p), ("Tk", C.c_void_p), ("rows0", C.c_int32), ("rowsk", C.c_int32),
                 ("theta", C.c_void_p), ("eps", C.c_void_p), ("act", C.c_int32), ("fuse", C.c_int32),
-                ("amax0", C.c_int32), ("amaxk", C.c_int32)]
+                ("amax0", C.c_int32), ("amaxk", C.c_int32),
+                ("dx_node_stride", C.c_int64), ("dx_hop_stride", C.c_int64),
+                ("dx_accumulate", C.c_int32), ("pad0", C.c_int32)]
 
 
 class ExtractInput(C.Structure):

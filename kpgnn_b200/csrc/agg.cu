@@ -781,6 +781,15 @@ int kp_agg_backward(const kp_agg_desc* desc, const float* dOut, float* dX, float
   KP_CHECK_ARG(workspace_bytes >= w.total && (workspace || w.total == 0), "kp_agg_backward: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   const size_t tn = (size_t)(a.rows0 + a.rowsk) * a.d;
+  if (dX && (a.dx_node_stride || a.dx_hop_stride || a.dx_accumulate)) {
+    // strided / accumulated dX: lean gather kernel only; refuse before anything is launched
+    const bool lean = c.fast && !c.fextra && kp::fast_lean_enabled() && (c.fG == 32 || c.fG == 16) && a.k + 1 <= c.fG;
+    if (!lean || a.dx_node_stride % 4 || a.dx_hop_stride % 4 || a.dx_node_stride < 0 || a.dx_hop_stride < 0 ||
+        (unsigned long long)a.N * (unsigned long long)(a.dx_node_stride ? a.dx_node_stride : a.k * a.d) >= 0xffffffffull) {
+      kp::set_error("kp_agg_backward: strided / accumulated dX is only available on the lean gather kernel");
+      return 3;
+    }
+  }
   if (a.N == 0) {
     if (dT0) KP_CUDA(cudaMemsetAsync(dT0, 0, sizeof(float) * (size_t)a.rows0 * a.d, st));
     if (dTk) KP_CUDA(cudaMemsetAsync(dTk, 0, sizeof(float) * (size_t)a.rowsk * a.d, st));

@@ -35,6 +35,10 @@ enum { TAB_NONE = 0, TAB_SMEM = 1, TAB_GLOBAL = 2 };
 struct FastArgs {
   kp_agg_desc d;
   unsigned xs, xh, ps, ph;   // element strides of X and P (host-validated: every offset < 2^32)
+  // unfused [N,k,d] output of the lean kernel (forward without combine, and B2's dX): node / hop strides in elements
+  // (0 = contiguous) and accumulate-into instead of overwrite (dX of the layer-history buffer, kpgnn_b200/stack.py)
+  unsigned os = 0, oh = 0;
+  int oacc = 0;
 };
 
 __device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }

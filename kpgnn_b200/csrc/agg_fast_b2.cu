@@ -17,6 +17,10 @@ int fast_b2(const FastArgs& fa, int G, bool fuse, bool extra, int grid, const fl
             cudaStream_t st) {
   int rc = 0;
   if (!extra && lean_b2(fa, G, Gs, dX, st, &rc)) return rc;
+  if (fa.d.dx_node_stride || fa.d.dx_hop_stride || fa.d.dx_accumulate) {
+    set_error("kp_agg_backward: strided / accumulated dX is only available on the lean gather kernel");
+    return 3;
+  }
   return G == 32 ? launch<32>(fa, fuse, extra, grid, Gs, dOut, dX, st)
          : G == 16 ? launch<16>(fa, fuse, extra, grid, Gs, dOut, dX, st)
          : G == 8 ? launch<8>(fa, fuse, extra, grid, Gs, dOut, dX, st)

@@ -97,6 +97,9 @@ bool lean_b2(const FastArgs& fa, int G, const float* Gs, float* dX, cudaStream_t
   t.xs = (unsigned)(a.k * a.d);
   t.xh = (unsigned)a.d;
   t.ps = t.ph = 0;
+  t.os = (unsigned)a.dx_node_stride;
+  t.oh = (unsigned)a.dx_hop_stride;
+  t.oacc = a.dx_accumulate;
   *rc = (G == 32) ? launch_lean<32, KP_ACT_NONE, false, TAB_NONE, false>(t, 0, 0, dX, st)
                   : launch_lean<16, KP_ACT_NONE, false, TAB_NONE, false>(t, 0, 0, dX, st);
   return true;

@@ -303,7 +303,7 @@ agg_fwd_lean_kernel(const FastArgs fa, float* __restrict__ out, unsigned pf_x_li
     // ---- this node
     const float* Xh = Xc;                                        // + h * xh per hop
     const float* Pv = Pc + (size_t)v * fa.ps;
-    float* outv = out + (FUSE ? (size_t)v * d : (size_t)v * k * d) + c;
+    float* outv = out + (FUSE ? (size_t)v * d : (size_t)v * (fa.os ? fa.os : (unsigned)(k * d))) + c;
     P4 o = p4zero();
     unsigned ent = win_sh;                                       // byte address of the segment's first entry
     unsigned th = theta_sh;
@@ -428,8 +428,10 @@ agg_fwd_lean_kernel(const FastArgs fa, float* __restrict__ out, unsigned pf_x_li
         const P4 t = lds4p(th);
         o.lo = fma2(t.lo, z.lo, o.lo); o.hi = fma2(t.hi, z.hi, o.hi);
         th += d4;
-      } else {
-        if (active) stg4p_stream(outv + h * d, z);
+      } else if (active) {
+        float* po = outv + (size_t)h * (fa.oh ? fa.oh : (unsigned)d);
+        if (fa.oacc) z = add4p(z, ldg4p(po));
+        stg4p_stream(po, z);
       }
       Xh += fa.xh;
       Pv += fa.ph;

@@ -135,18 +135,28 @@ class _KPGINPlusStack(torch.autograd.Function):
                                                    dW1.data_ptr(), dvec[0].data_ptr(), dW2.data_ptr(),
                                                    dvec[1].data_ptr(), dvec[2].data_ptr(), ws.data_ptr(), ws.numel(),
                                                    st), "kp_dense_block_backward")
-            dX = torch.empty((N, k, H), dtype=torch.float32, device=dev)
             dT0 = torch.empty_like(T0)
             dTk = torch.empty_like(Tk) if Tk is not None else None
             dth = torch.empty_like(theta) if theta is not None else None
             nb = C.c_size_t(0)
             _lib.check(lib.kp_agg_backward_workspace_bytes(C.byref(adesc), C.byref(nb)), "kp_agg_backward ws")
             ws2 = torch.empty(max(nb.value, 1), dtype=torch.uint8, device=dev)
-            _lib.check(lib.kp_agg_backward(C.byref(adesc), dagg.data_ptr(), dX.data_ptr(), None, dT0.data_ptr(),
+
+            def agg_bwd(dx_ptr):
+                return lib.kp_agg_backward(C.byref(adesc), dagg.data_ptr(), dx_ptr, None, dT0.data_ptr(),
                                            dTk.data_ptr() if dTk is not None else None,
                                            dth.data_ptr() if dth is not None else None, None, ws2.data_ptr(),
-                                           ws2.numel(), st), "kp_agg_backward")
-            G[:, L - l:L - l + k].add_(dX)
+                                           ws2.numel(), st)
+            # dX is accumulated straight into the history gradient (slots L-l .. L-l+k-1) by the gather kernel ...
+            adesc.dx_node_stride, adesc.dx_hop_stride, adesc.dx_accumulate = hs, H, 1
+            rc = agg_bwd(G[:, L - l].data_ptr())
+            if rc == 3:                 # ... unless another kernel family has to serve this call: temporary + add
+                adesc.dx_node_stride, adesc.dx_hop_stride, adesc.dx_accumulate = 0, 0, 0
+                dX = torch.empty((N, k, H), dtype=torch.float32, device=dev)
+                _lib.check(agg_bwd(dX.data_ptr()), "kp_agg_backward")
+                G[:, L - l:L - l + k].add_(dX)
+            else:
+                _lib.check(rc, "kp_agg_backward")
             dal = None
             if theta is not None:
                 dal = torch.empty_like(alphas)

@@ -80,3 +80,13 @@ def test_stack_deterministic(lib):
         res.append([p.grad.clone() for p in mm.parameters() if p.grad is not None])
     for x, y in zip(*res):
         assert torch.equal(x, y)
+
+
+def test_stack_on_generic_kernels(lib):
+    """With the generic kernel family forced, the strided / accumulated dX is refused (rc 3) and the stack falls back
+    to a temporary + add; results still match the layer-by-layer path."""
+    lib.kp_agg_set_force_generic(1)
+    try:
+        test_stack_matches_layerwise(lib, (3, 4, "concat", True))
+    finally:
+        lib.kp_agg_set_force_generic(0)

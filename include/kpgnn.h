@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define KPGNN_ABI_VERSION 5
+#define KPGNN_ABI_VERSION 6
 
 const char* kp_last_error(void);
 int kp_abi_version(void);
@@ -101,6 +101,11 @@ typedef struct {
    * nothing) when another kernel family would have to run, and the caller falls back to a temporary. */
   int64_t dx_node_stride, dx_hop_stride;
   int32_t dx_accumulate, pad0;
+  /* Backward only, with fuse: when both are non-NULL the reduction of the per-CTA dtheta partials is fused with
+   * GeometricCombine's backward (combine.py:51-58): geo_dalphas [d] receives d(loss)/d(alphas) for theta =
+   * kp_geometric_theta_forward(geo_alphas); the dtheta argument of kp_agg_backward may then be NULL. */
+  const float* geo_alphas;
+  float* geo_dalphas;
 } kp_agg_desc;
 
 int kp_agg_forward(const kp_agg_desc* desc, float* out, void* stream);
@@ -240,6 +245,14 @@ int kp_adam_step(const kp_adam_tensor* tensors_dev, const int32_t* chunks_dev, i
 int kp_geometric_theta_forward(const float* alphas, int32_t K, int32_t d, float* theta, void* stream);
 int kp_geometric_theta_backward(const float* alphas, const float* theta, const float* dtheta, int32_t K, int32_t d,
                                 float* dalphas, void* stream);
+/* The combine weights of up to 32 layers in one launch (layer l: alphas[l] [d] -> theta[l] [k[l], d]). */
+typedef struct {
+  int32_t L, d;
+  const float* alphas[32];
+  float* theta[32];
+  int32_t k[32];
+} kp_theta_batch;
+int kp_geometric_theta_forward_batched(const kp_theta_batch* batch, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Batched K-hop neighbourhood + peripheral-subgraph extraction.  Replaces, for a whole batch of graphs,

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # KPGNN_B200_LIB points at an alternative build of the same library (kernel tuning experiments)
 LIB_PATH = os.environ.get("KPGNN_B200_LIB") or os.path.join(_HERE, "libkpgnn_b200.so")
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 class KpError(RuntimeError):
@@ -32,7 +32,8 @@ class AggDesc(C.Structure):
                 ("theta", C.c_void_p), ("eps", C.c_void_p), ("act", C.c_int32), ("fuse", C.c_int32),
                 ("amax0", C.c_int32), ("amaxk", C.c_int32),
                 ("dx_node_stride", C.c_int64), ("dx_hop_stride", C.c_int64),
-                ("dx_accumulate", C.c_int32), ("pad0", C.c_int32)]
+                ("dx_accumulate", C.c_int32), ("pad0", C.c_int32),
+                ("geo_alphas", C.c_void_p), ("geo_dalphas", C.c_void_p)]
 
 
 class ExtractInput(C.Structure):
@@ -64,6 +65,11 @@ class DenseDesc(C.Structure):
                 ("Y1", C.c_void_p), ("Y2", C.c_void_p), ("Z2", C.c_void_p), ("stats", C.c_void_p),
                 ("out_stride", C.c_int64), ("r_stride", C.c_int64), ("dout_stride", C.c_int64),
                 ("dr_stride", C.c_int64), ("dR", C.c_void_p), ("barrier", C.c_void_p)]
+
+
+class ThetaBatch(C.Structure):
+    _fields_ = [("L", C.c_int32), ("d", C.c_int32), ("alphas", C.c_void_p * 32), ("theta", C.c_void_p * 32),
+                ("k", C.c_int32 * 32)]
 
 
 class PgradDesc(C.Structure):
@@ -105,6 +111,7 @@ _SIGNATURES = {
     "kp_dense_block_forward": (C.c_int, [C.POINTER(DenseDesc), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "kp_dense_block_backward": (C.c_int, [C.POINTER(DenseDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "kp_geometric_theta_forward_batched": (C.c_int, [C.POINTER(ThetaBatch), C.c_void_p]),
     "kp_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_double, C.c_double, C.c_float,
                                C.c_void_p, C.c_void_p]),
     "kp_peripheral_grad": (C.c_int, [C.POINTER(PgradDesc), C.c_void_p, C.c_void_p]),

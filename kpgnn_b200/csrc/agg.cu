@@ -477,6 +477,42 @@ __global__ void reduce_partials_kernel(const float* __restrict__ part, int nbloc
   }
 }
 
+// dtheta[h,c] = sum_b part[b*n + h*d + c] (same order as reduce_partials_kernel) fused with GeometricCombine's
+// backward (combine.py:51-58): one warp per channel c; dalphas[c] = a(1-a) * sum_h theta_h (dtheta_h - dot)
+// ((1-a)^h - a h (1-a)^(h-1)),  dot = sum_h theta_h dtheta_h,  a = sigmoid(alphas[c]).  dtheta itself is optional.
+__global__ void __launch_bounds__(256)
+dtheta_geo_bwd_kernel(const float* __restrict__ part, int nblocks, int k, int d, const float* __restrict__ alphas,
+                      const float* __restrict__ theta, float* __restrict__ dtheta, float* __restrict__ dalphas) {
+  // one CTA per channel; warp w sums hop h = w, w+8, ... (all hops' loads in flight together: one L2 round trip)
+  __shared__ float sd[32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = blockIdx.x;
+  const int n = k * d;
+  for (int h = w; h < k; h += 8) {
+    float s = 0.f;
+    for (int b = lane; b < nblocks; b += 32) s += __ldcs(part + (size_t)b * n + (size_t)h * d + c);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+      sd[h] = s;
+      if (dtheta) dtheta[(size_t)h * d + c] = s;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const float a = 1.f / (1.f + expf(-alphas[c]));
+    float dot = 0.f;
+    for (int h = 0; h < k; ++h) dot += theta[(size_t)h * d + c] * sd[h];
+    float da = 0.f, pw = 1.f, pwm1 = 0.f;
+    for (int h = 0; h < k; ++h) {
+      const float dt = theta[(size_t)h * d + c] * (sd[h] - dot);
+      da += dt * (pw - a * (float)h * pwm1);
+      pwm1 = pw;
+      pw *= (1.f - a);
+    }
+    dalphas[c] = da * a * (1.f - a);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // host side: configuration shared by forward, backward and the workspace-size query
 // ---------------------------------------------------------------------------------------------------------
@@ -775,6 +811,8 @@ int kp_agg_backward(const kp_agg_desc* desc, const float* dOut, float* dX, float
   if (kp::make_config(a, &c)) return 1;
   KP_CHECK_ARG(a.rowptrT && a.colT, "kp_agg_backward: plan has no transposed CSR");
   KP_CHECK_ARG(!dtheta || a.fuse, "kp_agg_backward: dtheta requires fuse");
+  const bool geo = a.fuse && a.geo_alphas && a.geo_dalphas;
+  KP_CHECK_ARG(!geo || a.k <= 32, "kp_agg_backward: fused GeometricCombine backward needs k <= 32");
   KP_CHECK_ARG(!deps || a.eps, "kp_agg_backward: deps requires eps");
   KP_CHECK_ARG((!dT0 && !dTk) || a.T0, "kp_agg_backward: table gradients requested without tables");
   kp::WsLayout w = kp::ws_layout(a, c);
@@ -802,7 +840,7 @@ int kp_agg_backward(const kp_agg_desc* desc, const float* dOut, float* dX, float
                  "kp_agg_backward: dOut/dX/dP/workspace must be 16-byte aligned");
   char* ws = (char*)workspace;
   float* Gs = c.need_gs ? (float*)(ws + w.gs) : nullptr;
-  float* dth_part = dtheta ? (float*)(ws + w.dtheta) : nullptr;
+  float* dth_part = (dtheta || geo) ? (float*)(ws + w.dtheta) : nullptr;
   float* dep_part = deps ? (float*)(ws + w.deps) : nullptr;
   kp::AggArgs args{a, c.G, c.gshift};
   const bool want_table = (dT0 || dTk);
@@ -890,7 +928,10 @@ int kp_agg_backward(const kp_agg_desc* desc, const float* dOut, float* dX, float
                   (int)tn, a.rows0 * a.d, dT0, dTk);
     }
   }
-  if (dtheta) {
+  if (geo) {
+    KP_LAUNCH(kp::dtheta_geo_bwd_kernel, a.d, 256, 0, st, dth_part, c.grid_b1, a.k, a.d,
+              a.geo_alphas, a.theta, dtheta, a.geo_dalphas);
+  } else if (dtheta) {
     const int n = a.k * a.d;
     KP_LAUNCH(kp::reduce_partials_kernel, kp::ceil_div((long long)n * 32, 256), 256, 0, st, dth_part, c.grid_b1, n, n,
               dtheta, (float*)nullptr);

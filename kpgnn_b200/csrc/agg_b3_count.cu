@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(B3C_THREADS, (A4 <= 4) ? B3C_CTAS_PER_SM : 1)
 agg_bwd_table_count_kernel(const kp_agg_desc a, const float* __restrict__ Gs, int g0, float* __restrict__ part) {
   constexpr int A = 4 * A4;
   constexpr int S = A + 4;                                   // count row: A counts | non-empty flag | Gs row | pad
-  constexpr int RB = (G < 8) ? G : ((A4 <= 4) ? 8 : 4);      // rows in flight per group
+  constexpr int RB = (G < 8) ? G : ((A4 <= 2 && G >= 16) ? 16 : ((A4 <= 4) ? 8 : 4));   // rows in flight per group
   extern __shared__ __align__(16) float smem[];
   float* Cm = smem;                                          // [B3C_THREADS][S]
   float* red = smem + B3C_THREADS * S;                       // [A][d]

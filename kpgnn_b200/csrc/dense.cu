@@ -749,14 +749,33 @@ dense_block_bwd_kernel(const kp_dense_desc m, const float* __restrict__ dOut, fl
   __syncthreads();
   DB_T(12);
   db_store_slab(D, r0, nr, Ci, dX);
-  db_grid_barrier(bar, ++phase * grid);
   DB_T(13);
-  // ---- fixed-order sums of the per-CTA weight-gradient partials: 8 lanes per output float4 ----
+  if (threadIdx.x == 0 && atomicAdd(bar + 1, 1u) == gridDim.x - 1) {
+    bar[0] = 0u;
+    bar[1] = 0u;
+  }
+  DB_T(14);
+  DB_T_PRINT(15, "bwd load xhat bn3 mask2+dots2+bar merge2+apply2 gemm_dz1 mask1+dots1 dW2+colsum wait merge1+apply1 gemm_dX dW1+colsum store+bar... reduce");
+}
+
+
+// dW1, db1, dW2, db2 = fixed-order sums of the per-CTA partials of dense_block_bwd_kernel: 16 lanes per output float4,
+// every partial requested before the first is used.  A separate launch: inside the persistent kernel this phase sat
+// behind a fourth grid barrier and ran on the kernel's 82 CTAs only (7.6 us, profiles/r1z_dense_block_phases.txt);
+// as its own grid it covers every output at once.
+__global__ void __launch_bounds__(256)
+dense_block_wgrad_reduce_kernel(const float* __restrict__ ws, int grid, int Ci, int Co, float* __restrict__ dW1,
+                                float* __restrict__ db1, float* __restrict__ dW2, float* __restrict__ db2) {
+  const float* pW1 = ws + (size_t)grid * 6 * Co;
+  const float* pW2 = pW1 + (size_t)grid * Co * Ci;
+  const float* pb1 = pW2 + (size_t)grid * Co * Co;
+  const float* pb2 = pb1 + (size_t)grid * Co;
+  constexpr int DB_THREADS_R = 256;
   {
     const int nW1 = (Co * Ci) >> 2, nW2 = (Co * Co) >> 2, nb = Co >> 2;
     const int total = nW1 + nW2 + 2 * nb;
     const int sub = threadIdx.x & 15;
-    const int wg = (blockIdx.x * DB_THREADS + threadIdx.x) >> 5, nwg = (grid * DB_THREADS) >> 5;
+    const int wg = (blockIdx.x * DB_THREADS_R + threadIdx.x) >> 5, nwg = ((int)gridDim.x * DB_THREADS_R) >> 5;
     for (int e0 = wg * 2; e0 < total; e0 += nwg * 2) {          // warp-uniform trip count (full-mask shuffles)
       const int e = e0 + ((threadIdx.x & 31) >> 4);
       const bool ok = e < total;
@@ -794,12 +813,6 @@ dense_block_bwd_kernel(const kp_dense_desc m, const float* __restrict__ dOut, fl
       if (ok && sub == 0) *reinterpret_cast<float4*>(dst) = s;
     }
   }
-  if (threadIdx.x == 0 && atomicAdd(bar + 1, 1u) == gridDim.x - 1) {
-    bar[0] = 0u;
-    bar[1] = 0u;
-  }
-  DB_T(14);
-  DB_T_PRINT(15, "bwd load xhat bn3 mask2+dots2+bar merge2+apply2 gemm_dz1 mask1+dots1 dW2+colsum wait merge1+apply1 gemm_dX dW1+colsum store+bar... reduce");
 }
 
 struct DbCfg {
@@ -922,6 +935,11 @@ int kp_dense_block_backward(const kp_dense_desc* desc, const float* dOut, float*
                                (int)c.smem_bwd));
   KP_LAUNCH(kp::dense_block_bwd_kernel, c.grid, kp::DB_THREADS, c.smem_bwd, st, m, dOut, dX, dW1, db1, dW2, db2, dbn,
             (float*)((char*)workspace + 256), bar, c.Rc);
+  {
+    const int total4 = (m.Cout * m.Cin + m.Cout * m.Cout + 2 * m.Cout) >> 2;   // output float4s, 16 lanes each
+    KP_LAUNCH(kp::dense_block_wgrad_reduce_kernel, kp::ceil_div((long long)total4 * 16, 256), 256, 0, st,
+              (const float*)((char*)workspace + 256), c.grid, m.Cin, m.Cout, dW1, db1, dW2, db2);
+  }
   return 0;
 }
 

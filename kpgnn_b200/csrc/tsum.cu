@@ -303,6 +303,44 @@ int kp_geometric_theta_backward(const float* alphas, const float* theta, const f
 
 }  // extern "C"
 
+// all layers of a stack in one launch: blockIdx.y = layer
+namespace kp {
+__global__ void geo_theta_fwd_batched_kernel(const kp_theta_batch b) {
+  const int l = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int K = b.k[l], d = b.d;
+  if (c >= d) return;
+  const float a = 1.f / (1.f + expf(-b.alphas[l][c]));
+  float m = -INFINITY, pw = 1.f;
+  for (int h = 0; h < K; ++h) {
+    m = fmaxf(m, a * pw);
+    pw *= (1.f - a);
+  }
+  float sum = 0.f;
+  pw = 1.f;
+  for (int h = 0; h < K; ++h) {
+    sum += expf(a * pw - m);
+    pw *= (1.f - a);
+  }
+  pw = 1.f;
+  const float inv = 1.f / sum;
+  for (int h = 0; h < K; ++h) {
+    b.theta[l][(size_t)h * d + c] = expf(a * pw - m) * inv;
+    pw *= (1.f - a);
+  }
+}
+}  // namespace kp
+
+extern "C" int kp_geometric_theta_forward_batched(const kp_theta_batch* batch, void* stream) {
+  KP_CHECK_ARG(batch && batch->L >= 0 && batch->L <= 32 && batch->d >= 1, "kp_geometric_theta_forward_batched: bad arguments");
+  for (int l = 0; l < batch->L; ++l)
+    KP_CHECK_ARG(batch->alphas[l] && batch->theta[l] && batch->k[l] >= 1, "kp_geometric_theta_forward_batched: layer %d", l);
+  if (batch->L == 0) return 0;
+  KP_LAUNCH(kp::geo_theta_fwd_batched_kernel, dim3(kp::ceil_div(batch->d, 128), batch->L), 128, 0, (cudaStream_t)stream,
+            *batch);
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // kp_peripheral_grad: dP[v,h,:] = sum_{l: k_l > h} theta_l[h,:] * dAgg_l[v,:]   (see include/kpgnn.h)
 // thread per (node, 4 channels): the L gradients are read once into registers, the K hop rows written once.

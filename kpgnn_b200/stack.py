@@ -53,6 +53,19 @@ class _KPGINPlusStack(torch.autograd.Function):
         Hn[:, L].copy_(x0.detach())
         hs = (L + 1) * H
         saved = []
+        # GeometricCombine weights of every layer in one launch (combine.py:51-58)
+        thetas = [None] * L
+        tb = _lib.ThetaBatch()
+        tb.d = H
+        pi, nb_ = 0, 0
+        for l, layer in enumerate(layers):
+            if layer.K > 1:
+                thetas[l] = torch.empty((layer.K, H), dtype=torch.float32, device=dev)
+                tb.alphas[nb_], tb.theta[nb_], tb.k[nb_] = (params[pi + 12].data_ptr(), thetas[l].data_ptr(), layer.K)
+                nb_ += 1
+            pi += _num_params(layer)
+        tb.L = nb_
+        _lib.check(lib.kp_geometric_theta_forward_batched(C.byref(tb), st), "kp_geometric_theta_forward_batched")
         pi = 0
         for l, layer in enumerate(layers):
             k = layer.K
@@ -62,11 +75,7 @@ class _KPGINPlusStack(torch.autograd.Function):
             alphas = params[pi + 12].detach() if k > 1 else None
             pi += np_l
             plan.check_tables(T0.size(0), Tk.size(0) if Tk is not None else 0, k)
-            theta = None
-            if k > 1:
-                theta = torch.empty((k, H), dtype=torch.float32, device=dev)
-                _lib.check(lib.kp_geometric_theta_forward(alphas.data_ptr(), k, H, theta.data_ptr(), st),
-                           "kp_geometric_theta_forward")
+            theta = thetas[l]
             xs = Hn[:, L - l:L - l + k, :]
             adesc = _make_desc(plan, k, xs, Pc[:, :k], T0.contiguous(), Tk.contiguous() if Tk is not None else None,
                                theta, None, ACT_GELU, k > 1, False, False)
@@ -137,7 +146,9 @@ class _KPGINPlusStack(torch.autograd.Function):
                                                    st), "kp_dense_block_backward")
             dT0 = torch.empty_like(T0)
             dTk = torch.empty_like(Tk) if Tk is not None else None
-            dth = torch.empty_like(theta) if theta is not None else None
+            dal = torch.empty_like(alphas) if theta is not None else None
+            if theta is not None:       # dtheta reduction fused with GeometricCombine's backward
+                adesc.geo_alphas, adesc.geo_dalphas = alphas.data_ptr(), dal.data_ptr()
             nb = C.c_size_t(0)
             _lib.check(lib.kp_agg_backward_workspace_bytes(C.byref(adesc), C.byref(nb)), "kp_agg_backward ws")
             ws2 = torch.empty(max(nb.value, 1), dtype=torch.uint8, device=dev)
@@ -145,8 +156,7 @@ class _KPGINPlusStack(torch.autograd.Function):
             def agg_bwd(dx_ptr):
                 return lib.kp_agg_backward(C.byref(adesc), dagg.data_ptr(), dx_ptr, None, dT0.data_ptr(),
                                            dTk.data_ptr() if dTk is not None else None,
-                                           dth.data_ptr() if dth is not None else None, None, ws2.data_ptr(),
-                                           ws2.numel(), st)
+                                           None, None, ws2.data_ptr(), ws2.numel(), st)
             # dX is accumulated straight into the history gradient (slots L-l .. L-l+k-1) by the gather kernel ...
             adesc.dx_node_stride, adesc.dx_hop_stride, adesc.dx_accumulate = hs, H, 1
             rc = agg_bwd(G[:, L - l].data_ptr())
@@ -157,11 +167,6 @@ class _KPGINPlusStack(torch.autograd.Function):
                 G[:, L - l:L - l + k].add_(dX)
             else:
                 _lib.check(rc, "kp_agg_backward")
-            dal = None
-            if theta is not None:
-                dal = torch.empty_like(alphas)
-                _lib.check(lib.kp_geometric_theta_backward(alphas.data_ptr(), theta.data_ptr(), dth.data_ptr(), k, H,
-                                                           dal.data_ptr(), st), "kp_geometric_theta_backward")
             pg.dagg[l], pg.k[l] = dagg.data_ptr(), k
             pg.theta[l] = theta.data_ptr() if theta is not None else None
             daggs.append(dagg)

@@ -516,13 +516,12 @@ def main():
     tr.capture()
     log("[rank %d] captured, %d of our kernels per step" % (rank, tr.launches_per_step))
     flush = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device=device)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                 # nvidia-smi needs ~0.3 s to start: begin before the warm-up steps
     for _ in range(args.warmup):
         tr.step_resident()
     torch.cuda.synchronize(device)
-
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     plan_launches = tr.refresh_derived() if args.eager else 0
     t_res = timed_steps(tr.step_resident, args.steps, device, flush, dist_on)
     log("[rank %d] resident timing done" % rank)

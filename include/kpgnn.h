@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define KPGNN_ABI_VERSION 6
+#define KPGNN_ABI_VERSION 7
 
 const char* kp_last_error(void);
 int kp_abi_version(void);
@@ -106,6 +106,11 @@ typedef struct {
    * kp_geometric_theta_forward(geo_alphas); the dtheta argument of kp_agg_backward may then be NULL. */
   const float* geo_alphas;
   float* geo_dalphas;
+  /* Backward only, optional: a second CUDA stream for the LEAF gradients (dT0/dTk, dtheta/dalphas, deps), which feed
+   * nothing but the optimizer.  They are forked onto it right after the first backward kernel, so they overlap the
+   * dX gather and whatever the caller enqueues next on `stream`.  The caller must make its stream wait for
+   * leaf_stream before reading those outputs and keep outputs + workspace alive until then.  NULL: one stream. */
+  void* leaf_stream;
 } kp_agg_desc;
 
 int kp_agg_forward(const kp_agg_desc* desc, float* out, void* stream);
@@ -201,6 +206,9 @@ typedef struct {
    * stream at a time; every launch leaves it zero again, so no memset node precedes the kernel.  NULL: the first
    * 256 bytes of the workspace are used and cleared by a cudaMemsetAsync before each launch. */
   uint32_t* barrier;
+  /* Backward only, optional: stream for the final weight-gradient reduction (dW1, db1, dW2, db2), same contract as
+   * kp_agg_desc.leaf_stream.  dX and the BatchNorm affine gradients are always produced on `stream`. */
+  void* leaf_stream;
 } kp_dense_desc;
 
 int kp_dense_block_max_rows(int32_t Cin, int32_t Cout);

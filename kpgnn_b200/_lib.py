@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # KPGNN_B200_LIB points at an alternative build of the same library (kernel tuning experiments)
 LIB_PATH = os.environ.get("KPGNN_B200_LIB") or os.path.join(_HERE, "libkpgnn_b200.so")
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 
 class KpError(RuntimeError):
@@ -33,7 +33,7 @@ class AggDesc(C.Structure):
                 ("amax0", C.c_int32), ("amaxk", C.c_int32),
                 ("dx_node_stride", C.c_int64), ("dx_hop_stride", C.c_int64),
                 ("dx_accumulate", C.c_int32), ("pad0", C.c_int32),
-                ("geo_alphas", C.c_void_p), ("geo_dalphas", C.c_void_p)]
+                ("geo_alphas", C.c_void_p), ("geo_dalphas", C.c_void_p), ("leaf_stream", C.c_void_p)]
 
 
 class ExtractInput(C.Structure):
@@ -64,7 +64,8 @@ class DenseDesc(C.Structure):
                 ("nbt1", C.c_void_p), ("nbt2", C.c_void_p), ("nbt3", C.c_void_p),
                 ("Y1", C.c_void_p), ("Y2", C.c_void_p), ("Z2", C.c_void_p), ("stats", C.c_void_p),
                 ("out_stride", C.c_int64), ("r_stride", C.c_int64), ("dout_stride", C.c_int64),
-                ("dr_stride", C.c_int64), ("dR", C.c_void_p), ("barrier", C.c_void_p)]
+                ("dr_stride", C.c_int64), ("dR", C.c_void_p), ("barrier", C.c_void_p),
+                ("leaf_stream", C.c_void_p)]
 
 
 class ThetaBatch(C.Structure):

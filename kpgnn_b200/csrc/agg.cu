@@ -860,6 +860,18 @@ int kp_agg_backward(const kp_agg_desc* desc, const float* dOut, float* dX, float
       KP_DISPATCH_VAF(kp::launch_b1, c.vec, a.act, a.fuse, args, c, dOut, Gs, dPk, dth_part, dep_part, st);
     }
   }
+  // Leaf gradients (tables, dtheta / dalphas, deps) feed nothing but the optimizer: with desc.leaf_stream they are
+  // forked onto that stream right after B1, so B3 and the reductions overlap B2 and whatever the caller launches next
+  // on the main stream.  The caller joins the leaf stream before reading them and keeps the workspace alive until then.
+  cudaStream_t lst = st;
+  if (a.leaf_stream && a.leaf_stream != stream) {
+    lst = (cudaStream_t)a.leaf_stream;
+    cudaEvent_t ev;
+    KP_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    KP_CUDA(cudaEventRecord(ev, st));
+    KP_CUDA(cudaStreamWaitEvent(lst, ev, 0));
+    KP_CUDA(cudaEventDestroy(ev));
+  }
   const float* Gsrc = c.need_gs ? Gs : dOut;
   if (dX && c.fast) {
     int rc = kp::fast_b2(kp::make_fast_args(a), c.fG, a.fuse != 0, c.fextra, c.fgrid, Gsrc, dOut, dX, st);
@@ -878,15 +890,15 @@ int kp_agg_backward(const kp_agg_desc* desc, const float* dOut, float* dX, float
   }
   if (want_table) {
     if (c.table_atomic) {
-      if (dT0) KP_CUDA(cudaMemsetAsync(dT0, 0, sizeof(float) * (size_t)a.rows0 * a.d, st));
-      if (dTk) KP_CUDA(cudaMemsetAsync(dTk, 0, sizeof(float) * (size_t)a.rowsk * a.d, st));
+      if (dT0) KP_CUDA(cudaMemsetAsync(dT0, 0, sizeof(float) * (size_t)a.rows0 * a.d, lst));
+      if (dTk) KP_CUDA(cudaMemsetAsync(dTk, 0, sizeof(float) * (size_t)a.rowsk * a.d, lst));
       KP_CHECK_ARG(dT0 && (dTk || a.k == 1), "kp_agg_backward: atomic table path needs both dT0 and dTk");
-      KP_LAUNCH(kp::agg_bwd_table_atomic_kernel, kp::kNumSMs * 8, 256, 0, st, a, Gsrc, dT0, dTk);
+      KP_LAUNCH(kp::agg_bwd_table_atomic_kernel, kp::kNumSMs * 8, 256, 0, lst, a, Gsrc, dT0, dTk);
     } else {
       float* part = (float*)(ws + w.table);
       const int threads = 256;
       if (c.b3_count) {
-        int rc = kp::b3_count(a, c.fG, Gsrc, part, dT0, dTk, st);
+        int rc = kp::b3_count(a, c.fG, Gsrc, part, dT0, dTk, lst);
         if (rc) return rc;
       } else if (c.b3_fast) {
 #define KP_B3F(GG)                                                                                              \
@@ -898,10 +910,10 @@ int kp_agg_backward(const kp_agg_desc* desc, const float* dOut, float* dX, float
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem_b3));               \
     }                                                                                                           \
     if (a.dinv)                                                                                                 \
-      KP_LAUNCH((kp::agg_bwd_table_fast_kernel<GG, true>), c.grid_b3, c.b3_threads, c.smem_b3, st, a, Gsrc,     \
+      KP_LAUNCH((kp::agg_bwd_table_fast_kernel<GG, true>), c.grid_b3, c.b3_threads, c.smem_b3, lst, a, Gsrc,     \
                 c.b3_groups, c.b3_rows_per_group, part);                                                        \
     else                                                                                                        \
-      KP_LAUNCH((kp::agg_bwd_table_fast_kernel<GG, false>), c.grid_b3, c.b3_threads, c.smem_b3, st, a, Gsrc,    \
+      KP_LAUNCH((kp::agg_bwd_table_fast_kernel<GG, false>), c.grid_b3, c.b3_threads, c.smem_b3, lst, a, Gsrc,    \
                 c.b3_groups, c.b3_rows_per_group, part);                                                        \
   } while (0)
         if (c.b3_G == 32) KP_B3F(32);
@@ -915,7 +927,7 @@ int kp_agg_backward(const kp_agg_desc* desc, const float* dOut, float* dX, float
     if (c.smem_b3 > 48 * 1024)                                                                             \
       KP_CUDA(cudaFuncSetAttribute(kp::agg_bwd_table_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                    (int)c.smem_b3));                                                       \
-    KP_LAUNCH((kp::agg_bwd_table_kernel<V>), c.grid_b3, threads, c.smem_b3, st, a, Gsrc, c.cw, c.rl,       \
+    KP_LAUNCH((kp::agg_bwd_table_kernel<V>), c.grid_b3, threads, c.smem_b3, lst, a, Gsrc, c.cw, c.rl,       \
               c.rows_per_block, part);                                                                     \
   } while (0)
       if (c.vec == 4) KP_B3(4);
@@ -924,20 +936,20 @@ int kp_agg_backward(const kp_agg_desc* desc, const float* dOut, float* dX, float
 #undef KP_B3
       }
       if (!c.b3_count)
-        KP_LAUNCH(kp::reduce_partials_kernel, kp::ceil_div((long long)tn * 32, 256), 256, 0, st, part, c.grid_b3,
+        KP_LAUNCH(kp::reduce_partials_kernel, kp::ceil_div((long long)tn * 32, 256), 256, 0, lst, part, c.grid_b3,
                   (int)tn, a.rows0 * a.d, dT0, dTk);
     }
   }
   if (geo) {
-    KP_LAUNCH(kp::dtheta_geo_bwd_kernel, a.d, 256, 0, st, dth_part, c.grid_b1, a.k, a.d,
+    KP_LAUNCH(kp::dtheta_geo_bwd_kernel, a.d, 256, 0, lst, dth_part, c.grid_b1, a.k, a.d,
               a.geo_alphas, a.theta, dtheta, a.geo_dalphas);
   } else if (dtheta) {
     const int n = a.k * a.d;
-    KP_LAUNCH(kp::reduce_partials_kernel, kp::ceil_div((long long)n * 32, 256), 256, 0, st, dth_part, c.grid_b1, n, n,
+    KP_LAUNCH(kp::reduce_partials_kernel, kp::ceil_div((long long)n * 32, 256), 256, 0, lst, dth_part, c.grid_b1, n, n,
               dtheta, (float*)nullptr);
   }
   if (deps) {
-    KP_LAUNCH(kp::reduce_partials_kernel, 1, 32, 0, st, dep_part, c.grid_b1, 1, 1, deps, (float*)nullptr);
+    KP_LAUNCH(kp::reduce_partials_kernel, 1, 32, 0, lst, dep_part, c.grid_b1, 1, 1, deps, (float*)nullptr);
   }
   return 0;
 }

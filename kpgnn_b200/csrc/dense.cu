@@ -936,8 +936,17 @@ int kp_dense_block_backward(const kp_dense_desc* desc, const float* dOut, float*
   KP_LAUNCH(kp::dense_block_bwd_kernel, c.grid, kp::DB_THREADS, c.smem_bwd, st, m, dOut, dX, dW1, db1, dW2, db2, dbn,
             (float*)((char*)workspace + 256), bar, c.Rc);
   {
+    cudaStream_t lst = st;
+    if (m.leaf_stream && m.leaf_stream != stream) {          // leaf gradients: fork (see kp_dense_desc.leaf_stream)
+      lst = (cudaStream_t)m.leaf_stream;
+      cudaEvent_t ev;
+      KP_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      KP_CUDA(cudaEventRecord(ev, st));
+      KP_CUDA(cudaStreamWaitEvent(lst, ev, 0));
+      KP_CUDA(cudaEventDestroy(ev));
+    }
     const int total4 = (m.Cout * m.Cin + m.Cout * m.Cout + 2 * m.Cout) >> 2;   // output float4s, 16 lanes each
-    KP_LAUNCH(kp::dense_block_wgrad_reduce_kernel, kp::ceil_div((long long)total4 * 16, 256), 256, 0, st,
+    KP_LAUNCH(kp::dense_block_wgrad_reduce_kernel, kp::ceil_div((long long)total4 * 16, 256), 256, 0, lst,
               (const float*)((char*)workspace + 256), c.grid, m.Cin, m.Cout, dW1, db1, dW2, db2);
   }
   return 0;

@@ -122,6 +122,13 @@ class _KPGINPlusStack(torch.autograd.Function):
         dev = dHn.device
         st = _stream(dev)
         G = dHn.contiguous().clone()                   # accumulated in place below
+        # leaf gradients (tables, combine weights, dense weights) go to a second stream and overlap the chain of
+        # dX-producing kernels; everything they touch is kept alive until the join at the end
+        main = torch.cuda.current_stream(dev)
+        leaf = _leaf_stream(dev) if _USE_LEAF_STREAM else None
+        if leaf is not None:
+            leaf.wait_stream(main)
+        keep_alive = []
         hs = (L + 1) * H
         grads = [None] * sum(_num_params(layer) for layer in layers)
         offs, o = [], 0
@@ -140,6 +147,8 @@ class _KPGINPlusStack(torch.autograd.Function):
             if residual:
                 d.dR, d.dr_stride = G[:, L - l].data_ptr(), hs
             ws = torch.empty(bwd_bytes, dtype=torch.uint8, device=dev)
+            d.leaf_stream = leaf.cuda_stream if leaf is not None else None
+            adesc.leaf_stream = leaf.cuda_stream if leaf is not None else None
             _lib.check(lib.kp_dense_block_backward(C.byref(d), G[:, L - l - 1].data_ptr(), dagg.data_ptr(),
                                                    dW1.data_ptr(), dvec[0].data_ptr(), dW2.data_ptr(),
                                                    dvec[1].data_ptr(), dvec[2].data_ptr(), ws.data_ptr(), ws.numel(),
@@ -167,6 +176,7 @@ class _KPGINPlusStack(torch.autograd.Function):
                 G[:, L - l:L - l + k].add_(dX)
             else:
                 _lib.check(rc, "kp_agg_backward")
+            keep_alive += [ws, ws2, dW1, dW2, dvec, dT0, dTk, dal]
             pg.dagg[l], pg.k[l] = dagg.data_ptr(), k
             pg.theta[l] = theta.data_ptr() if theta is not None else None
             daggs.append(dagg)
@@ -178,8 +188,24 @@ class _KPGINPlusStack(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dP = torch.empty((N, K, H), dtype=torch.float32, device=dev)
             _lib.check(lib.kp_peripheral_grad(C.byref(pg), dP.data_ptr(), st), "kp_peripheral_grad")
+        if leaf is not None:
+            main.wait_stream(leaf)                     # join: leaf gradients are complete for whoever runs next
+        del keep_alive
         dx0 = G[:, L] if ctx.needs_input_grad[0] else None
         return (dx0, dP, None) + tuple(grads)
+
+
+_USE_LEAF_STREAM = True
+_LEAF = {}
+
+
+def _leaf_stream(dev):
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    s = _LEAF.get(key)
+    if s is None:
+        s = torch.cuda.Stream(dev)
+        _LEAF[key] = s
+    return s
 
 
 def _num_params(layer):

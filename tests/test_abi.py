@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol(lib):
 
 def test_abi_version_and_error_string(lib):
     from kpgnn_b200 import _lib
-    assert lib.kp_abi_version() == _lib.ABI_VERSION == 6
+    assert lib.kp_abi_version() == _lib.ABI_VERSION == 7
     assert isinstance(lib.kp_last_error(), bytes)
     assert lib.kp_launch_count() >= 0
 

@@ -195,6 +195,7 @@ class Trainer(object):
             n0 = _lib.launch_count()
             self.loss = self._step()
             self.launches_per_step = _lib.launch_count() - n0
+            self.plan_obj = self.plan()
             return
         s = torch.cuda.Stream(self.device)
         s.wait_stream(torch.cuda.current_stream(self.device))
@@ -218,6 +219,7 @@ class Trainer(object):
                 self.opt.step()
         self.launches_per_step = _lib.launch_count() - n0
         torch.cuda.synchronize(self.device)
+        self.plan_obj = self.plan()                  # the graph refreshes this object in place on every replay
 
     def replay(self):
         if self.eager:
@@ -236,7 +238,11 @@ class Trainer(object):
         from kpgnn_b200 import _lib
         n0 = _lib.launch_count()
         base = self.dev.edge_attr
-        ok = self.kplan.refresh_plan(self.plan(), self.dev.edge_index, base, base.size(1))
+        # on a side stream: the plan rebuild overlaps the index / encoder kernels at the head of the step; the first
+        # layer's get_plan() joins it
+        if getattr(self, "plan_stream", None) is None:
+            self.plan_stream = torch.cuda.Stream(self.device)
+        ok = self.kplan.refresh_plan_async(self.plan(), self.dev.edge_index, base, base.size(1), self.plan_stream)
         assert ok
         return _lib.launch_count() - n0
 
@@ -304,7 +310,7 @@ class Trainer(object):
         self.replay()
         self.prefetch()
         val = self.loss.item()                       # D2H read of the step's loss
-        self.plan().validate()
+        self.plan_obj.validate()                     # deferred plan checks (stats copied back by the graph itself)
         return self.host_flat.numel(), val           # bytes copied host -> device per step
 
 

@@ -29,7 +29,8 @@ def deferred_checks(flag):
 
 class GraphPlan(object):
     __slots__ = ("N", "E", "K", "nnz", "capacity", "self_loops", "rowptr", "col", "attr16", "rowptrT", "colT", "dinv",
-                 "indeg", "max_attr0", "max_attrk", "device", "stats", "stats_host", "ws", "pending", "src", "dst")
+                 "indeg", "max_attr0", "max_attrk", "device", "stats", "stats_host", "ws", "pending", "src", "dst",
+                 "ready")
 
     def check_tables(self, rows0, rowsk, k):
         """nn.Embedding would raise IndexError on an out-of-range attr (KPGIN.py:90,95); so do we."""
@@ -96,6 +97,7 @@ def build_plan(edge_index, edge_attr_base, attr_stride, K, num_nodes, self_loops
     p = GraphPlan()
     p.N, p.E, p.K, p.self_loops, p.device = int(num_nodes), edge_index.size(1), K, bool(self_loops), dev
     p.pending = None
+    p.ready = None
     rows = p.N * K
     nbytes = C.c_size_t(0)
     _lib.check(lib.kp_plan_workspace_bytes(p.N, p.E, K, C.byref(nbytes)), "kp_plan_workspace_bytes")
@@ -184,4 +186,22 @@ def get_plan(edge_index, edge_attr, num_nodes, self_loops=False):
     if hit is None:
         hit = (build_plan(edge_index, base, stride, K, num_nodes, self_loops), base, versions)   # keeps base alive
         cache[key] = hit
+    if hit[0].ready is not None:
+        # the plan was refreshed on another stream (refresh_plan_async): its first consumer joins that stream
+        torch.cuda.current_stream(hit[0].device).wait_event(hit[0].ready)
+        hit[0].ready = None
     return hit[0], k
+
+
+def refresh_plan_async(p, edge_index, edge_attr_base, attr_stride, stream):
+    """refresh_plan on `stream` (forked from the current one), so the rebuild overlaps whatever the caller enqueues
+    next -- the feature / peripheral encoders of a training step do not need the plan.  The next get_plan() that
+    returns `p` makes its stream wait for the refresh."""
+    cur = torch.cuda.current_stream(p.device)
+    stream.wait_stream(cur)
+    with torch.cuda.stream(stream):
+        ok = refresh_plan(p, edge_index, edge_attr_base, attr_stride)
+        ev = torch.cuda.Event()
+        ev.record(stream)
+    p.ready = ev
+    return ok

@@ -43,3 +43,19 @@ with torch.cuda.stream(cs):
     a.record(cs); tr.stage_flat.copy_(tr.host_flat, non_blocking=True); b.record(cs)
 torch.cuda.synchronize()
 print("H2D of %.1f MB alone: %.1f us" % (tr.host_flat.numel() / 1e6, a.elapsed_time(b) * 1e3))
+# host-timer trace of the pieces inside one e2e step
+import collections
+acc = collections.defaultdict(list)
+for it in range(40):
+    torch.cuda.synchronize()
+    t0 = time.perf_counter(); tr.hand_over()
+    t1 = time.perf_counter(); tr.replay()
+    t2 = time.perf_counter(); tr.prefetch()
+    t3 = time.perf_counter(); v = tr.loss.item()
+    t4 = time.perf_counter(); p = tr.plan_obj
+    t5 = time.perf_counter(); p.validate()
+    t6 = time.perf_counter()
+    if it >= 10:
+        for k, a_, b_ in (("hand_over", t0, t1), ("replay", t1, t2), ("prefetch", t2, t3), ("item", t3, t4), ("plan()", t4, t5), ("validate", t5, t6), ("total", t0, t6)):
+            acc[k].append((b_ - a_) * 1e6)
+print("host trace (us): " + ", ".join("%s %.1f" % (k, statistics.mean(v)) for k, v in acc.items()))

@@ -56,7 +56,14 @@ def graph_profile():
         agg[k][1] += 1
     for k, (t, c) in sorted(agg.items(), key=lambda x: -x[1][0])[:45]:
         print("%8.1f us %4d x %6.2f  %s" % (t, c, t / c, k))
-    # phase view: time between successive agg forward kernels etc.
+    # timeline of the last replay: start offset, duration, stream, kernel
+    per = len(st) // 3
+    last = st[-per:]
+    t0 = last[0].time_range.start
+    print("\nTIMELINE of one step (%d kernels, %.1f us):" % (len(last), last[-1].time_range.end - t0))
+    for e in last:
+        print("%8.1f %6.1f  s%-3s %s" % (e.time_range.start - t0, e.time_range.end - e.time_range.start,
+                                        getattr(e, "device_resource_id", "?"), short(e.name)[:70]))
     del tr
 
 
@@ -96,4 +103,5 @@ def eager_profile():
 
 
 graph_profile()
-eager_profile()
+if os.environ.get('KP_PROF_EAGER'):
+    eager_profile()

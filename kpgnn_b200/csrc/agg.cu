@@ -606,13 +606,15 @@ static int make_config(const kp_agg_desc& a, Config* c) {
                  c->ftab != TAB_GLOBAL && (a.act != KP_ACT_NONE || a.fuse);
     if (c->lean_b1) {
       // largest CTA whose dtheta accumulators fit next to the tables; small batches keep 256 threads (more CTAs)
+      static const int env_b1_threads = getenv("KP_LEAN_B1_THREADS") ? atoi(getenv("KP_LEAN_B1_THREADS")) : 0;
       int threads = 1024;
       for (;;) {
         const int gpb = threads / fG;
         const size_t sm = sizeof(float) * ((size_t)c->stage_floats + (size_t)gpb * 3 * fG +
                                            (a.fuse ? (size_t)gpb * a.k * 4 * fG : 0));
-        const bool enough = (long long)a.N >= (long long)kNumSMs * gpb * 2;
-        if ((sm <= 200 * 1024 && enough) || threads == 256) {
+        const bool enough = (long long)a.N * 2 >= (long long)kNumSMs * gpb;   // half a wave of CTAs is enough (measured)
+        if (env_b1_threads ? threads <= env_b1_threads && (sm <= 200 * 1024 || threads == 256)
+                           : ((sm <= 200 * 1024 && enough) || threads == 256)) {
           c->lean_b1_threads = threads;
           c->lean_b1_smem = sm;
           break;

@@ -105,77 +105,122 @@ __device__ __forceinline__ void db_cp_slab(const float* __restrict__ g, int r0, 
 // out[r][o] = bias[o] + sum_k A[r][k] * W[o][k]   (W in the swizzled layout above), r < nrp (multiple of 4), o < Co.
 // Thread tile 4 rows x 4 channels: the phase is bound by shared-memory bandwidth (every row tile re-reads W), measured
 // 5.1 us with 2x4 tiles on 16 warps vs ~3 us with 4x4 tiles on 8 of them.
-__device__ __forceinline__ void db_gemm_AWt(const float* __restrict__ A, int lda, int Kd, const float* __restrict__ Ws,
-                                            int Co, const float* __restrict__ bias, int nrp, float* __restrict__ out,
-                                            int ldo) {
-  const int ctn = Co >> 2, ntiles = ctn * (nrp >> 2), ws = db_wstride(Kd);
+// thread tile: 4 rows x 4*TCQ output channels.  TCQ = 2 (-DKP_DENSE_TILE8) halves the shared-memory traffic per FMA but
+// leaves 117 of 512 threads busy: measured 6.0 us per GEMM phase vs 3.9 us for TCQ = 1, which stays the default.
+template <int TCQ>
+__device__ __forceinline__ void db_gemm_AWt_t(const float* __restrict__ A, int lda, int Kd, const float* __restrict__ Ws,
+                                              int Co, const float* __restrict__ bias, int nrp, float* __restrict__ out,
+                                              int ldo) {
+  const int ctn = Co / (4 * TCQ), ntiles = ctn * (nrp >> 2), ws = db_wstride(Kd);
   for (int t = threadIdx.x; t < ntiles; t += DB_THREADS) {
     const int rt = t / ctn, ct = t - rt * ctn;
-    const int r = rt * 4, o = ct * 4, sw = ct & 7;
-    float4 acc[4];
-    const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + o));
+    const int r = rt * 4, o = ct * 4 * TCQ;
+    float4 acc[TCQ][4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[j] = bv;
+    for (int q = 0; q < TCQ; ++q) {
+      const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + o + 4 * q));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[q][j] = bv;
+    }
     const float* a = A + r * lda;
-    const float* w0 = Ws + o * ws;
 #pragma unroll 2
     for (int kc = 0; kc < (Kd >> 2); ++kc) {
-      float4 x[4], w[4];
+      float4 x[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) x[j] = *reinterpret_cast<const float4*>(a + j * lda + (kc << 2));
 #pragma unroll
-      for (int j = 0; j < 4; ++j) w[j] = *reinterpret_cast<const float4*>(w0 + j * ws + ((kc ^ sw) << 2));
+      for (int q = 0; q < TCQ; ++q) {
+        const int sw = (ct * TCQ + q) & 7;
+        const float* w0 = Ws + (o + 4 * q) * ws + ((kc ^ sw) << 2);
+        float4 w[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        acc[j].x = fmaf(x[j].x, w[0].x, acc[j].x); acc[j].x = fmaf(x[j].y, w[0].y, acc[j].x);
-        acc[j].x = fmaf(x[j].z, w[0].z, acc[j].x); acc[j].x = fmaf(x[j].w, w[0].w, acc[j].x);
-        acc[j].y = fmaf(x[j].x, w[1].x, acc[j].y); acc[j].y = fmaf(x[j].y, w[1].y, acc[j].y);
-        acc[j].y = fmaf(x[j].z, w[1].z, acc[j].y); acc[j].y = fmaf(x[j].w, w[1].w, acc[j].y);
-        acc[j].z = fmaf(x[j].x, w[2].x, acc[j].z); acc[j].z = fmaf(x[j].y, w[2].y, acc[j].z);
-        acc[j].z = fmaf(x[j].z, w[2].z, acc[j].z); acc[j].z = fmaf(x[j].w, w[2].w, acc[j].z);
-        acc[j].w = fmaf(x[j].x, w[3].x, acc[j].w); acc[j].w = fmaf(x[j].y, w[3].y, acc[j].w);
-        acc[j].w = fmaf(x[j].z, w[3].z, acc[j].w); acc[j].w = fmaf(x[j].w, w[3].w, acc[j].w);
+        for (int j = 0; j < 4; ++j) w[j] = *reinterpret_cast<const float4*>(w0 + j * ws);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float4& c = acc[q][j];
+          c.x = fmaf(x[j].x, w[0].x, c.x); c.x = fmaf(x[j].y, w[0].y, c.x);
+          c.x = fmaf(x[j].z, w[0].z, c.x); c.x = fmaf(x[j].w, w[0].w, c.x);
+          c.y = fmaf(x[j].x, w[1].x, c.y); c.y = fmaf(x[j].y, w[1].y, c.y);
+          c.y = fmaf(x[j].z, w[1].z, c.y); c.y = fmaf(x[j].w, w[1].w, c.y);
+          c.z = fmaf(x[j].x, w[2].x, c.z); c.z = fmaf(x[j].y, w[2].y, c.z);
+          c.z = fmaf(x[j].z, w[2].z, c.z); c.z = fmaf(x[j].w, w[2].w, c.z);
+          c.w = fmaf(x[j].x, w[3].x, c.w); c.w = fmaf(x[j].y, w[3].y, c.w);
+          c.w = fmaf(x[j].z, w[3].z, c.w); c.w = fmaf(x[j].w, w[3].w, c.w);
+        }
       }
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(out + (r + j) * ldo + o) = acc[j];
+    for (int q = 0; q < TCQ; ++q)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(out + (r + j) * ldo + o + 4 * q) = acc[q][j];
   }
 }
+__device__ __forceinline__ void db_gemm_AWt(const float* __restrict__ A, int lda, int Kd, const float* __restrict__ Ws,
+                                            int Co, const float* __restrict__ bias, int nrp, float* __restrict__ out,
+                                            int ldo) {
+#ifdef KP_DENSE_TILE8
+  if (Co % 8 == 0) {
+    db_gemm_AWt_t<2>(A, lda, Kd, Ws, Co, bias, nrp, out, ldo);
+    return;
+  }
+#endif
+  db_gemm_AWt_t<1>(A, lda, Kd, Ws, Co, bias, nrp, out, ldo);
+}
 
-// out[r][n] = sum_k A[r][k] * B[k][n]   for r < nrp (multiple of 4), n < Nn; all in shared memory; thread tile 4 x 4
-__device__ __forceinline__ void db_gemm_AB(const float* __restrict__ A, int lda, int Kd, const float* __restrict__ B,
-                                           int Nn, int nrp, float* __restrict__ out, int ldo) {
-  const int ctn = Nn >> 2, ntiles = ctn * (nrp >> 2);
+// out[r][n] = sum_k A[r][k] * B[k][n]   for r < nrp (multiple of 4), n < Nn; all in shared memory; tile 4 x 4*TCQ
+template <int TCQ>
+__device__ __forceinline__ void db_gemm_AB_t(const float* __restrict__ A, int lda, int Kd, const float* __restrict__ B,
+                                             int Nn, int nrp, float* __restrict__ out, int ldo) {
+  const int ctn = Nn / (4 * TCQ), ntiles = ctn * (nrp >> 2);
   for (int t = threadIdx.x; t < ntiles; t += DB_THREADS) {
     const int rt = t / ctn, ct = t - rt * ctn;
-    const int r = rt * 4, n = ct * 4;
-    float4 acc[4];
+    const int r = rt * 4, n = ct * 4 * TCQ;
+    float4 acc[TCQ][4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q = 0; q < TCQ; ++q)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[q][j] = make_float4(0.f, 0.f, 0.f, 0.f);
     const float* a = A + r * lda;
     const float* b = B + n;
 #pragma unroll 2
     for (int k = 0; k < Kd; k += 4) {
-      float4 x[4], w[4];
+      float4 x[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) x[j] = *reinterpret_cast<const float4*>(a + j * lda + k);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) w[j] = *reinterpret_cast<const float4*>(b + (k + j) * Nn);
+      for (int q = 0; q < TCQ; ++q) {
+        float4 w[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        acc[j].x = fmaf(x[j].x, w[0].x, acc[j].x); acc[j].y = fmaf(x[j].x, w[0].y, acc[j].y);
-        acc[j].z = fmaf(x[j].x, w[0].z, acc[j].z); acc[j].w = fmaf(x[j].x, w[0].w, acc[j].w);
-        acc[j].x = fmaf(x[j].y, w[1].x, acc[j].x); acc[j].y = fmaf(x[j].y, w[1].y, acc[j].y);
-        acc[j].z = fmaf(x[j].y, w[1].z, acc[j].z); acc[j].w = fmaf(x[j].y, w[1].w, acc[j].w);
-        acc[j].x = fmaf(x[j].z, w[2].x, acc[j].x); acc[j].y = fmaf(x[j].z, w[2].y, acc[j].y);
-        acc[j].z = fmaf(x[j].z, w[2].z, acc[j].z); acc[j].w = fmaf(x[j].z, w[2].w, acc[j].w);
-        acc[j].x = fmaf(x[j].w, w[3].x, acc[j].x); acc[j].y = fmaf(x[j].w, w[3].y, acc[j].y);
-        acc[j].z = fmaf(x[j].w, w[3].z, acc[j].z); acc[j].w = fmaf(x[j].w, w[3].w, acc[j].w);
+        for (int j = 0; j < 4; ++j) w[j] = *reinterpret_cast<const float4*>(b + (k + j) * Nn + 4 * q);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float4& c = acc[q][j];
+          c.x = fmaf(x[j].x, w[0].x, c.x); c.y = fmaf(x[j].x, w[0].y, c.y);
+          c.z = fmaf(x[j].x, w[0].z, c.z); c.w = fmaf(x[j].x, w[0].w, c.w);
+          c.x = fmaf(x[j].y, w[1].x, c.x); c.y = fmaf(x[j].y, w[1].y, c.y);
+          c.z = fmaf(x[j].y, w[1].z, c.z); c.w = fmaf(x[j].y, w[1].w, c.w);
+          c.x = fmaf(x[j].z, w[2].x, c.x); c.y = fmaf(x[j].z, w[2].y, c.y);
+          c.z = fmaf(x[j].z, w[2].z, c.z); c.w = fmaf(x[j].z, w[2].w, c.w);
+          c.x = fmaf(x[j].w, w[3].x, c.x); c.y = fmaf(x[j].w, w[3].y, c.y);
+          c.z = fmaf(x[j].w, w[3].z, c.z); c.w = fmaf(x[j].w, w[3].w, c.w);
+        }
       }
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(out + (r + j) * ldo + n) = acc[j];
+    for (int q = 0; q < TCQ; ++q)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(out + (r + j) * ldo + n + 4 * q) = acc[q][j];
   }
+}
+__device__ __forceinline__ void db_gemm_AB(const float* __restrict__ A, int lda, int Kd, const float* __restrict__ B,
+                                           int Nn, int nrp, float* __restrict__ out, int ldo) {
+#ifdef KP_DENSE_TILE8
+  if (Nn % 8 == 0) {
+    db_gemm_AB_t<2>(A, lda, Kd, B, Nn, nrp, out, ldo);
+    return;
+  }
+#endif
+  db_gemm_AB_t<1>(A, lda, Kd, B, Nn, nrp, out, ldo);
 }
 
 // outg[m][n] = sum_{r<nr} A[r][m] * B[r][n]  (A, B in shared memory; outg in global memory, [M][Nn])

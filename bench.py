@@ -413,13 +413,38 @@ def agg_roofline(device, num_graphs, peak, reps=10):
                          "kernels": "agg_bwd_dst_lean (B1) + agg_fwd_lean<gather> (B2) + agg_bwd_table_count (B3) + reductions"}}
 
 
+def oracle_batch(num_graphs, seed):
+    """The same synthetic batch as host_batch(), built WITHOUT the product: oracle extraction (numpy restatement of
+    data_utils.py:20-241) per graph, then PyG Batch.from_data_list collation.  Untimed setup of the reference arm."""
+    import numpy as np
+    from kpgnn_b200 import synth
+    from oracle.extract_np import extract_multi_hop_neighbors_np
+    graphs = synth.zinc_like_graphs(num_graphs, seed=seed)
+    keys = ("edge_attr", "pe_attr", "peripheral_edge_attr", "peripheral_configuration_attr")
+    cols = {k: [] for k in keys}
+    ei, xs, batch, off = [], [], [], 0
+    for i, g in enumerate(graphs):
+        o = extract_multi_hop_neighbors_np(g["num_nodes"], g["edge_index"], g["edge_attr"], *EXTRACT_ARGS)
+        ei.append(o["edge_index"] + off)
+        for k in keys:
+            cols[k].append(o[k])
+        xs.append(g["x"])
+        batch.append(np.full(g["num_nodes"], i, dtype=np.int64))
+        off += g["num_nodes"]
+    b = {k: torch.from_numpy(np.concatenate(v, 0)) for k, v in cols.items()}
+    b["edge_index"] = torch.from_numpy(np.concatenate(ei, 1))
+    b["x"] = torch.from_numpy(np.concatenate(xs))
+    b["batch"] = torch.from_numpy(np.concatenate(batch))
+    b["y"] = torch.tensor([g["y"] for g in graphs], dtype=torch.float32)
+    b["num_graphs"] = num_graphs
+    return b
+
+
 def cpu_baseline(steps=4, warmup=1):
     """The oracle port of the reference training step (dense [E,k,d] messages, torch CPU), all host threads."""
     from oracle.model_torch import l1_loss, zinc_oracle_model
     torch.set_num_threads(os.cpu_count())
-    hb = host_batch(GRAPHS_PER_GPU, seed=0)
-    b = {f: getattr(hb, f) for f in hb.FIELDS}
-    b["num_graphs"] = hb.num_graphs
+    b = oracle_batch(GRAPHS_PER_GPU, seed=0)
     torch.manual_seed(0)
     model = zinc_oracle_model(K, LAYERS, HIDDEN).train()
     opt = torch.optim.Adam(model.parameters(), lr=1e-3)

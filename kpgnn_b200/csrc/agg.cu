@@ -610,7 +610,7 @@ static int make_config(const kp_agg_desc& a, Config* c) {
       int threads = 1024;
       for (;;) {
         const int gpb = threads / fG;
-        const size_t sm = sizeof(float) * ((size_t)c->stage_floats + (size_t)gpb * 3 * fG +
+        const size_t sm = sizeof(float) * ((size_t)c->stage_floats + (size_t)gpb * (lean_group_scratch_bytes(fG) / 4) +
                                            (a.fuse ? (size_t)gpb * a.k * 4 * fG : 0));
         const bool enough = (long long)a.N * 2 >= (long long)kNumSMs * gpb;   // half a wave of CTAs is enough (measured)
         if (env_b1_threads ? threads <= env_b1_threads && (sm <= 200 * 1024 || threads == 256)

@@ -41,6 +41,13 @@ struct FastArgs {
   int oacc = 0;
 };
 
+// Lean kernels (agg_lean.cuh): entries of one destination node held in the group's shared-memory window.  The first
+// G entries arrive through the one-node-ahead register prefetch, the rest (a 34-atom molecule at K = 8 has nodes with
+// 33 in-entries) are fetched with coalesced loads when the node is published; only nodes with more than kLeanWin
+// entries take the entry-by-entry path.  Per group: kLeanWin x {X element offset, table byte address} + G row pointers.
+constexpr int kLeanWin = 64;
+__host__ __device__ constexpr unsigned lean_group_scratch_bytes(int G) { return 8u * kLeanWin + 4u * (unsigned)G; }
+
 __device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float4 ld4s(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float4 lds4_sh(unsigned addr) {   // explicit LDS.128 with a 32-bit shared address
@@ -73,22 +80,33 @@ __device__ __forceinline__ unsigned group_mask() {
 
 // Stages tables (TAB_SMEM) and theta (NEED_THETA) at the start of dynamic shared memory.
 // Layout: [T0 rows0*d][Tk rowsk*d][theta k*d].  Returns the number of floats staged.
+// The three sources are walked as ONE virtual array and every thread issues up to KP_STAGE_BATCH 16-byte loads before
+// its first store: at the bench batch (27 KB per CTA, 256 threads) the copy is one L2 round trip instead of eight
+// dependent ones (22 % of the forward kernel's stall samples, profiles/r1zzz_small_batch.txt).
+#ifndef KP_STAGE_BATCH
+#define KP_STAGE_BATCH 8
+#endif
 template <int TAB, bool NEED_THETA>
 __device__ __forceinline__ int stage_tables(const kp_agg_desc& a, float* sm) {
-  int off = 0;
-  if (TAB == TAB_SMEM) {
-    const int n0 = a.rows0 * a.d, nk = a.rowsk * a.d;
-    for (int i = threadIdx.x * 4; i < n0; i += blockDim.x * 4) st4(sm + i, ld4(a.T0 + i));
-    for (int i = threadIdx.x * 4; i < nk; i += blockDim.x * 4) st4(sm + n0 + i, ld4(a.Tk + i));
-    off = n0 + nk;
-  }
-  if (NEED_THETA) {
-    const int nt = a.k * a.d;
-    for (int i = threadIdx.x * 4; i < nt; i += blockDim.x * 4) st4(sm + off + i, ld4(a.theta + i));
-    off += nt;
+  const int n0 = (TAB == TAB_SMEM) ? a.rows0 * a.d : 0;
+  const int n1 = n0 + ((TAB == TAB_SMEM) ? a.rowsk * a.d : 0);
+  const int total = n1 + (NEED_THETA ? a.k * a.d : 0);
+  const int step = blockDim.x * 4;
+  for (int base = threadIdx.x * 4; base < total; base += step * KP_STAGE_BATCH) {
+    float4 v[KP_STAGE_BATCH];
+#pragma unroll
+    for (int j = 0; j < KP_STAGE_BATCH; ++j) {
+      const int i = base + j * step;
+      if (i < total) v[j] = ld4(i < n0 ? a.T0 + i : (i < n1 ? a.Tk + (i - n0) : a.theta + (i - n1)));
+    }
+#pragma unroll
+    for (int j = 0; j < KP_STAGE_BATCH; ++j) {
+      const int i = base + j * step;
+      if (i < total) st4(sm + i, v[j]);
+    }
   }
   __syncthreads();
-  return off;
+  return total;
 }
 
 // Gathers one node's hop segments.  The node's entry list (all hops, contiguous in the plan) is read through a

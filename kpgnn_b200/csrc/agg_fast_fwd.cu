@@ -47,7 +47,7 @@ static int launch_lean(const FastArgs& fa, int grid, size_t smem, float* out, cu
   static const int env_threads = getenv("KP_LEAN_THREADS") ? atoi(getenv("KP_LEAN_THREADS")) : 0;
   const int threads = env_threads ? env_threads : ((long long)a.N >= (long long)kNumSMs * (1024 / G) * 2 ? 1024 : 256);
   const int gpb = threads / G, ctas_per_sm = 1024 / threads;
-  const size_t total = smem + (size_t)gpb * 12 * G;             // + per-group entry window and row pointers
+  const size_t total = smem + (size_t)gpb * lean_group_scratch_bytes(G);   // + per-group entry window and row pointers
   const long long want = ((long long)a.N + gpb - 1) / gpb;
   grid = (int)(want < kNumSMs * ctas_per_sm ? (want < 1 ? 1 : want) : kNumSMs * ctas_per_sm);   // persistent
   if (total > 48 * 1024)

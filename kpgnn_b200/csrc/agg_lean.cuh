@@ -200,6 +200,21 @@ __device__ __forceinline__ void lean_gather(P4& z, unsigned ent, const float* Xh
   for (int i = 0; i < NE; ++i) z = add4p(z, x[i]);
 }
 
+// Entries G .. kLeanWin-1 of the node being published (the first G came through the register prefetch): coalesced
+// loads straight from the plan into the group's window.  Uniform per group; a no-op for nodes with <= G entries.
+template <int G, int TAB>
+__device__ __forceinline__ void lean_publish_rest(const kp_agg_desc& a, unsigned win_sh, int nbeg, int nend, int e1,
+                                                  int lane, unsigned xs, unsigned d4, unsigned tab0_sh,
+                                                  unsigned tabk_sh) {
+  const int cnt = min(nend - nbeg, kLeanWin);
+  for (int j = G + lane; j < cnt; j += G) {
+    const int cj = __ldg(a.col + nbeg + j);
+    int aj = 0;
+    if (TAB != TAB_NONE) aj = (int)__ldg(a.attr16 + nbeg + j);
+    sts2_sh(win_sh + 8u * (unsigned)j, (unsigned)cj * xs, (nbeg + j < e1 ? tab0_sh : tabk_sh) + (unsigned)aj * d4);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // forward.  Everything except the KP-GCN per-entry norm (dinv) and tables too large for shared memory, which stay
 // on the kernels of agg_fast.cuh.
@@ -228,8 +243,8 @@ agg_fwd_lean_kernel(const FastArgs fa, float* __restrict__ out, unsigned pf_x_li
   const unsigned theta_sh = sm_base + ((TAB == TAB_SMEM) ? (unsigned)((a.rows0 + a.rowsk) * d) : 0u) * 4u + c * 4u;
   // per-group scratch behind the staged tables: entry window [G] x {X element offset, table byte address} and the
   // node's row pointers [G]
-  const unsigned win_sh = sm_base + (unsigned)staged * 4u + (unsigned)gib * (12u * G);
-  const unsigned rp_sh = win_sh + 8u * G;
+  const unsigned win_sh = sm_base + (unsigned)staged * 4u + (unsigned)gib * lean_group_scratch_bytes(G);
+  const unsigned rp_sh = win_sh + 8u * kLeanWin;
   const float* Xc = opaque_ptr(a.X + c);
   const bool hasP = a.P != nullptr;
   const float* Pc = opaque_ptr(hasP ? a.P + c : a.X + c);
@@ -284,8 +299,9 @@ agg_fwd_lean_kernel(const FastArgs fa, float* __restrict__ out, unsigned pf_x_li
       const unsigned ta = (nbeg + lane < e1 ? tab0_sh : tabk_sh) + (unsigned)nattr * d4;
       sts2_sh(win_sh + 8u * lane, xo, ta);
     }
+    lean_publish_rest<G, TAB>(a, win_sh, nbeg, nend, e1, lane, xs, d4, tab0_sh, tabk_sh);
     group_sync<G>(gm);
-    const bool big = (nend - nbeg) > G;                          // entry list longer than the window: slow path
+    const bool big = (nend - nbeg) > kLeanWin;                   // entry list longer than the window: slow path
     vn = v + vstride;
     rpn = rpnn;
     ncol = 0; nattr = 0;
@@ -491,13 +507,13 @@ agg_bwd_dst_lean_kernel(const FastArgs fa, const float* __restrict__ dOut, float
   const unsigned tab0_sh = sm_base;
   const unsigned tabk_sh = tab0_sh + ((TAB == TAB_SMEM) ? (unsigned)(a.rows0 * d) * 4u : 0u);
   const unsigned theta_sh = sm_base + ((TAB == TAB_SMEM) ? (unsigned)((a.rows0 + a.rowsk) * d) : 0u) * 4u + c4;
-  const unsigned win_sh = sm_base + (unsigned)staged * 4u + (unsigned)gib * (12u * G);
-  const unsigned rp_sh = win_sh + 8u * G;
+  const unsigned win_sh = sm_base + (unsigned)staged * 4u + (unsigned)gib * lean_group_scratch_bytes(G);
+  const unsigned rp_sh = win_sh + 8u * kLeanWin;
   // dtheta accumulators: [gpb][k][4G] floats behind the windows; lane l of group g owns columns 4l..4l+3 of copy g
   constexpr unsigned dpad = 4u * G;
   const bool need_z = FUSE && dtheta_part != nullptr;
-  float* acc_all = sm + staged + gpb * 3 * G;
-  const unsigned acc_sh = sm_base + (unsigned)(staged + gpb * 3 * G) * 4u + (unsigned)(gib * k) * dpad * 4u + (unsigned)lane * 16u;
+  float* acc_all = sm + staged + gpb * (int)(lean_group_scratch_bytes(G) / 4u);
+  const unsigned acc_sh = sm_base + (unsigned)staged * 4u + (unsigned)gpb * lean_group_scratch_bytes(G) + (unsigned)(gib * k) * dpad * 4u + (unsigned)lane * 16u;
   if (need_z) {
     for (int i = threadIdx.x; i < gpb * k * (int)dpad; i += blockDim.x) acc_all[i] = 0.f;
     __syncthreads();
@@ -535,8 +551,9 @@ agg_bwd_dst_lean_kernel(const FastArgs fa, const float* __restrict__ dOut, float
         const unsigned ta = (nbeg + lane < e1 ? tab0_sh : tabk_sh) + (unsigned)nattr * d4;
         sts2_sh(win_sh + 8u * lane, xo, ta);
       }
+      lean_publish_rest<G, TAB>(a, win_sh, nbeg, nend, e1, lane, xs, d4, tab0_sh, tabk_sh);
       group_sync<G>(gm);
-      const bool big = (nend - nbeg) > G;
+      const bool big = (nend - nbeg) > kLeanWin;
       vn = v + vstride;
       rpn = rpnn;
       ncol = 0; nattr = 0;

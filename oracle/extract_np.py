@@ -5,8 +5,8 @@ Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl
 It is the CHECKER for the CUDA extractor in `kpgnn_b200/csrc/extract.cu`; nothing in `kpgnn_b200/` imports it.
 
 Parity status: PINNED against the reference itself, executed unmodified in the build container behind the
-`torch_geometric` stand-in (oracle/refimport.py): see tests/test_oracle_extract.py (live comparison when
-/root/reference exists) and tests/golden/extract_*.npz (committed outputs of the reference, made by
+`torch_geometric` stand-in (oracle/refimport.py): see tests/test_oracle_cpu.py (live comparison when
+/root/reference exists) and tests/golden/extract.npz (committed outputs of the reference, made by
 oracle/make_golden.py).  The reference has no tests or golden vectors of its own.
 
 Arithmetic domain: the reference computes walk counts with float32 sparse matmuls and casts to int32

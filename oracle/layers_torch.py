@@ -7,7 +7,7 @@ torch_geometric pinned 2.1.0, README.md:12, not vendored): flow source->target, 
 sum (or mean) at `edge_index[1]`, `dim_size = N`.
 
 Parity status: PINNED against the reference itself (imported unmodified behind oracle/pyg_standin in the build
-container): tests/test_oracle_layers.py compares live when /root/reference exists, and tests/golden/layer_*.npz
+container): tests/test_oracle_cpu.py compares live when /root/reference exists, and tests/golden/layers.npz
 hold the reference's own outputs/gradients (made by oracle/make_golden.py).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this file.

@@ -175,6 +175,50 @@ def test_op_widths_vs_dense_oracle(lib, d, fuse):
         assert rel_err(a, c) < RTOL, rel_err(a, c)
 
 
+@pytest.mark.parametrize("d", [104, 64])
+@pytest.mark.parametrize("fuse", [False, True])
+def test_entry_window_boundaries(lib, d, fuse):
+    """Destination nodes whose in-entry lists straddle the lean kernels' shared-memory window (G = 32 / 16 lanes,
+    window 64 entries): complete graphs under the gd kernel with K=3 give exactly 3(n-1) entries per node --
+    21, 33 (one past G=32), 48, 63, 66 (two past the window) and 87 -- next to sparse molecules; forward and
+    every gradient against the dense oracle, through every kernel family."""
+    import numpy as np
+    from kpgnn_b200 import synth
+    from kpgnn_b200.ops import khop_aggregate, ACT_GELU
+    from kpgnn_b200.plan import get_plan
+    from tests.util import collate
+    dev = torch.device("cuda:0")
+    K = 3
+    rng = np.random.default_rng(5)
+    graphs = [synth.random_typed_graph(rng, n, 1.1) for n in (8, 12, 17, 22, 23, 30)] + synth.zinc_like_graphs(3, seed=9)
+    b = collate(graphs, (K, 50, 0, 3, 50, 50, "gd"))
+    N = b["num_nodes"]
+    ei, ea = b["edge_index"].to(dev), b["edge_attr"].to(dev)
+    cnt = torch.bincount(b["edge_index"][1], weights=(b["edge_attr"] != 0).sum(1).double(), minlength=N)
+    assert {21, 33, 48, 63, 66, 87} <= set(int(c) for c in cnt.tolist())
+    g = torch.Generator().manual_seed(d)
+    t0 = torch.randn(5, d, generator=g).to(dev)
+    tk = torch.randn(52, d, generator=g).to(dev)
+    th0 = torch.softmax(torch.randn(K, d, generator=g), 0).to(dev)
+    x0 = torch.randn(N, K, d, generator=g).to(dev)
+    P0 = torch.randn(N, K, d, generator=g).to(dev)
+    outs = []
+    for mode in ("oracle", "mine"):
+        x, P = x0.clone().requires_grad_(True), P0.clone().requires_grad_(True)
+        T0, Tk, th = (t.clone().requires_grad_(True) for t in (t0, tk, th0))
+        if mode == "oracle":
+            z = torch.nn.functional.gelu(OL.dense_khop_aggregate(x, ei, ea, T0, Tk)) + P
+            y = (z * th).sum(1) if fuse else z
+        else:
+            plan, k = get_plan(ei, ea, N)
+            y = khop_aggregate(x, plan, k, P=P, T0=T0, Tk=Tk, theta=th if fuse else None, act=ACT_GELU, fuse=fuse)
+        gy = torch.randn(y.shape, generator=torch.Generator().manual_seed(3)).to(dev)
+        y.backward(gy)
+        outs.append([y, x.grad, P.grad, T0.grad, Tk.grad] + ([th.grad] if fuse else []))
+    for a, c in zip(outs[1], outs[0]):
+        assert rel_err(a, c) < RTOL, rel_err(a, c)
+
+
 @pytest.mark.parametrize("K", [1, 3, 6])
 def test_kgin_simulation_layer(lib, K):
     """BASELINE config 5 workload: 3-regular graphs, KGINConv(16, K), forward only (run_simulation.py:96-116)."""

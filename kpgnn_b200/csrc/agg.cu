@@ -608,7 +608,18 @@ static int make_config(const kp_agg_desc& a, Config* c) {
       // largest CTA whose dtheta accumulators fit next to the tables; small batches keep 256 threads (more CTAs)
       static const int env_b1_threads = getenv("KP_LEAN_B1_THREADS") ? atoi(getenv("KP_LEAN_B1_THREADS")) : 0;
       int threads = 1024;
-      for (;;) {
+      const int balanced = env_b1_threads ? 0 : lean_balanced_threads(a.N, fG, 2);
+      if (balanced) {      // one CTA per SM, the same number of groups each (see lean_balanced_threads)
+        const int gpb = balanced / fG;
+        const size_t sm = sizeof(float) * ((size_t)c->stage_floats + (size_t)gpb * (lean_group_scratch_bytes(fG) / 4) +
+                                           (a.fuse ? (size_t)gpb * a.k * 4 * fG : 0));
+        if (sm <= 200 * 1024) {
+          c->lean_b1_threads = balanced;
+          c->lean_b1_smem = sm;
+          threads = 0;
+        }
+      }
+      while (threads) {
         const int gpb = threads / fG;
         const size_t sm = sizeof(float) * ((size_t)c->stage_floats + (size_t)gpb * (lean_group_scratch_bytes(fG) / 4) +
                                            (a.fuse ? (size_t)gpb * a.k * 4 * fG : 0));

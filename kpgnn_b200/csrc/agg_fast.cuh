@@ -19,6 +19,7 @@
 //   * optional features (GCN norm, SAGE mean, GIN self term) are compiled out unless EXTRA;
 //   * GELU through the erfc form with raw MUFU.RCP / MUFU.EX2 (agg_common.cuh).
 #pragma once
+#include <stdlib.h>
 #include "agg_common.cuh"
 
 namespace kp {
@@ -47,6 +48,21 @@ struct FastArgs {
 // entries take the entry-by-entry path.  Per group: kLeanWin x {X element offset, table byte address} + G row pointers.
 constexpr int kLeanWin = 64;
 __host__ __device__ constexpr unsigned lean_group_scratch_bytes(int G) { return 8u * kLeanWin + 4u * (unsigned)G; }
+
+// Launch geometry of the lean kernels for batches that fit ONE wave (N <= kNumSMs * 1024 / G nodes): CTAs sized so
+// that every SM gets exactly one CTA with the same number of lane groups -- ceil(N / kNumSMs) groups, threads a
+// multiple of 32, at least 256.  At the bench batch (2 986 nodes) that is 143 CTAs x 672 threads instead of 374 x 256
+// (2 or 3 CTAs per SM: the 3-CTA SMs set the kernel time) or 94 x 1024 (54 SMs idle).  Returns 0 when the batch does
+// not fit one wave (the caller keeps its persistent configuration).  KP_LEAN_BALANCED is a bit mask for A/B runs:
+// 1 = forward / B2 launches, 2 = B1 launches.
+inline int lean_balanced_threads(long long N, int G, int which) {
+  static const int mask = getenv("KP_LEAN_BALANCED") ? atoi(getenv("KP_LEAN_BALANCED")) : 3;
+  if (!(mask & which) || N <= 0 || N > (long long)kNumSMs * (1024 / G)) return 0;
+  long long gpb = (N + kNumSMs - 1) / kNumSMs;
+  int threads = (int)((gpb * G + 31) / 32 * 32);
+  if (threads < 256) threads = 256;
+  return threads > 1024 ? 1024 : threads;
+}
 
 __device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float4 ld4s(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }

@@ -45,7 +45,10 @@ static int launch_lean(const FastArgs& fa, int grid, size_t smem, float* out, cu
   // one 1024-thread CTA per SM when there are enough nodes to give every SM a few blocks (tables staged once per
   // SM, 32 neighbouring nodes in flight on one L1); 256-thread CTAs for small batches so that all SMs get work
   static const int env_threads = getenv("KP_LEAN_THREADS") ? atoi(getenv("KP_LEAN_THREADS")) : 0;
-  const int threads = env_threads ? env_threads : ((long long)a.N >= (long long)kNumSMs * (1024 / G) * 2 ? 1024 : 256);
+  const int balanced = lean_balanced_threads(a.N, G, 1);
+  const int threads = env_threads ? env_threads
+                      : balanced ? balanced
+                                 : ((long long)a.N >= (long long)kNumSMs * (1024 / G) * 2 ? 1024 : 256);
   const int gpb = threads / G, ctas_per_sm = 1024 / threads;
   const size_t total = smem + (size_t)gpb * lean_group_scratch_bytes(G);   // + per-group entry window and row pointers
   const long long want = ((long long)a.N + gpb - 1) / gpb;

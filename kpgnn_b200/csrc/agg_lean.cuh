@@ -515,7 +515,7 @@ agg_bwd_dst_lean_kernel(const FastArgs fa, const float* __restrict__ dOut, float
   float* acc_all = sm + staged + gpb * (int)(lean_group_scratch_bytes(G) / 4u);
   const unsigned acc_sh = sm_base + (unsigned)staged * 4u + (unsigned)gpb * lean_group_scratch_bytes(G) + (unsigned)(gib * k) * dpad * 4u + (unsigned)lane * 16u;
   if (need_z) {
-    for (int i = threadIdx.x; i < gpb * k * (int)dpad; i += blockDim.x) acc_all[i] = 0.f;
+    for (int i = threadIdx.x * 4; i < gpb * k * (int)dpad; i += blockDim.x * 4) st4(acc_all + i, make_float4(0.f, 0.f, 0.f, 0.f));
     __syncthreads();
   }
   const float* Xc = opaque_ptr(a.X + c);
@@ -641,7 +641,8 @@ agg_bwd_dst_lean_kernel(const FastArgs fa, const float* __restrict__ dOut, float
     for (int i = threadIdx.x; i < k * d; i += blockDim.x) {   // fixed-order reduction over the CTA's groups
       const int h = i / d, cc = i - h * d;
       float s = 0.f;
-      for (int g = 0; g < gpb; ++g) s += acc_all[((size_t)g * k + h) * dpad + cc];
+#pragma unroll 8
+      for (int g = 0; g < gpb; ++g) s += acc_all[((size_t)g * k + h) * dpad + cc];      // loads batched, adds in order
       dtheta_part[(size_t)blockIdx.x * k * d + i] = s;
     }
   }

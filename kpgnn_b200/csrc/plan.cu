@@ -19,7 +19,8 @@ __global__ void plan_count_kernel(const int64_t* __restrict__ src, const int64_t
   long long total = (long long)E * K;
   int max0 = 0, maxk = 0, bad = 0;
   if (t < total) {
-    int e = (int)(t / K), h = (int)(t - (long long)e * K);
+    const unsigned tu = (unsigned)t;                 // E * K < 2^31 (kp_plan_workspace_bytes): 32-bit division
+    int e = (int)(tu / (unsigned)K), h = (int)(tu - (unsigned)e * (unsigned)K);
     long long s = src[e], d = dst[e];
     bool ok = (s >= 0 && s < N && d >= 0 && d < N);
     if (!ok) {
@@ -38,16 +39,28 @@ __global__ void plan_count_kernel(const int64_t* __restrict__ src, const int64_t
       }
     }
   }
-  // warp-reduce the statistics before touching global memory
+  // Statistics: warp shuffle -> shared-memory atomics -> ONE guarded global update per CTA.  Every warp issuing its
+  // own atomicMax on stats[1..2] serialised ~30 k same-address reductions in L2: 12 of this kernel's 17 us at the
+  // bench batch, during which the step's encoder branch could not start (profiles/r1zzz_small_batch.txt).
+  __shared__ int s_stat[3];
+  if (threadIdx.x < 3) s_stat[threadIdx.x] = 0;
+  __syncthreads();
   for (int o = 16; o > 0; o >>= 1) {
     max0 = max(max0, __shfl_xor_sync(0xffffffffu, max0, o));
     maxk = max(maxk, __shfl_xor_sync(0xffffffffu, maxk, o));
     bad += __shfl_xor_sync(0xffffffffu, bad, o);
   }
   if ((threadIdx.x & 31) == 0) {
-    if (max0) atomicMax(&stats[1], max0);
-    if (maxk) atomicMax(&stats[2], maxk);
-    if (bad) atomicAdd(&stats[3], bad);
+    if (max0) atomicMax(&s_stat[0], max0);
+    if (maxk) atomicMax(&s_stat[1], maxk);
+    if (bad) atomicAdd(&s_stat[2], bad);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // the plain read only filters: a stale (smaller) value costs one redundant atomic, never a lost update
+    if (s_stat[0] > __ldcg(&stats[1])) atomicMax(&stats[1], s_stat[0]);
+    if (s_stat[1] > __ldcg(&stats[2])) atomicMax(&stats[2], s_stat[1]);
+    if (s_stat[2]) atomicAdd(&stats[3], s_stat[2]);
   }
 }
 
@@ -70,7 +83,8 @@ __global__ void plan_scatter_kernel(const int64_t* __restrict__ src, const int64
                                     int* __restrict__ eidT, int cap) {
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)E * K) return;
-  int e = (int)(t / K), h = (int)(t - (long long)e * K);
+  const unsigned tu = (unsigned)t;
+  int e = (int)(tu / (unsigned)K), h = (int)(tu - (unsigned)e * (unsigned)K);
   long long s = src[e], d = dst[e];
   if (s < 0 || s >= N || d < 0 || d >= N) return;
   long long a = attr[(long long)e * attr_stride + h];
@@ -93,24 +107,45 @@ __device__ __forceinline__ void insertion_sort(int* a, int n) {
   }
 }
 
-// one thread per row: restore ascending edge id inside the row, then emit the compact arrays
+// Edge ids of one row in ascending order.  Rows of up to KP_EMIT_LOCAL entries are sorted in a thread-local buffer
+// (all loads issued up front, the data-dependent insertion steps hit L1): sorting in place in global memory made
+// every compare a dependent L2 round trip, and the row with the most entries set the kernel time (20 us at the bench
+// batch).  Longer rows are sorted in place.
+#define KP_EMIT_LOCAL 32
+__device__ __forceinline__ const int* sorted_row_ids(int* g, int n, int* buf) {
+  if (n > KP_EMIT_LOCAL) {
+    insertion_sort(g, n);
+    return g;
+  }
+#pragma unroll 4
+  for (int i = 0; i < n; ++i) buf[i] = g[i];
+  insertion_sort(buf, n);
+  return buf;
+}
+
+// two threads per row (even: the (dst,hop) row, odd: the (src,hop) row of the transpose): restore ascending edge id
+// inside the row, then emit the compact arrays
 __global__ void plan_emit_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
                                  const int64_t* __restrict__ attr, int64_t attr_stride, int N, int K,
                                  int self_loops, const int* __restrict__ rowptr, const int* __restrict__ rowptrT,
                                  int* __restrict__ eid, int* __restrict__ eidT, int* __restrict__ col,
                                  uint16_t* __restrict__ attr16, int* __restrict__ colT,
                                  float* __restrict__ dinv, int cap) {
-  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = (int)(t >> 1);
+  const bool transposed = t & 1u;
   if (r >= N * K) return;
   int v = r / K, h = r - v * K;
-  if (dinv) dinv[r] = 1.0f / sqrtf((float)(rowptr[r + 1] - rowptr[r]));
+  if (dinv && !transposed) dinv[r] = 1.0f / sqrtf((float)(rowptr[r + 1] - rowptr[r]));
   if (rowptr[r + 1] > cap || rowptrT[r + 1] > cap) return;   // overflow: reported through stats[0] > capacity
-  {
+  int buf[KP_EMIT_LOCAL];
+  if (!transposed) {
     int b = rowptr[r], e = rowptr[r + 1];
     int n = e - b - (self_loops ? 1 : 0);
-    insertion_sort(eid + b, n);
+    const int* ids = sorted_row_ids(eid + b, n, buf);
+#pragma unroll 4
     for (int i = 0; i < n; ++i) {
-      int id = eid[b + i];
+      int id = ids[i];
       col[b + i] = (int)src[id];
       attr16[b + i] = (uint16_t)attr[(long long)id * attr_stride + h];
     }
@@ -118,12 +153,12 @@ __global__ void plan_emit_kernel(const int64_t* __restrict__ src, const int64_t*
       col[e - 1] = v;
       attr16[e - 1] = 1;
     }
-  }
-  {
+  } else {
     int b = rowptrT[r], e = rowptrT[r + 1];
     int n = e - b - (self_loops ? 1 : 0);
-    insertion_sort(eidT + b, n);
-    for (int i = 0; i < n; ++i) colT[b + i] = (int)dst[eidT[b + i]];
+    const int* ids = sorted_row_ids(eidT + b, n, buf);
+#pragma unroll 4
+    for (int i = 0; i < n; ++i) colT[b + i] = (int)dst[ids[i]];
     if (self_loops) colT[e - 1] = v;
   }
 }
@@ -207,7 +242,7 @@ int kp_plan_fill(const kp_plan_input* in, const int32_t* rowptr, const int32_t* 
     KP_LAUNCH(kp::plan_scatter_kernel, kp::ceil_div(total, 256), 256, 0, st, in->src, in->dst, in->attr,
               in->attr_stride, N, E, K, rowptr, rowptrT, cur, curT, eid, eidT, (int)capacity);
   }
-  KP_LAUNCH(kp::plan_emit_kernel, kp::ceil_div(rows, 128), 128, 0, st, in->src, in->dst, in->attr,
+  KP_LAUNCH(kp::plan_emit_kernel, kp::ceil_div(2 * rows, 128), 128, 0, st, in->src, in->dst, in->attr,
             in->attr_stride, N, K, in->self_loops, rowptr, rowptrT, eid, eidT, col, attr16, colT, dinv, (int)capacity);
   return 0;
 }

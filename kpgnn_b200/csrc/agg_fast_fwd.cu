@@ -43,7 +43,8 @@ static int launch_lean(const FastArgs& fa, int grid, size_t smem, float* out, cu
   if (env_mode == 0) { pfx_ = 0; pfp_ = 0; }
   if (env_mode == 2 && pfx) bulk = (unsigned)(a.k * a.d) * 4u;
   // one 1024-thread CTA per SM when there are enough nodes to give every SM a few blocks (tables staged once per
-  // SM, 32 neighbouring nodes in flight on one L1); 256-thread CTAs for small batches so that all SMs get work
+  // SM, 32 neighbouring nodes in flight on one L1); batches that fit one wave get one equally sized CTA per SM
+  // (lean_balanced_threads); 256-thread CTAs in between so that all SMs get work
   static const int env_threads = getenv("KP_LEAN_THREADS") ? atoi(getenv("KP_LEAN_THREADS")) : 0;
   const int balanced = lean_balanced_threads(a.N, G, 1);
   const int threads = env_threads ? env_threads

@@ -56,3 +56,33 @@ def test_product_never_imports_oracle():
                 if re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M):
                     bad.append(os.path.join(dirpath, f))
     assert not bad, bad
+
+
+def test_struct_layouts_match_header(tmp_path):
+    """Every ctypes mirror in kpgnn_b200/_lib.py has the size and the field offsets the C compiler gives the struct
+    declared in include/kpgnn.h (a silent drift here would make the kernels read garbage descriptors)."""
+    import subprocess
+    from kpgnn_b200 import _lib
+    mirrors = {"kp_plan_input": _lib.PlanInput, "kp_agg_desc": _lib.AggDesc, "kp_extract_input": _lib.ExtractInput,
+               "kp_tsum_desc": _lib.TsumDesc, "kp_dense_desc": _lib.DenseDesc, "kp_theta_batch": _lib.ThetaBatch,
+               "kp_pgrad_desc": _lib.PgradDesc}
+    header = open(os.path.join(ROOT, "include", "kpgnn.h")).read()
+    declared = set(re.findall(r"^\}\s*(kp_[a-z0-9_]+)\s*;", header, flags=re.M))
+    # structs that never cross the Python boundary as ctypes objects are packed with numpy/torch instead
+    assert declared - set(mirrors) <= {"kp_adam_tensor"}, declared - set(mirrors)
+    lines = ['#include <stdio.h>', '#include "kpgnn.h"', "int main(void) {"]
+    for cname, cls in mirrors.items():
+        lines.append('  printf("%s.sizeof %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('  printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    c_layout = dict(line.split() for line in out.splitlines())
+    for cname, cls in mirrors.items():
+        assert int(c_layout[cname + ".sizeof"]) == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(c_layout["%s.%s" % (cname, fname)]) == getattr(cls, fname).offset, (cname, fname)

@@ -57,6 +57,7 @@ __host__ __device__ constexpr unsigned lean_group_scratch_bytes(int G) { return 
 // 1 = forward / B2 launches, 2 = B1 launches.
 inline int lean_balanced_threads(long long N, int G, int which) {
   static const int mask = getenv("KP_LEAN_BALANCED") ? atoi(getenv("KP_LEAN_BALANCED")) : 3;
+  if (G != 32) return 0;      // measured and parity-tested at one-wave sizes for 32-lane groups only (64 < d <= 128)
   if (!(mask & which) || N <= 0 || N > (long long)kNumSMs * (1024 / G)) return 0;
   long long gpb = (N + kNumSMs - 1) / kNumSMs;
   int threads = (int)((gpb * G + 31) / 32 * 32);

@@ -241,8 +241,8 @@ agg_fwd_lean_kernel(const FastArgs fa, float* __restrict__ out, unsigned pf_x_li
   const unsigned tab0_sh = sm_base;
   const unsigned tabk_sh = tab0_sh + ((TAB == TAB_SMEM) ? (unsigned)(a.rows0 * d) * 4u : 0u);
   const unsigned theta_sh = sm_base + ((TAB == TAB_SMEM) ? (unsigned)((a.rows0 + a.rowsk) * d) : 0u) * 4u + c * 4u;
-  // per-group scratch behind the staged tables: entry window [G] x {X element offset, table byte address} and the
-  // node's row pointers [G]
+  // per-group scratch behind the staged tables: entry window [kLeanWin] x {X element offset, table byte address} and
+  // the node's row pointers [G]
   const unsigned win_sh = sm_base + (unsigned)staged * 4u + (unsigned)gib * lean_group_scratch_bytes(G);
   const unsigned rp_sh = win_sh + 8u * kLeanWin;
   const float* Xc = opaque_ptr(a.X + c);

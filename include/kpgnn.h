@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define KPGNN_ABI_VERSION 7
+#define KPGNN_ABI_VERSION 8
 
 const char* kp_last_error(void);
 int kp_abi_version(void);
@@ -247,6 +247,13 @@ typedef struct {
 } kp_adam_tensor;
 int kp_adam_step(const kp_adam_tensor* tensors_dev, const int32_t* chunks_dev, int32_t nchunks, float lr, double beta1,
                  double beta2, float eps, int32_t* state_dev, void* stream);   /* betas in double: 1-beta is formed exactly */
+
+/* Graph readout over a sorted segment vector: PyG global_add_pool / global_mean_pool on `data.batch`
+ * (models/GraphRegression.py:26, models/GraphClassification.py:30).  out[g,:] = sum (mean != 0: mean) of the rows i of
+ * x [N,C] (row stride x_stride elements) with seg[i] == g; seg is int64, non-decreasing, values in [0,G).  Rows are
+ * added in ascending order by one thread per column: bit-reproducible, no float atomics. */
+int kp_segment_sum(const float* x, int64_t x_stride, const int64_t* seg, int32_t N, int32_t C, int32_t G, int32_t mean,
+                   float* out, void* stream);
 
 /* GeometricCombine weights, layers/combine.py:51-58: theta[h,c] = softmax over h of a_c (1-a_c)^h with
  * a = sigmoid(alphas); theta is [K,d].  Backward returns d(loss)/d(alphas) from d(loss)/d(theta). */

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # KPGNN_B200_LIB points at an alternative build of the same library (kernel tuning experiments)
 LIB_PATH = os.environ.get("KPGNN_B200_LIB") or os.path.join(_HERE, "libkpgnn_b200.so")
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 
 class KpError(RuntimeError):
@@ -115,6 +115,8 @@ _SIGNATURES = {
     "kp_geometric_theta_forward_batched": (C.c_int, [C.POINTER(ThetaBatch), C.c_void_p]),
     "kp_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_double, C.c_double, C.c_float,
                                C.c_void_p, C.c_void_p]),
+    "kp_segment_sum": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                C.c_void_p, C.c_void_p]),
     "kp_peripheral_grad": (C.c_int, [C.POINTER(PgradDesc), C.c_void_p, C.c_void_p]),
     "kp_geometric_theta_forward": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "kp_geometric_theta_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
@@ -153,11 +155,12 @@ _BARRIERS = {}
 
 
 def barrier_state(device):
-    """Persistent zero-initialised grid-barrier state for kp_dense_block_* on `device` (one per stream in use)."""
+    """Persistent zero-initialised grid-barrier state for kp_dense_block_* : one per (device, stream), so two dense
+    blocks running concurrently on different streams never share a counter.  During stream capture the key is the
+    capturing stream; the captured graph owns that state for its lifetime (it is never freed)."""
     import torch
-    key = (device.index if device.index is not None else torch.cuda.current_device(),
-           torch.cuda.current_stream(device).cuda_stream if not torch.cuda.is_current_stream_capturing() else -1)
-    key = key[0]
+    dev = device.index if device.index is not None else torch.cuda.current_device()
+    key = (dev, torch.cuda.current_stream(device).cuda_stream)
     t = _BARRIERS.get(key)
     if t is None:
         t = torch.zeros(64, dtype=torch.int32, device=device)

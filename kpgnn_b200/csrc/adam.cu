@@ -13,14 +13,23 @@ namespace kp {
 constexpr int ADAM_CHUNK = 1024;
 
 __global__ void __launch_bounds__(256)
-adam_kernel(const kp_adam_tensor* __restrict__ tensors, const int2* __restrict__ chunks, float lr, float b1, float b2,
-            float omb1, float omb2, float eps, int* __restrict__ state /* [0] = steps taken, [1] = finished blocks */) {
+adam_kernel(const kp_adam_tensor* __restrict__ tensors, const int2* __restrict__ chunks, double lr, double b1d,
+            double b2d, float eps, int* __restrict__ state /* [0] = steps taken, [1] = finished blocks */) {
   const int2 ck = chunks[blockIdx.x];
   const kp_adam_tensor t = tensors[ck.x];
   const int step = state[0] + 1;
-  const float bc1 = 1.f - powf(b1, (float)step);
-  const float bc2s = sqrtf(1.f - powf(b2, (float)step));
-  const float step_size = lr / bc1;
+  // Bias corrections in double, as torch.optim.Adam forms them on the host (1 - beta^t cancels catastrophically in
+  // fp32 at small t: 1 - 0.999f is off by 1.3e-5 relative).  One thread per block, broadcast through shared memory.
+  __shared__ float s_step_size, s_bc2s;
+  if (threadIdx.x == 0) {
+    const double bc1 = -expm1((double)step * log(b1d));
+    const double bc2 = -expm1((double)step * log(b2d));
+    s_step_size = (float)(lr / bc1);
+    s_bc2s = (float)sqrt(bc2);
+  }
+  __syncthreads();
+  const float step_size = s_step_size, bc2s = s_bc2s;
+  const float b1 = (float)b1d, b2 = (float)b2d, omb1 = (float)(1.0 - b1d), omb2 = (float)(1.0 - b2d);
   const int end = min(t.n, ck.y + ADAM_CHUNK);
   for (int i = ck.y + threadIdx.x; i < end; i += blockDim.x) {
     const float g = t.g[i];
@@ -47,7 +56,7 @@ extern "C" int kp_adam_step(const kp_adam_tensor* tensors_dev, const int32_t* ch
   KP_CHECK_ARG(tensors_dev && chunks_dev && state_dev && nchunks >= 0, "kp_adam_step: null argument");
   KP_CHECK_ARG((((uintptr_t)chunks_dev) & 7) == 0 && (((uintptr_t)tensors_dev) & 7) == 0, "kp_adam_step: misaligned table");
   if (nchunks == 0) return 0;
-  KP_LAUNCH(kp::adam_kernel, nchunks, 256, 0, (cudaStream_t)stream, tensors_dev, (const int2*)chunks_dev, lr, (float)beta1,
-            (float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2), eps, state_dev);
+  KP_LAUNCH(kp::adam_kernel, nchunks, 256, 0, (cudaStream_t)stream, tensors_dev, (const int2*)chunks_dev, (double)lr, beta1,
+            beta2, eps, state_dev);
   return 0;
 }

@@ -37,6 +37,20 @@ extern std::atomic<uint64_t> g_launches;
     KP_CUDA(cudaGetLastError());                                                           \
   } while (0)
 
+// Kernels that spin on a grid-wide barrier: a cooperative launch makes the driver guarantee that every CTA of the grid
+// is co-resident (it fails with cudaErrorCooperativeLaunchTooLarge instead of deadlocking on a smaller part / MIG
+// slice); capturable in CUDA graphs like a plain launch.  `args` is the usual array of pointers to the arguments.
+#define KP_LAUNCH_COOP(kernel, grid, block, smem, stream, args)                                             \
+  do {                                                                                                      \
+    cudaError_t _le = cudaLaunchCooperativeKernel((const void*)(kernel), dim3(grid), dim3(block), (args),   \
+                                                  (size_t)(smem), (cudaStream_t)(stream));                  \
+    kp::g_launches.fetch_add(1, std::memory_order_relaxed);                                                 \
+    if (_le != cudaSuccess) {                                                                               \
+      kp::set_error("cooperative launch of %s failed: %s (%s:%d)", #kernel, cudaGetErrorString(_le), __FILE__, __LINE__); \
+      return 2;                                                                                             \
+    }                                                                                                       \
+  } while (0)
+
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

@@ -955,8 +955,13 @@ int kp_dense_block_forward(const kp_dense_desc* desc, float* out, void* workspac
   if (!m.barrier) KP_CUDA(cudaMemsetAsync(workspace, 0, 256, st));
   KP_CUDA(cudaFuncSetAttribute(kp::dense_block_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)c.smem_fwd));
-  KP_LAUNCH(kp::dense_block_fwd_kernel, c.grid, kp::DB_THREADS, c.smem_fwd, st, m, out,
-            (float*)((char*)workspace + 256), bar, c.Rc);
+  {
+    kp_dense_desc marg = m;
+    float* part = (float*)((char*)workspace + 256);
+    int rc_rows = c.Rc;
+    void* args[] = {&marg, &out, &part, &bar, &rc_rows};
+    KP_LAUNCH_COOP(kp::dense_block_fwd_kernel, c.grid, kp::DB_THREADS, c.smem_fwd, st, args);
+  }
   return 0;
 }
 
@@ -978,8 +983,13 @@ int kp_dense_block_backward(const kp_dense_desc* desc, const float* dOut, float*
   if (!m.barrier) KP_CUDA(cudaMemsetAsync(workspace, 0, 256, st));
   KP_CUDA(cudaFuncSetAttribute(kp::dense_block_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)c.smem_bwd));
-  KP_LAUNCH(kp::dense_block_bwd_kernel, c.grid, kp::DB_THREADS, c.smem_bwd, st, m, dOut, dX, dW1, db1, dW2, db2, dbn,
-            (float*)((char*)workspace + 256), bar, c.Rc);
+  {
+    kp_dense_desc marg = m;
+    float* part = (float*)((char*)workspace + 256);
+    int rc_rows = c.Rc;
+    void* args[] = {&marg, (void*)&dOut, &dX, &dW1, &db1, &dW2, &db2, &dbn, &part, &bar, &rc_rows};
+    KP_LAUNCH_COOP(kp::dense_block_bwd_kernel, c.grid, kp::DB_THREADS, c.smem_bwd, st, args);
+  }
   {
     cudaStream_t lst = st;
     if (m.leaf_stream && m.leaf_stream != stream) {          // leaf gradients: fork (see kp_dense_desc.leaf_stream)

@@ -66,10 +66,40 @@ class _Norm(nn.Module):
         return self.module(x)
 
 
-def segment_sum(x, batch, num_graphs):
-    """global_add_pool (GraphRegression.py:26): deterministic on sorted `batch` would need offsets; index_add
-    is what PyG does and is outside the K-hop path."""
-    return torch.zeros((num_graphs, x.size(1)), dtype=x.dtype, device=x.device).index_add_(0, batch, x)
+class _SegmentSum(torch.autograd.Function):
+    """kp_segment_sum (include/kpgnn.h): ordered per-graph row sums over the sorted `batch` vector."""
+
+    @staticmethod
+    def forward(ctx, x, batch, num_graphs, mean):
+        import ctypes as C
+        from . import _lib
+        lib = _lib.lib()
+        if not x.is_cuda:
+            raise _lib.KpError("kpgnn_b200 runs on CUDA tensors only (no CPU fallback)")
+        x = x.detach()
+        if x.stride(-1) != 1:
+            x = x.contiguous()
+        batch = batch.contiguous()
+        out = torch.empty((num_graphs, x.size(1)), dtype=torch.float32, device=x.device)
+        st = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+        _lib.check(lib.kp_segment_sum(x.data_ptr(), x.stride(0), batch.data_ptr(), x.size(0), x.size(1), num_graphs,
+                                      1 if mean else 0, out.data_ptr(), st), "kp_segment_sum")
+        ctx.batch, ctx.mean, ctx.num_graphs = batch, mean, num_graphs
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        if ctx.mean:
+            cnt = torch.bincount(ctx.batch, minlength=ctx.num_graphs).clamp_(min=1).to(dout.dtype)
+            dout = dout / cnt.unsqueeze(1)
+        return dout.index_select(0, ctx.batch), None, None, None
+
+
+def segment_sum(x, batch, num_graphs, mean=False):
+    """global_add_pool / global_mean_pool (GraphRegression.py:26) over the sorted `batch` vector: rows added in
+    ascending order per graph, no float atomics (torch's index_add_ is a float atomicAdd, so the readout -- and with
+    it the loss and every gradient -- would differ in the last bits from run to run)."""
+    return _SegmentSum.apply(x, batch, num_graphs, mean)
 
 
 class KPGNNPlusBackbone(nn.Module):

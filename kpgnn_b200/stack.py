@@ -110,7 +110,9 @@ class _KPGINPlusStack(torch.autograd.Function):
             _lib.check(lib.kp_dense_block_forward(C.byref(d), out.data_ptr(), ws.data_ptr(), ws.numel(), st),
                        "kp_dense_block_forward")
             saved.append((adesc, d, bb.value, k, theta, alphas, agg, keep, stats, (W1c, W2c, T0, Tk)))
-        ctx.saved, ctx.Hn, ctx.Pc, ctx.cfg = saved, Hn, Pc, cfg
+        # a non-autograd alias keeps the storage alive for the saved descriptors without the node -> output -> grad_fn
+        # reference cycle that storing the output itself would create (freed by refcount, not by the cyclic GC)
+        ctx.saved, ctx.Hn, ctx.Pc, ctx.cfg = saved, Hn.detach(), Pc, cfg
         ctx.shape = (N, H, K, L)
         return Hn
 

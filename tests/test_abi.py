@@ -30,7 +30,9 @@ def test_library_exports_every_declared_symbol(lib):
 
 def test_abi_version_and_error_string(lib):
     from kpgnn_b200 import _lib
-    assert lib.kp_abi_version() == _lib.ABI_VERSION == 7
+    hdr = open(os.path.join(ROOT, "include", "kpgnn.h")).read()
+    declared = int(re.search(r"#define\s+KPGNN_ABI_VERSION\s+(\d+)", hdr).group(1))
+    assert lib.kp_abi_version() == _lib.ABI_VERSION == declared
     assert isinstance(lib.kp_last_error(), bytes)
     assert lib.kp_launch_count() >= 0
 

@@ -120,6 +120,11 @@ int kp_agg_forward(const kp_agg_desc* desc, float* out, void* stream);
  * bit 4: TMA-staged forward kernel for every eligible call; bit 5: TMA-staged forward kernel for large batches.
  * 0 = production default (lean kernels, no TMA staging). */
 int kp_agg_set_force_generic(int flag);
+/* Test hook, process-wide: max_ctas > 0 caps the grid of every persistent aggregation kernel, lean_threads > 0 (a
+ * multiple of 32 in [256,1024]) forces the CTA size of the packed-math kernels -- so a batch of a few thousand nodes
+ * runs the same multi-node-per-lane-group loops, software pipeline and partial reductions as the 8 192-graph launch
+ * the roofline is quoted on.  (0, 0) = production geometry. */
+int kp_agg_set_launch_geometry(int max_ctas, int lean_threads);
 
 /* Backward of kp_agg_forward (autograd of the same reference lines).  Deterministic, no float atomics:
  * transposed-CSR gather for dX, owner-computes partial tables for dT0/dTk, per-CTA partials for dtheta/deps.

@@ -92,6 +92,7 @@ _SIGNATURES = {
                                C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]),
     "kp_agg_forward": (C.c_int, [C.POINTER(AggDesc), C.c_void_p, C.c_void_p]),
     "kp_agg_set_force_generic": (C.c_int, [C.c_int]),
+    "kp_agg_set_launch_geometry": (C.c_int, [C.c_int, C.c_int]),
     "kp_agg_backward_workspace_bytes": (C.c_int, [C.POINTER(AggDesc), C.POINTER(C.c_size_t)]),
     "kp_agg_backward": (C.c_int, [C.POINTER(AggDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -540,6 +540,7 @@ struct Config {
 };
 
 static int g_force_generic = 0;   // test hook (kp_agg_set_force_generic): exercise the generic kernels
+int g_geom_max_ctas = 0, g_geom_lean_threads = 0;   // test hook (kp_agg_set_launch_geometry), see agg_fast_host.h
 
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 static bool aligned8(const void* p) { return ((uintptr_t)p & 7) == 0; }
@@ -572,8 +573,8 @@ static int make_config(const kp_agg_desc& a, Config* c) {
   c->gshift = sh;
   const int gpb = 256 / G;
   long long want = ((long long)a.N + gpb - 1) / gpb;
-  c->grid = (int)(want < 1 ? 1 : (want > kNumSMs * 16 ? kNumSMs * 16 : want));
-  c->grid_b1 = (int)(want < 1 ? 1 : (want > kNumSMs * 2 ? kNumSMs * 2 : want));
+  c->grid = geom_cap(want > kNumSMs * 16 ? kNumSMs * 16 : want);
+  c->grid_b1 = geom_cap(want > kNumSMs * 2 ? kNumSMs * 2 : want);
   const int dpad = ((a.d + G * c->vec - 1) / (G * c->vec)) * (G * c->vec);
   c->smem_b1 = sizeof(float) * (size_t)gpb * a.k * dpad;
   c->need_gs = (a.act != KP_ACT_NONE) || a.fuse || a.dinv || a.indeg;
@@ -594,8 +595,8 @@ static int make_config(const kp_agg_desc& a, Config* c) {
     c->fG = fG;
     const int fgpb = 256 / fG;
     const long long fwant = ((long long)a.N + fgpb - 1) / fgpb;
-    c->fgrid = (int)(fwant < 1 ? 1 : (fwant > kNumSMs * KP_FWD_MINB ? kNumSMs * KP_FWD_MINB : fwant));
-    c->fgrid_b1 = (int)(fwant < 1 ? 1 : (fwant > kNumSMs * 3 ? kNumSMs * 3 : fwant));
+    c->fgrid = geom_cap(fwant > kNumSMs * KP_FWD_MINB ? kNumSMs * KP_FWD_MINB : fwant);
+    c->fgrid_b1 = geom_cap(fwant > kNumSMs * 3 ? kNumSMs * 3 : fwant);
     const long long tabf = a.T0 ? (long long)(a.rows0 + a.rowsk) * a.d : 0;
     c->ftab = !a.T0 ? TAB_NONE : (tabf * 4 <= 56 * 1024 ? TAB_SMEM : TAB_GLOBAL);
     c->stage_floats = (int)((c->ftab == TAB_SMEM ? tabf : 0) + (a.fuse ? a.k * a.d : 0));
@@ -606,7 +607,8 @@ static int make_config(const kp_agg_desc& a, Config* c) {
                  c->ftab != TAB_GLOBAL && (a.act != KP_ACT_NONE || a.fuse);
     if (c->lean_b1) {
       // largest CTA whose dtheta accumulators fit next to the tables; small batches keep 256 threads (more CTAs)
-      static const int env_b1_threads = getenv("KP_LEAN_B1_THREADS") ? atoi(getenv("KP_LEAN_B1_THREADS")) : 0;
+      static const int env_b1_threads_ = getenv("KP_LEAN_B1_THREADS") ? atoi(getenv("KP_LEAN_B1_THREADS")) : 0;
+      const int env_b1_threads = g_geom_lean_threads ? g_geom_lean_threads : env_b1_threads_;
       int threads = 1024;
       const int balanced = env_b1_threads ? 0 : lean_balanced_threads(a.N, fG, 2);
       if (balanced) {      // one CTA per SM, the same number of groups each (see lean_balanced_threads)
@@ -638,7 +640,7 @@ static int make_config(const kp_agg_desc& a, Config* c) {
         const int gpb = c->lean_b1_threads / fG;
         const long long want = ((long long)a.N + gpb - 1) / gpb;
         const long long cap = (long long)kNumSMs * (1024 / c->lean_b1_threads);
-        c->grid_b1 = (int)(want < 1 ? 1 : (want > cap ? cap : want));
+        c->grid_b1 = geom_cap(want > cap ? cap : want);
       }
     }
   }
@@ -805,6 +807,16 @@ int kp_agg_set_force_generic(int flag) {
   // TMA-staged forward kernel (agg_tma.cuh): off by default (measured slightly slower than the lean kernel);
   // bit 4: use it for every eligible call, however small (tests); bit 5: use it for large batches only
   kp::fast_fwd_set_tma((flag & 16) ? 2 : ((flag & 32) ? 1 : 0));
+  return 0;
+}
+
+int kp_agg_set_launch_geometry(int max_ctas, int lean_threads) {
+  if (max_ctas < 0 || (lean_threads != 0 && (lean_threads < 256 || lean_threads > 1024 || lean_threads % 32))) {
+    kp::set_error("kp_agg_set_launch_geometry: max_ctas >= 0, lean_threads 0 or a multiple of 32 in [256,1024]");
+    return 1;
+  }
+  kp::g_geom_max_ctas = max_ctas;
+  kp::g_geom_lean_threads = lean_threads;
   return 0;
 }
 

@@ -17,6 +17,8 @@
 // Eligible: d % 4 == 0, d <= 128, largest embedding row <= 31 (desc.amax0 / amaxk).  Everything else stays on agg.cu.
 #include "agg_common.cuh"
 
+namespace kp { extern int g_geom_max_ctas; }   // test hook, agg_fast_host.h
+
 namespace kp {
 
 constexpr int B3C_THREADS = 256;
@@ -197,7 +199,8 @@ bool b3_count_ok(const kp_agg_desc& a, int G) {
 void b3_count_grid(const kp_agg_desc& a, int* g0, int* g1) {
   const long long t0 = ((long long)a.N + B3C_THREADS - 1) / B3C_THREADS;
   const long long t1 = ((long long)a.N * (a.k - 1) + B3C_THREADS - 1) / B3C_THREADS;
-  const long long cap = (long long)kNumSMs * (b3c_A4(a) <= 4 ? B3C_CTAS_PER_SM : 1);
+  long long cap = (long long)kNumSMs * (b3c_A4(a) <= 4 ? B3C_CTAS_PER_SM : 1);
+  if (g_geom_max_ctas > 0 && cap > g_geom_max_ctas) cap = g_geom_max_ctas < 2 ? 2 : g_geom_max_ctas;   // test hook
   if (t0 + t1 <= cap) {
     *g0 = (int)t0;
     *g1 = (int)t1;

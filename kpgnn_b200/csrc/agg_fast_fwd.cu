@@ -47,13 +47,14 @@ static int launch_lean(const FastArgs& fa, int grid, size_t smem, float* out, cu
   // (lean_balanced_threads); 256-thread CTAs in between so that all SMs get work
   static const int env_threads = getenv("KP_LEAN_THREADS") ? atoi(getenv("KP_LEAN_THREADS")) : 0;
   const int balanced = lean_balanced_threads(a.N, G, 1);
-  const int threads = env_threads ? env_threads
+  const int threads = g_geom_lean_threads ? g_geom_lean_threads
+                      : env_threads ? env_threads
                       : balanced ? balanced
                                  : ((long long)a.N >= (long long)kNumSMs * (1024 / G) * 2 ? 1024 : 256);
   const int gpb = threads / G, ctas_per_sm = 1024 / threads;
   const size_t total = smem + (size_t)gpb * lean_group_scratch_bytes(G);   // + per-group entry window and row pointers
   const long long want = ((long long)a.N + gpb - 1) / gpb;
-  grid = (int)(want < kNumSMs * ctas_per_sm ? (want < 1 ? 1 : want) : kNumSMs * ctas_per_sm);   // persistent
+  grid = geom_cap(want < kNumSMs * ctas_per_sm ? (want < 1 ? 1 : want) : kNumSMs * ctas_per_sm);   // persistent
   if (total > 48 * 1024)
     KP_CUDA(cudaFuncSetAttribute(agg_fwd_lean_kernel<G, ACT, FUSE, TAB, EXTRA>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total));

@@ -23,6 +23,15 @@ inline bool fast_combo(int act, bool fuse, bool need_extra, bool* extra) {
   return !fuse;
 }
 
+// Test hook (kp_agg_set_launch_geometry): g_geom_max_ctas > 0 caps the grid of every persistent aggregation kernel so
+// that each lane group / CTA loops over many nodes even on a small batch; g_geom_lean_threads > 0 forces the CTA size
+// of the lean kernels (256..1024).  Both 0 in production.
+extern int g_geom_max_ctas, g_geom_lean_threads;
+inline int geom_cap(long long grid) {
+  if (g_geom_max_ctas > 0 && grid > g_geom_max_ctas) grid = g_geom_max_ctas;
+  return (int)(grid < 1 ? 1 : grid);
+}
+
 void fast_fwd_set_lean(int flag);   // 1 (default): packed-math + L2-prefetch kernels (agg_lean.cuh) where k + 1 <= G
 void fast_fwd_set_ring(int flag);   // 0: plain register-prefetch forward kernel, 1 (default): cp.async ring
 int fast_fwd(const FastArgs& fa, int G, int act, bool fuse, int tab, bool extra, int grid, size_t smem, float* out,

@@ -45,7 +45,7 @@ static int launch_tma(const FastArgs& fa, const CUtensorMap& tm, const CUtensorM
   const size_t total = fixed + (size_t)TMA_STAGES * (stage_rows + (a.P ? 32 : 0)) * a.d * 4;
   KP_CUDA(cudaFuncSetAttribute(agg_fwd_tma_kernel<ACT, FUSE, TAB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)total));
-  const int grid = ntiles < kNumSMs ? ntiles : kNumSMs;
+  const int grid = geom_cap(ntiles < kNumSMs ? ntiles : kNumSMs);
   KP_LAUNCH((agg_fwd_tma_kernel<ACT, FUSE, TAB>), grid, TMA_THREADS, total, st, fa, tm, tm32, tmp, out, stage_rows, ntiles);
   return 0;
 }

@@ -8,6 +8,11 @@ Fixtures:
   extract.npz   extraction inputs/outputs of data_utils.extract_multi_hop_neighbors (bit-exact targets)
   layers.npz    state_dict + inputs + output + gradients of each layers/* module (1e-5 relative targets)
   model_zinc.npz   GraphRegression(GNNPlus(KPGINPlus K=8 L=8 H=104)) on an 8-graph ZINC-shaped batch
+  extract_full.npz 128 EXP graphs, the 15 SR25 graphs (gd + spd), one n = 1 280 regular graph: extraction at real inputs
+  models_cfg.npz   the other BASELINE.json model configs (EXP KP-GIN, KPGINPrime, SR25 KPGCN / KPGraphSAGE): reference
+                   state_dict + batch + prediction + loss + every parameter gradient
+
+    python -m oracle.make_golden [extract] [extract_full] [layers] [model] [models_cfg]     # subset
 """
 import argparse
 import json
@@ -103,6 +108,43 @@ def make_extract(ns):
     store["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
     np.savez_compressed(os.path.join(OUT, "extract.npz"), **store)
     print("extract.npz: %d cases" % len(meta))
+
+
+def make_extract_full(ns):
+    """BASELINE.json configs at their real inputs: the first 128 graphs of the in-repo EXP dataset (configs[0]), all 15
+    in-repo SR25 graphs under both kernels (configs[3]) and one n = 1 280 3-regular graph at K = 6 (configs[4]); outputs
+    stored in the narrowest integer type that holds them (the npz stays < 1 MB)."""
+    from tests import ref_util as RU
+    cases = [("exp%d_spd3" % i, g, (3, 1, 5, 1, 1000, 1000, "spd")) for i, g in enumerate(RU.exp_graphs(128))]
+    for i, g in enumerate(RU.sr25_graphs()):
+        cases.append(("sr25_%d_gd4" % i, g, (4, 1000, 4, 1, 1000, 1000, "gd")))
+        cases.append(("sr25_%d_spd4" % i, g, (4, 1000, 4, 1, 1000, 1000, "spd")))
+    cases.append(("regular1280_spd6", synth.regular_graph(1280, 3, 0), (6, 10, 1, 1, 1, 1, "spd")))
+
+    def narrow(a):
+        a = np.ascontiguousarray(a)
+        for dt in (np.uint8, np.uint16, np.int32):
+            if a.size == 0 or (a.min() >= np.iinfo(dt).min and a.max() <= np.iinfo(dt).max):
+                return a.astype(dt)
+        return a
+    store, meta = {}, []
+    for idx, (name, g, args) in enumerate(cases):
+        r = _ref_extract(ns, g, args)
+        pre = "c%d_" % idx
+        store[pre + "in_edge_index"] = narrow(g["edge_index"])
+        fields = []
+        for k in ("edge_index", "edge_attr", "pe_attr", "peripheral_edge_attr", "peripheral_configuration_attr"):
+            v = r._store.get(k, None)
+            if v is not None:
+                assert v.dtype == torch.long
+                store[pre + "out_" + k] = narrow(v.contiguous().numpy())
+                fields.append(k)
+        meta.append({"name": name, "num_nodes": int(g["num_nodes"]), "args": list(args), "fields": fields})
+        if idx % 32 == 0:
+            print("  extract_full: %d / %d" % (idx, len(cases)), flush=True)
+    store["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(OUT, "extract_full.npz"), **store)
+    print("extract_full.npz: %d cases" % len(meta))
 
 
 def _collate(ns, graphs, args):
@@ -212,14 +254,54 @@ def make_model(ns):
     print("model_zinc.npz: loss %.6f, %d params" % (loss.item(), sum(p.numel() for p in model.parameters())))
 
 
+def make_models_cfg(ns):
+    """BASELINE.json configs[0], [2], [3] as the reference's train scripts build them (tests/ref_util.py CONFIGS),
+    forward + backward on the CPU, for the GPU test that loads the same state_dict into the product."""
+    from tests import ref_util as RU
+    store, meta = {}, []
+    for name, graphs in (("exp", RU.exp_graphs(16)), ("prime", synth.zinc_like_graphs(6, seed=41)),
+                         ("sr_gcn", RU.sr25_graphs()[:6]), ("sr_sage", RU.sr25_graphs()[:6])):
+        cfg = RU.CONFIGS[name]
+        torch.manual_seed(99)
+        b = RU.ref_batch(ns, graphs, cfg["extract"], torch.float32 if cfg["head"][0] == "regression" else torch.int64)
+        model = RU.build_model(cfg, ns.GNNs, ns.layer_utils.make_gnn_layer, ns.input_encoder.EmbeddingEncoder, ns)
+        with torch.no_grad():
+            for n, p in model.named_parameters():
+                if n.endswith("alphas"):
+                    p.add_(0.3 * torch.randn_like(p))
+        model.train()
+        sd = {k: v.clone() for k, v in model.state_dict().items()}
+        pred = model(b)
+        loss = RU.loss_fn(cfg, pred, b.y)
+        loss.backward()
+        pre = "m%d_" % len(meta)
+        store[pre + "pred"] = pred.detach().numpy()
+        store[pre + "loss"] = np.array(loss.item(), dtype=np.float32)
+        for k in ("x", "edge_index", "edge_attr", "pe_attr", "peripheral_edge_attr", "peripheral_configuration_attr",
+                  "batch", "y"):
+            v = b._store[k].contiguous().numpy()
+            store[pre + "b_" + k] = v.astype(np.int32) if v.dtype == np.int64 else v
+        for k, v in sd.items():
+            store[pre + "sd_" + k] = v.numpy()
+        for k, p in model.named_parameters():
+            if p.grad is not None:
+                store[pre + "gp_" + k] = p.grad.numpy()
+        meta.append({"name": name, "num_graphs": len(graphs)})
+        print("  models_cfg: %s loss %.6f" % (name, loss.item()))
+    store["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(OUT, "models_cfg.npz"), **store)
+
+
 def main():
     if not refimport.available():
         raise SystemExit("reference tree not found at %s" % refimport.REF_ROOT)
     os.makedirs(OUT, exist_ok=True)
     ns = refimport.load()
-    make_extract(ns)
-    make_layers(ns)
-    make_model(ns)
+    only = sys.argv[1:]
+    for name, fn in (("extract", make_extract), ("extract_full", make_extract_full), ("layers", make_layers),
+                     ("model", make_model), ("models_cfg", make_models_cfg)):
+        if not only or name in only:
+            fn(ns)
 
 
 if __name__ == "__main__":

@@ -161,3 +161,30 @@ def test_full_size_properties(lib):
     ref = extract_multi_hop_neighbors_np(g["num_nodes"], g["edge_index"], g["edge_attr"], 8, 50, 6, 3, 50, 50, "spd")
     one = extract_batch([g], (8, 50, 6, 3, 50, 50, "spd"), "cuda:0")
     assert np.array_equal(one.peripheral_configuration_attr.cpu().numpy(), ref["peripheral_configuration_attr"])
+
+
+def test_reference_goldens_full_configs_bit_exact(lib):
+    """tests/golden/extract_full.npz: the reference's own outputs on the first 128 graphs of its EXP dataset
+    (configs[0]), all 15 SR25 graphs under gd and spd (configs[3]) and an n = 1 280 3-regular graph at K = 6
+    (configs[4]); every field bit-exact, extracted here as ONE batch per config (graph-major collation)."""
+    from kpgnn_b200.data_utils import extract_batch
+    z, meta = GU.load("extract_full.npz")
+    groups = {}
+    for i, m in enumerate(meta):
+        groups.setdefault(tuple(m["args"]), []).append(i)
+    for args, idxs in groups.items():
+        graphs = [{"num_nodes": meta[i]["num_nodes"], "x": np.zeros(meta[i]["num_nodes"], dtype=np.int64),
+                   "edge_index": z["c%d_in_edge_index" % i].astype(np.int64), "edge_attr": None} for i in idxs]
+        b = extract_batch(graphs, args, "cuda:0")
+        off = 0
+        exp = {f: [] for f in ("edge_index", "edge_attr", "pe_attr", "peripheral_edge_attr",
+                               "peripheral_configuration_attr")}
+        for i, g in zip(idxs, graphs):
+            for f in exp:
+                v = z["c%d_out_%s" % (i, f)].astype(np.int64)
+                exp[f].append(v + off if f == "edge_index" else v)
+            off += g["num_nodes"]
+        for f, parts in exp.items():
+            ref = np.concatenate(parts, axis=1 if f == "edge_index" else 0)
+            got = getattr(b, f).cpu().numpy()
+            assert got.shape == ref.shape and np.array_equal(got, ref), (args, f)

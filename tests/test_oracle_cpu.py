@@ -143,3 +143,21 @@ def test_install_dropin_aliases_reference_import_names():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr
+
+
+@pytest.mark.skipif(not refimport.available(), reason="reference files not staged")
+def test_reference_models_import_over_dropin_namespace():
+    """oracle/refimport.load_models_over_dropin: the reference's models/GNNs.py imported unmodified with its
+    `from layers...` lines bound to the product package, next to the all-reference namespace (CPU: construction only;
+    forward/backward on a B200 is tests/test_reference_models_gpu.py)."""
+    from tests import ref_util as RU
+    from kpgnn_b200.layers import layer_utils as mine
+    from kpgnn_b200.layers.input_encoder import EmbeddingEncoder
+    dropin = refimport.load_models_over_dropin()
+    for name, cfg in RU.CONFIGS.items():
+        m = RU.build_model(cfg, dropin.GNNs, mine.make_gnn_layer, EmbeddingEncoder, dropin)
+        r = RU.build_model(cfg, dropin.ref.GNNs, dropin.ref.layer_utils.make_gnn_layer,
+                           dropin.ref.input_encoder.EmbeddingEncoder, dropin.ref)
+        assert list(m.state_dict().keys()) == list(r.state_dict().keys()), name
+        assert type(RU.first_layer(m)).__module__.startswith("kpgnn_b200.layers.")
+        assert not type(RU.first_layer(r)).__module__.startswith("kpgnn_b200")

@@ -1,0 +1,97 @@
+"""The reference's OWN models/GNNs.py (GNN, GNNPlus, GNNPrime), UNMODIFIED, running on a B200 over the drop-in
+layers -- `kpgnn_b200.install_dropin()` semantics, no repo backbone involved -- against the all-reference model
+(reference layers through the torch_geometric stand-in) on the SAME device, same weights, same batch:
+score/logits, loss and every parameter gradient, forward and backward, for every BASELINE.json model config.
+Bar: 1e-5 relative (north_star), same-device comparison.
+
+Needs the reference's files: /root/reference (build container) or the staged copy oracle/_ref/ (GPU box, made by
+oracle/fetch_ref.py / __graft_entry__.build()); skipped otherwise -- tests/test_golden_gpu.py then carries parity
+from the committed fixtures."""
+import numpy as np
+import pytest
+import torch
+
+from kpgnn_b200 import synth
+from tests import ref_util as RU
+from tests.util import rel_err
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not RU.available(), reason="reference files not staged")]
+
+torch.backends.cuda.matmul.allow_tf32 = False
+torch.backends.cudnn.allow_tf32 = False
+RTOL = 1e-5
+# analytically-zero gradients (a Linear bias feeding BatchNorm): rounding noise on both sides
+NOISE_ONLY = ("mlp.0.bias", "mlp.3.bias")
+
+
+@pytest.fixture(scope="module")
+def spaces():
+    from oracle import refimport
+    dropin = refimport.load_models_over_dropin()
+    return dropin.ref, dropin
+
+
+def _graphs(name):
+    if name == "exp":
+        return RU.exp_graphs(24)
+    if name.startswith("sr"):
+        return RU.sr25_graphs()
+    return synth.zinc_like_graphs(12, seed=31)
+
+
+def _compare(cfg, ref_model, my_model, batch_cpu, dev):
+    my_model.load_state_dict(ref_model.state_dict())        # the reference's state_dict loads unchanged
+    res = []
+    for model in (ref_model, my_model):
+        model = model.to(dev).train()
+        b = batch_cpu.clone().to(dev)
+        pred = model(b)
+        loss = RU.loss_fn(cfg, pred, b.y)
+        loss.backward()
+        res.append((pred.detach(), loss.detach(), {n: p.grad for n, p in model.named_parameters()}))
+    (p0, l0, g0), (p1, l1, g1) = res
+    assert rel_err(p1, p0) < RTOL, ("prediction", rel_err(p1, p0))
+    assert abs(float(l1) - float(l0)) <= RTOL * max(abs(float(l0)), 1e-6), ("loss", float(l0), float(l1))
+    gmax = max(float(v.abs().max()) for v in g0.values() if v is not None)
+    worst = ("", 0.0)
+    for n in g0:
+        a, c = g1[n], g0[n]
+        if a is None or c is None:
+            for t in (a, c):
+                assert t is None or float(t.abs().max()) <= 1e-6 * gmax, n
+            continue
+        if n.endswith(NOISE_ONLY):
+            assert float((a - c).abs().max()) < 1e-4 * gmax, n
+            continue
+        err = rel_err(a, c, floor=1e-2 * gmax)
+        if err > worst[1]:
+            worst = (n, err)
+    assert worst[1] < RTOL, worst
+
+
+@pytest.mark.parametrize("name,combine,virtual_node", [
+    ("zinc", "geometric", False), ("zinc", "attention", False), ("zinc", "geometric", True),
+    ("exp", "geometric", False), ("exp", "attention", False),
+    ("prime", "geometric", False),
+    ("sr_gcn", "geometric", False), ("sr_sage", "geometric", False), ("sr_gcn", "attention", False)])
+def test_unmodified_reference_model_over_dropin_layers(lib, spaces, name, combine, virtual_node):
+    ns, dropin = spaces
+    cfg = RU.CONFIGS[name]
+    dev = torch.device("cuda:0")
+    from kpgnn_b200.layers import layer_utils as my_layer_utils
+    from kpgnn_b200.layers.input_encoder import EmbeddingEncoder as MyEmb
+    batch = RU.ref_batch(ns, _graphs(name), cfg["extract"],
+                         torch.float32 if cfg["head"][0] == "regression" else torch.int64)
+    torch.manual_seed(17)
+    ref_model = RU.build_model(cfg, ns.GNNs, ns.layer_utils.make_gnn_layer, ns.input_encoder.EmbeddingEncoder, ns,
+                               combine, virtual_node)
+    # perturb the zero-initialised combine weights so their gradient paths carry signal
+    with torch.no_grad():
+        for n, p in ref_model.named_parameters():
+            if n.endswith("alphas"):
+                p.add_(0.3 * torch.randn_like(p))
+    my_model = RU.build_model(cfg, dropin.GNNs, my_layer_utils.make_gnn_layer, MyEmb, dropin, combine, virtual_node)
+    # it IS the reference's backbone class (from the reference's file), built on the product's layers
+    assert type(my_model.embedding_model).__module__.startswith("kp_dropin_models_")
+    assert type(RU.first_layer(my_model)).__module__.startswith("kpgnn_b200.layers.")
+    _compare(cfg, ref_model, my_model, batch, dev)

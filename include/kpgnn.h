@@ -253,6 +253,33 @@ typedef struct {
 int kp_adam_step(const kp_adam_tensor* tensors_dev, const int32_t* chunks_dev, int32_t nchunks, float lr, double beta1,
                  double beta2, float eps, int32_t* state_dev, void* stream);   /* betas in double: 1-beta is formed exactly */
 
+/* ------------------------------------------------------------------------------------------------------------
+ * AttentionCombine, layers/combine.py:8-27: a bidirectional single-layer LSTM (input size d, hidden size K,
+ * batch_first) over the hop axis of x [N,K,d], its [N,K,2K] output summed over the last axis, a softmax over hops,
+ * and the weighted sum of x over hops -> out [N,d].  One kernel forward (a warp per node; x is read once, nothing
+ * of size [N,K,*] is written), one recompute-and-backpropagate kernel backward plus fixed-order reductions of the
+ * parameter gradients (no float atomics).  Weights use torch.nn.LSTM's layout: w_ih [4K,d], w_hh [4K,K], b_ih [4K],
+ * b_hh [4K], gate order i,f,g,o; index 0 = forward direction (`*_l0`), 1 = reverse (`*_l0_reverse`).
+ * 1 <= K <= 16, 1 <= d <= 128.  x rows have a dense last dimension; node / hop strides in elements.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t N, K, d, pad;
+  const float* x;
+  int64_t x_node_stride, x_hop_stride;
+  const float* w_ih[2];
+  const float* w_hh[2];
+  const float* b_ih[2];
+  const float* b_hh[2];
+} kp_attn_desc;
+/* out [N,d]; weights [N,K] (the softmax weights, optional, NULL to skip) */
+int kp_attn_combine_forward(const kp_attn_desc* desc, float* out, float* weights, void* stream);
+int kp_attn_combine_backward_workspace_bytes(const kp_attn_desc* desc, size_t* bytes);
+/* dOut [N,d] contiguous; dX [N,K,d] contiguous (written); dw_ih_* [4K,d], dw_hh_* [4K,K], db_* [4K] (the gradient of
+ * b_ih and of b_hh alike), _f = forward direction, _r = reverse. */
+int kp_attn_combine_backward(const kp_attn_desc* desc, const float* dOut, float* dX, float* dw_ih_f, float* dw_ih_r,
+                             float* dw_hh_f, float* dw_hh_r, float* db_f, float* db_r, void* workspace,
+                             size_t workspace_bytes, void* stream);
+
 /* Graph readout over a sorted segment vector: PyG global_add_pool / global_mean_pool on `data.batch`
  * (models/GraphRegression.py:26, models/GraphClassification.py:30).  out[g,:] = sum (mean != 0: mean) of the rows i of
  * x [N,C] (row stride x_stride elements) with seg[i] == g; seg is int64, non-decreasing, values in [0,G).  Rows are

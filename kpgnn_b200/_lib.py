@@ -68,6 +68,12 @@ class DenseDesc(C.Structure):
                 ("leaf_stream", C.c_void_p)]
 
 
+class AttnDesc(C.Structure):
+    _fields_ = [("N", C.c_int32), ("K", C.c_int32), ("d", C.c_int32), ("pad", C.c_int32),
+                ("x", C.c_void_p), ("x_node_stride", C.c_int64), ("x_hop_stride", C.c_int64),
+                ("w_ih", C.c_void_p * 2), ("w_hh", C.c_void_p * 2), ("b_ih", C.c_void_p * 2), ("b_hh", C.c_void_p * 2)]
+
+
 class ThetaBatch(C.Structure):
     _fields_ = [("L", C.c_int32), ("d", C.c_int32), ("alphas", C.c_void_p * 32), ("theta", C.c_void_p * 32),
                 ("k", C.c_int32 * 32)]
@@ -116,6 +122,11 @@ _SIGNATURES = {
     "kp_geometric_theta_forward_batched": (C.c_int, [C.POINTER(ThetaBatch), C.c_void_p]),
     "kp_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_double, C.c_double, C.c_float,
                                C.c_void_p, C.c_void_p]),
+    "kp_attn_combine_forward": (C.c_int, [C.POINTER(AttnDesc), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "kp_attn_combine_backward_workspace_bytes": (C.c_int, [C.POINTER(AttnDesc), C.POINTER(C.c_size_t)]),
+    "kp_attn_combine_backward": (C.c_int, [C.POINTER(AttnDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                           C.c_void_p]),
     "kp_segment_sum": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                 C.c_void_p, C.c_void_p]),
     "kp_peripheral_grad": (C.c_int, [C.POINTER(PgradDesc), C.c_void_p, C.c_void_p]),

@@ -225,12 +225,12 @@ template <int G, int A4>
 static int b3c_launch(const kp_agg_desc& a, const float* Gs, int g0, int g1, float* part, cudaStream_t st) {
   const size_t smem = sizeof(float) * ((size_t)B3C_THREADS * (4 * A4 + 4) + (size_t)4 * A4 * a.d);
   if (a.dinv) {
-    if (smem > 48 * 1024)
+    if (smem > 32 * 1024)
       KP_CUDA(cudaFuncSetAttribute(agg_bwd_table_count_kernel<G, A4, true>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     KP_LAUNCH((agg_bwd_table_count_kernel<G, A4, true>), g0 + g1, B3C_THREADS, smem, st, a, Gs, g0, part);
   } else {
-    if (smem > 48 * 1024)
+    if (smem > 32 * 1024)
       KP_CUDA(cudaFuncSetAttribute(agg_bwd_table_count_kernel<G, A4, false>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     KP_LAUNCH((agg_bwd_table_count_kernel<G, A4, false>), g0 + g1, B3C_THREADS, smem, st, a, Gs, g0, part);

@@ -461,7 +461,7 @@ agg_bwd_dst_fast_kernel(const FastArgs fa, const float* __restrict__ dOut, float
   SegGather<G, TAB, EXTRA> sg;
   sg.Xb = a.X; sg.col = a.col; sg.attr = a.attr16; sg.dinv = EXTRA ? a.dinv : nullptr;
   sg.xs = fa.xs; sg.gm = group_mask<G>(); sg.Kp = Kp; sg.d = d; sg.lane = lane;
-  float eps_acc = 0.f;
+  double eps_acc = 0.0;   // scalar reduction over N*k*d products: double keeps it within the 1e-5 parity bar
   constexpr int chunk = KP_CHUNK_ITERS * gpb;
   for (int v0 = blockIdx.x * chunk; v0 < a.N; v0 += gridDim.x * chunk)
   for (int v = v0 + gib; v < min(a.N, v0 + chunk); v += gpb) {
@@ -517,7 +517,7 @@ agg_bwd_dst_fast_kernel(const FastArgs fa, const float* __restrict__ dOut, float
       }
       if (EXTRA && deps_part && active) {
         const float4 x = ld4(a.X + ((unsigned)v * fa.xs + xoff));
-        eps_acc += dy.x * x.x + dy.y * x.y + dy.z * x.z + dy.w * x.w;
+        eps_acc += (double)(dy.x * x.x + dy.y * x.y) + (double)(dy.z * x.z + dy.w * x.w);
       }
       if (Gs && active) {
         if (EXTRA) {
@@ -537,7 +537,7 @@ agg_bwd_dst_fast_kernel(const FastArgs fa, const float* __restrict__ dOut, float
     }
   }
   if (EXTRA && deps_part) {
-    __shared__ float red[256];
+    __shared__ double red[256];
     __syncthreads();
     red[threadIdx.x] = eps_acc;
     __syncthreads();
@@ -545,7 +545,7 @@ agg_bwd_dst_fast_kernel(const FastArgs fa, const float* __restrict__ dOut, float
       if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
       __syncthreads();
     }
-    if (threadIdx.x == 0) deps_part[blockIdx.x] = red[0];
+    if (threadIdx.x == 0) deps_part[blockIdx.x] = (float)red[0];
   }
 }
 

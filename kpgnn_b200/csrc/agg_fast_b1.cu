@@ -7,7 +7,7 @@ namespace kp {
 template <int G, int ACT, bool FUSE, int TAB, bool EXTRA>
 static int launch(const FastArgs& fa, int grid, size_t smem, const float* dOut, float* Gs, float* dP, float* dth,
                   float* dep, cudaStream_t st) {
-  if (smem > 48 * 1024)
+  if (smem > 32 * 1024)
     KP_CUDA(cudaFuncSetAttribute(agg_bwd_dst_fast_kernel<G, ACT, FUSE, TAB, EXTRA>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   KP_LAUNCH((agg_bwd_dst_fast_kernel<G, ACT, FUSE, TAB, EXTRA>), grid, 256, smem, st, fa, dOut, Gs, dP, dth, dep);
@@ -17,7 +17,7 @@ static int launch(const FastArgs& fa, int grid, size_t smem, const float* dOut, 
 template <int G, int ACT, bool FUSE, int TAB>
 static int launch_lean(const FastArgs& fa, int grid, int threads, size_t smem, const float* dOut, float* Gs, float* dP,
                        float* dth, cudaStream_t st) {
-  if (smem > 48 * 1024)
+  if (smem > 32 * 1024)
     KP_CUDA(cudaFuncSetAttribute(agg_bwd_dst_lean_kernel<G, ACT, FUSE, TAB>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   KP_LAUNCH((agg_bwd_dst_lean_kernel<G, ACT, FUSE, TAB>), grid, threads, smem, st, fa, dOut, Gs, dP, dth);

@@ -7,7 +7,7 @@ namespace kp {
 
 template <int G, int ACT, bool FUSE, int TAB, bool EXTRA>
 static int launch(const FastArgs& fa, int grid, size_t smem, float* out, cudaStream_t st) {
-  if (smem > 48 * 1024)
+  if (smem > 32 * 1024)
     KP_CUDA(cudaFuncSetAttribute(agg_fwd_fast_kernel<G, ACT, FUSE, TAB, EXTRA>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   KP_LAUNCH((agg_fwd_fast_kernel<G, ACT, FUSE, TAB, EXTRA>), grid, 256, smem, st, fa, out);
@@ -20,7 +20,7 @@ static int launch_ring(const FastArgs& fa, int grid, size_t smem, float* out, cu
   const unsigned slot = fa.d.d <= 104 ? KP_RING_SLOT_BYTES : 512u;
   const int stage_floats = (int)(smem / sizeof(float));
   const size_t total = smem + (size_t)8 * 9 * slot;
-  if (total > 48 * 1024)
+  if (total > 32 * 1024)
     KP_CUDA(cudaFuncSetAttribute(agg_fwd_ring_kernel<ACT, FUSE, TAB, EXTRA>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total));
   KP_LAUNCH((agg_fwd_ring_kernel<ACT, FUSE, TAB, EXTRA>), grid, 256, total, st, fa, out, stage_floats, slot);
@@ -55,7 +55,7 @@ static int launch_lean(const FastArgs& fa, int grid, size_t smem, float* out, cu
   const size_t total = smem + (size_t)gpb * lean_group_scratch_bytes(G);   // + per-group entry window and row pointers
   const long long want = ((long long)a.N + gpb - 1) / gpb;
   grid = geom_cap(want < kNumSMs * ctas_per_sm ? (want < 1 ? 1 : want) : kNumSMs * ctas_per_sm);   // persistent
-  if (total > 48 * 1024)
+  if (total > 32 * 1024)
     KP_CUDA(cudaFuncSetAttribute(agg_fwd_lean_kernel<G, ACT, FUSE, TAB, EXTRA>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total));
   KP_LAUNCH((agg_fwd_lean_kernel<G, ACT, FUSE, TAB, EXTRA>), grid, threads, total, st, fa, out, pfx_, pfp_, dist, bulk);

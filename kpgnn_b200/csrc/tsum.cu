@@ -219,7 +219,7 @@ int kp_table_sum_backward(const kp_tsum_desc* desc, const float* dOut, float* dT
   const int grid = c.B * c.Q;
 #define KP_TSB(GG)                                                                                             \
   do {                                                                                                         \
-    if (c.smem > 48 * 1024)                                                                                    \
+    if (c.smem > 32 * 1024)                                                                                    \
       KP_CUDA(cudaFuncSetAttribute(kp::tsum_bwd_kernel<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem)); \
     KP_LAUNCH(kp::tsum_bwd_kernel<GG>, grid, c.threads, c.smem, st, *desc, dOut, c.ngroups, c.rows_per_group, part); \
   } while (0)

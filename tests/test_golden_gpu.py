@@ -183,10 +183,13 @@ def test_other_config_models_match_reference_golden(lib, idx):
     pred = model(b)
     loss = RU.loss_fn(cfg, pred, b.y)
     loss.backward()
-    assert rel_err(pred, torch.from_numpy(_ZC[pre + "pred"])) < 1e-5
-    assert abs(loss.item() - float(_ZC[pre + "loss"])) < 1e-5 * abs(float(_ZC[pre + "loss"]))
+    own = m["own32"]            # the reference's own fp32-vs-float64 distance per tensor (oracle/make_golden.py)
+
+    def bar(key):
+        return max(1e-5, 4.0 * own.get(key, 0.0))
+    assert rel_err(pred, torch.from_numpy(_ZC[pre + "pred"])) < bar("pred")
+    assert abs(loss.item() - float(_ZC[pre + "loss"])) < bar("loss") * abs(float(_ZC[pre + "loss"]))
     gmax = max(float(np.abs(_ZC[k]).max()) for k in _ZC.files if k.startswith(pre + "gp_"))
-    worst = ("", 0.0)
     for n, p in model.named_parameters():
         key = pre + "gp_" + n
         if key not in _ZC.files:
@@ -194,10 +197,8 @@ def test_other_config_models_match_reference_golden(lib, idx):
             continue
         ref = torch.from_numpy(_ZC[key])
         g = p.grad if p.grad is not None else torch.zeros_like(ref)
-        if n.endswith(NOISE_ONLY):
+        if n.endswith(NOISE_ONLY + ("combine_proj.bias",)):      # a bias feeding BatchNorm: analytically zero gradient
+            assert float((g.cpu().double() - ref.double()).abs().max()) < 1e-4 * gmax, n
             continue
         err = rel_err(g, ref, floor=1e-2 * gmax)
-        if err > worst[1]:
-            worst = (n, err)
-    # CPU reference vs GPU: the dense GEMM / BatchNorm reductions both sides share run in different orders
-    assert worst[1] < 5e-5, worst
+        assert err < bar("gp_" + n), (n, err, own.get("gp_" + n))

@@ -46,17 +46,23 @@ def _run_pair(mine, ora, batch, make_x, P_shape, use_pe, gine=False):
         pe = torch.randint(0, 5, (N, K - 1), generator=g)
     elif K > 1 and not gine:
         pe = batch["pe_attr"]
+    # AttentionCombine: the product runs its own LSTM kernel (exact expf / tanhf), the oracle's nn.LSTM is cuDNN's fp32
+    # approximation -- evaluate the oracle in float64 there, so the comparison sees the product's error only
+    f64 = any("attention_lstm" in n for n, _ in ora.named_parameters())
+    if f64:
+        ora = ora.double()
     outs = []
     for layer in (ora, mine):
         d = dev
-        x = x0.clone().to(d).requires_grad_(True)
-        P = P0.clone().to(d).requires_grad_(True) if P0 is not None else None
+        dt = torch.float64 if (f64 and layer is ora) else torch.float32
+        x = x0.clone().to(d, dt).requires_grad_(True)
+        P = P0.clone().to(d, dt).requires_grad_(True) if P0 is not None else None
         ei, ea = batch["edge_index"].to(d), batch["edge_attr"].to(d)
         if gine:
             y = layer(x * 1.0, ei, ea[:, :1])
         else:
             y = layer(x * 1.0, ei, ea, pe.to(d) if pe is not None else None, P)
-        gy = torch.randn(y.shape, generator=torch.Generator().manual_seed(11)).to(d)
+        gy = torch.randn(y.shape, generator=torch.Generator().manual_seed(11)).to(d, dt)
         y.backward(gy)
         grads = {"x": x.grad}
         if P is not None:
@@ -78,7 +84,7 @@ def _run_pair(mine, ora, batch, make_x, P_shape, use_pe, gine=False):
             assert float((g1[n] - g0[n]).abs().max()) < 1e-4 * gmax, n
             continue
         err = rel_err(g1[n], g0[n], floor=1e-3 * gmax)
-        assert err < 5 * RTOL, (n, err)
+        assert err < RTOL, (n, err)
 
 
 CASES = [(K, kern, comb, pe) for K in (1, 3, 8) for kern in ("spd", "gd") for comb in ("geometric", "attention")
@@ -211,7 +217,7 @@ def test_bench_size_parity(lib):
         del y
     names = ("out", "dX", "dP", "dT0", "dTk", "dtheta")
     for n, a, c in zip(names, outs[1], outs[0]):
-        tol = RTOL if n in ("out", "dX", "dP") else 5 * RTOL       # parameter gradients: the golden tests' bar
+        tol = RTOL
         assert rel_err(a, c) < tol, (n, rel_err(a, c))
 
 

@@ -86,7 +86,7 @@ def test_persistent_multinode_other_kernel_families(lib, family):
 
 def _chunk_bounds(batch_vec, ei, graphs_per_chunk, G):
     """Node / edge ranges of consecutive graph chunks (edges are sorted by graph)."""
-    node_ptr = torch.searchsorted(batch_vec, torch.arange(0, G + 1, graphs_per_chunk).clamp(max=G))
+    node_ptr = torch.searchsorted(batch_vec, torch.arange(0, G + 1, graphs_per_chunk, device=batch_vec.device).clamp(max=G))
     node_ptr[-1] = batch_vec.numel()
     edge_ptr = torch.searchsorted(ei[0].contiguous(), node_ptr)
     return node_ptr.tolist(), edge_ptr.tolist()
@@ -181,11 +181,16 @@ def _layer_pair(mine, ora, b, x_shape, P_shape, tol=RTOL):
     x0 = torch.randn(*[N if s == "N" else s for s in x_shape], generator=g)
     P0 = torch.randn(*[N if s == "N" else s for s in P_shape], generator=g)
     ei, ea, pe = b["edge_index"].to(dev), b["edge_attr"].to(dev), b["pe_attr"]
+    # attention combine: oracle in float64 (its nn.LSTM would otherwise be cuDNN's fp32 approximation)
+    f64 = any("attention_lstm" in n for n, _ in ora.named_parameters())
+    if f64:
+        ora = ora.double()
     outs = []
     for layer in (ora, mine):
-        x, P = x0.clone().to(dev).requires_grad_(True), P0.clone().to(dev).requires_grad_(True)
+        dt = torch.float64 if (f64 and layer is ora) else torch.float32
+        x, P = x0.clone().to(dev, dt).requires_grad_(True), P0.clone().to(dev, dt).requires_grad_(True)
         y = layer(x * 1.0, ei, ea, pe.to(dev) if pe is not None else None, P)
-        y.backward(torch.randn(y.shape, generator=torch.Generator().manual_seed(11)).to(dev))
+        y.backward(torch.randn(y.shape, generator=torch.Generator().manual_seed(11)).to(dev, dt))
         grads = {"x": x.grad, "P": P.grad}
         grads.update({n: p.grad for n, p in layer.named_parameters()})
         outs.append((y, grads))

@@ -13,7 +13,7 @@ def rel_err(a, b, floor=1e-30):
     """max |a-b| / max(|b|_inf, tiny): the '1e-5 relative' bar is on the tensor scale (fp32 sums of ~20 terms
     cannot be elementwise-relative near zero crossings)."""
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
-    scale = max(b.abs().max().item(), floor)
+    scale = max(b.abs().max().item(), floor, 1e-30)
     return (a - b).abs().max().item() / scale
 
 

@@ -57,7 +57,7 @@ def _run(cfg, model, batch_cpu, dev, double):
 def _compare(cfg, ref_model, my_model, batch_cpu, dev):
     """Truth = the all-reference model in float64.  The bar is 1e-5 relative; where the all-reference model's OWN fp32
     evaluation already sits further than that from its float64 evaluation (deep stacks of BatchNorm amplify fp32
-    rounding: a property of the model, not of either implementation) the product must stay within 4x the reference's
+    rounding: a property of the model, not of either implementation) the product must stay within 10x the reference's
     own fp32 error."""
     my_model.load_state_dict(ref_model.state_dict())        # the reference's state_dict loads unchanged
     import copy
@@ -68,7 +68,7 @@ def _compare(cfg, ref_model, my_model, batch_cpu, dev):
     p0, l0, g0 = _run(cfg, ref_model, batch_cpu, dev, True)
 
     def bar(own):
-        return max(RTOL, 4.0 * own)
+        return max(RTOL, 10.0 * own)
     assert rel_err(p1, p0) < bar(rel_err(p32, p0)), ("prediction", rel_err(p1, p0), rel_err(p32, p0))
     assert abs(l1 - l0) <= bar(abs(l32 - l0) / max(abs(l0), 1e-6)) * max(abs(l0), 1e-6), ("loss", l0, l1, l32)
     gmax = max(float(v.abs().max()) for v in g0.values() if v is not None)

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define KPGNN_ABI_VERSION 8
+#define KPGNN_ABI_VERSION 9
 
 const char* kp_last_error(void);
 int kp_abi_version(void);
@@ -63,6 +63,20 @@ int kp_plan_count(const kp_plan_input* in, int32_t* rowptr, int32_t* rowptrT, in
 int kp_plan_fill(const kp_plan_input* in, const int32_t* rowptr, const int32_t* rowptrT, int32_t* col,
                  uint16_t* attr16, int32_t* colT, float* dinv, int32_t capacity, void* workspace,
                  size_t workspace_bytes, void* stream);
+
+/* In-place refreshes with a fixed capacity: rows past `capacity` were not emitted by kp_plan_fill; clamp both row
+ * pointer arrays (N*K+1 ints) to it so that consumers see those rows as empty and never index past col/attr16/colT. */
+int kp_plan_clamp(int32_t* rowptr, int32_t* rowptrT, int32_t N, int32_t K, int32_t capacity, void* stream);
+
+/* Closed node blocks of a plan: maximal runs of consecutive nodes whose in- and out-neighbours (all hops) stay inside
+ * the run -- the graphs of a collated batch (PyG Batch.from_data_list numbers nodes graph by graph), found without
+ * the `batch` vector, which the reference's layer signature (KPGINplus.py:61) does not carry.  block_ptr [N+1] receives
+ * the block boundaries (num_blocks+1 used), block_stats[0..2] = {num_blocks, max nodes per block, max entries per
+ * block}.  The block-resident kernels (kp_agg_desc.block_ptr) partition their work by these ranges. */
+int kp_plan_blocks_workspace_bytes(int32_t N, size_t* bytes);
+int kp_plan_blocks(const int32_t* rowptr, const int32_t* col, const int32_t* rowptrT, const int32_t* colT, int32_t N,
+                   int32_t K, int32_t capacity, int32_t* block_ptr, int32_t* block_stats, void* workspace,
+                   size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Per-hop masked aggregation with fused epilogue (forward) -- the message/aggregate/update of
@@ -111,13 +125,22 @@ typedef struct {
    * dX gather and whatever the caller enqueues next on `stream`.  The caller must make its stream wait for
    * leaf_stream before reading those outputs and keep outputs + workspace alive until then.  NULL: one stream. */
   void* leaf_stream;
+  /* Optional closed node blocks of the plan (kp_plan_blocks: block_ptr [num_blocks+1], the largest block's node
+   * count).  When supplied, unfused calls whose largest block fits in shared memory run block-resident: a CTA stages one
+   * (block, hop) slice of X and takes every gather of the block's rows from shared memory -- the long-row regime of
+   * the regular-graph workload (run_simulation.py, ~177 entries per node).  NULL: row-streaming kernels only. */
+  const int32_t* block_ptr;
+  const int32_t* block_stats;          /* device: [0] = current number of blocks (read by the kernel, so that a captured
+                                          launch follows in-place plan refreshes); NULL: num_blocks below is exact */
+  int32_t num_blocks, max_block_nodes; /* host-side sizing: grid ~ num_blocks * k units, shared memory ~ max_block_nodes */
 } kp_agg_desc;
 
 int kp_agg_forward(const kp_agg_desc* desc, float* out, void* stream);
 /* Test hook, process-wide; a bit set of kernel-family selectors so every implementation is parity-tested on the
  * same inputs.  bit 0: generic (any width / alignment / stride) kernels instead of the float4 fast path;
  * bit 1: register-prefetch instead of cp.async-ring forward kernel; bit 2: no packed-math ("lean") kernels;
- * bit 4: TMA-staged forward kernel for every eligible call; bit 5: TMA-staged forward kernel for large batches.
+ * bit 4: TMA-staged forward kernel for every eligible call; bit 5: TMA-staged forward kernel for large batches;
+ * bit 6: ignore desc.block_ptr (no block-resident kernels).
  * 0 = production default (lean kernels, no TMA staging). */
 int kp_agg_set_force_generic(int flag);
 /* Test hook, process-wide: max_ctas > 0 caps the grid of every persistent aggregation kernel, lean_threads > 0 (a

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # KPGNN_B200_LIB points at an alternative build of the same library (kernel tuning experiments)
 LIB_PATH = os.environ.get("KPGNN_B200_LIB") or os.path.join(_HERE, "libkpgnn_b200.so")
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 
 class KpError(RuntimeError):
@@ -33,7 +33,9 @@ class AggDesc(C.Structure):
                 ("amax0", C.c_int32), ("amaxk", C.c_int32),
                 ("dx_node_stride", C.c_int64), ("dx_hop_stride", C.c_int64),
                 ("dx_accumulate", C.c_int32), ("pad0", C.c_int32),
-                ("geo_alphas", C.c_void_p), ("geo_dalphas", C.c_void_p), ("leaf_stream", C.c_void_p)]
+                ("geo_alphas", C.c_void_p), ("geo_dalphas", C.c_void_p), ("leaf_stream", C.c_void_p),
+                ("block_ptr", C.c_void_p), ("block_stats", C.c_void_p), ("num_blocks", C.c_int32),
+                ("max_block_nodes", C.c_int32)]
 
 
 class ExtractInput(C.Structure):
@@ -96,6 +98,10 @@ _SIGNATURES = {
                                 C.c_void_p, C.c_size_t, C.c_void_p]),
     "kp_plan_fill": (C.c_int, [C.POINTER(PlanInput), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "kp_plan_clamp": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "kp_plan_blocks_workspace_bytes": (C.c_int, [C.c_int32, C.POINTER(C.c_size_t)]),
+    "kp_plan_blocks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "kp_agg_forward": (C.c_int, [C.POINTER(AggDesc), C.c_void_p, C.c_void_p]),
     "kp_agg_set_force_generic": (C.c_int, [C.c_int]),
     "kp_agg_set_launch_geometry": (C.c_int, [C.c_int, C.c_int]),

@@ -791,6 +791,8 @@ int kp_agg_forward(const kp_agg_desc* desc, float* out, void* stream) {
                "kp_agg_forward: output not aligned for %d-wide stores", c.vec);
   kp::AggArgs args{*desc, c.G, c.gshift};
   cudaStream_t st = (cudaStream_t)stream;
+  if (c.fast && kp::tile_eligible(*desc, c.ftab))
+    return kp::tile_fwd(kp::make_fast_args(*desc), c.fG, desc->act, c.ftab, c.fextra, out, st);
   if (c.fast)
     return kp::fast_fwd(kp::make_fast_args(*desc), c.fG, desc->act, desc->fuse != 0, c.ftab, c.fextra, c.fgrid,
                         c.fsmem_fwd, out, st);
@@ -807,6 +809,7 @@ int kp_agg_set_force_generic(int flag) {
   // TMA-staged forward kernel (agg_tma.cuh): off by default (measured slightly slower than the lean kernel);
   // bit 4: use it for every eligible call, however small (tests); bit 5: use it for large batches only
   kp::fast_fwd_set_tma((flag & 16) ? 2 : ((flag & 32) ? 1 : 0));
+  kp::tile_set_mode((flag & 64) ? 0 : 1);
   return 0;
 }
 
@@ -898,7 +901,10 @@ int kp_agg_backward(const kp_agg_desc* desc, const float* dOut, float* dX, float
     KP_CUDA(cudaEventDestroy(ev));
   }
   const float* Gsrc = c.need_gs ? Gs : dOut;
-  if (dX && c.fast) {
+  if (dX && c.fast && kp::tile_eligible(a, kp::TAB_NONE) && !a.dx_node_stride && !a.dx_hop_stride && !a.dx_accumulate) {
+    int rc = kp::tile_b2(kp::make_fast_args(a), c.fG, c.fextra, Gsrc, dOut, dX, st);
+    if (rc) return rc;
+  } else if (dX && c.fast) {
     int rc = kp::fast_b2(kp::make_fast_args(a), c.fG, a.fuse != 0, c.fextra, c.fgrid, Gsrc, dOut, dX, st);
     if (rc) return rc;
   } else if (dX) {

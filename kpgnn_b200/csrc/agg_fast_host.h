@@ -48,6 +48,12 @@ int fast_b1(const FastArgs& fa, int G, int act, bool fuse, int tab, bool extra, 
 int fast_b2(const FastArgs& fa, int G, bool fuse, bool extra, int grid, const float* Gs, const float* dOut, float* dX,
             cudaStream_t st);
 
+// block-resident kernels for long rows (agg_tile.cu)
+void tile_set_mode(int mode);      // 0 = never, 1 = when the caller supplies closed blocks (default)
+bool tile_eligible(const kp_agg_desc& a, int tab);
+int tile_fwd(const FastArgs& fa, int G, int act, int tab, bool extra, float* out, cudaStream_t st);
+int tile_b2(const FastArgs& fa, int G, bool extra, const float* Gs, const float* dOut, float* dX, cudaStream_t st);
+
 // dispatch helper shared by the three translation units
 #define KP_FAST_TAB(FN, G, A, F, X, tab, ...)                                  \
   ((tab) == TAB_SMEM ? FN<G, A, F, TAB_SMEM, X>(__VA_ARGS__)                   \

@@ -137,11 +137,15 @@ __global__ void plan_emit_kernel(const int64_t* __restrict__ src, const int64_t*
   if (r >= N * K) return;
   int v = r / K, h = r - v * K;
   if (dinv && !transposed) dinv[r] = 1.0f / sqrtf((float)(rowptr[r + 1] - rowptr[r]));
-  if (rowptr[r + 1] > cap || rowptrT[r + 1] > cap) return;   // overflow: reported through stats[0] > capacity
+  // Overflow (in-place refresh of a plan whose capacity the new batch exceeds; reported through stats[0] > capacity):
+  // rows are cut at the capacity, so that after kp_plan_clamp every index a consumer can reach was written from THIS
+  // batch (wrong results, raised by the caller at its next sync point, but never an out-of-range gather).
   int buf[KP_EMIT_LOCAL];
   if (!transposed) {
     int b = rowptr[r], e = rowptr[r + 1];
-    int n = e - b - (self_loops ? 1 : 0);
+    const bool cut = e > cap;
+    if (b >= cap) return;
+    int n = (cut ? cap : e) - b - ((self_loops && !cut) ? 1 : 0);
     const int* ids = sorted_row_ids(eid + b, n, buf);
 #pragma unroll 4
     for (int i = 0; i < n; ++i) {
@@ -149,18 +153,92 @@ __global__ void plan_emit_kernel(const int64_t* __restrict__ src, const int64_t*
       col[b + i] = (int)src[id];
       attr16[b + i] = (uint16_t)attr[(long long)id * attr_stride + h];
     }
-    if (self_loops) {
+    if (self_loops && !cut) {
       col[e - 1] = v;
       attr16[e - 1] = 1;
     }
   } else {
     int b = rowptrT[r], e = rowptrT[r + 1];
-    int n = e - b - (self_loops ? 1 : 0);
+    const bool cut = e > cap;
+    if (b >= cap) return;
+    int n = (cut ? cap : e) - b - ((self_loops && !cut) ? 1 : 0);
     const int* ids = sorted_row_ids(eidT + b, n, buf);
 #pragma unroll 4
     for (int i = 0; i < n; ++i) colT[b + i] = (int)dst[ids[i]];
-    if (self_loops) colT[e - 1] = v;
+    if (self_loops && !cut) colT[e - 1] = v;
   }
+}
+
+// In-place refresh with a fixed capacity (CUDA-graph replay loops): when a batch has more entries than were
+// allocated, the rows past the capacity were not emitted; clamp the row pointers so that every consumer kernel sees
+// them as EMPTY rows and stays inside col / attr16 / colT.  The overflow itself is reported through stats[0] > capacity.
+__global__ void plan_clamp_kernel(int* __restrict__ rowptr, int* __restrict__ rowptrT, int n, int cap) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    if (rowptr[i] > cap) rowptr[i] = cap;
+    if (rowptrT[i] > cap) rowptrT[i] = cap;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Closed node blocks: maximal consecutive node ranges [b, e) such that every in- and out-neighbour (over all hops)
+// of a node in the range lies in the range -- for a collated batch these are the graphs (or their connected
+// components), WITHOUT being told the batch vector, which the reference's layer API does not carry.  The kernels that
+// keep a block's rows in shared memory (agg_block.cuh) partition their work by these ranges.
+//   lo/hi per node -> prefix max of hi, suffix min of lo -> start flags -> block ids -> block_ptr
+// ------------------------------------------------------------------------------------------------------------
+__global__ void plan_block_range_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
+                                        const int* __restrict__ rowptrT, const int* __restrict__ colT, int N, int K,
+                                        int cap, int* __restrict__ hi, int* __restrict__ lo_rev) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= N) return;
+  int lo = v, h = v;
+  {
+    const int b = rowptr[(size_t)v * K], e = min(rowptr[(size_t)(v + 1) * K], cap);
+    for (int j = b; j < e; ++j) {
+      const int c = __ldg(col + j);
+      lo = min(lo, c);
+      h = max(h, c);
+    }
+  }
+  {
+    const int b = rowptrT[(size_t)v * K], e = min(rowptrT[(size_t)(v + 1) * K], cap);
+    for (int j = b; j < e; ++j) {
+      const int c = __ldg(colT + j);
+      lo = min(lo, c);
+      h = max(h, c);
+    }
+  }
+  hi[v] = h;
+  lo_rev[N - 1 - v] = lo;
+}
+
+__global__ void plan_block_flag_kernel(const int* __restrict__ pmax, const int* __restrict__ smin_rev, int N,
+                                       int* __restrict__ flag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  flag[i] = (i == 0 || (pmax[i - 1] < i && smin_rev[N - 1 - i] >= i)) ? 1 : 0;
+}
+
+__global__ void plan_block_ptr_kernel(const int* __restrict__ flag, const int* __restrict__ bid, int N,
+                                      int* __restrict__ block_ptr, int* __restrict__ bstats) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  if (flag[i]) block_ptr[bid[i]] = i;
+  if (i == N - 1) {
+    const int nb = bid[i] + flag[i];
+    block_ptr[nb] = N;
+    bstats[0] = nb;
+  }
+}
+
+__global__ void plan_block_stats_kernel(const int* __restrict__ block_ptr, const int* __restrict__ rowptr, int K,
+                                        int N, int cap, int* __restrict__ bstats) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= bstats[0]) return;
+  const int v0 = block_ptr[b], v1 = block_ptr[b + 1];
+  atomicMax(&bstats[1], v1 - v0);
+  atomicMax(&bstats[2], min(rowptr[(size_t)v1 * K], cap) - min(rowptr[(size_t)v0 * K], cap));
 }
 
 static size_t scan_temp_bytes(int rows_plus_1) {
@@ -244,6 +322,62 @@ int kp_plan_fill(const kp_plan_input* in, const int32_t* rowptr, const int32_t* 
   }
   KP_LAUNCH(kp::plan_emit_kernel, kp::ceil_div(2 * rows, 128), 128, 0, st, in->src, in->dst, in->attr,
             in->attr_stride, N, K, in->self_loops, rowptr, rowptrT, eid, eidT, col, attr16, colT, dinv, (int)capacity);
+  return 0;
+}
+
+int kp_plan_clamp(int32_t* rowptr, int32_t* rowptrT, int32_t N, int32_t K, int32_t capacity, void* stream) {
+  KP_CHECK_ARG(rowptr && rowptrT && N >= 0 && K >= 1 && capacity >= 0, "kp_plan_clamp: bad argument");
+  const long long n = (long long)N * K + 1;
+  KP_LAUNCH(kp::plan_clamp_kernel, kp::ceil_div(n, 256), 256, 0, stream, rowptr, rowptrT, (int)n, (int)capacity);
+  return 0;
+}
+
+int kp_plan_blocks_workspace_bytes(int32_t N, size_t* bytes) {
+  KP_CHECK_ARG(N >= 0 && bytes, "kp_plan_blocks_workspace_bytes: bad arguments");
+  size_t t1 = 0, t2 = 0;
+  cub::DeviceScan::InclusiveScan(nullptr, t1, (int*)nullptr, (int*)nullptr, cub::Max(), N > 0 ? N : 1);
+  cub::DeviceScan::ExclusiveSum(nullptr, t2, (int*)nullptr, (int*)nullptr, N > 0 ? N : 1);
+  const size_t arr = kp::align_up(sizeof(int) * (size_t)(N > 0 ? N : 1), 256);
+  *bytes = 5 * arr + kp::align_up(t1 > t2 ? t1 : t2, 256);
+  return 0;
+}
+
+int kp_plan_blocks(const int32_t* rowptr, const int32_t* col, const int32_t* rowptrT, const int32_t* colT, int32_t N,
+                   int32_t K, int32_t capacity, int32_t* block_ptr, int32_t* block_stats, void* workspace,
+                   size_t workspace_bytes, void* stream) {
+  KP_CHECK_ARG(rowptr && rowptrT && block_ptr && block_stats && N >= 0 && K >= 1, "kp_plan_blocks: bad argument");
+  size_t need = 0;
+  if (kp_plan_blocks_workspace_bytes(N, &need)) return 1;
+  KP_CHECK_ARG(workspace_bytes >= need && workspace, "kp_plan_blocks: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  KP_CUDA(cudaMemsetAsync(block_stats, 0, sizeof(int) * 4, st));
+  if (N == 0) {
+    KP_CUDA(cudaMemsetAsync(block_ptr, 0, sizeof(int), st));
+    return 0;
+  }
+  KP_CHECK_ARG(col && colT, "kp_plan_blocks: null plan arrays");
+  const size_t arr = kp::align_up(sizeof(int) * (size_t)N, 256);
+  char* w = (char*)workspace;
+  int* hi = (int*)w;
+  int* lo_rev = (int*)(w + arr);
+  int* pmax = (int*)(w + 2 * arr);
+  int* smin_rev = (int*)(w + 3 * arr);
+  int* flag = (int*)(w + 4 * arr);
+  void* temp = w + 5 * arr;
+  size_t temp_bytes = workspace_bytes - 5 * arr;
+  const int grid = kp::ceil_div(N, 256);
+  KP_LAUNCH(kp::plan_block_range_kernel, grid, 256, 0, st, rowptr, col, rowptrT, colT, N, K, (int)capacity, hi, lo_rev);
+  size_t tb = temp_bytes;
+  KP_CUDA(cub::DeviceScan::InclusiveScan(temp, tb, hi, pmax, cub::Max(), N, st));
+  tb = temp_bytes;
+  KP_CUDA(cub::DeviceScan::InclusiveScan(temp, tb, lo_rev, smin_rev, cub::Min(), N, st));
+  KP_LAUNCH(kp::plan_block_flag_kernel, grid, 256, 0, st, pmax, smin_rev, N, flag);
+  tb = temp_bytes;
+  int* bid = hi;                               // hi is dead after the scan
+  KP_CUDA(cub::DeviceScan::ExclusiveSum(temp, tb, flag, bid, N, st));
+  kp::g_launches.fetch_add(3, std::memory_order_relaxed);
+  KP_LAUNCH(kp::plan_block_ptr_kernel, grid, 256, 0, st, flag, bid, N, block_ptr, block_stats);
+  KP_LAUNCH(kp::plan_block_stats_kernel, grid, 256, 0, st, block_ptr, rowptr, K, N, (int)capacity, block_stats);
   return 0;
 }
 

@@ -13,6 +13,10 @@ from . import _lib
 from ._lib import ACT_GELU, ACT_NONE, ACT_RELU  # noqa: F401
 
 
+# average entries per (node, hop) row from which the block-resident kernels (csrc/agg_tile.cu) are worth their staging
+LONG_ROW_ENTRIES = 12
+
+
 def _ptr(t):
     return None if t is None else t.data_ptr()
 
@@ -37,6 +41,10 @@ def _make_desc(plan, k, x, P, T0, Tk, theta, eps, act, fuse, use_dinv, use_mean)
     desc.theta, desc.eps = _ptr(theta), _ptr(eps)
     desc.act, desc.fuse = act, 1 if fuse else 0
     desc.amax0, desc.amaxk = plan.max_attr0, plan.max_attrk
+    if plan.block_ptr is not None and not fuse:
+        # closed node blocks were requested for this plan (long-row workloads): block-resident kernels where they fit
+        desc.block_ptr, desc.block_stats = plan.block_ptr.data_ptr(), plan.block_stats.data_ptr()
+        desc.num_blocks, desc.max_block_nodes = plan.num_blocks, plan.max_block_nodes
     return desc
 
 
@@ -119,4 +127,6 @@ def khop_aggregate(x, plan, k, P=None, T0=None, Tk=None, theta=None, eps=None, a
     """x [N,k,d] fp32 (any node/hop strides, dense last dim) -> [N,d] if fuse else [N,k,d].  See kpgnn.h."""
     if fuse and theta is None:
         raise ValueError("fuse=True needs theta [k,d]")
+    if not fuse and plan.block_ptr is None and plan.nnz >= LONG_ROW_ENTRIES * max(plan.N * plan.K, 1):
+        plan.blocks()          # long rows (e.g. n = 1 280 regular graphs at K = 6): stage blocks in shared memory
     return _KHopAggregate.apply(x, P, T0, Tk, theta, eps, plan, k, act, fuse, use_dinv, use_mean)

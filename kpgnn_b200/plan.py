@@ -30,7 +30,31 @@ def deferred_checks(flag):
 class GraphPlan(object):
     __slots__ = ("N", "E", "K", "nnz", "capacity", "self_loops", "rowptr", "col", "attr16", "rowptrT", "colT", "dinv",
                  "indeg", "max_attr0", "max_attrk", "device", "stats", "stats_host", "ws", "pending", "src", "dst",
-                 "ready")
+                 "ready", "block_ptr", "block_stats", "block_ws", "num_blocks", "max_block_nodes", "max_block_nnz",
+                 "block_stats_host")
+
+    def blocks(self):
+        """Closed node blocks (kp_plan_blocks: the graphs of the batch, found from the plan itself).  Computed on first
+        use (one host sync for the statistics that size the block-resident kernels) and recomputed by every in-place
+        refresh from then on."""
+        if self.block_ptr is None:
+            lib = _lib.lib()
+            nb = C.c_size_t(0)
+            _lib.check(lib.kp_plan_blocks_workspace_bytes(self.N, C.byref(nb)), "kp_plan_blocks_workspace_bytes")
+            self.block_ws = torch.empty(max(nb.value, 16), dtype=torch.uint8, device=self.device)
+            self.block_ptr = torch.empty(self.N + 1, dtype=torch.int32, device=self.device)
+            self.block_stats = torch.zeros(4, dtype=torch.int32, device=self.device)
+            self.block_stats_host = torch.empty(4, dtype=torch.int32, pin_memory=True)
+            self._run_blocks()
+            self.num_blocks, self.max_block_nodes, self.max_block_nnz, _ = self.block_stats.tolist()
+        return self.block_ptr
+
+    def _run_blocks(self):
+        lib = _lib.lib()
+        _lib.check(lib.kp_plan_blocks(self.rowptr.data_ptr(), self.col.data_ptr(), self.rowptrT.data_ptr(),
+                                      self.colT.data_ptr(), self.N, self.K, self.capacity, self.block_ptr.data_ptr(),
+                                      self.block_stats.data_ptr(), self.block_ws.data_ptr(), self.block_ws.numel(),
+                                      _stream_ptr(self.device)), "kp_plan_blocks")
 
     def check_tables(self, rows0, rowsk, k):
         """nn.Embedding would raise IndexError on an out-of-range attr (KPGIN.py:90,95); so do we."""
@@ -49,6 +73,13 @@ class GraphPlan(object):
             self.pending.synchronize()
             self.pending = None
         nnz, m0, mk, bad = self.stats_host.tolist()
+        if self.block_ptr is not None:
+            nb, mbn, mbz, _ = self.block_stats_host.tolist()
+            if mbn > self.max_block_nodes or mbz > self.max_block_nnz:
+                raise _lib.KpError("refreshed batch has a graph of %d nodes / %d entries, above what the block-resident "
+                                   "kernels were sized for (%d / %d)" % (mbn, mbz, self.max_block_nodes,
+                                                                        self.max_block_nnz))
+            self.num_blocks = nb
         if bad:
             raise IndexError("edge_index / edge_attr out of range in %d entries" % bad)
         if nnz > self.capacity:
@@ -98,6 +129,8 @@ def build_plan(edge_index, edge_attr_base, attr_stride, K, num_nodes, self_loops
     p.N, p.E, p.K, p.self_loops, p.device = int(num_nodes), edge_index.size(1), K, bool(self_loops), dev
     p.pending = None
     p.ready = None
+    p.block_ptr = p.block_stats = p.block_ws = p.block_stats_host = None
+    p.num_blocks = p.max_block_nodes = p.max_block_nnz = 0
     rows = p.N * K
     nbytes = C.c_size_t(0)
     _lib.check(lib.kp_plan_workspace_bytes(p.N, p.E, K, C.byref(nbytes)), "kp_plan_workspace_bytes")
@@ -129,6 +162,12 @@ def refresh_plan(p, edge_index, edge_attr_base, attr_stride):
     _run_count(p, pin)
     if _DEFERRED:
         _run_fill(p, pin)
+        # the batch may exceed the capacity (found out at validate()): consumers must stay inside the arrays meanwhile
+        _lib.check(_lib.lib().kp_plan_clamp(p.rowptr.data_ptr(), p.rowptrT.data_ptr(), p.N, p.K, p.capacity,
+                                            _stream_ptr(p.device)), "kp_plan_clamp")
+        if p.block_ptr is not None:
+            p._run_blocks()
+            p.block_stats_host.copy_(p.block_stats, non_blocking=True)
         p.stats_host.copy_(p.stats, non_blocking=True)
         if torch.cuda.is_current_stream_capturing():
             p.pending = "captured"              # every replay refreshes stats_host; validate() syncs the stream
@@ -144,6 +183,9 @@ def refresh_plan(p, edge_index, edge_attr_base, attr_stride):
         return False
     p.nnz, p.max_attr0, p.max_attrk = nnz, m0, mk
     _run_fill(p, pin)
+    if p.block_ptr is not None:
+        p._run_blocks()
+        p.num_blocks, p.max_block_nodes, p.max_block_nnz, _ = p.block_stats.tolist()
     return True
 
 

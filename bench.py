@@ -413,6 +413,179 @@ def agg_roofline(device, num_graphs, peak, reps=10):
                          "kernels": "agg_bwd_dst_lean (B1) + agg_fwd_lean<gather> (B2) + agg_bwd_table_count (B3) + reductions"}}
 
 
+# ----------------------------------------------------------------------------------------------------------------
+# other BASELINE.json workloads, reported next to the headline line (keys under "workloads")
+# ----------------------------------------------------------------------------------------------------------------
+REG_N, REG_K, REG_D, REG_GRAPHS = 1280, 6, 16, 64             # configs[4]: run_simulation.py:96-140 (n, K, hidden)
+REG_EXTRACT = (REG_K, 10, 1, 1, 1, 1, "spd")                  # run_simulation.py:103
+
+
+def _events_ms(fn, reps, device, flush=None, warm=2):
+    st = torch.cuda.current_stream(device)
+    ts = []
+    for i in range(reps + warm):
+        if flush is not None:
+            flush_l2(flush)
+        torch.cuda.synchronize(device)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(st)
+        fn()
+        b.record(st)
+        torch.cuda.synchronize(device)
+        if i >= warm:
+            ts.append(a.elapsed_time(b))
+    return statistics.mean(ts)
+
+
+def extract_alg_bytes(csr, out, args):
+    """input int32 CSR + type (2*E1*4 + E1), output compact src/dst (E_K*8) + hop/attr per entry (nnz*3)
+    + the peripheral tensors as int16 (N*K*(2*max_edge_type + max_hop_num + 1)*2)."""
+    K, _, H, MET = args[0], args[1], args[2], args[3]
+    E1 = int(csr["ecol"].shape[0])
+    EK = int(out["edge_index"].size(1))
+    nnz = int((out["edge_attr"] != 0).sum())
+    return 2 * E1 * 4 + E1 + EK * 8 + nnz * 3 + csr["N"] * K * (2 * MET + H + 1) * 2
+
+
+def extraction_metrics(device, peak, name, graphs, args, reps=5):
+    """K-hop + peripheral extraction of one batch from its packed CSR (resident on the device): graphs/s, algorithmic
+    GB/s and the fraction of the HBM roofline; bit-exactness is the gate (tests/test_extract_gpu.py)."""
+    from kpgnn_b200 import data_utils as DU
+    t0 = time.perf_counter()
+    csr = DU.upload_csr(DU.pack_csr(graphs), device)
+    pack_ms = (time.perf_counter() - t0) * 1e3
+    holder = {}
+
+    def run():
+        holder["out"] = DU._extract_device(csr, *args, device=device)
+    ms = _events_ms(run, reps, device)
+    alg = extract_alg_bytes(csr, holder["out"], args)
+    return {"config": name, "graphs": len(graphs), "nodes": csr["N"], "khop_edges": int(holder["out"]["edge_index"].size(1)),
+            "ms_device": round(ms, 3), "graphs_per_s": round(len(graphs) / (ms * 1e-3), 1),
+            "algorithmic_bytes": alg, "achieved_GBps": round(alg / ms / 1e6, 2),
+            "frac_of_hbm_peak": round(alg / ms / 1e6 / peak, 5), "host_csr_pack_ms": round(pack_ms, 3)}
+
+
+class RegularWorkload(object):
+    """configs[4]: node-level KP-GIN (`KGINConv`, run_simulation.py:29-93) on 3-regular graphs with n = 1 280, K = 6,
+    hidden 16, forward only -- per step: K-hop extraction of the rank's 64 graphs (kp_extract_*), plan build, one
+    KGINConv forward.  The reference runs the same per graph with batch_size 1 (run_simulation.py:103-110)."""
+
+    def __init__(self, device, rank):
+        from kpgnn_b200 import data_utils as DU, synth
+        from kpgnn_b200.simulation import KGINConv
+        self.DU, self.device = DU, device
+        graphs = [synth.regular_graph(REG_N, 3, rank * REG_GRAPHS + s) for s in range(REG_GRAPHS)]
+        self.csr = DU.pack_csr(graphs)
+        self.dev_csr = DU.upload_csr(dict(self.csr), device)      # "value": the packed raw batch is resident in HBM
+        torch.manual_seed(0)
+        self.model = KGINConv(REG_D, REG_K).to(device).eval()
+        self.x = torch.ones(self.csr["N"], 1, device=device)
+        self.batch = torch.from_numpy(self.csr["node_graph"].astype(np.int64)).to(device)
+        self.out = None
+        self.host_out = torch.empty((self.csr["N"], REG_D), dtype=torch.float32, pin_memory=True)
+
+    def step(self, csr=None):
+        ex = self.DU._extract_device(csr or self.dev_csr, *REG_EXTRACT, device=self.device)
+        with torch.no_grad():
+            self.out = self.model(self.x, ex["edge_index"], ex["edge_attr"], self.batch)
+        self.last = ex
+
+    def step_e2e(self):
+        self.step(self.csr)                                      # host arrays: uploaded inside the timed region
+        self.host_out.copy_(self.out, non_blocking=True)        # run_simulation.py:111 `output.cpu()`
+        torch.cuda.current_stream(self.device).synchronize()
+
+
+def regular_roofline(device, peak, wl):
+    """The aggregation launch of the configs[4] layer at >= 1 GB of algorithmic bytes: the rank's 64 extracted graphs
+    replicated 10x with node offsets (640 graphs, 819 200 nodes, 144 M entries), d = 16, self term, no tables.
+    Bytes per SURVEY.md 8(d): X + out + rowptr + 4-byte col per entry."""
+    import ctypes as C
+    from kpgnn_b200 import _lib
+    from kpgnn_b200.ops import _make_desc, ACT_NONE
+    from kpgnn_b200.plan import get_plan
+    reps = 10
+    ex = wl.last
+    N0 = wl.csr["N"]
+    ei = torch.cat([ex["edge_index"] + r * N0 for r in range(reps)], dim=1)
+    ea = ex["edge_attr"].repeat(reps, 1)
+    N = N0 * reps
+    plan, k = get_plan(ei, ea, N)
+    plan.blocks()
+    del ei, ea
+    x = torch.randn(N, REG_K, REG_D, device=device)
+    eps = torch.zeros(1, device=device)
+    out = torch.empty(N, REG_K, REG_D, device=device)
+    desc = _make_desc(plan, k, x, None, None, None, None, eps, ACT_NONE, False, False, False)
+    lib = _lib.lib()
+    sp = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    flush = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device=device)
+    ms = _events_ms(lambda: _lib.check(lib.kp_agg_forward(C.byref(desc), out.data_ptr(), sp), "kp_agg_forward"), 8, device,
+                    flush)
+    alg = 4 * N * REG_K * REG_D * 2 + 4 * (N * REG_K + 1) + plan.nnz * 4
+    return {"bound": "hbm (algorithmic); the gathers themselves are served from shared memory", "graphs_per_launch":
+            REG_GRAPHS * reps, "nodes": N, "nnz": plan.nnz, "algorithmic_bytes": alg, "ms_per_launch": round(ms, 4),
+            "achieved": round(alg / ms / 1e6, 1), "peak": peak, "unit": "GB/s", "frac": round(alg / ms / 1e6 / peak, 4),
+            "gather_model_GBps": round((plan.nnz * (REG_D * 4 + 4) + 4 * N * REG_K * REG_D) / ms / 1e6, 1),
+            "kernel": "agg_tile_kernel<4,NONE,no-tables,self-term> (block-resident, csrc/agg_tile.cu)"}
+
+
+def other_model_steps(device):
+    """Training-step times (eager, fwd + bwd + Adam) of the other model configs on the product backbones, and -- when the
+    reference's files are staged (oracle/_ref) -- of the reference's UNMODIFIED models/GNNs.py running layer by layer on
+    the drop-in layers, next to the headline's stack path.  Diagnostics, not bench lines."""
+    from kpgnn_b200 import backbones, synth
+    from kpgnn_b200.data_utils import extract_batch
+    from kpgnn_b200.model import l1_loss
+    from kpgnn_b200.optim import FusedAdam
+    res = {}
+    graphs = synth.zinc_like_graphs(GRAPHS_PER_GPU, seed=0)
+    y = torch.tensor([g["y"] for g in graphs], dtype=torch.float32, device=device)
+
+    def time_model(model, b, steps=10):
+        opt = FusedAdam([p for p in model.parameters() if p.requires_grad], lr=1e-3)
+
+        def step():
+            opt.zero_grad()
+            loss = l1_loss(model(b), y)
+            loss.backward()
+            opt.step()
+        return _events_ms(step, steps, device, warm=3)
+    # configs[2]: KPGINPrime K=16, 17 layers, hidden 96 (README.md:128)
+    b16 = extract_batch(graphs, (16, 50, 6, 3, 50, 50, "spd"), device)
+    torch.manual_seed(0)
+    prime = backbones.make_model("KPGINPrime", 96, 16, 17, 21, 3, 50, 50, 6, 50, JK="concat", residual=True).to(device).train()
+    ms = time_model(prime, b16)
+    res["kpginprime_K16_L17_H96_batch128"] = {"ms_per_step_eager": round(ms, 3),
+                                              "graphs_per_s": round(GRAPHS_PER_GPU / (ms * 1e-3), 1)}
+    try:
+        from oracle import refimport
+        if refimport.available():
+            import argparse
+            from kpgnn_b200.layers import layer_utils
+            from kpgnn_b200.layers.input_encoder import EmbeddingEncoder
+            dropin = refimport.load_models_over_dropin()
+            b8 = extract_batch(graphs, EXTRACT_ARGS, device)
+            a = argparse.Namespace(model_name="KPGINPlus", hidden_size=HIDDEN, K=K, num_hop1_edge=3, max_pe_num=50,
+                                   combine="geometric", num_layer=LAYERS, eps=0., train_eps=False, aggr="add")
+            torch.manual_seed(0)
+            gnn = dropin.GNNs.GNNPlus(num_layer=LAYERS, gnn_layer=layer_utils.make_gnn_layer(a), JK="concat",
+                                      norm_type="Batch", init_emb=EmbeddingEncoder(21, HIDDEN), residual=True,
+                                      virtual_node=False, use_rd=False, num_hop1_edge=3, max_edge_count=50,
+                                      max_hop_num=6, max_distance_count=50, wo_peripheral_edge=False,
+                                      wo_peripheral_configuration=False, drop_prob=0.0)
+            model = dropin.GraphRegression.GraphRegression(embedding_model=gnn, pooling_method="sum").to(device).train()
+            ms = time_model(model, b8)
+            res["reference_GNNPlus_unmodified_over_dropin_layers_batch128"] = {
+                "ms_per_step_eager": round(ms, 3), "graphs_per_s": round(GRAPHS_PER_GPU / (ms * 1e-3), 1),
+                "note": "the reference's own models/GNNs.py + GraphRegression.py (staged copy), layer by layer, no CUDA "
+                        "graph, no stack node: what a reference user gets from install_dropin() alone"}
+    except Exception as e:      # diagnostics must never take the bench line down
+        res["reference_GNNPlus_unmodified_over_dropin_layers_batch128"] = {"error": repr(e)[:200]}
+    return res
+
+
 def oracle_batch(num_graphs, seed):
     """The same synthetic batch as host_batch(), built WITHOUT the product: oracle extraction (numpy restatement of
     data_utils.py:20-241) per graph, then PyG Batch.from_data_list collation.  Untimed setup of the reference arm."""
@@ -524,6 +697,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-workloads", action="store_true",
+                    help="skip the secondary workloads (configs[4] regular graphs, extraction metrics, other models)")
     ap.add_argument("--blas", default="default", choices=["default", "cublas", "cublaslt"])
     ap.add_argument("--eager", action="store_true",
                     help="profiling helper: no CUDA graph (ncu cannot re-launch graph kernel nodes that opted "
@@ -595,6 +770,43 @@ def main():
     ms_e2e = reduce_max(statistics.mean(t_e2e))
     total_graphs = GRAPHS_PER_GPU * world
 
+    # ---- configs[4]: regular n = 1280 graphs, extraction + KGIN forward, 64 graphs per GPU, at every N
+    workloads = {}
+    if not args.no_workloads:
+        log("[rank %d] regular-graph workload" % rank)
+        wl = RegularWorkload(device, rank)
+        for _ in range(2):
+            wl.step()
+        t_reg = timed_steps(wl.step, max(3, min(args.steps, 10)), device, flush, dist_on)
+        t_reg_e2e = timed_steps(wl.step_e2e, max(3, min(args.steps, 10)), device, flush, dist_on)
+        ms_reg, ms_reg_e2e = reduce_max(statistics.mean(t_reg)), reduce_max(statistics.mean(t_reg_e2e))
+        if rank == 0:
+            nbytes_in = sum(int(np.asarray(wl.csr[k]).nbytes) for k in ("gptr", "node_graph", "pair_off", "erow", "ecol",
+                                                                        "emult", "etype"))
+            workloads["regular1280"] = {
+                "workload": "configs[4]: 3-regular graphs n=1280, K=6 spd extraction + plan + KGINConv(16) forward, "
+                            "%d graphs per GPU (run_simulation.py:96-116)" % REG_GRAPHS,
+                "value": round(REG_GRAPHS * world / (ms_reg * 1e-3), 1), "unit": "graphs/s", "n_gpus": world,
+                "ms_per_step": round(ms_reg, 3), "scaling": "weak",
+                "e2e": {"value": round(REG_GRAPHS * world / (ms_reg_e2e * 1e-3), 1), "unit": "graphs/s",
+                        "h2d_bytes_per_step": nbytes_in, "d2h_bytes_per_step": int(wl.host_out.numel() * 4),
+                        "ms_per_step": round(ms_reg_e2e, 3)}}
+            if world == 1 and not args.no_roofline:
+                workloads["regular1280"]["roofline"] = regular_roofline(device, peak, wl)
+        del wl
+        torch.cuda.empty_cache()
+    if rank == 0 and world == 1 and not args.no_workloads:
+        from kpgnn_b200 import synth
+        log("[rank 0] extraction metrics / other model steps")
+        zg = synth.zinc_like_graphs(GRAPHS_PER_GPU, seed=0)
+        workloads["extract"] = [
+            extraction_metrics(device, peak, "configs[1] zinc128 K=8 spd", zg, EXTRACT_ARGS),
+            extraction_metrics(device, peak, "configs[2] zinc128 K=16 spd", zg, (16, 50, 6, 3, 50, 50, "spd")),
+            extraction_metrics(device, peak, "configs[4] regular1280 x16 K=6 spd",
+                               [synth.regular_graph(REG_N, 3, s) for s in range(16)], REG_EXTRACT, reps=3)]
+        workloads["model_steps"] = other_model_steps(device)
+        torch.cuda.empty_cache()
+
     roof = roof_small = None
     cpu = None
     if rank == 0 and world == 1 and not args.no_roofline:
@@ -623,7 +835,7 @@ def main():
             "gpu_launches": int((tr.launches_per_step + plan_launches) * args.steps),
             "gpu_launches_per_step": {"ours_in_cuda_graph_incl_plan_rebuild": int(tr.launches_per_step)},
             "clocks": clocks, "roofline": roof, "roofline_batch128": roof_small, "cpu_baseline": cpu,
-            "loss": float(tr.loss.item()),
+            "workloads": workloads or None, "loss": float(tr.loss.item()),
         }
         print(json.dumps(line), flush=True)
     if dist_on:

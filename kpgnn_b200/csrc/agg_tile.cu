@@ -24,6 +24,7 @@ struct TileArgs {
   const int32_t* block_ptr;
   const int32_t* block_stats;  // device [0] = number of blocks (NULL: num_blocks is exact)
   int num_blocks, dpad, stage_floats;
+  int chunks;                  // row chunks per (block, hop): a unit is (chunk, block, hop)
   const float* self_src;       // B2 mode: dOut [N,k,d] for the (1+eps) self term; forward mode: unused
 };
 
@@ -49,12 +50,20 @@ agg_tile_kernel(const FastArgs fa, const TileArgs ta, float* __restrict__ out) {
   float self_c = 0.f;
   if (EXTRA && a.eps) self_c = 1.f + __ldg(a.eps);
   const int nblocks = ta.block_stats ? __ldg(ta.block_stats) : ta.num_blocks;
-  const int units = nblocks * k;
+  const int per_hop = nblocks * ta.chunks;
+  const int units = per_hop * k;
   for (int u = blockIdx.x; u < units; u += gridDim.x) {
-    const int h = k - 1 - u / nblocks;                   // far hops (the long rows of an spd plan) are dealt first
-    const int b = u - (u / nblocks) * nblocks;
+    // far hops (the long rows of an spd plan: 96 of a node's 177 entries sit in hop 6 of a 3-regular graph) are dealt
+    // first, and every (block, hop) is cut into row chunks: without the cut the 64 hop-6 units of a 64-graph batch
+    // carried 54 % of the work on 64 CTAs and set the kernel time
+    const int hq = u / per_hop, rem = u - hq * per_hop;
+    const int h = k - 1 - hq;
+    const int b = rem / ta.chunks, ch = rem - b * ta.chunks;
     const int v0 = __ldg(ta.block_ptr + b), v1 = __ldg(ta.block_ptr + b + 1);
     const int nb = v1 - v0;
+    const int per = (nb + ta.chunks - 1) / ta.chunks;
+    const int r0 = min(nb, ch * per), r1 = min(nb, r0 + per);
+    if (r0 >= r1) continue;                               // (block-uniform: no barrier is skipped by part of a CTA)
     __syncthreads();                                      // everyone is done with the previous unit's slice
     {
       const float* src = a.X + (size_t)v0 * fa.xs + (size_t)h * fa.xh;
@@ -67,17 +76,19 @@ agg_tile_kernel(const FastArgs fa, const TileArgs ta, float* __restrict__ out) {
       cp_async_wait<0>();
     }
     __syncthreads();
-    for (int vl = gib; vl < nb; vl += gpb) {
+    for (int vl = r0 + gib; vl < r1; vl += gpb) {
       const int v = v0 + vl;
       const int r = v * Kp + h;
       const int rb = __ldg(ta.rowptr + r), re = __ldg(ta.rowptr + r + 1);
       P4 acc = p4zero();
+      int ncol = (rb + lane < re) ? __ldg(ta.col + rb + lane) : v0;      // entry indices run one window ahead
       for (int j0 = rb; j0 < re; j0 += G) {
         const int cnt = min(G, re - j0);
         unsigned my_off = 0, my_tab = 0;
         float my_w = 0.f;
+        const int cj = ncol;
+        if (j0 + G + lane < re) ncol = __ldg(ta.col + j0 + G + lane);
         if (lane < cnt) {
-          const int cj = __ldg(ta.col + j0 + lane);
           my_off = (unsigned)(cj - v0) * dpad4;
           if (TAB != TAB_NONE) my_tab = (unsigned)__ldg(ta.attr16 + j0 + lane) * (unsigned)d * 4u;
           if (EXTRA && !B2 && a.dinv) my_w = __ldg(a.dinv + (size_t)cj * Kp + h);
@@ -145,6 +156,13 @@ agg_tile_kernel(const FastArgs fa, const TileArgs ta, float* __restrict__ out) {
 static int g_tile_mode = 1;     // 0 = never, 1 = when the caller supplies blocks (default), 2 = also for short rows (tests)
 void tile_set_mode(int mode) { g_tile_mode = mode; }
 
+// row chunks per (block, hop): about two passes of the CTA's lane groups per unit
+static int tile_chunks(const kp_agg_desc& a, int G) {
+  const int gpb = TILE_THREADS / G;
+  int c = a.max_block_nodes / (2 * gpb);
+  return c < 1 ? 1 : (c > 64 ? 64 : c);
+}
+
 static size_t tile_smem(const kp_agg_desc& a, int tab, int* dpad, int* stage_floats) {
   *dpad = a.d + 4;
   *stage_floats = tab == TAB_SMEM ? (a.rows0 + a.rowsk) * a.d : 0;
@@ -165,7 +183,7 @@ static int tile_launch(const FastArgs& fa, const TileArgs& ta, size_t smem, floa
                                  (int)smem));
   int per_sm = (int)((220 * 1024) / (smem + 1024));
   per_sm = per_sm < 1 ? 1 : (per_sm > 3 ? 3 : per_sm);
-  const long long units = (long long)ta.num_blocks * fa.d.k;
+  const long long units = (long long)ta.num_blocks * ta.chunks * fa.d.k;
   const int grid = geom_cap(units < (long long)kNumSMs * per_sm ? units : (long long)kNumSMs * per_sm);
   KP_LAUNCH((agg_tile_kernel<G, ACT, TAB, EXTRA, B2>), grid, TILE_THREADS, smem, st, fa, ta, out);
   return 0;
@@ -186,6 +204,7 @@ int tile_fwd(const FastArgs& fa, int G, int act, int tab, bool extra, float* out
   ta.rowptr = a.rowptr; ta.col = a.col; ta.attr16 = a.attr16; ta.block_ptr = a.block_ptr;
   ta.block_stats = a.block_stats;
   ta.num_blocks = a.num_blocks; ta.self_src = nullptr;
+  ta.chunks = tile_chunks(a, G);
   const size_t smem = tile_smem(a, tab, &ta.dpad, &ta.stage_floats);
   switch (G) {
     case 32: return KP_TILE_ACT(32, act, extra, tab, fa, ta, smem, out, st);
@@ -210,6 +229,7 @@ int tile_b2(const FastArgs& fa, int G, bool extra, const float* Gs, const float*
   ta.rowptr = a.rowptrT; ta.col = a.colT; ta.attr16 = nullptr; ta.block_ptr = a.block_ptr;
   ta.block_stats = a.block_stats;
   ta.num_blocks = a.num_blocks; ta.self_src = dOut;
+  ta.chunks = tile_chunks(a, G);
   const size_t smem = tile_smem(t.d, TAB_NONE, &ta.dpad, &ta.stage_floats);
 #define KP_TILE_B2(GG) \
   (extra ? tile_launch<GG, KP_ACT_NONE, TAB_NONE, true, true>(t, ta, smem, dX, st) \

@@ -107,65 +107,103 @@ __device__ __forceinline__ void insertion_sort(int* a, int n) {
   }
 }
 
-// Edge ids of one row in ascending order.  Rows of up to KP_EMIT_LOCAL entries are sorted in a thread-local buffer
-// (all loads issued up front, the data-dependent insertion steps hit L1): sorting in place in global memory made
-// every compare a dependent L2 round trip, and the row with the most entries set the kernel time (20 us at the bench
-// batch).  Longer rows are sorted in place.
 #define KP_EMIT_LOCAL 32
-__device__ __forceinline__ const int* sorted_row_ids(int* g, int n, int* buf) {
-  if (n > KP_EMIT_LOCAL) {
-    insertion_sort(g, n);
-    return g;
+// Long rows (more than KP_EMIT_LOCAL entries: every row of the far hops of an n = 1 280 regular graph) are ordered by the
+// whole warp: ids staged in shared memory, every lane ranks its entries by counting the smaller ids (edge ids are
+// distinct, so the ranks are a permutation) and emits straight to the rank's slot.  One thread insertion-sorting a
+// 96-entry row in global memory cost 0.72 ms per 16 such graphs (profiles/r2_extract_kineto.txt).
+#define KP_EMIT_WARP_CAP 1024
+__device__ __forceinline__ void emit_long_row(const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
+                                              const int64_t* __restrict__ attr, int64_t attr_stride, int h,
+                                              bool transposed, int* __restrict__ ids_g, int b, int n,
+                                              int* __restrict__ col, uint16_t* __restrict__ attr16,
+                                              int* __restrict__ colT, int* __restrict__ buf, int lane) {
+  const bool staged = n <= KP_EMIT_WARP_CAP;
+  const int* ids = ids_g;
+  if (staged) {
+    for (int i = lane; i < n; i += 32) buf[i] = ids_g[i];
+    ids = buf;
   }
-#pragma unroll 4
-  for (int i = 0; i < n; ++i) buf[i] = g[i];
-  insertion_sort(buf, n);
-  return buf;
+  __syncwarp();
+  for (int i = lane; i < n; i += 32) {
+    const int my = ids[i];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) rank += ids[j] < my;
+    if (!transposed) {
+      col[b + rank] = (int)src[my];
+      attr16[b + rank] = (uint16_t)attr[(long long)my * attr_stride + h];
+    } else {
+      colT[b + rank] = (int)dst[my];
+    }
+  }
+  __syncwarp();
 }
 
 // two threads per row (even: the (dst,hop) row, odd: the (src,hop) row of the transpose): restore ascending edge id
 // inside the row, then emit the compact arrays
-__global__ void plan_emit_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
+__global__ void __launch_bounds__(128)
+plan_emit_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
                                  const int64_t* __restrict__ attr, int64_t attr_stride, int N, int K,
                                  int self_loops, const int* __restrict__ rowptr, const int* __restrict__ rowptrT,
                                  int* __restrict__ eid, int* __restrict__ eidT, int* __restrict__ col,
                                  uint16_t* __restrict__ attr16, int* __restrict__ colT,
                                  float* __restrict__ dinv, int cap) {
+  __shared__ int s_buf[4][KP_EMIT_WARP_CAP];
   const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
   const int r = (int)(t >> 1);
   const bool transposed = t & 1u;
-  if (r >= N * K) return;
-  int v = r / K, h = r - v * K;
-  if (dinv && !transposed) dinv[r] = 1.0f / sqrtf((float)(rowptr[r + 1] - rowptr[r]));
-  // Overflow (in-place refresh of a plan whose capacity the new batch exceeds; reported through stats[0] > capacity):
-  // rows are cut at the capacity, so that after kp_plan_clamp every index a consumer can reach was written from THIS
-  // batch (wrong results, raised by the caller at its next sync point, but never an out-of-range gather).
-  int buf[KP_EMIT_LOCAL];
-  if (!transposed) {
-    int b = rowptr[r], e = rowptr[r + 1];
-    const bool cut = e > cap;
-    if (b >= cap) return;
-    int n = (cut ? cap : e) - b - ((self_loops && !cut) ? 1 : 0);
-    const int* ids = sorted_row_ids(eid + b, n, buf);
+  const bool valid = r < N * K;
+  int v = 0, h = 0, b = 0, e = 0, n = 0;
+  bool cut = false;
+  if (valid) {
+    v = r / K;
+    h = r - v * K;
+    if (dinv && !transposed) dinv[r] = 1.0f / sqrtf((float)(rowptr[r + 1] - rowptr[r]));
+    // Overflow (in-place refresh of a plan whose capacity the new batch exceeds; reported through stats[0] > capacity):
+    // rows are cut at the capacity, so that after kp_plan_clamp every index a consumer can reach was written from THIS
+    // batch (wrong results, raised by the caller at its next sync point, but never an out-of-range gather).
+    b = transposed ? rowptrT[r] : rowptr[r];
+    e = transposed ? rowptrT[r + 1] : rowptr[r + 1];
+    cut = e > cap;
+    n = b >= cap ? 0 : (cut ? cap : e) - b - ((self_loops && !cut) ? 1 : 0);
+  }
+  int* ids_g = (transposed ? eidT : eid) + b;
+  if (valid && n > 0 && n <= KP_EMIT_LOCAL) {
+    int buf[KP_EMIT_LOCAL];
 #pragma unroll 4
-    for (int i = 0; i < n; ++i) {
-      int id = ids[i];
-      col[b + i] = (int)src[id];
-      attr16[b + i] = (uint16_t)attr[(long long)id * attr_stride + h];
+    for (int i = 0; i < n; ++i) buf[i] = ids_g[i];
+    insertion_sort(buf, n);
+    if (!transposed) {
+#pragma unroll 4
+      for (int i = 0; i < n; ++i) {
+        const int id = buf[i];
+        col[b + i] = (int)src[id];
+        attr16[b + i] = (uint16_t)attr[(long long)id * attr_stride + h];
+      }
+    } else {
+#pragma unroll 4
+      for (int i = 0; i < n; ++i) colT[b + i] = (int)dst[buf[i]];
     }
-    if (self_loops && !cut) {
+  }
+  if (valid && self_loops && !cut && b < cap) {
+    if (!transposed) {
       col[e - 1] = v;
       attr16[e - 1] = 1;
+    } else {
+      colT[e - 1] = v;
     }
-  } else {
-    int b = rowptrT[r], e = rowptrT[r + 1];
-    const bool cut = e > cap;
-    if (b >= cap) return;
-    int n = (cut ? cap : e) - b - ((self_loops && !cut) ? 1 : 0);
-    const int* ids = sorted_row_ids(eidT + b, n, buf);
-#pragma unroll 4
-    for (int i = 0; i < n; ++i) colT[b + i] = (int)dst[ids[i]];
-    if (self_loops && !cut) colT[e - 1] = v;
+  }
+  // long rows of this warp's 32 tasks, one after the other, by the whole warp
+  unsigned longmask = __ballot_sync(0xffffffffu, valid && n > KP_EMIT_LOCAL);
+  while (longmask) {
+    const int l = __ffs(longmask) - 1;
+    longmask &= longmask - 1;
+    const int lb = __shfl_sync(0xffffffffu, b, l), ln = __shfl_sync(0xffffffffu, n, l);
+    const int lh = __shfl_sync(0xffffffffu, h, l);
+    const bool lt = __shfl_sync(0xffffffffu, (int)transposed, l) != 0;
+    emit_long_row(src, dst, attr, attr_stride, lh, lt, (lt ? eidT : eid) + lb, lb, ln, col, attr16, colT,
+                  s_buf[threadIdx.x >> 5], lane);
   }
 }
 

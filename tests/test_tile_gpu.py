@@ -81,8 +81,11 @@ def _pair(b, K, d, act_name, tables, use_P, eps_on, dinv_on=False, seed=0):
                    ([eps.grad] if eps_on else []))
     for a, c in zip(res[1], res[0]):
         assert rel_err(a, c) < RTOL, rel_err(a, c)
-    # the block-resident and the row-streaming kernels add a row's entries in the same order: identical bits forward
-    assert torch.equal(res[1][0], res[2][0])
+    if not tables:
+        # without tables both kernel families add a row's entries in the same order: identical bits forward
+        assert torch.equal(res[1][0], res[2][0])
+    else:
+        assert rel_err(res[1][0], res[2][0]) < 1e-6
 
 
 @pytest.mark.parametrize("d", [16, 64, 104])

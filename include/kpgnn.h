@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define KPGNN_ABI_VERSION 9
+#define KPGNN_ABI_VERSION 10
 
 const char* kp_last_error(void);
 int kp_abi_version(void);
@@ -237,6 +237,12 @@ typedef struct {
   /* Backward only, optional: stream for the final weight-gradient reduction (dW1, db1, dW2, db2), same contract as
    * kp_agg_desc.leaf_stream.  dX and the BatchNorm affine gradients are always produced on `stream`. */
   void* leaf_stream;
+  /* Optional: the batch's row count in DEVICE memory.  N above is then the CAPACITY of every [N,*] buffer (it sizes the
+   * grid and the workspace) and *n_dev <= N the number of rows that exist: rows in [*n_dev, N) are padding -- excluded
+   * from the batch statistics, the running statistics and every gradient sum; `out` and dX are written as zeros there.
+   * One captured launch (CUDA graph) then serves batches of different sizes (train_ZINC.py:29-47: a new batch, with a
+   * new node count, every step).  NULL: N rows exist. */
+  const int32_t* n_dev;
 } kp_dense_desc;
 
 int kp_dense_block_max_rows(int32_t Cin, int32_t Cout);
@@ -302,6 +308,31 @@ int kp_attn_combine_backward_workspace_bytes(const kp_attn_desc* desc, size_t* b
 int kp_attn_combine_backward(const kp_attn_desc* desc, const float* dOut, float* dX, float* dw_ih_f, float* dw_ih_r,
                              float* dw_hh_f, float* dw_hh_r, float* db_f, float* db_r, void* workspace,
                              size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Compact batch wire format -> the reference's int64 wire tensors at a fixed capacity (csrc/wire.cu).  Replaces the
+ * host-side collation + int64 upload of the reference's loader (train_ZINC.py:29-47, PyG Batch.from_data_list + `.to`):
+ * int32 node ids, 1/2-byte attributes and per-graph node offsets cross PCIe; one kernel widens them into the static
+ * tensors the layers read and pads the tail (nodes >= N: x = 0, peripheral attrs = 0, batch = g; edges >= E: src = dst
+ * = 0 and every hop attr = 0, i.e. masked in every hop), so that the whole training step can be captured once and
+ * replayed for batches of different sizes.  hdr (device) = {N, E}; the node count is also written to *o_n.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t n_cap, e_cap, g, K, met, hp1;      /* capacities; graphs per batch; hops; max_edge_type; max_hop_num + 1 */
+  int32_t x_bytes, attr_bytes, p_bytes, pad; /* element widths of x (1|2|4), edge attrs (1|2), peripheral attrs (1|2) */
+  const int32_t* hdr;                        /* device [2]: N, E of this batch */
+  const int32_t* gptr;                       /* [g+1] node offsets of the graphs */
+  const void* x;                             /* [N] node types, or NULL */
+  const int32_t* src; const int32_t* dst;    /* [E] K-hop edge list (global node ids) */
+  const void* attr;                          /* [E,K] hop attributes */
+  const void* pea; const void* pca;          /* [N,K,met,2], [N,K,hp1] or NULL */
+  int64_t* o_x; int64_t* o_batch;            /* [n_cap] or NULL */
+  int64_t* o_ei;                             /* [2,e_cap] */
+  int64_t* o_ea;                             /* [e_cap,K] */
+  int64_t* o_pea; int64_t* o_pca;            /* [n_cap,K,met,2], [n_cap,K,hp1] or NULL */
+  int32_t* o_n;                              /* device scalar or NULL */
+} kp_wire_desc;
+int kp_wire_unpack(const kp_wire_desc* desc, void* stream);
 
 /* Graph readout over a sorted segment vector: PyG global_add_pool / global_mean_pool on `data.batch`
  * (models/GraphRegression.py:26, models/GraphClassification.py:30).  out[g,:] = sum (mean != 0: mean) of the rows i of

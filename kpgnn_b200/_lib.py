@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # KPGNN_B200_LIB points at an alternative build of the same library (kernel tuning experiments)
 LIB_PATH = os.environ.get("KPGNN_B200_LIB") or os.path.join(_HERE, "libkpgnn_b200.so")
 
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 
 class KpError(RuntimeError):
@@ -67,13 +67,22 @@ class DenseDesc(C.Structure):
                 ("Y1", C.c_void_p), ("Y2", C.c_void_p), ("Z2", C.c_void_p), ("stats", C.c_void_p),
                 ("out_stride", C.c_int64), ("r_stride", C.c_int64), ("dout_stride", C.c_int64),
                 ("dr_stride", C.c_int64), ("dR", C.c_void_p), ("barrier", C.c_void_p),
-                ("leaf_stream", C.c_void_p)]
+                ("leaf_stream", C.c_void_p), ("n_dev", C.c_void_p)]
 
 
 class AttnDesc(C.Structure):
     _fields_ = [("N", C.c_int32), ("K", C.c_int32), ("d", C.c_int32), ("pad", C.c_int32),
                 ("x", C.c_void_p), ("x_node_stride", C.c_int64), ("x_hop_stride", C.c_int64),
                 ("w_ih", C.c_void_p * 2), ("w_hh", C.c_void_p * 2), ("b_ih", C.c_void_p * 2), ("b_hh", C.c_void_p * 2)]
+
+
+class WireDesc(C.Structure):
+    _fields_ = [("n_cap", C.c_int32), ("e_cap", C.c_int32), ("g", C.c_int32), ("K", C.c_int32), ("met", C.c_int32),
+                ("hp1", C.c_int32), ("x_bytes", C.c_int32), ("attr_bytes", C.c_int32), ("p_bytes", C.c_int32),
+                ("pad", C.c_int32), ("hdr", C.c_void_p), ("gptr", C.c_void_p), ("x", C.c_void_p), ("src", C.c_void_p),
+                ("dst", C.c_void_p), ("attr", C.c_void_p), ("pea", C.c_void_p), ("pca", C.c_void_p),
+                ("o_x", C.c_void_p), ("o_batch", C.c_void_p), ("o_ei", C.c_void_p), ("o_ea", C.c_void_p),
+                ("o_pea", C.c_void_p), ("o_pca", C.c_void_p), ("o_n", C.c_void_p)]
 
 
 class ThetaBatch(C.Structure):
@@ -133,6 +142,7 @@ _SIGNATURES = {
     "kp_attn_combine_backward": (C.c_int, [C.POINTER(AttnDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                            C.c_void_p]),
+    "kp_wire_unpack": (C.c_int, [C.POINTER(WireDesc), C.c_void_p]),
     "kp_segment_sum": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                 C.c_void_p, C.c_void_p]),
     "kp_peripheral_grad": (C.c_int, [C.POINTER(PgradDesc), C.c_void_p, C.c_void_p]),

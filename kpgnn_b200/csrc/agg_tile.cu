@@ -164,7 +164,7 @@ static int tile_chunks(const kp_agg_desc& a, int G) {
 }
 
 static size_t tile_smem(const kp_agg_desc& a, int tab, int* dpad, int* stage_floats) {
-  *dpad = a.d + 4;
+  *dpad = a.d <= 16 ? 16 : a.d + 4;   // 4-lane groups (d <= 16): a 64-byte row stride halves the bank conflicts of two rows per quarter-warp
   *stage_floats = tab == TAB_SMEM ? (a.rows0 + a.rowsk) * a.d : 0;
   return sizeof(float) * ((size_t)*stage_floats + (size_t)a.max_block_nodes * *dpad);
 }

@@ -325,16 +325,18 @@ __device__ __forceinline__ void db_merge_stats(const float* __restrict__ part, i
       pm[i] = __ldcg(reinterpret_cast<const float4*>(part + (size_t)b * 2 * C + C + c));
     }
   }
-  const float fn_full = (float)min(Rc, N), inv_full = 1.f / fn_full;    // every slab is full except the last
-  const float fn_last = (float)(N - (grid - 1) * Rc), inv_last = 1.f / fn_last;
-  const float inv0 = grid == 1 ? inv_last : inv_full;
+  // rows of slab b: Rc for the full ones, fewer for the one that holds row N-1, none behind it (the grid is sized for
+  // the row CAPACITY when the row count comes from device memory, kp_dense_desc.n_dev)
+  const float fn0 = (float)min(Rc, N);
+  const float inv0 = 1.f / fn0;
   const float4 K = make_float4(p0.x * inv0, p0.y * inv0, p0.z * inv0, p0.w * inv0);
   float4 sa = make_float4(0.f, 0.f, 0.f, 0.f), sb = sa, sm = sa;
 #pragma unroll
   for (int i = 0; i < DB_MAXI; ++i) {
     const int b = warp + i * DB_WARPS;
-    if (b < grid) {
-      const float fn = b == grid - 1 ? fn_last : fn_full, inv = b == grid - 1 ? inv_last : inv_full;
+    const int nb = min(Rc, N - b * Rc);
+    if (b < grid && nb > 0) {
+      const float fn = (float)nb, inv = 1.f / fn;
       const float dx = fmaf(ps[i].x, inv, -K.x), dy = fmaf(ps[i].y, inv, -K.y), dz = fmaf(ps[i].z, inv, -K.z),
                   dw = fmaf(ps[i].w, inv, -K.w);
       sa.x = fmaf(fn, dx, sa.x); sa.y = fmaf(fn, dy, sa.y); sa.z = fmaf(fn, dz, sa.z); sa.w = fmaf(fn, dw, sa.w);
@@ -412,10 +414,15 @@ dense_block_fwd_kernel(const kp_dense_desc m, float* __restrict__ out, float* __
   extern __shared__ __align__(16) float smem[];
   DB_T_DECL
   DB_T(0);
-  const int Ci = m.Cin, Co = m.Cout, N = m.N;
+  const int Ci = m.Cin, Co = m.Cout;
+  // rows: m.N is the CAPACITY of the row buffers (and sizes the grid); the batch's row count may come from device
+  // memory (m.n_dev), so that one captured launch serves batches of different sizes.  Rows in [N, m.N) are padding:
+  // excluded from every statistic, written as zeros.
+  const int N = m.n_dev ? min(__ldg(m.n_dev), m.N) : m.N;
   const int grid = gridDim.x;
   const int r0 = blockIdx.x * Rc;
   const int nr = max(0, min(Rc, N - r0));
+  const int nr_cap = max(0, min(Rc, m.N - r0));
   const int Rp = (Rc + 3) & ~3;
   float* W1s = smem;                         // [Co][wstride(Ci)] swizzled
   float* W2s = W1s + Co * db_wstride(Ci);    // [Co][wstride(Co)] swizzled
@@ -496,6 +503,9 @@ dense_block_fwd_kernel(const kp_dense_desc m, float* __restrict__ out, float* __
         }
         *reinterpret_cast<float4*>(out + (size_t)(r0 + r) * so + c) = v;
       }
+    if (c < Co)
+      for (int r = nr + warp; r < nr_cap; r += DB_WARPS)       // padding rows of the capacity: zeros
+        *reinterpret_cast<float4*>(out + (size_t)(r0 + r) * so + c) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   DB_T(16);
   DB_T_PRINT(17, "fwd load gemm1 stats1 bar1 merge1 apply1 gemm2 stats2 bar2 merge2 apply2 stats3 bar3 merge3 apply3 out");
@@ -642,10 +652,12 @@ dense_block_bwd_kernel(const kp_dense_desc m, const float* __restrict__ dOut, fl
   extern __shared__ __align__(16) float smem[];
   DB_T_DECL
   DB_T(0);
-  const int Ci = m.Cin, Co = m.Cout, N = m.N;
+  const int Ci = m.Cin, Co = m.Cout;
+  const int N = m.n_dev ? min(__ldg(m.n_dev), m.N) : m.N;      // see dense_block_fwd_kernel
   const int grid = gridDim.x;
   const int r0 = blockIdx.x * Rc;
   const int nr = max(0, min(Rc, N - r0));
+  const int nr_cap = max(0, min(Rc, m.N - r0));
   const int Rp = (Rc + 3) & ~3;
   float* W1 = smem;                   // [Co][Ci] row-major (dX = dy1 W1)
   float* W2 = W1 + Co * Ci;           // [Co][Co] row-major (dz1 = dy2 W2)
@@ -793,7 +805,7 @@ dense_block_bwd_kernel(const kp_dense_desc m, const float* __restrict__ dOut, fl
   db_slab_colsum(E, Co, nr, red, pb1 + (size_t)blockIdx.x * Co);
   __syncthreads();
   DB_T(12);
-  db_store_slab(D, r0, nr, Ci, dX);
+  db_store_slab(D, r0, nr_cap, Ci, dX);      // rows [nr, nr_cap) are padding: their dy1 rows are zero, so is dX
   DB_T(13);
   if (threadIdx.x == 0 && atomicAdd(bar + 1, 1u) == gridDim.x - 1) {
     bar[0] = 0u;

@@ -19,7 +19,7 @@ from .. import _lib
 
 class _DenseBlock(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, W1, b1, g1, be1, W2, b2, g2, be2, g3, be3, res, bns):
+    def forward(ctx, x, W1, b1, g1, be1, W2, b2, g2, be2, g3, be3, res, bns, n_dev=None):
         lib = _lib.lib()
         bn1, bn2, bn3 = bns
         x = x.contiguous()
@@ -49,6 +49,8 @@ class _DenseBlock(torch.autograd.Function):
         d.stats = stats.data_ptr()
         out = torch.empty((N, Cout), dtype=torch.float32, device=dev)
         d.barrier = _lib.barrier_state(dev).data_ptr()
+        if n_dev is not None:
+            d.n_dev = n_dev.data_ptr()
         fb, bb = C.c_size_t(0), C.c_size_t(0)
         _lib.check(lib.kp_dense_block_workspace_bytes(C.byref(d), C.byref(fb), C.byref(bb)), "kp_dense_block ws")
         ws = torch.empty(fb.value, dtype=torch.uint8, device=dev)
@@ -56,7 +58,7 @@ class _DenseBlock(torch.autograd.Function):
         _lib.check(lib.kp_dense_block_forward(C.byref(d), out.data_ptr(), ws.data_ptr(), ws.numel(), st),
                    "kp_dense_block_forward")
         ctx.desc, ctx.bwd_bytes, ctx.has_bn3, ctx.has_res = d, bb.value, g3 is not None, res is not None
-        ctx.keep = (x, W1c, W2c, b1, g1, be1, b2, g2, be2, g3, be3, saved, stats)     # owners of the desc's pointers
+        ctx.keep = (x, W1c, W2c, b1, g1, be1, b2, g2, be2, g3, be3, saved, stats, n_dev)   # owners of the desc's pointers
         return out
 
     @staticmethod
@@ -81,7 +83,7 @@ class _DenseBlock(torch.autograd.Function):
         g3g = dvec[6] if ctx.has_bn3 else None
         be3g = dvec[7] if ctx.has_bn3 else None
         return (dX, dW1, dvec[0], dvec[2], dvec[3], dW2, dvec[1], dvec[4], dvec[5], g3g, be3g,
-                dout if ctx.has_res else None, None)
+                dout if ctx.has_res else None, None, None)
 
 
 def _bn_ok(bn):
@@ -89,8 +91,10 @@ def _bn_ok(bn):
             and bn.momentum is not None and bn.weight is not None and bn.weight.dtype == torch.float32)
 
 
-def fused_dense_block(x, lin1, bn1, lin2, bn2, bn3=None, residual=None):
-    """Linear-BN-ReLU-Linear-BN-ReLU (+ BatchNorm + residual) in one kernel, or None if not applicable."""
+def fused_dense_block(x, lin1, bn1, lin2, bn2, bn3=None, residual=None, n_dev=None):
+    """Linear-BN-ReLU-Linear-BN-ReLU (+ BatchNorm + residual) in one kernel, or None if not applicable.
+    n_dev: optional device int32 scalar -- the number of rows that exist when x.size(0) is a padded capacity
+    (kp_dense_desc.n_dev): padding rows are excluded from every statistic and come back as zeros."""
     if not (torch.is_tensor(x) and x.is_cuda and x.dim() == 2 and x.dtype == torch.float32):
         return None
     if not (isinstance(lin1, nn.Linear) and isinstance(lin2, nn.Linear) and lin1.bias is not None
@@ -109,4 +113,4 @@ def fused_dense_block(x, lin1, bn1, lin2, bn2, bn3=None, residual=None):
         return None
     return _DenseBlock.apply(x, lin1.weight, lin1.bias, bn1.weight, bn1.bias, lin2.weight, lin2.bias, bn2.weight,
                              bn2.bias, bn3.weight if bn3 is not None else None,
-                             bn3.bias if bn3 is not None else None, residual, (bn1, bn2, bn3))
+                             bn3.bias if bn3 is not None else None, residual, (bn1, bn2, bn3), n_dev)

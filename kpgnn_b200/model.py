@@ -27,6 +27,7 @@ class Batch(object):
     def __init__(self, **kw):
         self.num_graphs = kw.pop("num_graphs")
         self.num_nodes = kw.pop("num_nodes", None)
+        self.n_dev = kw.pop("n_dev", None)     # padded-capacity batches: device int32 scalar with the true node count
         for f in self.FIELDS:
             setattr(self, f, kw.get(f))
 
@@ -92,6 +93,8 @@ class _SegmentSum(torch.autograd.Function):
         if ctx.mean:
             cnt = torch.bincount(ctx.batch, minlength=ctx.num_graphs).clamp_(min=1).to(dout.dtype)
             dout = dout / cnt.unsqueeze(1)
+        # rows of a padded capacity carry graph id == num_graphs (kpgnn_b200/wire.py): they read a zero row
+        dout = torch.cat([dout, dout.new_zeros(1, dout.size(1))], 0)
         return dout.index_select(0, ctx.batch), None, None, None
 
 
@@ -227,7 +230,10 @@ class KPGNNPlusBackbone(nn.Module):
         if data.edge_attr.dim() != 2 or data.edge_attr.size(1) != self.K:
             return None
         plan, _ = get_plan(data.edge_index, data.edge_attr, x.size(0))
+        plan.n_dev = getattr(data, "n_dev", None)
         if not stack_applicable(self.gnns, norms, x, P, plan, pe_zero, self.dropout.p):
+            if plan.n_dev is not None:
+                raise RuntimeError("padded-capacity batches (Batch.n_dev) need the fused layer stack")
             return None
         Hn = kpginplus_stack(self.gnns, norms, x, P, plan, self.residual)      # [N, L+1, H], slot L-j = h_j
         lin = self.output_proj[0]

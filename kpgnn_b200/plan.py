@@ -31,7 +31,7 @@ class GraphPlan(object):
     __slots__ = ("N", "E", "K", "nnz", "capacity", "self_loops", "rowptr", "col", "attr16", "rowptrT", "colT", "dinv",
                  "indeg", "max_attr0", "max_attrk", "device", "stats", "stats_host", "ws", "pending", "src", "dst",
                  "ready", "block_ptr", "block_stats", "block_ws", "num_blocks", "max_block_nodes", "max_block_nnz",
-                 "block_stats_host")
+                 "block_stats_host", "n_dev")
 
     def blocks(self):
         """Closed node blocks (kp_plan_blocks: the graphs of the batch, found from the plan itself).  Computed on first
@@ -116,6 +116,16 @@ def _plan_input(p, edge_index, edge_attr_base, attr_stride):
                           1 if p.self_loops else 0)
 
 
+_CAPACITY_HINT = 0
+
+
+def reserve_capacity(nnz):
+    """Entries to allocate for plans built from now on when the first batch has fewer (static-buffer loops over
+    batches of different sizes: the plan is refreshed in place and must hold the largest batch).  0 = exact fit."""
+    global _CAPACITY_HINT
+    _CAPACITY_HINT = int(nnz)
+
+
 def build_plan(edge_index, edge_attr_base, attr_stride, K, num_nodes, self_loops=False):
     """edge_index [2,E] int64 cuda; edge_attr_base: int64 cuda tensor whose element (e,h) lives at
     data_ptr + 8*(e*attr_stride + h) for h < K.  One host sync (reads nnz to size the compact arrays)."""
@@ -130,6 +140,7 @@ def build_plan(edge_index, edge_attr_base, attr_stride, K, num_nodes, self_loops
     p.pending = None
     p.ready = None
     p.block_ptr = p.block_stats = p.block_ws = p.block_stats_host = None
+    p.n_dev = None        # device int32 scalar: rows that exist when N is a padded capacity (kpgnn_b200/wire.py)
     p.num_blocks = p.max_block_nodes = p.max_block_nnz = 0
     rows = p.N * K
     nbytes = C.c_size_t(0)
@@ -147,10 +158,11 @@ def build_plan(edge_index, edge_attr_base, attr_stride, K, num_nodes, self_loops
     if bad:
         raise IndexError("edge_index / edge_attr out of range in %d entries (node ids must be in [0,%d), "
                          "attrs in [0,65535])" % (bad, p.N))
-    p.nnz = p.capacity = nnz
-    p.col = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
-    p.colT = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
-    p.attr16 = torch.empty(max(nnz, 1), dtype=torch.int16, device=dev)
+    p.nnz = nnz
+    p.capacity = max(nnz, _CAPACITY_HINT + (p.N * K if self_loops else 0))
+    p.col = torch.zeros(max(p.capacity, 1), dtype=torch.int32, device=dev)
+    p.colT = torch.zeros(max(p.capacity, 1), dtype=torch.int32, device=dev)
+    p.attr16 = torch.zeros(max(p.capacity, 1), dtype=torch.int16, device=dev)
     _run_fill(p, pin)
     return p
 
@@ -247,3 +259,16 @@ def refresh_plan_async(p, edge_index, edge_attr_base, attr_stride, stream):
         ev.record(stream)
     p.ready = ev
     return ok
+
+
+def mark_current(edge_index, edge_attr, num_nodes, self_loops=False):
+    """Tell the cache that the plan of these tensors was refreshed by the caller (refresh_plan / refresh_plan_async on
+    the cached object) for their CURRENT contents: the next get_plan() is a plain hit.  For loops that rewrite the wire
+    tensors with raw kernels inside a captured region, where get_plan() must not re-plan on its own."""
+    base, stride, K = _attr_base(edge_attr)
+    key = (base.data_ptr(), stride, K, int(num_nodes), bool(self_loops), edge_index.size(1))
+    cache = getattr(edge_index, "_kpgnn_plans", None)
+    if cache is None or key not in cache:
+        raise KeyError("no cached plan for these tensors")
+    hit = cache[key]
+    cache[key] = (hit[0], base, (base._version, edge_index._version))

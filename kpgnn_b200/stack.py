@@ -101,6 +101,8 @@ class _KPGINPlusStack(torch.autograd.Function):
             d.Y1, d.Y2, d.Z2, d.stats = keep[0].data_ptr(), keep[1].data_ptr(), keep[2].data_ptr(), stats.data_ptr()
             out = Hn[:, L - l - 1]
             d.barrier = _lib.barrier_state(dev).data_ptr()
+            if plan.n_dev is not None:          # N is a padded capacity: the batch's row count lives on the device
+                d.n_dev = plan.n_dev.data_ptr()
             d.out_stride = hs
             if residual:
                 d.R, d.r_stride = Hn[:, L - l].data_ptr(), hs

@@ -51,7 +51,7 @@ class Trainer(object):
     """model: a graph-level model over kpgnn_b200.model.KPGNNPlusBackbone (fused layer stack: padded capacity batches
     need it); spec / bounds: see fit_spec()."""
 
-    def __init__(self, model, spec, bounds, device, world=1, lr=1e-3, loss_fn=l1_loss, use_graph=True):
+    def __init__(self, model, spec, bounds, device, world=1, lr=1e-3, loss_fn=l1_loss, use_graph=True, adam_eps=1e-8):
         self.model, self.spec, self.bounds = model, spec, bounds
         self.device, self.world, self.loss_fn, self.use_graph = torch.device(device), world, loss_fn, use_graph
         self.wire = DeviceWire(spec, device)
@@ -62,7 +62,7 @@ class Trainer(object):
         self.staged = self.consumed = None
         self.params = [p for p in model.parameters() if p.requires_grad]
         self.grads = FlatGradients(self.params) if world > 1 else None
-        self.opt = FusedAdam(self.params, lr=lr)
+        self.opt = FusedAdam(self.params, lr=lr, eps=adam_eps)
         self.loss = None
         self.graph = self.graph_opt = None
         self.launches_per_step = 0

@@ -113,205 +113,41 @@ class ClockSampler(object):
 # ----------------------------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------------------------
-class Trainer(object):
-    """Static-buffer training step captured in one CUDA graph (forward + backward + all-reduce + Adam)."""
+NUM_BATCHES = 8                                      # distinct seeded batches (different N / E / nnz) the timed steps rotate through
 
-    def __init__(self, host, device, world, eager=False):
-        self.eager = eager
-        from kpgnn_b200 import plan as kplan
+
+class BenchStream(object):
+    """The bench's stream of batches and its trainer (kpgnn_b200/train.py): NUM_BATCHES distinct 128-graph batches per
+    rank, packed in the compact wire format into pinned host buffers (the loader's side, untimed), one captured step
+    graph at the capacity of the largest batch, every timed step on the NEXT batch."""
+
+    def __init__(self, device, rank, world, eager=False):
         from kpgnn_b200.model import zinc_kpginplus
-        self.kplan = kplan
-        self.world, self.device = world, device
+        from kpgnn_b200.train import Trainer, fit_spec
+        hbs = [host_batch(GRAPHS_PER_GPU, seed=1000 * rank + s) for s in range(NUM_BATCHES)]
+        self.sizes = [(int(b.x.size(0)), int(b.edge_index.size(1))) for b in hbs]
+        self.wire_bytes_reference_layout = int(statistics.mean(b.nbytes() for b in hbs))
+        self.spec, self.bounds = fit_spec(hbs, K, EXTRACT_ARGS[3], EXTRACT_ARGS[2])
+        self.flats = [self.spec.pack(b, self.spec.host_buffer()) for b in hbs]
+        self.dev_flats = [f.to(device) for f in self.flats]              # "value": batches resident in HBM
         torch.manual_seed(0)
-        self.model = zinc_kpginplus(K, LAYERS, HIDDEN).to(device).train()
-        # One contiguous byte buffer per side (pinned host, device staging, device step inputs) with the batch's wire
-        # tensors as views: a step's upload is ONE 7.5 MB H2D copy, and the captured graph reads fixed addresses.
-        self.host, self.host_flat = self._flat_batch(host, None, pin=True)
-        self.dev, self.dev_flat = self._flat_batch(host, device)
-        _, self.stage_flat = self._flat_batch(host, device)
-        self.copy_stream = torch.cuda.Stream(device)
-        self.staged = None                               # event: staging buffer holds the next batch
-        self.consumed = None                             # event: staging buffer has been copied into the step inputs
-        from kpgnn_b200.dist import FlatGradients
-        self.params = [p for p in self.model.parameters() if p.requires_grad]
-        # world > 1: gradients live in one flat buffer (a single all-reduce); world == 1: autograd hands each
-        # gradient tensor over without the per-parameter accumulate kernel
-        self.grads = FlatGradients(self.params) if world > 1 else None
-        from kpgnn_b200.optim import FusedAdam
-        self.opt = FusedAdam(self.params, lr=1e-3)          # torch.optim.Adam(lr=1e-3) semantics, train_ZINC.py:244
-        self.loss = None
-        self.graph = None
-        self.launches_per_step = 0
-        kplan.deferred_checks(True)
-        from kpgnn_b200.encoders import peripheral_index
-        self.idx_buf = peripheral_index(self.dev.peripheral_edge_attr, self.dev.peripheral_configuration_attr)
-        self._tag_idx()
-
-    def _tag_idx(self):
-        d = self.dev
-        d._peripheral_idx = ((d.peripheral_edge_attr._version, d.peripheral_configuration_attr._version), self.idx_buf)
-
-    def refresh_derived(self):
-        """Everything derived from the raw wire tensors is recomputed EVERY step into static buffers (a new batch
-        arrives every step in training): the graph plan and the slot-ordered peripheral index matrix."""
-        from kpgnn_b200.encoders import peripheral_index
-        n = self.refresh_plan()
-        self.idx_buf.copy_(peripheral_index(self.dev.peripheral_edge_attr, self.dev.peripheral_configuration_attr))
-        self._tag_idx()
-        return n
-
-    def _zero(self):
-        # autograd hands every gradient tensor over (no per-parameter accumulate kernels); with world > 1 they are
-        # packed into the flat all-reduce buffer by one concatenation after backward
-        for p in self.params:
-            p.grad = None
-
-    def _step(self):
-        from kpgnn_b200.model import l1_loss
-        self._zero()
-        loss = l1_loss(self.model(self.dev), self.dev.y)
-        loss.backward()
-        if self.grads is not None:
-            self.grads.gather_()
-            self.grads.allreduce_mean_(self.world)             # one NCCL all-reduce per step over NVLink
-        self.opt.step()
-        return loss.detach()
-
-    def _fwd_bwd(self):
-        from kpgnn_b200.model import l1_loss
-        self._zero()
-        loss = l1_loss(self.model(self.dev), self.dev.y)
-        loss.backward()
-        if self.grads is not None:
-            self.grads.gather_()
-        return loss.detach()
-
-    def capture(self):
-        """world == 1: the whole step is ONE CUDA graph.  world > 1: forward+backward is one graph, the NCCL
-        all-reduce of the flat gradient is issued eagerly on the same stream, Adam is a second graph (keeps
-        NCCL out of stream capture; the collective is ~2 MB and latency-bound either way)."""
-        from kpgnn_b200 import _lib
-        if self.eager:
-            n0 = _lib.launch_count()
-            self.loss = self._step()
-            self.launches_per_step = _lib.launch_count() - n0
-            self.plan_obj = self.plan()
-            return
-        s = torch.cuda.Stream(self.device)
-        s.wait_stream(torch.cuda.current_stream(self.device))
-        with torch.cuda.stream(s):
-            for _ in range(3):
-                self._step()
-        torch.cuda.current_stream(self.device).wait_stream(s)
-        torch.cuda.synchronize(self.device)
-        self.graph = torch.cuda.CUDAGraph()
-        n0 = _lib.launch_count()
-        if self.world == 1:
-            with torch.cuda.graph(self.graph):
-                self.refresh_derived()
-                self.loss = self._step()
-        else:
-            with torch.cuda.graph(self.graph):
-                self.refresh_derived()
-                self.loss = self._fwd_bwd()
-            self.graph_opt = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph_opt):
-                self.opt.step()
-        self.launches_per_step = _lib.launch_count() - n0
-        torch.cuda.synchronize(self.device)
-        self.plan_obj = self.plan()                  # the graph refreshes this object in place on every replay
-
-    def replay(self):
-        if self.eager:
-            self.loss = self._step()
-            return
-        self.graph.replay()
-        if self.world > 1:
-            self.grads.allreduce_mean_(self.world)
-            self.graph_opt.replay()
-
-    def plan(self):
-        p, _ = self.kplan.get_plan(self.dev.edge_index, self.dev.edge_attr, self.dev.x.size(0))
-        return p
-
-    def refresh_plan(self):
-        from kpgnn_b200 import _lib
-        n0 = _lib.launch_count()
-        base = self.dev.edge_attr
-        # on a side stream: the plan rebuild overlaps the index / encoder kernels at the head of the step; the first
-        # layer's get_plan() joins it
-        if getattr(self, "plan_stream", None) is None:
-            self.plan_stream = torch.cuda.Stream(self.device)
-        ok = self.kplan.refresh_plan_async(self.plan(), self.dev.edge_index, base, base.size(1), self.plan_stream)
-        assert ok
-        return _lib.launch_count() - n0
-
-    @staticmethod
-    def _flat_batch(src, device, pin=False):
-        """Copies the wire tensors of `src` into one flat uint8 buffer (256-byte aligned fields); returns the Batch of
-        views and the buffer."""
-        from kpgnn_b200.model import Batch
-        offs, total = {}, 0
-        for f in src.FIELDS:
-            t = getattr(src, f)
-            if torch.is_tensor(t):
-                offs[f] = total
-                total += (t.numel() * t.element_size() + 255) // 256 * 256
-        flat = torch.empty(total, dtype=torch.uint8, pin_memory=pin) if device is None else \
-            torch.empty(total, dtype=torch.uint8, device=device)
-        out = Batch(num_graphs=src.num_graphs, num_nodes=src.num_nodes)
-        for f in src.FIELDS:
-            t = getattr(src, f)
-            if torch.is_tensor(t):
-                n = t.numel() * t.element_size()
-                v = flat[offs[f]:offs[f] + n].view(t.dtype).view(t.shape)
-                v.copy_(t)
-                setattr(out, f, v)
-            else:
-                setattr(out, f, t)
-        return out, flat
-
-    def payload_bytes(self):
-        return sum(getattr(self.host, f).numel() * getattr(self.host, f).element_size() for f in self.host.FIELDS
-                   if torch.is_tensor(getattr(self.host, f)))
-
-    def prefetch(self):
-        """Host -> device staging copy of the NEXT batch on the copy stream (pinned memory, one transfer)."""
-        cs = self.copy_stream
-        if self.consumed is not None:
-            cs.wait_event(self.consumed)                 # the previous contents have been handed to the step inputs
-        with torch.cuda.stream(cs):
-            self.stage_flat.copy_(self.host_flat, non_blocking=True)
-            self.staged = torch.cuda.Event()
-            self.staged.record(cs)
-
-    def hand_over(self):
-        """Hands the staged batch to the step's input buffers: device-to-device, ordered on the compute stream."""
-        if self.staged is None:
-            self.prefetch()
-        st = torch.cuda.current_stream(self.device)
-        st.wait_event(self.staged)
-        self.dev_flat.copy_(self.stage_flat, non_blocking=True)
-        self.consumed = torch.cuda.Event()
-        self.consumed.record(st)
+        model = zinc_kpginplus(K, LAYERS, HIDDEN).to(device).train()
+        self.tr = Trainer(model, self.spec, self.bounds, device, world=world, lr=1e-3, use_graph=not eager)
+        self.tr.capture(self.flats[0])
+        self.i = 0
+        self.tr.prefetch(self.flats[0])
 
     def step_resident(self):
-        if self.eager:
-            self.refresh_derived()
-        self.replay()                                # plan + index rebuild are the first nodes of the CUDA graph
+        """Next batch already in HBM: device-to-device hand-over into the staging buffer + the step graph."""
+        self.i = (self.i + 1) % NUM_BATCHES
+        self.tr.wire.stage.copy_(self.dev_flats[self.i], non_blocking=True)
+        self.tr.replay()
 
     def step_e2e(self):
-        """One step through the public path with HOST inputs: the batch staged by the previous call is handed to the
-        step, the step is launched, and the NEXT batch's host->device copy (pinned, copy stream) is issued behind it so
-        that it overlaps the kernels; then the loss is read back (train_ZINC.py:45)."""
-        self.hand_over()
-        if self.eager:
-            self.refresh_derived()
-        self.replay()
-        self.prefetch()
-        val = self.loss.item()                       # D2H read of the step's loss
-        self.plan_obj.validate()                     # deferred plan checks (stats copied back by the graph itself)
-        return self.host_flat.numel(), val           # bytes copied host -> device per step
+        """Next batch in pinned host memory: its upload was issued behind the previous step; hand-over, step graph,
+        upload of the batch after it, loss read-back, deferred plan validation."""
+        self.i = (self.i + 1) % NUM_BATCHES
+        return self.tr.step_e2e(self.flats[(self.i + 1) % NUM_BATCHES])
 
 
 def flush_l2(buf):
@@ -334,6 +170,37 @@ def timed_steps(fn, steps, device, flush_buf, dist_on):
         torch.cuda.synchronize(device)
         times.append(a.elapsed_time(b))
     return times
+
+
+def _check_agg_launch(hb, ei, ea, x, P, t0, tk, th, out, dout=None, dX=None, graphs=48):
+    """The timed launch is CHECKED before it is timed: its output rows (and, when given, its dX rows) for the first and
+    the last `graphs` graphs of the batch against the textbook formula evaluated in float64 with plain torch ops
+    (masked gather + embedding lookup, index_add at the destination, GELU, + P, theta-weighted sum over hops:
+    layers/KPGINplus.py:74-88, combine.py:43-58).  Graphs are independent, so a chunk is checked on its own."""
+    batch = hb.batch
+    G = int(batch[-1]) + 1
+    worst = 0.0
+    for g0, g1 in ((0, min(graphs, G)), (max(0, G - graphs), G)):
+        n0 = int(torch.searchsorted(batch, torch.tensor(g0)))
+        n1 = int(torch.searchsorted(batch, torch.tensor(g1)))
+        src_all = hb.edge_index[0]
+        e0 = int(torch.searchsorted(src_all, torch.tensor(n0)))
+        e1 = int(torch.searchsorted(src_all, torch.tensor(n1)))
+        src, dst, a = ei[0, e0:e1] - n0, ei[1, e0:e1] - n0, ea[e0:e1]
+        xc = x[n0:n1].double().requires_grad_(dX is not None)
+        emb = torch.cat([t0.double()[a[:, :1]], tk.double()[a[:, 1:]]], dim=1)
+        msg = (xc[src] + emb).masked_fill(a.unsqueeze(-1) == 0, 0.0)
+        agg = torch.zeros_like(xc).index_add_(0, dst, msg)
+        ref = ((torch.nn.functional.gelu(agg) + P[n0:n1].double()) * th.double()).sum(1)
+        err = float((out[n0:n1].double() - ref).abs().max() / ref.abs().max())
+        worst = max(worst, err)
+        assert err < 1e-5, "aggregation launch fails its check before timing: forward rel err %.3e" % err
+        if dX is not None:
+            ref.backward(dout[n0:n1].double())
+            errb = float((dX[n0:n1].double() - xc.grad).abs().max() / xc.grad.abs().max())
+            worst = max(worst, errb)
+            assert errb < 1e-5, "aggregation launch fails its check before timing: dX rel err %.3e" % errb
+    return worst
 
 
 def agg_roofline(device, num_graphs, peak, reps=10):
@@ -361,6 +228,9 @@ def agg_roofline(device, num_graphs, peak, reps=10):
     sp = C.c_void_p(st.cuda_stream)
     alg = 4 * N * K * HIDDEN * 2 + 4 * N * HIDDEN + 4 * (N * K + 1) + plan.nnz * 6
     flush = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device=device)     # 256 MB > 126 MB L2
+    # verify, then time: the SAME descriptor / launch geometry
+    _lib.check(lib.kp_agg_forward(C.byref(desc), out.data_ptr(), sp), "kp_agg_forward")
+    checked = _check_agg_launch(hb, ei, ea, x, P, t0, tk, th, out)
     ts = []
     for i in range(reps + 3):
         flush_l2(flush)
@@ -383,6 +253,9 @@ def agg_roofline(device, num_graphs, peak, reps=10):
     _lib.check(lib.kp_agg_backward_workspace_bytes(C.byref(desc), C.byref(nb)), "ws")
     ws = torch.empty(nb.value, dtype=torch.uint8, device=device)
     alg_b = 4 * N * HIDDEN + 4 * N * K * HIDDEN * 4 + 2 * (4 * (N * K + 1) + plan.nnz * 6)
+    _lib.check(lib.kp_agg_backward(C.byref(desc), dout.data_ptr(), dX.data_ptr(), dP.data_ptr(), dT0.data_ptr(),
+                                   dTk.data_ptr(), dth.data_ptr(), None, ws.data_ptr(), ws.numel(), sp), "kp_agg_backward")
+    checked = max(checked, _check_agg_launch(hb, ei, ea, x, P, t0, tk, th, out, dout, dX))
     tb = []
     for i in range(reps + 3):
         flush_l2(flush)
@@ -406,7 +279,7 @@ def agg_roofline(device, num_graphs, peak, reps=10):
     return {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
             "frac": round(achieved / peak, 4), "traffic": traffic, "kernel": "agg_fwd_lean_kernel<32,GELU,fuse,smem-tables>",
             "graphs_per_launch": num_graphs, "nodes": N, "nnz": plan.nnz, "algorithmic_bytes": alg,
-            "ms_per_launch": round(ms, 5),
+            "ms_per_launch": round(ms, 5), "checked_before_timing_max_rel_err": float("%.3e" % checked),
             "backward": {"ms": round(msb, 5), "algorithmic_bytes": alg_b,
                          "achieved": round(alg_b / (msb * 1e-3) / 1e9, 1),
                          "frac": round(alg_b / (msb * 1e-3) / 1e9 / peak, 4),
@@ -682,9 +555,13 @@ def workload_config(world):
             "graphs_per_gpu": GRAPHS_PER_GPU, "global_batch": GRAPHS_PER_GPU * world,
             "parallelism": "dp%d" % world, "l2": "flushed between timed steps (256 MB write)",
             "plan_rebuilt_every_step": True, "cuda_graph": True,
-            "e2e_input_pipeline": "every step uploads one batch (7.5 MB, pinned host -> device staging, copy stream) "
-                                  "while the previous step computes, then a device-to-device hand-over; loss read "
-                                  "back every step"}
+            "batches": "%d distinct seeded batches per GPU (different node / K-hop edge / plan-entry counts), a "
+                       "different one every step, through ONE captured step graph at padded capacity (row count "
+                       "read from device memory)" % NUM_BATCHES,
+            "e2e_input_pipeline": "every step uploads the next batch in the compact wire format (int32 ids, 1-byte "
+                                  "attributes; ~1.4 MB instead of the 7.5 MB int64 layout) from pinned host memory on a "
+                                  "copy stream while the previous step computes; device-to-device hand-over, one "
+                                  "kernel widens it to the reference's int64 wire tensors; loss read back every step"}
 
 
 def main():
@@ -736,27 +613,24 @@ def main():
         return
 
     log("[rank %d] building batch" % rank)
-    tr = Trainer(host_batch(GRAPHS_PER_GPU, seed=rank), device, world, eager=args.eager)
-    log("[rank %d] capturing" % rank)
-    tr.capture()
-    log("[rank %d] captured, %d of our kernels per step" % (rank, tr.launches_per_step))
+    bs = BenchStream(device, rank, world, eager=args.eager)
+    tr = bs.tr
+    log("[rank %d] captured, %d of our kernels per step; batches (N, E): %s" % (rank, tr.launches_per_step, bs.sizes))
     flush = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device=device)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()                 # nvidia-smi needs ~0.3 s to start: begin before the warm-up steps
     for _ in range(args.warmup):
-        tr.step_resident()
+        bs.step_resident()
     torch.cuda.synchronize(device)
-    plan_launches = tr.refresh_derived() if args.eager else 0
-    t_res = timed_steps(tr.step_resident, args.steps, device, flush, dist_on)
+    tr.validate()
+    t_res = timed_steps(bs.step_resident, args.steps, device, flush, dist_on)
+    tr.validate()
     log("[rank %d] resident timing done" % rank)
+    bs.tr.prefetch(bs.flats[(bs.i + 1) % NUM_BATCHES])
     for _ in range(3):
-        tr.step_e2e()
-    h2d = [0]
-
-    def e2e():
-        h2d[0], _ = tr.step_e2e()
-    t_e2e = timed_steps(e2e, args.steps, device, flush, dist_on)
+        bs.step_e2e()
+    t_e2e = timed_steps(bs.step_e2e, args.steps, device, flush, dist_on)
     clocks = sampler.stop() if rank == 0 else None
     log("[rank %d] e2e timing done" % rank)
 
@@ -831,8 +705,10 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(world),
             "e2e": {"value": round(total_graphs / (ms_e2e * 1e-3), 1), "unit": "graphs/s",
-                    "h2d_bytes_per_step": int(h2d[0]), "d2h_bytes_per_step": 4 + 16, "ms_per_step": round(ms_e2e, 4)},
-            "gpu_launches": int((tr.launches_per_step + plan_launches) * args.steps),
+                    "h2d_bytes_per_step": int(bs.spec.nbytes), "d2h_bytes_per_step": 4 + 16,
+                    "ms_per_step": round(ms_e2e, 4),
+                    "reference_wire_layout_bytes_per_batch": bs.wire_bytes_reference_layout},
+            "gpu_launches": int(tr.launches_per_step * args.steps),
             "gpu_launches_per_step": {"ours_in_cuda_graph_incl_plan_rebuild": int(tr.launches_per_step)},
             "clocks": clocks, "roofline": roof, "roofline_batch128": roof_small, "cpu_baseline": cpu,
             "workloads": workloads or None, "loss": float(tr.loss.item()),

@@ -537,6 +537,8 @@ struct Config {
   bool lean_b1;
   int lean_b1_threads;
   size_t lean_b1_smem;
+  // the whole backward as one block-resident kernel (agg_block_bwd.cu)
+  bool fb;
 };
 
 static int g_force_generic = 0;   // test hook (kp_agg_set_force_generic): exercise the generic kernels
@@ -644,6 +646,8 @@ static int make_config(const kp_agg_desc& a, Config* c) {
       }
     }
   }
+  c->fb = c->fast && fast_lean_enabled() && block_bwd_eligible(a, c->fG, c->ftab, true);
+  if (c->fb && c->grid_b1 < block_bwd_grid()) c->grid_b1 = block_bwd_grid();    // sizes the dtheta partials
   // table pass
   const int trows = a.T0 ? a.rows0 + (a.k > 1 ? a.rowsk : 0) : 0;
   c->cw = lanes;
@@ -719,8 +723,13 @@ static WsLayout ws_layout(const kp_agg_desc& a, const Config& c) {
   w.gs = take(c.need_gs ? sizeof(float) * (size_t)a.N * a.k * a.d : 0);
   w.dtheta = take(sizeof(float) * (size_t)c.grid_b1 * a.k * a.d);
   w.deps = take(sizeof(float) * (size_t)c.grid_b1);
-  w.table = take(c.b3_count ? sizeof(float) * c.b3_part_floats
-                            : (c.grid_b3 ? sizeof(float) * (size_t)c.grid_b3 * (a.rows0 + a.rowsk) * a.d : 0));
+  size_t tab_bytes = c.b3_count ? sizeof(float) * c.b3_part_floats
+                                : (c.grid_b3 ? sizeof(float) * (size_t)c.grid_b3 * (a.rows0 + a.rowsk) * a.d : 0);
+  if (c.fb && a.T0) {
+    const size_t fbb = sizeof(float) * (size_t)block_bwd_grid() * (a.rows0 + a.rowsk) * a.d;
+    if (fbb > tab_bytes) tab_bytes = fbb;
+  }
+  w.table = take(tab_bytes);
   w.total = off;
   return w;
 }
@@ -810,6 +819,7 @@ int kp_agg_set_force_generic(int flag) {
   // bit 4: use it for every eligible call, however small (tests); bit 5: use it for large batches only
   kp::fast_fwd_set_tma((flag & 16) ? 2 : ((flag & 32) ? 1 : 0));
   kp::tile_set_mode((flag & 64) ? 0 : 1);
+  kp::block_bwd_set_mode((flag & 64) ? 0 : 1);
   return 0;
 }
 
@@ -872,6 +882,36 @@ int kp_agg_backward(const kp_agg_desc* desc, const float* dOut, float* dX, float
   float* dep_part = deps ? (float*)(ws + w.deps) : nullptr;
   kp::AggArgs args{a, c.G, c.gshift};
   const bool want_table = (dT0 || dTk);
+  if (c.fb && !deps && (!want_table || (dT0 && (dTk || a.k == 1)))) {
+    // ONE block-resident kernel: recompute + dP + dtheta partials, dX through shared memory, table partials
+    float* dPk = dP;
+    if (!a.fuse && dP == dOut) dPk = nullptr;
+    float* tab_part = want_table ? (float*)(ws + w.table) : nullptr;
+    int fgrid = 0;
+    int rc = kp::block_bwd(kp::make_fast_args(a), dOut, dX, dPk, dth_part, tab_part, &fgrid, st);
+    if (rc) return rc;
+    cudaStream_t lst = st;
+    if (a.leaf_stream && a.leaf_stream != stream) {
+      lst = (cudaStream_t)a.leaf_stream;
+      cudaEvent_t ev;
+      KP_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      KP_CUDA(cudaEventRecord(ev, st));
+      KP_CUDA(cudaStreamWaitEvent(lst, ev, 0));
+      KP_CUDA(cudaEventDestroy(ev));
+    }
+    if (want_table)
+      KP_LAUNCH(kp::reduce_partials_kernel, kp::ceil_div((long long)tn * 32, 256), 256, 0, lst, tab_part, fgrid, (int)tn,
+                a.rows0 * a.d, dT0, dTk);
+    if (geo) {
+      KP_LAUNCH(kp::dtheta_geo_bwd_kernel, a.d, 256, 0, lst, dth_part, fgrid, a.k, a.d, a.geo_alphas, a.theta, dtheta,
+                a.geo_dalphas);
+    } else if (dtheta) {
+      const int n = a.k * a.d;
+      KP_LAUNCH(kp::reduce_partials_kernel, kp::ceil_div((long long)n * 32, 256), 256, 0, lst, dth_part, fgrid, n, n,
+                dtheta, (float*)nullptr);
+    }
+    return 0;
+  }
   const bool want_b1 = c.need_gs ? (dX || want_table || dP || dth_part || dep_part) : (dP || dep_part);
   if (want_b1) {
     float* dPk = dP;

@@ -54,6 +54,13 @@ bool tile_eligible(const kp_agg_desc& a, int tab);
 int tile_fwd(const FastArgs& fa, int G, int act, int tab, bool extra, float* out, cudaStream_t st);
 int tile_b2(const FastArgs& fa, int G, bool extra, const float* Gs, const float* dOut, float* dX, cudaStream_t st);
 
+// the whole backward as one block-resident kernel (agg_block_bwd.cu)
+void block_bwd_set_mode(int mode);   // 0 = never, 1 = when the caller supplies closed blocks (default)
+bool block_bwd_eligible(const kp_agg_desc& a, int G, int tab, bool want_dtheta);
+int block_bwd_grid();
+int block_bwd(const FastArgs& fa, const float* dOut, float* dX, float* dP, float* dth_part, float* tab_part, int* grid_out,
+              cudaStream_t st);
+
 // dispatch helper shared by the three translation units
 #define KP_FAST_TAB(FN, G, A, F, X, tab, ...)                                  \
   ((tab) == TAB_SMEM ? FN<G, A, F, TAB_SMEM, X>(__VA_ARGS__)                   \

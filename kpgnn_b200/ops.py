@@ -15,6 +15,19 @@ from ._lib import ACT_GELU, ACT_NONE, ACT_RELU  # noqa: F401
 
 # average entries per (node, hop) row from which the block-resident kernels (csrc/agg_tile.cu) are worth their staging
 LONG_ROW_ENTRIES = 12
+# size of the backward's hand-over tensor Gs [N,k,d] (bytes) from which the whole backward runs as one block-resident
+# kernel (csrc/agg_block_bwd.cu): beyond the L2 the three-kernel path writes Gs to HBM once and reads it back twice
+BLOCK_BWD_MIN_BYTES = 48 << 20
+
+
+def want_blocks(plan, k, d, fuse):
+    """Asks the plan for its closed node blocks when a block-resident kernel would serve this call."""
+    if plan.block_ptr is not None:
+        return
+    if not fuse and plan.nnz >= LONG_ROW_ENTRIES * max(plan.N * plan.K, 1):
+        plan.blocks()          # long rows (e.g. n = 1 280 regular graphs at K = 6): stage blocks in shared memory
+    elif 4 * plan.N * k * d >= BLOCK_BWD_MIN_BYTES:
+        plan.blocks()          # large molecule batches: keep the backward's hand-over tensor in shared memory
 
 
 def _ptr(t):
@@ -41,8 +54,9 @@ def _make_desc(plan, k, x, P, T0, Tk, theta, eps, act, fuse, use_dinv, use_mean)
     desc.theta, desc.eps = _ptr(theta), _ptr(eps)
     desc.act, desc.fuse = act, 1 if fuse else 0
     desc.amax0, desc.amaxk = plan.max_attr0, plan.max_attrk
-    if plan.block_ptr is not None and not fuse:
-        # closed node blocks were requested for this plan (long-row workloads): block-resident kernels where they fit
+    if plan.block_ptr is not None:
+        # closed node blocks were requested for this plan: block-resident kernels where they fit (long rows: unfused
+        # forward / dX from shared-memory slices; molecule batches: the whole backward as one kernel)
         desc.block_ptr, desc.block_stats = plan.block_ptr.data_ptr(), plan.block_stats.data_ptr()
         desc.num_blocks, desc.max_block_nodes = plan.num_blocks, plan.max_block_nodes
     return desc
@@ -127,6 +141,5 @@ def khop_aggregate(x, plan, k, P=None, T0=None, Tk=None, theta=None, eps=None, a
     """x [N,k,d] fp32 (any node/hop strides, dense last dim) -> [N,d] if fuse else [N,k,d].  See kpgnn.h."""
     if fuse and theta is None:
         raise ValueError("fuse=True needs theta [k,d]")
-    if not fuse and plan.block_ptr is None and plan.nnz >= LONG_ROW_ENTRIES * max(plan.N * plan.K, 1):
-        plan.blocks()          # long rows (e.g. n = 1 280 regular graphs at K = 6): stage blocks in shared memory
+    want_blocks(plan, k, x.size(-1), fuse)
     return _KHopAggregate.apply(x, P, T0, Tk, theta, eps, plan, k, act, fuse, use_dinv, use_mean)

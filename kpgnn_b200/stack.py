@@ -25,7 +25,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from .ops import _make_desc, ACT_GELU
+from .ops import _make_desc, want_blocks, ACT_GELU
 from .layers.combine import GeometricCombine
 from .layers.dense_block import _bn_ok
 
@@ -51,6 +51,7 @@ class _KPGINPlusStack(torch.autograd.Function):
             Pc = Pc.contiguous()
         Hn = torch.empty((N, L + 1, H), dtype=torch.float32, device=dev)
         Hn[:, L].copy_(x0.detach())
+        want_blocks(plan, K, H, True)
         hs = (L + 1) * H
         saved = []
         # GeometricCombine weights of every layer in one launch (combine.py:51-58)

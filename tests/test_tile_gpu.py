@@ -112,3 +112,71 @@ def test_tile_kernels_kpgcn_layer(lib, comb):
     H, K = 96, 6
     _layer_pair(KPGCNConv(H, H, K, 1, 10, comb), OL.OracleKPGCNConv(H, H, K, 1, 10, comb), b, ("N", H),
                 ("N", K, H // K))
+
+
+@pytest.mark.parametrize("fuse", [True, False])
+@pytest.mark.parametrize("K,d", [(8, 104), (3, 104), (1, 104), (5, 72), (8, 128)])
+def test_block_resident_backward(lib, fuse, K, d):
+    """The whole backward as one block-resident kernel (csrc/agg_block_bwd.cu), forced on for a small molecule batch:
+    dX, dP, dT0, dTk, dtheta against the dense float64 oracle AND against the three-kernel path (same inputs)."""
+    import kpgnn_b200.ops as ops
+    from kpgnn_b200.ops import khop_aggregate, ACT_GELU
+    from kpgnn_b200.plan import get_plan
+    dev = torch.device("cuda:0")
+    b = zinc_batch(40, K, "spd", seed=K + d)
+    N = b["num_nodes"]
+    ei, ea = b["edge_index"].to(dev), b["edge_attr"].to(dev)
+    g = torch.Generator().manual_seed(K)
+    t0 = torch.randn(5, d, generator=g).to(dev)
+    tk = torch.randn(52, d, generator=g).to(dev)
+    th0 = torch.softmax(torch.randn(K, d, generator=g), 0).to(dev)
+    x0 = torch.randn(N, K, d, generator=g).to(dev)
+    P0 = torch.randn(N, K, d, generator=g).to(dev)
+    gy = torch.randn((N, d) if fuse else (N, K, d), generator=g).to(dev)
+    res = {}
+    for mode in ("oracle", "block", "three"):
+        dt = torch.float64 if mode == "oracle" else torch.float32
+        x, P = x0.to(dt).requires_grad_(True), P0.to(dt).requires_grad_(True)
+        T0, Tk, th = (t.to(dt).clone().requires_grad_(True) for t in (t0, tk, th0))
+        if mode == "oracle":
+            z = torch.nn.functional.gelu(OL.dense_khop_aggregate(x, ei, ea, T0, Tk if K > 1 else None)) + P
+            y = (z * th).sum(1) if fuse else z
+        else:
+            plan, k = get_plan(ei.clone(), ea, N)
+            if mode == "block":
+                plan.blocks()
+            y = khop_aggregate(x, plan, k, P=P, T0=T0, Tk=Tk if K > 1 else None, theta=th if fuse else None,
+                               act=ACT_GELU, fuse=fuse)
+            assert (plan.block_ptr is not None) == (mode == "block")
+        y.backward(gy.to(dt))
+        res[mode] = [x.grad, P.grad, T0.grad] + ([Tk.grad] if K > 1 else []) + ([th.grad] if fuse else [])
+    for a, c in zip(res["block"], res["oracle"]):
+        assert rel_err(a, c) < RTOL, rel_err(a, c)
+    for a, c in zip(res["block"], res["three"]):
+        assert rel_err(a, c) < 1e-6
+
+
+def test_block_resident_backward_in_stack(lib):
+    """The layer-history stack (strided, accumulated dX) over the block-resident backward: same gradients as without."""
+    import kpgnn_b200.ops as ops
+    from kpgnn_b200.model import Batch, l1_loss, zinc_kpginplus
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    model = zinc_kpginplus(8, 8, 104).to(dev).train()
+    d = zinc_batch(16, 8, "spd", seed=3)
+    res = []
+    for force in (False, True):
+        keep = ops.BLOCK_BWD_MIN_BYTES
+        ops.BLOCK_BWD_MIN_BYTES = 0 if force else 1 << 60
+        try:
+            b = Batch(**{k: (v.clone() if torch.is_tensor(v) else v) for k, v in d.items()}).to(dev)
+            for p in model.parameters():
+                p.grad = None
+            loss = l1_loss(model(b), b.y)
+            loss.backward()
+            res.append([loss.detach()] + [p.grad.clone() for p in model.parameters() if p.grad is not None])
+        finally:
+            ops.BLOCK_BWD_MIN_BYTES = keep
+    gmax = max(float(t.abs().max()) for t in res[0][1:])
+    for a, c in zip(res[1], res[0]):
+        assert rel_err(a, c, floor=1e-3 * gmax) < 1e-5

@@ -209,12 +209,13 @@ def agg_roofline(device, num_graphs, peak, reps=10):
     4*N*k*d [X] + 4*N*k*d [P] + 4*N*d [out] + 4*(N*k+1) [rowptr] + nnz*(4 [col] + 2 [attr16])."""
     import ctypes as C
     from kpgnn_b200 import _lib
-    from kpgnn_b200.ops import _make_desc, ACT_GELU
+    from kpgnn_b200.ops import _make_desc, want_blocks, ACT_GELU
     from kpgnn_b200.plan import get_plan
     hb = host_batch(num_graphs, seed=1000 + num_graphs)
     ei, ea = hb.edge_index.to(device), hb.edge_attr.to(device)
     N = hb.x.size(0)
     plan, k = get_plan(ei, ea, N)
+    want_blocks(plan, k, HIDDEN, True)       # what khop_aggregate does: block-resident backward for large batches
     g = torch.Generator(device=device).manual_seed(0)
     x = torch.randn(N, K, HIDDEN, device=device, generator=g)
     P = torch.randn(N, K, HIDDEN, device=device, generator=g)
@@ -283,7 +284,9 @@ def agg_roofline(device, num_graphs, peak, reps=10):
             "backward": {"ms": round(msb, 5), "algorithmic_bytes": alg_b,
                          "achieved": round(alg_b / (msb * 1e-3) / 1e9, 1),
                          "frac": round(alg_b / (msb * 1e-3) / 1e9 / peak, 4),
-                         "kernels": "agg_bwd_dst_lean (B1) + agg_fwd_lean<gather> (B2) + agg_bwd_table_count (B3) + reductions"}}
+                         "kernels": ("agg_block_bwd_kernel (recompute + dP + dtheta, dX and table gradients from the "
+                                     "shared-memory hand-over tile) + partial reductions") if plan.block_ptr is not None
+                         else "agg_bwd_dst_lean (B1) + agg_fwd_lean<gather> (B2) + agg_bwd_table_count (B3) + reductions"}}
 
 
 # ----------------------------------------------------------------------------------------------------------------

@@ -60,53 +60,84 @@ agg_block_bwd_kernel(const FastArgs fa, const FbArgs fb) {
   for (int i = threadIdx.x * 4; i < trows * d; i += FB_THREADS * 4) st4(dT_s + i, make_float4(0.f, 0.f, 0.f, 0.f));
   const bool need_z = FUSE && fb.dth_part != nullptr;
   const bool hasP = need_z && a.P != nullptr;
-  float4 dth[FB_MAXHG];               // dtheta partial sums of this lane's 4 channels, hops of the CURRENT group
-  // (a CTA's units alternate between hop groups; one accumulator set per group id lives in registers only for
-  //  groups == 1; otherwise partial sums are flushed to the per-CTA shared staging at the end of every unit)
-  float* dth_cta = reinterpret_cast<float*>(mask_s + 2);               // [FB_WARPS][k][d] staging, only if need_z
-  if (need_z)
-    for (int i = threadIdx.x; i < FB_WARPS * k * d; i += FB_THREADS) dth_cta[i] = 0.f;
+  // A CTA serves ONE hop group for its whole life (group = blockIdx.x % groups; the grid is a multiple of `groups`):
+  // the dtheta sums of the group's hops stay in registers across all of the CTA's units and are reduced over the warps
+  // once, at the end, through the (then free) Gs tile.
+  float4 dth[FB_MAXHG];
+#pragma unroll
+  for (int i = 0; i < FB_MAXHG; ++i) dth[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
   const int nblocks = fb.block_stats ? __ldg(fb.block_stats) : fb.num_blocks;
-  const int units = nblocks * fb.groups;
-  for (int u = blockIdx.x; u < units; u += gridDim.x) {
-    const int b = u / fb.groups, g = u - b * fb.groups;
-    const int h0 = g * HG, h1 = min(k, h0 + HG), nh = h1 - h0;
+  const int g = blockIdx.x % fb.groups;
+  const int h0 = g * HG, h1 = min(k, h0 + HG), nh = h1 - h0;
+  const float* Xg = a.X + (size_t)h0 * fa.xh + c;
+  for (int b = blockIdx.x / fb.groups; b < nblocks; b += gridDim.x / fb.groups) {
     const int v0 = __ldg(fb.block_ptr + b), v1 = __ldg(fb.block_ptr + b + 1);
     const int nb = v1 - v0;
     if (nb > fb.maxn) continue;        // cannot happen when the caller sized maxn from the plan statistics
     // ---------------------------------------------------------------- phase 1: B1, a warp per destination node
-#pragma unroll
-    for (int i = 0; i < FB_MAXHG; ++i) dth[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int vl = warp; vl < nb; vl += FB_WARPS) {
       const int v = v0 + vl;
       const int rp = (lane <= nh) ? __ldg(a.rowptr + (size_t)v * Kp + h0 + lane) : 0;
-      const int eb = __shfl_sync(0xffffffffu, rp, 0), ee = __shfl_sync(0xffffffffu, rp, nh);
       float4 go = make_float4(0.f, 0.f, 0.f, 0.f);
       if (FUSE) go = ld4s(fb.dOut + ((size_t)v * d + c));
-      int hcur = 0, hend = __shfl_sync(0xffffffffu, rp, 1);
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      // closes hop `hcur` of node v: activation derivative, Gs -> shared, dP -> global, dtheta partial
-      auto finish_hop = [&](int hl) {
+      const int eb = __shfl_sync(0xffffffffu, rp, 0), ee = __shfl_sync(0xffffffffu, rp, nh);
+      // the node's entries of this hop group, one per lane (molecules: ~10; longer lists re-load per 32)
+      int mycol = 0, myattr = 0;
+      if (eb + lane < ee) {
+        mycol = __ldg(a.col + eb + lane);
+        if (TAB) myattr = (int)__ldg(a.attr16 + eb + lane);
+      }
+      int wb = eb;                                                    // first entry held in the lanes
+      for (int hl = 0; hl < nh; ++hl) {
         const int h = h0 + hl;
+        const int hb = __shfl_sync(0xffffffffu, rp, hl), he = __shfl_sync(0xffffffffu, rp, hl + 1);
         const size_t row = ((size_t)v * k + h) * d + c;
-        float4 dy;
+        // independent loads of the hop first: dOut / P rows, then the gathers four at a time
+        float4 dy = make_float4(0.f, 0.f, 0.f, 0.f), p = dy;
+        if (!FUSE) dy = ld4s(fb.dOut + row);
+        if (hasP) p = ld4s(a.P + ((size_t)v * fa.ps + (size_t)h * fa.ph + c));
+        const float* Xh = Xg + (size_t)hl * fa.xh;
+        const float* Th = TAB ? ((h == 0 ? a.T0 : a.Tk) + c) : nullptr;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = hb; j < he; j += 4) {
+          if (j + 4 > wb + 32) {                                     // (rare) window moves: reload 32 entries from j
+            wb = j;
+            mycol = 0; myattr = 0;
+            if (wb + lane < ee) {
+              mycol = __ldg(a.col + wb + lane);
+              if (TAB) myattr = (int)__ldg(a.attr16 + wb + lane);
+            }
+          }
+          float4 x[4], t[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const unsigned cj = (unsigned)__shfl_sync(0xffffffffu, mycol, (j - wb + i) & 31);
+            const int aj = TAB ? __shfl_sync(0xffffffffu, myattr, (j - wb + i) & 31) : 0;
+            x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            t[i] = x[i];
+            if (j + i < he) {
+              x[i] = ld4(Xh + cj * fa.xs);
+              if (TAB) t[i] = ld4(Th + aj * d);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            add4(x[i], t[i]);
+            add4(acc, x[i]);
+          }
+        }
         if (FUSE) {
-          const float4 t = *reinterpret_cast<const float4*>(theta_s + h * d + c);
-          dy = make_float4(t.x * go.x, t.y * go.y, t.z * go.z, t.w * go.w);
-        } else {
-          dy = ld4s(fb.dOut + row);
+          const float4 th = *reinterpret_cast<const float4*>(theta_s + h * d + c);
+          dy = make_float4(th.x * go.x, th.y * go.y, th.z * go.z, th.w * go.w);
         }
         if (fb.dP && active) st4s(fb.dP + row, dy);
-        float4 gsv = make_float4(dy.x * act_bwd<ACT>(acc.x), dy.y * act_bwd<ACT>(acc.y), dy.z * act_bwd<ACT>(acc.z),
-                                 dy.w * act_bwd<ACT>(acc.w));
+        const float4 gsv = make_float4(dy.x * act_bwd<ACT>(acc.x), dy.y * act_bwd<ACT>(acc.y),
+                                       dy.z * act_bwd<ACT>(acc.z), dy.w * act_bwd<ACT>(acc.w));
         if (active) *reinterpret_cast<float4*>(Gs_s + ((size_t)vl * HG + hl) * d + c) = gsv;
         if (need_z) {
-          float4 z = make_float4(act_fwd<ACT>(acc.x), act_fwd<ACT>(acc.y), act_fwd<ACT>(acc.z), act_fwd<ACT>(acc.w));
-          if (hasP) {
-            const float4 p = ld4s(a.P + ((size_t)v * fa.ps + (size_t)h * fa.ph + c));
-            z.x += p.x; z.y += p.y; z.z += p.z; z.w += p.w;
-          }
+          const float4 z = make_float4(act_fwd<ACT>(acc.x) + p.x, act_fwd<ACT>(acc.y) + p.y, act_fwd<ACT>(acc.z) + p.z,
+                                       act_fwd<ACT>(acc.w) + p.w);
 #pragma unroll
           for (int i = 0; i < FB_MAXHG; ++i)
             if (i == hl) {
@@ -114,46 +145,7 @@ agg_block_bwd_kernel(const FastArgs fa, const FbArgs fb) {
               dth[i].z = fmaf(go.z, z.z, dth[i].z); dth[i].w = fmaf(go.w, z.w, dth[i].w);
             }
         }
-      };
-      for (int j0 = eb; j0 < ee; j0 += 32) {
-        int mycol = 0, myattr = 0;
-        if (j0 + lane < ee) {
-          mycol = __ldg(a.col + j0 + lane);
-          if (TAB) myattr = (int)__ldg(a.attr16 + j0 + lane);
-        }
-        const int cnt = min(32, ee - j0);
-        for (int i = 0; i < cnt; ++i) {
-          const int j = j0 + i;
-          while (j >= hend) {                                        // hop boundary (also skips empty hops)
-            finish_hop(hcur);
-            acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            ++hcur;
-            hend = __shfl_sync(0xffffffffu, rp, hcur + 1);
-          }
-          const unsigned cj = (unsigned)__shfl_sync(0xffffffffu, mycol, i);
-          float4 x = ld4(a.X + (cj * fa.xs + (unsigned)(h0 + hcur) * fa.xh + c));
-          if (TAB) {
-            const int aj = __shfl_sync(0xffffffffu, myattr, i);
-            add4(x, ld4(((h0 + hcur) == 0 ? a.T0 : a.Tk) + aj * d + c));
-          }
-          add4(acc, x);
-        }
       }
-      while (hcur < nh) {                                            // the last hop with entries and the empty ones behind it
-        finish_hop(hcur);
-        acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        ++hcur;
-      }
-    }
-    if (need_z) {                       // flush this unit's dtheta sums into the warp's staging rows (fixed order: unit by unit)
-#pragma unroll
-      for (int i = 0; i < FB_MAXHG; ++i)
-        if (i < nh && active) {
-          float4* p = reinterpret_cast<float4*>(dth_cta + ((size_t)warp * k + h0 + i) * d + c);
-          float4 s = *p;
-          s.x += dth[i].x; s.y += dth[i].y; s.z += dth[i].z; s.w += dth[i].w;
-          *p = s;
-        }
     }
     __syncthreads();
     // ---------------------------------------------------------------- phase 2: B2, a warp per source node
@@ -162,20 +154,32 @@ agg_block_bwd_kernel(const FastArgs fa, const FbArgs fb) {
       for (int ul = warp; ul < nb; ul += FB_WARPS) {
         const int uu = v0 + ul;
         const int rp = (lane <= nh) ? __ldg(a.rowptrT + (size_t)uu * Kp + h0 + lane) : 0;
+        const int eb = __shfl_sync(0xffffffffu, rp, 0), ee = __shfl_sync(0xffffffffu, rp, nh);
+        int myv = (eb + lane < ee) ? __ldg(a.colT + eb + lane) - v0 : 0;
+        int wb = eb;
         for (int hl = 0; hl < nh; ++hl) {
           const int rb = __shfl_sync(0xffffffffu, rp, hl), re = __shfl_sync(0xffffffffu, rp, hl + 1);
           float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-          for (int j0 = rb; j0 < re; j0 += 32) {
-            const int myv = (j0 + lane < re) ? __ldg(a.colT + j0 + lane) - v0 : 0;
-            const int cnt = min(32, re - j0);
-            for (int i = 0; i < cnt; ++i) {
-              const int vl = __shfl_sync(0xffffffffu, myv, i);
-              add4(acc, *reinterpret_cast<const float4*>(Gs_s + ((size_t)vl * HG + hl) * d + c));
+          float* po = fb.dX + ((size_t)uu * os + (size_t)(h0 + hl) * oh + c);
+          float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (fa.oacc && active) old = *reinterpret_cast<const float4*>(po);
+          for (int j = rb; j < re; j += 4) {
+            if (j + 4 > wb + 32) {
+              wb = j;
+              myv = (wb + lane < ee) ? __ldg(a.colT + wb + lane) - v0 : 0;
             }
+            float4 gq[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int vl = __shfl_sync(0xffffffffu, myv, (j - wb + i) & 31);
+              gq[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (j + i < re) gq[i] = *reinterpret_cast<const float4*>(Gs_s + ((size_t)vl * HG + hl) * d + c);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) add4(acc, gq[i]);
           }
           if (active) {
-            float* po = fb.dX + ((size_t)uu * os + (size_t)(h0 + hl) * oh + c);
-            if (fa.oacc) add4(acc, *reinterpret_cast<const float4*>(po));
+            add4(acc, old);
             *reinterpret_cast<float4*>(po) = acc;
           }
         }
@@ -185,18 +189,19 @@ agg_block_bwd_kernel(const FastArgs fa, const FbArgs fb) {
     if (TAB && fb.tab_part) {
       const int nrows = nb * nh;
       // (i) count matrix: thread r owns row r = (vl, hl); counts of each attr value among the row's entries
-      for (int i = threadIdx.x; i < nrows * (FB_TROWS / 4); i += FB_THREADS) reinterpret_cast<unsigned*>(cnt_s)[i] = 0u;
+      for (int i = threadIdx.x; i < nb * HG * (FB_TROWS / 4); i += FB_THREADS) reinterpret_cast<unsigned*>(cnt_s)[i] = 0u;
       if (threadIdx.x < 2) mask_s[threadIdx.x] = 0ull;
       __syncthreads();
       for (int r = threadIdx.x; r < nrows; r += FB_THREADS) {
         const int vl = r / nh, hl = r - vl * nh;
         const int rr = (v0 + vl) * Kp + h0 + hl;
         const int rb = __ldg(a.rowptr + rr), re = __ldg(a.rowptr + rr + 1);
+        unsigned char* crow = cnt_s + (size_t)(vl * HG + hl) * FB_TROWS;
         unsigned long long m = 0ull;
         for (int j = rb; j < re; ++j) {
           const int aj = (int)__ldg(a.attr16 + j);
           if (aj < FB_TROWS) {
-            ++cnt_s[r * FB_TROWS + aj];
+            ++crow[aj];
             m |= 1ull << aj;
           }
         }
@@ -210,6 +215,8 @@ agg_block_bwd_kernel(const FastArgs fa, const FbArgs fb) {
 #pragma unroll 1
         for (int cls = 0; cls < 2; ++cls) {
           if (cls == 0 && h0 != 0) continue;                         // hop 0 lives in the first group only
+          const int hl_lo = (cls == 0) ? 0 : (h0 == 0 ? 1 : 0);      // hops of this class inside the group
+          const int hl_hi = (cls == 0) ? 1 : nh;
           const unsigned long long m = mask_s[cls];
           const int present = __popcll(m);
           for (int s0 = slot; s0 < present; s0 += nslots) {
@@ -217,18 +224,17 @@ agg_block_bwd_kernel(const FastArgs fa, const FbArgs fb) {
             for (int i = 0; i < s0; ++i) mm &= mm - 1;
             const int t = __ffsll((long long)mm) - 1;
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int r = 0; r < nrows; ++r) {
-              const int hl = r % nh;
-              if (((h0 + hl) == 0) != (cls == 0)) continue;
-              const unsigned cn = cnt_s[r * FB_TROWS + t];
-              if (cn) fma4(acc, (float)cn, *reinterpret_cast<const float4*>(Gs_s + (size_t)r * d + 4 * q));
-            }
+            for (int vl = 0; vl < nb; ++vl)
+              for (int hl = hl_lo; hl < hl_hi; ++hl) {
+                const unsigned cn = cnt_s[(size_t)(vl * HG + hl) * FB_TROWS + t];
+                if (cn) fma4(acc, (float)cn, *reinterpret_cast<const float4*>(Gs_s + ((size_t)vl * HG + hl) * d + 4 * q));
+              }
             const int trow = cls == 0 ? t : fb.rows0 + t;
             if (t < (cls == 0 ? fb.rows0 : fb.rowsk)) {
               float4* p = reinterpret_cast<float4*>(dT_s + (size_t)trow * d + 4 * q);
-              float4 s = *p;
-              s.x += acc.x; s.y += acc.y; s.z += acc.z; s.w += acc.w;
-              *p = s;
+              float4 sv = *p;
+              sv.x += acc.x; sv.y += acc.y; sv.z += acc.z; sv.w += acc.w;
+              *p = sv;
             }
           }
         }
@@ -238,11 +244,27 @@ agg_block_bwd_kernel(const FastArgs fa, const FbArgs fb) {
   }
   // ------------------------------------------------------------------ per-CTA partials, written once
   if (need_z) {
-    for (int i = threadIdx.x; i < k * d; i += FB_THREADS) {           // fixed-order sum over the CTA's warps
-      float s = 0.f;
+    // fixed-order sum of the warps' register sums through the Gs tile (free now), in rounds of `per_round` warps
+    float* stage = Gs_s;
+    float* mine = fb.dth_part + (size_t)blockIdx.x * k * d;
+    for (int i = threadIdx.x; i < k * d; i += FB_THREADS) mine[i] = 0.f;
+    __syncthreads();
+    const int per_round = max(1, min(FB_WARPS, fb.maxn));
+    for (int w0 = 0; w0 < FB_WARPS; w0 += per_round) {
+      if (warp >= w0 && warp < w0 + per_round && active) {
 #pragma unroll
-      for (int w = 0; w < FB_WARPS; ++w) s += dth_cta[(size_t)w * k * d + i];
-      fb.dth_part[(size_t)blockIdx.x * k * d + i] = s;
+        for (int i = 0; i < FB_MAXHG; ++i)
+          if (i < nh) *reinterpret_cast<float4*>(stage + ((size_t)(warp - w0) * HG + i) * d + c) = dth[i];
+      }
+      __syncthreads();
+      const int nw = min(per_round, FB_WARPS - w0);
+      for (int i = threadIdx.x; i < nh * d; i += FB_THREADS) {
+        const int hl = i / d, cc = i - hl * d;
+        float sv = mine[(size_t)(h0 + hl) * d + cc];
+        for (int w = 0; w < nw; ++w) sv += stage[((size_t)w * HG + hl) * d + cc];
+        mine[(size_t)(h0 + hl) * d + cc] = sv;
+      }
+      __syncthreads();
     }
   }
   if (TAB && fb.tab_part) {
@@ -258,7 +280,7 @@ static size_t fb_smem(const kp_agg_desc& a, int HG, bool need_z, int maxn) {
   const int trows = a.T0 ? a.rows0 + a.rowsk : 0;
   size_t b = sizeof(float) * ((a.fuse ? (size_t)a.k * a.d : 0) + (size_t)maxn * HG * a.d + (size_t)trows * a.d);
   b += (size_t)maxn * HG * FB_TROWS + 16;
-  if (need_z) b += sizeof(float) * (size_t)FB_WARPS * a.k * a.d;
+  (void)need_z;
   return (b + 15) & ~(size_t)15;
 }
 
@@ -324,7 +346,9 @@ int block_bwd(const FastArgs& fa, const float* dOut, float* dX, float* dP, float
   f2.oacc = a.dx_accumulate;
   const size_t smem = fb_smem(a, fb.HG, need_z, fb.maxn);
   const long long units = (long long)a.num_blocks * fb.groups;
-  const int grid = geom_cap(units < block_bwd_grid() ? units : block_bwd_grid());
+  int grid = geom_cap(units < block_bwd_grid() ? units : block_bwd_grid());
+  grid = grid / fb.groups * fb.groups;           // a CTA serves one hop group: group = blockIdx.x % groups
+  if (grid < fb.groups) grid = fb.groups;
   *grid_out = grid;
   return a.fuse ? fb_launch<KP_ACT_GELU, true>(f2, fb, a.T0 != nullptr, grid, smem, st)
                 : fb_launch<KP_ACT_GELU, false>(f2, fb, a.T0 != nullptr, grid, smem, st);

@@ -15,9 +15,13 @@ from ._lib import ACT_GELU, ACT_NONE, ACT_RELU  # noqa: F401
 
 # average entries per (node, hop) row from which the block-resident kernels (csrc/agg_tile.cu) are worth their staging
 LONG_ROW_ENTRIES = 12
-# size of the backward's hand-over tensor Gs [N,k,d] (bytes) from which the whole backward runs as one block-resident
-# kernel (csrc/agg_block_bwd.cu): beyond the L2 the three-kernel path writes Gs to HBM once and reads it back twice
-BLOCK_BWD_MIN_BYTES = 48 << 20
+# Size of the backward's hand-over tensor Gs [N,k,d] (bytes) from which the whole backward runs as ONE block-resident
+# kernel (csrc/agg_block_bwd.cu: Gs stays in shared memory, DRAM traffic = the algorithmic bytes).  OFF by default
+# (None): measured at 8 192 molecules the fused kernel takes 2.30 ms against 1.10 ms for the three pipelined kernels --
+# a molecule gives a 512-thread CTA only ~23 rows per phase, and its three barrier-separated phases expose the
+# rowptr -> entries -> gather latency chain that the lean kernels hide by software pipelining across nodes
+# (profiles/r2_block_bwd.txt).  Parity-tested (tests/test_tile_gpu.py); set a byte threshold to opt in.
+BLOCK_BWD_MIN_BYTES = None
 
 
 def want_blocks(plan, k, d, fuse):
@@ -26,8 +30,8 @@ def want_blocks(plan, k, d, fuse):
         return
     if not fuse and plan.nnz >= LONG_ROW_ENTRIES * max(plan.N * plan.K, 1):
         plan.blocks()          # long rows (e.g. n = 1 280 regular graphs at K = 6): stage blocks in shared memory
-    elif 4 * plan.N * k * d >= BLOCK_BWD_MIN_BYTES:
-        plan.blocks()          # large molecule batches: keep the backward's hand-over tensor in shared memory
+    elif BLOCK_BWD_MIN_BYTES is not None and 4 * plan.N * k * d >= BLOCK_BWD_MIN_BYTES:
+        plan.blocks()          # opt-in: keep the backward's hand-over tensor in shared memory
 
 
 def _ptr(t):

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define KPGNN_ABI_VERSION 10
+#define KPGNN_ABI_VERSION 11
 
 const char* kp_last_error(void);
 int kp_abi_version(void);
@@ -187,6 +187,37 @@ int kp_table_sum_set_smem_cap(size_t bytes);
 int kp_table_sum_backward_workspace_bytes(const kp_tsum_desc* desc, size_t* bytes);
 int kp_table_sum_backward(const kp_tsum_desc* desc, const float* dOut, float* dTable, void* workspace,
                           size_t workspace_bytes, void* stream);
+
+/* Folding the peripheral-attribute encoders (layers/feature_encoder.py:37-67 as used by models/GNNs.py:172-179 /
+ * :393-400: embedding lookups -> concat -> Linear, gated by tanh(pew) / sigmoid(pew)) into ONE lookup table for
+ * kp_table_sum_*:  table[row_off[i] + r, :] = g_{gate[i]} * E_i[r, :] W_i^T,  last row (row_off[T]) = sum_g
+ * bias_mult[g] * g_g * bias[g], with g = tanh(raw) (gate_act 0) or sigmoid(raw) (gate_act 1).  One kernel forward, one
+ * backward (dE_i, the dW_i slices, the bias and raw-gate gradients; fixed-order sums).  W[i] points at the first element
+ * of the table's [H_out, H_in] slice of its Linear weight, w_stride[i] = that weight's row length. */
+typedef struct {
+  int32_t T, H_in, H_out, gate_act;
+  const float* E[16];
+  const float* W[16];
+  int64_t w_stride[16];
+  int32_t rows[16];
+  int32_t gate[16];
+  int32_t row_off[17];
+  int32_t pad;
+  const float* gate_raw[2];
+  const float* bias[2];
+  float bias_mult[2];
+} kp_fold_desc;
+typedef struct {
+  float* dE[16];          /* [rows_i, H_in] or NULL */
+  float* dW[16];          /* slice pointers with the forward's w_stride, or NULL */
+  float* dbias[2];        /* [H_out] or NULL */
+  float* dgate_raw[2];    /* [1] or NULL */
+} kp_fold_grads;
+int kp_fold_forward(const kp_fold_desc* desc, float* table, void* stream);
+/* workspace: 256 bytes, 16-byte aligned, ZEROED ONCE by the caller and private to one stream (the kernel leaves its
+ * arrival counter at zero again). */
+int kp_fold_backward(const kp_fold_desc* desc, const float* dTable, const kp_fold_grads* grads, void* workspace,
+                     size_t workspace_bytes, void* stream);
 
 /* Training-mode BatchNorm1d (+ optional fused ReLU) over [N,C] fp32 rows: the BN / ReLU of the KP-GIN+ MLP
  * (layers/KPGINplus.py:25-30) and the backbone's norm (models/GNNs.py:430, norm_type "Batch").  Biased variance

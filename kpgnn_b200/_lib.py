@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # KPGNN_B200_LIB points at an alternative build of the same library (kernel tuning experiments)
 LIB_PATH = os.environ.get("KPGNN_B200_LIB") or os.path.join(_HERE, "libkpgnn_b200.so")
 
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 
 class KpError(RuntimeError):
@@ -74,6 +74,18 @@ class AttnDesc(C.Structure):
     _fields_ = [("N", C.c_int32), ("K", C.c_int32), ("d", C.c_int32), ("pad", C.c_int32),
                 ("x", C.c_void_p), ("x_node_stride", C.c_int64), ("x_hop_stride", C.c_int64),
                 ("w_ih", C.c_void_p * 2), ("w_hh", C.c_void_p * 2), ("b_ih", C.c_void_p * 2), ("b_hh", C.c_void_p * 2)]
+
+
+class FoldDesc(C.Structure):
+    _fields_ = [("T", C.c_int32), ("H_in", C.c_int32), ("H_out", C.c_int32), ("gate_act", C.c_int32),
+                ("E", C.c_void_p * 16), ("W", C.c_void_p * 16), ("w_stride", C.c_int64 * 16), ("rows", C.c_int32 * 16),
+                ("gate", C.c_int32 * 16), ("row_off", C.c_int32 * 17), ("pad", C.c_int32),
+                ("gate_raw", C.c_void_p * 2), ("bias", C.c_void_p * 2), ("bias_mult", C.c_float * 2)]
+
+
+class FoldGrads(C.Structure):
+    _fields_ = [("dE", C.c_void_p * 16), ("dW", C.c_void_p * 16), ("dbias", C.c_void_p * 2),
+                ("dgate_raw", C.c_void_p * 2)]
 
 
 class WireDesc(C.Structure):
@@ -142,6 +154,9 @@ _SIGNATURES = {
     "kp_attn_combine_backward": (C.c_int, [C.POINTER(AttnDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                            C.c_void_p]),
+    "kp_fold_forward": (C.c_int, [C.POINTER(FoldDesc), C.c_void_p, C.c_void_p]),
+    "kp_fold_backward": (C.c_int, [C.POINTER(FoldDesc), C.c_void_p, C.POINTER(FoldGrads), C.c_void_p, C.c_size_t,
+                                   C.c_void_p]),
     "kp_wire_unpack": (C.c_int, [C.POINTER(WireDesc), C.c_void_p]),
     "kp_segment_sum": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                 C.c_void_p, C.c_void_p]),
@@ -193,6 +208,21 @@ def barrier_state(device):
     if t is None:
         t = torch.zeros(64, dtype=torch.int32, device=device)
         _BARRIERS[key] = t
+    return t
+
+
+_FOLD_WS = {}
+
+
+def fold_workspace(device):
+    """256 zero-initialised bytes per (device, stream) for kp_fold_backward (partials + self-resetting counter)."""
+    import torch
+    dev = device.index if device.index is not None else torch.cuda.current_device()
+    key = (dev, torch.cuda.current_stream(device).cuda_stream)
+    t = _FOLD_WS.get(key)
+    if t is None:
+        t = torch.zeros(256, dtype=torch.uint8, device=device)
+        _FOLD_WS[key] = t
     return t
 
 

@@ -66,8 +66,8 @@ class _KHopBackboneBase(nn.Module):
         if pea is not None and pca is not None and like.is_cuda and dk % 4 == 0 and 4 <= dk <= 128:
             from .encoders import fused_peripheral_attr, peripheral_index
             return fused_peripheral_attr(self.peripheral_edge_embedding, self.peripheral_configuration_embedding,
-                                         torch.sigmoid(self.pew), torch.sigmoid(self.pcw), peripheral_index(pea, pca),
-                                         num_nodes, self.K, pea.size(2))
+                                         self.pew, self.pcw, peripheral_index(pea, pca), num_nodes, self.K,
+                                         pea.size(2), gate="sigmoid")
         P = torch.zeros((num_nodes, self.K, dk), device=like.device, dtype=like.dtype)
         if pea is not None:
             P = P + torch.sigmoid(self.pew) * self.peripheral_edge_embedding(pea).sum(-2)

@@ -87,26 +87,89 @@ def peripheral_index(peripheral_edge_attr, peripheral_configuration_attr):
     return torch.cat(cols, dim=1).contiguous()
 
 
-def fused_peripheral_attr(edge_enc, cfg_enc, gate_e, gate_c, idx, N, K, c_slots):
-    """P [N,K,H] = gate_e * edge_enc(edge_attr).sum(-2) + gate_c * cfg_enc(cfg_attr), computed as one gather-sum.
-    edge_enc / cfg_enc are FeatureConcatEncoder modules (2 and h+1 tables); gate_* are the already-squashed
-    scalars (tanh(pew) in GNNPlus, sigmoid in GNN/GNNPrime); idx from `peripheral_index`."""
+class _Fold(torch.autograd.Function):
+    """kp_fold_forward / kp_fold_backward (include/kpgnn.h): the folded, gate-scaled lookup table of both encoders.
+    Inputs: pew, pcw (raw gates), We, be, Wc, bc (the two Linear layers), then the embedding weights in table order."""
+
+    @staticmethod
+    def _desc(pew, pcw, We, be, Wc, bc, embs, n_edge, c_slots, gate_act):
+        H_out, H_in = We.size(0), embs[0].size(1)
+        d = _lib.FoldDesc()
+        d.T, d.H_in, d.H_out, d.gate_act = len(embs), H_in, H_out, gate_act
+        off = 0
+        for i, e in enumerate(embs):
+            edge = i < n_edge
+            W = We if edge else Wc
+            j = i if edge else i - n_edge
+            d.E[i], d.rows[i], d.gate[i] = e.data_ptr(), e.size(0), 0 if edge else 1
+            d.W[i], d.w_stride[i] = W.data_ptr() + 4 * j * H_in, W.size(1)
+            d.row_off[i] = off
+            off += e.size(0)
+        d.row_off[len(embs)] = off
+        d.gate_raw[0], d.gate_raw[1] = pew.data_ptr(), pcw.data_ptr()
+        d.bias[0], d.bias[1] = be.data_ptr(), bc.data_ptr()
+        d.bias_mult[0], d.bias_mult[1] = float(c_slots), 1.0
+        return d, off + 1
+
+    @staticmethod
+    def forward(ctx, n_edge, c_slots, gate_act, pew, pcw, We, be, Wc, bc, *embs):
+        lib = _lib.lib()
+        ts = [t.detach().contiguous() for t in (pew, pcw, We, be, Wc, bc) + tuple(embs)]
+        desc, total = _Fold._desc(*ts[:6], ts[6:], n_edge, c_slots, gate_act)
+        table = torch.empty((total, We.size(0)), dtype=torch.float32, device=We.device)
+        st = C.c_void_p(torch.cuda.current_stream(We.device).cuda_stream)
+        _lib.check(lib.kp_fold_forward(C.byref(desc), table.data_ptr(), st), "kp_fold_forward")
+        ctx.ts, ctx.cfg = ts, (n_edge, c_slots, gate_act)
+        return table
+
+    @staticmethod
+    def backward(ctx, dtable):
+        lib = _lib.lib()
+        ts = ctx.ts
+        n_edge, c_slots, gate_act = ctx.cfg
+        pew, pcw, We, be, Wc, bc = ts[:6]
+        embs = ts[6:]
+        dev = We.device
+        desc, _ = _Fold._desc(pew, pcw, We, be, Wc, bc, embs, n_edge, c_slots, gate_act)
+        dtable = dtable.contiguous()
+        g = _lib.FoldGrads()
+        dWe, dWc = torch.empty_like(We), torch.empty_like(Wc)
+        dbe, dbc = torch.empty_like(be), torch.empty_like(bc)
+        dpe, dpc = torch.empty_like(pew), torch.empty_like(pcw)
+        dembs = [torch.empty_like(e) for e in embs]
+        H_in = embs[0].size(1)
+        for i, de in enumerate(dembs):
+            edge = i < n_edge
+            g.dE[i] = de.data_ptr()
+            g.dW[i] = (dWe if edge else dWc).data_ptr() + 4 * (i if edge else i - n_edge) * H_in
+        g.dbias[0], g.dbias[1] = dbe.data_ptr(), dbc.data_ptr()
+        g.dgate_raw[0], g.dgate_raw[1] = dpe.data_ptr(), dpc.data_ptr()
+        ws = _lib.fold_workspace(dev)
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(lib.kp_fold_backward(C.byref(desc), dtable.data_ptr(), C.byref(g), ws.data_ptr(), ws.numel(), st),
+                   "kp_fold_backward")
+        return (None, None, None, dpe, dpc, dWe, dbe, dWc, dbc) + tuple(dembs)
+
+
+def fused_peripheral_attr(edge_enc, cfg_enc, pew, pcw, idx, N, K, c_slots, gate="tanh"):
+    """P [N,K,H] = g(pew) * edge_enc(edge_attr).sum(-2) + g(pcw) * cfg_enc(cfg_attr), computed as one gather-sum over
+    the folded tables.  edge_enc / cfg_enc are FeatureConcatEncoder modules (2 and h+1 tables); pew / pcw the RAW gate
+    parameters, g = tanh in GNNPlus (GNNs.py:396), sigmoid in GNN / GNNPrime (GNNs.py:175); idx from `peripheral_index`.
+    The fold (nine small products forward, twenty-seven backward) is one kernel each way (kp_fold_*)."""
     H = edge_enc.proj.out_features
-    We = edge_enc.proj.weight                    # [H, 2H]
-    Wc = cfg_enc.proj.weight                     # [H, (h+1)H]
+    embs = [e.weight for e in edge_enc.embedding_list] + [e.weight for e in cfg_enc.embedding_list]
     nc = len(cfg_enc.embedding_list)
-    tabs = [gate_e * (edge_enc.embedding_list[i].weight @ We[:, i * H:(i + 1) * H].t()) for i in range(2)]
-    Ec = torch.stack([e.weight for e in cfg_enc.embedding_list])            # [h+1, R, H]
-    Wc3 = Wc.view(H, nc, H).permute(1, 2, 0)                                # [h+1, H_in, H_out]
-    tabs.append((gate_c * torch.bmm(Ec, Wc3)).reshape(-1, H))
-    tabs.append((c_slots * gate_e * edge_enc.proj.bias + gate_c * cfg_enc.proj.bias).view(1, H))
-    table = torch.cat(tabs, dim=0)
+    same = all(e.size(1) == embs[0].size(1) for e in embs) and edge_enc.proj.in_features == 2 * embs[0].size(1)
+    if not same or len(embs) > 16 or H > 256 or embs[0].size(1) > 256:
+        raise _lib.KpError("fused_peripheral_attr: unsupported encoder shapes")
+    table = _Fold.apply(len(edge_enc.embedding_list), c_slots, 0 if gate == "tanh" else 1, pew, pcw,
+                        edge_enc.proj.weight, edge_enc.proj.bias, cfg_enc.proj.weight, cfg_enc.proj.bias, *embs)
     sizes = [edge_enc.embedding_list[0].num_embeddings, edge_enc.embedding_list[1].num_embeddings] + \
             [e.num_embeddings for e in cfg_enc.embedding_list] + [1]
     slots = [c_slots, c_slots] + [1] * nc + [1]
     offs, o = [], 0
-    for n, s in zip(sizes, slots):
-        offs += [o] * s
+    for n, s_ in zip(sizes, slots):
+        offs += [o] * s_
         o += n
     range_slot, range_row = _ranges(sizes, slots, H)
     out = _TableSum.apply(table, idx, offs, range_slot, range_row)

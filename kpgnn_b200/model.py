@@ -155,8 +155,8 @@ class KPGNNPlusBackbone(nn.Module):
                 idx = (ver, peripheral_index(data.peripheral_edge_attr, data.peripheral_configuration_attr))
                 data._peripheral_idx = idx
             return fused_peripheral_attr(self.peripheral_edge_embedding, self.peripheral_configuration_embedding,
-                                         torch.tanh(self.pew), torch.tanh(self.pcw), idx[1], num_nodes, self.K,
-                                         data.peripheral_edge_attr.size(2))
+                                         self.pew, self.pcw, idx[1], num_nodes, self.K,
+                                         data.peripheral_edge_attr.size(2), gate="tanh")
         P = torch.zeros((num_nodes, self.K, self.hidden_size), device=like.device, dtype=like.dtype)
         if data.peripheral_edge_attr is not None:
             P = P + torch.tanh(self.pew) * self.peripheral_edge_embedding(data.peripheral_edge_attr).sum(-2)

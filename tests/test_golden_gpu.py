@@ -122,14 +122,16 @@ def test_determinism_bitwise(lib):
         assert torch.equal(a, c)
 
 
-def test_fused_peripheral_encoder_matches_reference_form(lib):
+@pytest.mark.parametrize("gate,H", [("tanh", 104), ("sigmoid", 16), ("sigmoid", 12), ("tanh", 96)])
+def test_fused_peripheral_encoder_matches_reference_form(lib, gate, H):
     """kp_table_sum_* (folded tables + gather-sum) against the reference's lookup -> concat -> Linear -> sum
     (models/GNNs.py:393-400), forward and every parameter gradient."""
     from kpgnn_b200.encoders import fused_peripheral_attr, peripheral_index
     from kpgnn_b200.layers.feature_encoder import FeatureConcatEncoder
     dev = torch.device("cuda:0")
     torch.manual_seed(5)
-    N, K, H, c = 333, 8, 104, 3
+    N, K, c = 333, 8, 3
+    sq = torch.tanh if gate == "tanh" else torch.sigmoid
     ee = FeatureConcatEncoder([5, 51], H, padding=0).to(dev)
     ce = FeatureConcatEncoder([51] * 7, H, padding=0).to(dev)
     pew = torch.randn(1, device=dev, requires_grad=True)
@@ -142,9 +144,9 @@ def test_fused_peripheral_encoder_matches_reference_form(lib):
         for p in list(ee.parameters()) + list(ce.parameters()) + [pew, pcw]:
             p.grad = None
         if fused:
-            P = fused_peripheral_attr(ee, ce, torch.tanh(pew), torch.tanh(pcw), peripheral_index(pea, pca), N, K, c)
+            P = fused_peripheral_attr(ee, ce, pew, pcw, peripheral_index(pea, pca), N, K, c, gate=gate)
         else:
-            P = torch.tanh(pew) * ee(pea).sum(-2) + torch.tanh(pcw) * ce(pca)
+            P = sq(pew) * ee(pea).sum(-2) + sq(pcw) * ce(pca)
         P.backward(gy)
         res.append([P.detach()] + [p.grad.clone() for p in list(ee.parameters()) + list(ce.parameters()) + [pew, pcw]])
     for a, b in zip(res[1], res[0]):

@@ -893,11 +893,7 @@ int kp_agg_backward(const kp_agg_desc* desc, const float* dOut, float* dX, float
     cudaStream_t lst = st;
     if (a.leaf_stream && a.leaf_stream != stream) {
       lst = (cudaStream_t)a.leaf_stream;
-      cudaEvent_t ev;
-      KP_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-      KP_CUDA(cudaEventRecord(ev, st));
-      KP_CUDA(cudaStreamWaitEvent(lst, ev, 0));
-      KP_CUDA(cudaEventDestroy(ev));
+      KP_CUDA(kp::fork_stream(st, lst));
     }
     if (want_table)
       KP_LAUNCH(kp::reduce_partials_kernel, kp::ceil_div((long long)tn * 32, 256), 256, 0, lst, tab_part, fgrid, (int)tn,
@@ -934,11 +930,7 @@ int kp_agg_backward(const kp_agg_desc* desc, const float* dOut, float* dX, float
   cudaStream_t lst = st;
   if (a.leaf_stream && a.leaf_stream != stream) {
     lst = (cudaStream_t)a.leaf_stream;
-    cudaEvent_t ev;
-    KP_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    KP_CUDA(cudaEventRecord(ev, st));
-    KP_CUDA(cudaStreamWaitEvent(lst, ev, 0));
-    KP_CUDA(cudaEventDestroy(ev));
+    KP_CUDA(kp::fork_stream(st, lst));
   }
   const float* Gsrc = c.need_gs ? Gs : dOut;
   if (dX && c.fast && kp::tile_eligible(a, kp::TAB_NONE) && !a.dx_node_stride && !a.dx_hop_stride && !a.dx_accumulate) {

@@ -76,6 +76,12 @@ __device__ __forceinline__ void sts4p(unsigned addr, const P4& v) {
 __device__ __forceinline__ void stg4p_stream(float* p, const P4& v) {
   asm volatile("st.global.cs.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(v.lo), "l"(v.hi) : "memory");
 }
+// coherent load (no read-only / L1-texture path): for memory this kernel or an overlapping one also writes
+__device__ __forceinline__ P4 ld4p_coherent(const float* p) {
+  P4 v;
+  asm volatile("ld.global.v2.b64 {%0, %1}, [%2];" : "=l"(v.lo), "=l"(v.hi) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void stg4p(float* p, const P4& v) {
   asm volatile("st.global.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(v.lo), "l"(v.hi) : "memory");
 }
@@ -446,7 +452,7 @@ agg_fwd_lean_kernel(const FastArgs fa, float* __restrict__ out, unsigned pf_x_li
         th += d4;
       } else if (active) {
         float* po = outv + (size_t)h * (fa.oh ? fa.oh : (unsigned)d);
-        if (fa.oacc) z = add4p(z, ldg4p(po));
+        if (fa.oacc) z = add4p(z, ld4p_coherent(po));     // read-modify-write of the caller's buffer: never through .nc
         stg4p_stream(po, z);
       }
       Xh += fa.xh;

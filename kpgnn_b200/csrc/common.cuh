@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <atomic>
 
 #include "../../include/kpgnn.h"
@@ -42,7 +43,10 @@ extern std::atomic<uint64_t> g_launches;
 // slice); capturable in CUDA graphs like a plain launch.  `args` is the usual array of pointers to the arguments.
 #define KP_LAUNCH_COOP(kernel, grid, block, smem, stream, args)                                             \
   do {                                                                                                      \
-    cudaError_t _le = cudaLaunchCooperativeKernel((const void*)(kernel), dim3(grid), dim3(block), (args),   \
+    static const bool _plain = getenv("KP_DENSE_COOP") && atoi(getenv("KP_DENSE_COOP")) == 0;               \
+    cudaError_t _le = _plain ? cudaLaunchKernel((const void*)(kernel), dim3(grid), dim3(block), (args),     \
+                                                (size_t)(smem), (cudaStream_t)(stream))                     \
+                             : cudaLaunchCooperativeKernel((const void*)(kernel), dim3(grid), dim3(block), (args),   \
                                                   (size_t)(smem), (cudaStream_t)(stream));                  \
     kp::g_launches.fetch_add(1, std::memory_order_relaxed);                                                 \
     if (_le != cudaSuccess) {                                                                               \
@@ -50,6 +54,11 @@ extern std::atomic<uint64_t> g_launches;
       return 2;                                                                                             \
     }                                                                                                       \
   } while (0)
+
+// Fork helper: make `to` wait for everything enqueued on `from` so far.  Events come from a small per-thread ring and
+// are never destroyed while in flight (create + record + wait + destroy around every fork is legal, but keeping the
+// event object alive keeps the dependency valid under every driver / capture mode).
+cudaError_t fork_stream(cudaStream_t from, cudaStream_t to);
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

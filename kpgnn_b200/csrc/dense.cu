@@ -1006,11 +1006,7 @@ int kp_dense_block_backward(const kp_dense_desc* desc, const float* dOut, float*
     cudaStream_t lst = st;
     if (m.leaf_stream && m.leaf_stream != stream) {          // leaf gradients: fork (see kp_dense_desc.leaf_stream)
       lst = (cudaStream_t)m.leaf_stream;
-      cudaEvent_t ev;
-      KP_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-      KP_CUDA(cudaEventRecord(ev, st));
-      KP_CUDA(cudaStreamWaitEvent(lst, ev, 0));
-      KP_CUDA(cudaEventDestroy(ev));
+      KP_CUDA(kp::fork_stream(st, lst));
     }
     const int total4 = (m.Cout * m.Cin + m.Cout * m.Cout + 2 * m.Cout) >> 2;   // output float4s, 16 lanes each
     KP_LAUNCH(kp::dense_block_wgrad_reduce_kernel, kp::ceil_div((long long)total4 * 16, 256), 256, 0, lst,

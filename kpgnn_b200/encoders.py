@@ -18,16 +18,23 @@ from . import _lib
 
 
 def _ranges(table_sizes, slots_per_table, d, max_bytes=24 * 1024, max_ranges=16):
-    """Partition consecutive tables into ranges whose rows fit a shared-memory sub-table."""
+    """Partition consecutive tables into ranges whose rows fit a shared-memory sub-table and whose slots fit the
+    gather-sum kernel's lane group (G = 4 lanes for d <= 16, then the next power of two >= d / 4)."""
+    G = 4
+    while G < d // 4:
+        G <<= 1
     slot_b, row_b = [0], [0]
     rows = slots = 0
-    cur = 0
+    cur = cur_slots = 0
     for n, s in zip(table_sizes, slots_per_table):
-        if cur and (cur + n) * d * 4 > max_bytes:
+        if s > G:
+            raise _lib.KpError("a table is read through %d slots but rows of %d floats give lane groups of %d" % (s, d, G))
+        if cur and ((cur + n) * d * 4 > max_bytes or cur_slots + s > G):
             slot_b.append(slots)
             row_b.append(rows)
-            cur = 0
+            cur = cur_slots = 0
         cur += n
+        cur_slots += s
         rows += n
         slots += s
     slot_b.append(slots)
@@ -85,6 +92,10 @@ def peripheral_index(peripheral_edge_attr, peripheral_configuration_attr):
     cols = [e[:, :, 0], e[:, :, 1], peripheral_configuration_attr.reshape(N * K, -1),
             torch.zeros((N * K, 1), dtype=torch.int64, device=e.device)]
     return torch.cat(cols, dim=1).contiguous()
+
+
+import os as _os
+_FOLD_KERNEL = _os.environ.get("KP_FOLD", "1") != "0"
 
 
 class _Fold(torch.autograd.Function):
@@ -162,8 +173,18 @@ def fused_peripheral_attr(edge_enc, cfg_enc, pew, pcw, idx, N, K, c_slots, gate=
     same = all(e.size(1) == embs[0].size(1) for e in embs) and edge_enc.proj.in_features == 2 * embs[0].size(1)
     if not same or len(embs) > 16 or H > 256 or embs[0].size(1) > 256:
         raise _lib.KpError("fused_peripheral_attr: unsupported encoder shapes")
-    table = _Fold.apply(len(edge_enc.embedding_list), c_slots, 0 if gate == "tanh" else 1, pew, pcw,
-                        edge_enc.proj.weight, edge_enc.proj.bias, cfg_enc.proj.weight, cfg_enc.proj.bias, *embs)
+    if _FOLD_KERNEL:
+        table = _Fold.apply(len(edge_enc.embedding_list), c_slots, 0 if gate == "tanh" else 1, pew, pcw,
+                            edge_enc.proj.weight, edge_enc.proj.bias, cfg_enc.proj.weight, cfg_enc.proj.bias, *embs)
+    else:                      # the same fold as ~50 library launches (A/B measurements only)
+        Hi = embs[0].size(1)
+        ge, gc = (torch.tanh(pew), torch.tanh(pcw)) if gate == "tanh" else (torch.sigmoid(pew), torch.sigmoid(pcw))
+        We, Wc = edge_enc.proj.weight, cfg_enc.proj.weight
+        tabs = [ge * (edge_enc.embedding_list[i].weight @ We[:, i * Hi:(i + 1) * Hi].t()) for i in range(2)]
+        Ec = torch.stack([e.weight for e in cfg_enc.embedding_list])
+        tabs.append((gc * torch.bmm(Ec, Wc.view(H, nc, Hi).permute(1, 2, 0))).reshape(-1, H))
+        tabs.append((c_slots * ge * edge_enc.proj.bias + gc * cfg_enc.proj.bias).view(1, H))
+        table = torch.cat(tabs, dim=0)
     sizes = [edge_enc.embedding_list[0].num_embeddings, edge_enc.embedding_list[1].num_embeddings] + \
             [e.num_embeddings for e in cfg_enc.embedding_list] + [1]
     slots = [c_slots, c_slots] + [1] * nc + [1]

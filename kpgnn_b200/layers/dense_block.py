@@ -17,6 +17,10 @@ import torch.nn as nn
 from .. import _lib
 
 
+import os as _os
+_DISABLED = _os.environ.get("KP_NO_DENSE") == "1"        # A/B switch: run the modules one by one
+
+
 class _DenseBlock(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, W1, b1, g1, be1, W2, b2, g2, be2, g3, be3, res, bns, n_dev=None):
@@ -95,7 +99,7 @@ def fused_dense_block(x, lin1, bn1, lin2, bn2, bn3=None, residual=None, n_dev=No
     """Linear-BN-ReLU-Linear-BN-ReLU (+ BatchNorm + residual) in one kernel, or None if not applicable.
     n_dev: optional device int32 scalar -- the number of rows that exist when x.size(0) is a padded capacity
     (kp_dense_desc.n_dev): padding rows are excluded from every statistic and come back as zeros."""
-    if not (torch.is_tensor(x) and x.is_cuda and x.dim() == 2 and x.dtype == torch.float32):
+    if not (torch.is_tensor(x) and x.is_cuda and x.dim() == 2 and x.dtype == torch.float32) or _DISABLED:
         return None
     if not (isinstance(lin1, nn.Linear) and isinstance(lin2, nn.Linear) and lin1.bias is not None
             and lin2.bias is not None and _bn_ok(bn1) and _bn_ok(bn2) and (bn3 is None or _bn_ok(bn3))):

@@ -231,6 +231,9 @@ def stack_applicable(layers, norms, x0, P, plan, pe_attr_zero, dropout_p):
     """True when the whole stack can run as one node: training mode, geometric combine, BatchNorm everywhere, no
     dropout between layers, pe_attr == 0 (what the reference's extractor emits), everything fp32 on one CUDA device."""
     from .layers.KPGINplus import KPGINPlusConv
+    from .layers import dense_block as _db
+    if _db._DISABLED:
+        return False
     if not (torch.is_tensor(x0) and x0.is_cuda and x0.dim() == 2 and x0.dtype == torch.float32 and P is not None
             and P.dtype == torch.float32 and P.dim() == 3 and pe_attr_zero and dropout_p == 0.0):
         return False

@@ -134,28 +134,39 @@ def test_captured_step_over_distinct_batches_matches_oracle(lib):
         return ob
     oparams = dict(ora.named_parameters())
     # ---- (a)
+    # The product path is bit-reproducible; the ORACLE on a GPU is not: its index_add_ sums are atomically ordered, and a
+    # batch that happens to hold an activation within rounding of a ReLU / |.| kink then yields one of two discrete
+    # gradients from run to run (observed on 2 of these 6 batches: the oracle differed from ITSELF by 2.7e-2 between
+    # runs while 48 replays of the product were bitwise identical).  So the oracle is evaluated up to 4 times per batch
+    # and the product has to match one of its outcomes.
     for i, hb in enumerate(hbs):
         reset()
         tr.prefetch(flats[i])
         mine = tr.step_e2e(flats[i])
-        for p in ora.parameters():
-            p.grad = None
+        mygrads = {n: (p.grad.clone() if p.grad is not None else torch.zeros_like(p)) for n, p in model.named_parameters()}
         ob = oracle_batch(hb)
-        loss = ol1(ora(ob), ob["y"])
-        loss.backward()
-        ref = float(loss.detach())
-        assert abs(mine - ref) <= 1e-5 * max(abs(ref), 1e-3), (i, mine, ref)
-        gmax = max(float(p.grad.abs().max()) for p in oparams.values() if p.grad is not None)
-        for n, p in model.named_parameters():
-            if n.endswith(("mlp.0.bias", "mlp.3.bias")):
-                continue
-            zero = torch.zeros_like(p)
-            g = p.grad if p.grad is not None else zero
-            og = oparams[n].grad if oparams[n].grad is not None else zero
-            err = rel_err(g, og, floor=1e-2 * gmax)
-            # the scalar gates pew / pcw are sums of ~N*K*H signed products that cancel to ~1 % of their running partial
-            # sums: fp32 summation order alone (the oracle's index_add_ is atomically ordered) moves them by ~1e-3
-            assert err < (1e-2 if p.numel() == 1 else 1e-4), (i, n, err)
+        worst = None
+        for attempt in range(4):
+            for p in ora.parameters():
+                p.grad = None
+            loss = ol1(ora(ob), ob["y"])
+            loss.backward()
+            ref = float(loss.detach())
+            assert abs(mine - ref) <= 1e-5 * max(abs(ref), 1e-3), (i, mine, ref)
+            gmax = max(float(p.grad.abs().max()) for p in oparams.values() if p.grad is not None)
+            worst = None
+            for n, g in mygrads.items():
+                if n.endswith(("mlp.0.bias", "mlp.3.bias")):
+                    continue
+                og = oparams[n].grad if oparams[n].grad is not None else torch.zeros_like(g)
+                err = rel_err(g, og, floor=1e-2 * gmax)
+                # the scalar gates pew / pcw are sums of ~N*K*H signed products that cancel to ~1 % of their running
+                # partial sums: fp32 summation order alone moves them by ~1e-3
+                if err >= (1e-2 if g.numel() == 1 else 1e-4) and (worst is None or err > worst[1]):
+                    worst = (n, err)
+            if worst is None:
+                break
+        assert worst is None, (i, worst)
     # ---- (b)
     reset()
     opt = torch.optim.Adam(ora.parameters(), lr=1e-3)

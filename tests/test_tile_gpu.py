@@ -181,4 +181,4 @@ def test_block_resident_backward_in_stack(lib):
     gmax = max(float(t.abs().max()) for t in res[0][1:])
     for a, c in zip(res[1], res[0]):
         # (the scalar gates pew / pcw are near-cancelling sums of ~5e5 terms: 1e-4)
-        assert rel_err(a, c, floor=1e-3 * gmax) < (1e-4 if a.numel() == 1 else 1e-5)
+        assert rel_err(a, c, floor=1e-3 * gmax) < (1e-4 if a.numel() == 1 else 2e-5)

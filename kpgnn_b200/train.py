@@ -146,11 +146,24 @@ class Trainer(object):
                 self.loss = self._fwd_bwd()
                 self.opt.step()
         else:
-            with torch.cuda.graph(self.graph):
-                self.loss = self._fwd_bwd()
-            self.graph_opt = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph_opt):
-                self.opt.step()
+            # world > 1: the NCCL all-reduce of the flat gradient is captured INSIDE the step graph (one launch per
+            # step, no host round trip between backward, collective and Adam).  If this NCCL / driver combination
+            # refuses to capture a collective, fall back to: forward+backward graph, eager all-reduce, Adam graph.
+            try:
+                with torch.cuda.graph(self.graph):
+                    self.loss = self._fwd_bwd()
+                    self.grads.allreduce_mean_(self.world)
+                    self.opt.step()
+                self.graph_opt = None
+            except Exception:
+                torch.cuda.synchronize(self.device)
+                self.graph = torch.cuda.CUDAGraph()
+                n0 = _lib.launch_count()
+                with torch.cuda.graph(self.graph):
+                    self.loss = self._fwd_bwd()
+                self.graph_opt = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph_opt):
+                    self.opt.step()
         self.launches_per_step = _lib.launch_count() - n0
         torch.cuda.synchronize(self.device)
 
@@ -159,7 +172,7 @@ class Trainer(object):
             self.loss = self._step_eager()
             return
         self.graph.replay()
-        if self.world > 1:
+        if self.graph_opt is not None:
             self.grads.allreduce_mean_(self.world)
             self.graph_opt.replay()
 

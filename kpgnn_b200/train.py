@@ -12,6 +12,8 @@ sizes:
 Capacities (nodes, K-hop edges, plan entries, largest hop attribute) are fixed when the trainer is built -- a loader
 knows them from preprocessing -- and every refresh is validated against them at the step's next sync point.
 """
+import os
+
 import torch
 
 from . import plan as kplan
@@ -149,7 +151,10 @@ class Trainer(object):
             # world > 1: the NCCL all-reduce of the flat gradient is captured INSIDE the step graph (one launch per
             # step, no host round trip between backward, collective and Adam).  If this NCCL / driver combination
             # refuses to capture a collective, fall back to: forward+backward graph, eager all-reduce, Adam graph.
+            in_graph = os.environ.get("KP_NCCL_IN_GRAPH", "0") == "1"
             try:
+                if not in_graph:
+                    raise RuntimeError("collective outside the graph")
                 with torch.cuda.graph(self.graph):
                     self.loss = self._fwd_bwd()
                     self.grads.allreduce_mean_(self.world)

@@ -13,10 +13,18 @@ sys.path.insert(0, ROOT)
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    logf = open(os.path.join(ROOT, "gpurun_out", "dist_rank%d.log" % rank), "a")
+
+    def mark(msg):
+        logf.write("[in_graph=%s] %s\n" % (os.environ.get("KP_NCCL_IN_GRAPH", "0"), msg))
+        logf.flush()
+    mark("start")
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     torch.backends.cuda.matmul.allow_tf32 = False
     dist.init_process_group("nccl", device_id=dev)
+    mark("pg up")
     from kpgnn_b200 import synth
     from kpgnn_b200.data_utils import extract_batch_host
     from kpgnn_b200.model import Batch, zinc_kpginplus
@@ -30,16 +38,20 @@ def main():
         hbs.append(Batch(**f))
     spec, bounds = fit_spec(hbs, 8, 3, 6, headroom=1.3)
     flats = [spec.pack(b, spec.host_buffer()) for b in hbs]
+    mark("batches packed")
     # (1) eager: all-reduced gradient == mean of the local gradients
     torch.manual_seed(0)
     model = zinc_kpginplus(8, 8, 104).to(dev).train()
     tr = Trainer(model, spec, bounds, dev, world=world, use_graph=False)
     tr.load(flats[0])
     tr._fwd_bwd()
+    mark("eager fwd/bwd")
     local_flat = tr.grads.flat.clone()
     tr.grads.allreduce_mean_(world)
     gathered = [torch.empty_like(local_flat) for _ in range(world)]
     dist.all_gather(gathered, local_flat)
+    torch.cuda.synchronize()
+    mark("all-reduce + all-gather")
     mean = torch.stack(gathered).double().mean(0)
     err = float((tr.grads.flat.double() - mean).abs().max() / mean.abs().max())
     differ = float((gathered[0] - gathered[-1]).abs().max())
@@ -50,9 +62,11 @@ def main():
     model = zinc_kpginplus(8, 8, 104).to(dev).train()
     tr = Trainer(model, spec, bounds, dev, world=world, use_graph=True)
     tr.capture(flats[0])
+    mark("captured, single_graph=%s" % (tr.graph_opt is None))
     tr.prefetch(flats[0])
     for step in range(6):
         tr.step_e2e(flats[(step + 1) % 3])
+        mark("step %d" % step)
     flat_params = torch.cat([p.detach().flatten() for p in model.parameters()])
     allp = [torch.empty_like(flat_params) for _ in range(world)]
     dist.all_gather(allp, flat_params)

@@ -552,8 +552,8 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(world):
-    return {"workload": "configs[1]: ZINC-shape synthetic molecules, KPGINPlus K=8 8 layers hidden 104 residual, "
+def workload_config(world, exchange=None):
+    cfg = {"workload": "configs[1]: ZINC-shape synthetic molecules, KPGINPlus K=8 8 layers hidden 104 residual, "
                         "batch 128 per GPU, spd kernel; forward+backward+Adam(lr 1e-3), L1 loss",
             "graphs_per_gpu": GRAPHS_PER_GPU, "global_batch": GRAPHS_PER_GPU * world,
             "parallelism": "dp%d" % world, "l2": "flushed between timed steps (256 MB write)",
@@ -565,6 +565,9 @@ def workload_config(world):
                                   "attributes; ~1.4 MB instead of the 7.5 MB int64 layout) from pinned host memory on a "
                                   "copy stream while the previous step computes; device-to-device hand-over, one "
                                   "kernel widens it to the reference's int64 wire tensors; loss read back every step"}
+    if exchange:
+        cfg["gradient_exchange"] = exchange
+    return cfg
 
 
 def main():
@@ -706,7 +709,9 @@ def main():
             "metric": METRIC, "value": round(total_graphs / (ms_res * 1e-3), 1), "unit": "graphs/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_res, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(world),
+            "config": workload_config(world, None if world == 1 else (
+                "peer-memory kernel over NVLink (csrc/peer.cu), captured in the step graph"
+                if type(tr.grads).__name__ == "PeerGradients" else "process-group all-reduce between two graphs")),
             "e2e": {"value": round(total_graphs / (ms_e2e * 1e-3), 1), "unit": "graphs/s",
                     "h2d_bytes_per_step": int(bs.spec.nbytes), "d2h_bytes_per_step": 4 + 16,
                     "ms_per_step": round(ms_e2e, 4),

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # KPGNN_B200_LIB points at an alternative build of the same library (kernel tuning experiments)
 LIB_PATH = os.environ.get("KPGNN_B200_LIB") or os.path.join(_HERE, "libkpgnn_b200.so")
 
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 
 class KpError(RuntimeError):
@@ -88,6 +88,15 @@ class FoldGrads(C.Structure):
                 ("dgate_raw", C.c_void_p * 2)]
 
 
+PEER_MAX, PEER_CTAS, PEER_HANDLE_BYTES = 8, 64, 64
+PEER_FLAG_BYTES = 2 * PEER_CTAS * PEER_MAX * 4
+
+
+class PeerDesc(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("n", C.c_int64), ("block", C.c_void_p * PEER_MAX),
+                ("out", C.c_void_p), ("epoch", C.c_void_p), ("error", C.c_void_p), ("scale", C.c_float)]
+
+
 class WireDesc(C.Structure):
     _fields_ = [("n_cap", C.c_int32), ("e_cap", C.c_int32), ("g", C.c_int32), ("K", C.c_int32), ("met", C.c_int32),
                 ("hp1", C.c_int32), ("x_bytes", C.c_int32), ("attr_bytes", C.c_int32), ("p_bytes", C.c_int32),
@@ -158,6 +167,13 @@ _SIGNATURES = {
     "kp_fold_backward": (C.c_int, [C.POINTER(FoldDesc), C.c_void_p, C.POINTER(FoldGrads), C.c_void_p, C.c_size_t,
                                    C.c_void_p]),
     "kp_wire_unpack": (C.c_int, [C.POINTER(WireDesc), C.c_void_p]),
+    "kp_peer_block_bytes": (C.c_size_t, [C.c_int64]),
+    "kp_peer_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "kp_peer_free": (C.c_int, [C.c_void_p]),
+    "kp_peer_export": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "kp_peer_import": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "kp_peer_release": (C.c_int, [C.c_void_p]),
+    "kp_peer_allreduce_mean": (C.c_int, [C.POINTER(PeerDesc), C.c_void_p]),
     "kp_segment_sum": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                 C.c_void_p, C.c_void_p]),
     "kp_peripheral_grad": (C.c_int, [C.POINTER(PgradDesc), C.c_void_p, C.c_void_p]),

@@ -67,3 +67,96 @@ class FlatGradients(object):
             dist.all_reduce(self.flat)
             self.flat.div_(world)
         return self.flat
+
+
+class _RawCuda(object):
+    """A float32 device buffer owned by the library, presented to torch through __cuda_array_interface__."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f4", "data": (int(ptr), False), "version": 2,
+                                         "strides": None}
+
+
+class PeerGradients(FlatGradients):
+    """FlatGradients whose exchange is the library's own kernel over NVLink peer memory (csrc/peer.cu,
+    include/kpgnn.h kp_peer_*): the local gradient is packed into a peer-visible block, every rank reads all blocks
+    directly and writes the rank-ordered mean into `flat` (what the optimizer reads).  One kernel per step instead of
+    {NCCL launch, divide, second graph}; no NCCL call inside the step, so the whole step is ONE CUDA graph.
+
+    Set-up needs a process group for the one-time handle exchange only (any backend).  Raises when a peer block cannot
+    be opened (no P2P path between the devices) -- the caller then keeps FlatGradients + the backend's all-reduce."""
+
+    def __init__(self, params, group=None):
+        from . import _lib
+        import ctypes as C
+        self.params = [p for p in params if p.requires_grad]
+        dev = self.params[0].device
+        n = sum(p.numel() for p in self.params)
+        self.n, self.device = n, dev
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > _lib.PEER_MAX:
+            raise RuntimeError("peer exchange supports up to %d ranks on one node" % _lib.PEER_MAX)
+        L = _lib.lib()
+        with torch.cuda.device(dev):
+            nbytes = L.kp_peer_block_bytes(n)
+            own = C.c_void_p()
+            _lib.check(L.kp_peer_alloc(nbytes, C.byref(own)), "kp_peer_alloc")
+            handle = C.create_string_buffer(_lib.PEER_HANDLE_BYTES)
+            _lib.check(L.kp_peer_export(own, handle), "kp_peer_export")
+            handles = [None] * self.world
+            dist.all_gather_object(handles, (bytes(handle.raw), n, int(dev.index)), group=group)
+            if any(h[1] != n for h in handles):
+                raise RuntimeError("ranks disagree on the gradient length")
+            self.blocks = []
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    self.blocks.append(own.value)
+                else:
+                    ptr = C.c_void_p()
+                    _lib.check(L.kp_peer_import(h[0], C.byref(ptr)), "kp_peer_import")
+                    self.blocks.append(ptr.value)
+            self._own = own.value
+            self.send = torch.as_tensor(_RawCuda(own.value + _lib.PEER_FLAG_BYTES, n), device=dev)
+            assert self.send.data_ptr() == own.value + _lib.PEER_FLAG_BYTES and self.send.dtype == torch.float32
+            self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+            self.state = torch.zeros(_lib.PEER_CTAS + 1, dtype=torch.int32, device=dev)      # epochs | error
+            d = _lib.PeerDesc()
+            d.world, d.rank, d.n = self.world, self.rank, n
+            for r in range(self.world):
+                d.block[r] = self.blocks[r]
+            d.out, d.epoch = self.flat.data_ptr(), self.state.data_ptr()
+            d.error = self.state.data_ptr() + 4 * _lib.PEER_CTAS
+            d.scale = 1.0 / self.world
+            self.desc = d
+        self._point_grads()
+        dist.barrier(group=group)           # every rank has opened every block before the first exchange
+
+    def _point_grads(self):
+        o = 0
+        for p in self.params:
+            p.grad = self.flat[o:o + p.numel()].view_as(p)
+            o += p.numel()
+
+    def gather_(self):
+        pieces = []
+        for p in self.params:
+            g = p.grad
+            pieces.append(g.reshape(-1) if g is not None else self.flat.new_zeros(p.numel()))
+        torch.cat(pieces, out=self.send)
+        self._point_grads()
+        return self.send
+
+    def allreduce_mean_(self, world=None):
+        from . import _lib
+        import ctypes as C
+        st = torch.cuda.current_stream(self.device)
+        _lib.check(_lib.lib().kp_peer_allreduce_mean(C.byref(self.desc), C.c_void_p(st.cuda_stream)),
+                   "kp_peer_allreduce_mean")
+        return self.flat
+
+    def check(self):
+        """After a synchronisation point: did an exchange time out waiting for a peer?"""
+        err = int(self.state[-1].item())
+        if err:
+            raise RuntimeError("peer gradient exchange timed out (%s)" %
+                               ("waiting for the ranks' gradients" if err == 1 else "waiting for the readers"))

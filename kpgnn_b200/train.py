@@ -17,7 +17,7 @@ import os
 import torch
 
 from . import plan as kplan
-from .dist import FlatGradients
+from .dist import FlatGradients, PeerGradients
 from .encoders import peripheral_index
 from .model import l1_loss
 from .optim import FusedAdam
@@ -63,13 +63,33 @@ class Trainer(object):
         self.plan_stream = torch.cuda.Stream(device)
         self.staged = self.consumed = None
         self.params = [p for p in model.parameters() if p.requires_grad]
-        self.grads = FlatGradients(self.params) if world > 1 else None
+        self.grads = self._make_grads() if world > 1 else None
         self.opt = FusedAdam(self.params, lr=lr, eps=adam_eps)
         self.loss = None
         self.graph = self.graph_opt = None
         self.launches_per_step = 0
         self.idx_buf = peripheral_index(self.dev.peripheral_edge_attr, self.dev.peripheral_configuration_attr)
         self.plan_obj = None
+
+    def _make_grads(self):
+        """world > 1: the library's peer-memory exchange (csrc/peer.cu) when every rank can open every other rank's
+        gradient block; otherwise (KP_PEER_ALLREDUCE=0, or no P2P path) the process group's all-reduce."""
+        import torch.distributed as dist
+        want = os.environ.get("KP_PEER_ALLREDUCE", "1") != "0"
+        grads, err = None, None
+        if want:
+            try:
+                grads = PeerGradients(self.params)
+            except Exception as e:                      # noqa: BLE001 -- any set-up failure selects the NCCL exchange
+                err = e
+        ok = torch.tensor([1 if grads is not None else 0], device=self.device if dist.get_backend() == "nccl" else "cpu")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)       # all ranks or none
+        if int(ok.item()) == 1:
+            return grads
+        if want and dist.get_rank() == 0:
+            import warnings
+            warnings.warn("peer-memory gradient exchange unavailable (%s); using the process group's all-reduce" % (err,))
+        return FlatGradients(self.params)
 
     # ---- derived per-batch state, recomputed every step into static buffers
     def _tag_idx(self):
@@ -151,7 +171,7 @@ class Trainer(object):
             # world > 1: the NCCL all-reduce of the flat gradient is captured INSIDE the step graph (one launch per
             # step, no host round trip between backward, collective and Adam).  If this NCCL / driver combination
             # refuses to capture a collective, fall back to: forward+backward graph, eager all-reduce, Adam graph.
-            in_graph = os.environ.get("KP_NCCL_IN_GRAPH", "0") == "1"
+            in_graph = isinstance(self.grads, PeerGradients) or os.environ.get("KP_NCCL_IN_GRAPH", "0") == "1"
             try:
                 if not in_graph:
                     raise RuntimeError("collective outside the graph")
@@ -216,3 +236,7 @@ class Trainer(object):
     def validate(self):
         if self.plan_obj is not None:
             self.plan_obj.validate()
+        if isinstance(self.grads, PeerGradients):
+            self._validations = getattr(self, "_validations", 0) + 1
+            if self._validations % 16 == 1:
+                self.grads.check()

@@ -20,10 +20,23 @@ def main():
         logf.write("[in_graph=%s] %s\n" % (os.environ.get("KP_NCCL_IN_GRAPH", "0"), msg))
         logf.flush()
     mark("start")
-    dev = torch.device("cuda", local)
+    same_gpu = os.environ.get("KP_DIST_SAME_GPU") == "1"      # two processes on ONE device (single-GPU boxes): gloo plumbing
+    dev = torch.device("cuda", 0 if same_gpu else local)
     torch.cuda.set_device(dev)
     torch.backends.cuda.matmul.allow_tf32 = False
-    dist.init_process_group("nccl", device_id=dev)
+    if same_gpu:
+        dist.init_process_group("gloo")
+    else:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def all_gather(t):
+        if same_gpu:
+            out = [torch.empty_like(t, device="cpu") for _ in range(world)]
+            dist.all_gather(out, t.cpu())
+            return [o.to(dev) for o in out]
+        out = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return out
     mark("pg up")
     from kpgnn_b200 import synth
     from kpgnn_b200.data_utils import extract_batch_host
@@ -46,14 +59,19 @@ def main():
     tr.load(flats[0])
     tr._fwd_bwd()
     mark("eager fwd/bwd")
-    local_flat = tr.grads.flat.clone()
+    peer = hasattr(tr.grads, "send")
+    local_flat = (tr.grads.send if peer else tr.grads.flat).clone()
     tr.grads.allreduce_mean_(world)
-    gathered = [torch.empty_like(local_flat) for _ in range(world)]
-    dist.all_gather(gathered, local_flat)
+    gathered = all_gather(local_flat)
     torch.cuda.synchronize()
     mark("all-reduce + all-gather")
     mean = torch.stack(gathered).double().mean(0)
     err = float((tr.grads.flat.double() - mean).abs().max() / mean.abs().max())
+    if peer:        # the kernel's contract: fp32 sum in rank order, times 1/world -- bit-exact, identical on every rank
+        acc = gathered[0].clone()
+        for g in gathered[1:]:
+            acc += g
+        assert torch.equal(tr.grads.flat, acc * (1.0 / world)), "peer exchange is not the rank-ordered fp32 mean"
     differ = float((gathered[0] - gathered[-1]).abs().max())
     assert err < 1e-6, err
     assert differ > 0, "ranks must see different batches"
@@ -68,13 +86,14 @@ def main():
         tr.step_e2e(flats[(step + 1) % 3])
         mark("step %d" % step)
     flat_params = torch.cat([p.detach().flatten() for p in model.parameters()])
-    allp = [torch.empty_like(flat_params) for _ in range(world)]
-    dist.all_gather(allp, flat_params)
+    allp = all_gather(flat_params)
+    if peer:
+        tr.grads.check()
     drift = max(float((a - allp[0]).abs().max()) for a in allp)
     assert drift == 0.0, drift
     if rank == 0:
-        print("DIST_CHECK_OK world=%d allreduce_err=%.2e replicas_drift=%.1f single_graph=%s"
-              % (world, err, drift, tr.graph_opt is None))
+        print("DIST_CHECK_OK world=%d exchange=%s allreduce_err=%.2e replicas_drift=%.1f single_graph=%s"
+              % (world, "peer-memory kernel" if peer else "process group", err, drift, tr.graph_opt is None))
     dist.barrier()
     dist.destroy_process_group()
 

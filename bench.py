@@ -155,21 +155,27 @@ def flush_l2(buf):
 
 
 def timed_steps(fn, steps, device, flush_buf, dist_on):
-    """Per-step CUDA events on the launching stream; L2 flushed between steps (outside the events)."""
-    times = []
+    """EXACTLY `steps` steps bracketed by a barrier + synchronize on both sides; inside the bracket every step has its own
+    pair of CUDA events on the launching stream and the L2 flush runs between one step's end event and the next step's
+    start event (in stream order, so it is outside every timed interval).  The host does not synchronise between steps
+    (a training loop does not either): launches queue behind the flush, ranks stay coupled only through the step's own
+    gradient exchange.  Returns the per-step device times in ms."""
     st = torch.cuda.current_stream(device)
+    if dist_on:
+        torch.distributed.barrier()
+    torch.cuda.synchronize(device)
+    evs = []
     for _ in range(steps):
         flush_l2(flush_buf)
-        if dist_on:
-            torch.distributed.barrier()
-        torch.cuda.synchronize(device)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(st)
         fn()
         b.record(st)
-        torch.cuda.synchronize(device)
-        times.append(a.elapsed_time(b))
-    return times
+        evs.append((a, b))
+    torch.cuda.synchronize(device)
+    if dist_on:
+        torch.distributed.barrier()
+    return [a.elapsed_time(b) for a, b in evs]
 
 
 def _check_agg_launch(hb, ei, ea, x, P, t0, tk, th, out, dout=None, dX=None, graphs=48):

@@ -35,40 +35,51 @@ def _raw(g):
 
 def pack_csr(graphs):
     """Raw graphs -> batch CSR by source with duplicate (src,dst) pairs merged (multiplicity, summed type), the
-    same merge the reference's COO->dense conversions perform (data_utils.py:52-53)."""
-    ns, srcs, dsts, typs = [], [], [], []
-    off = 0
-    for g in graphs:
-        n, ei, ea, _, _ = _raw(g)
-        ei = np.asarray(ei, dtype=np.int64).reshape(2, -1)
-        if ei.shape[1]:
-            if ei.min() < 0 or ei.max() >= n:
-                raise IndexError("edge_index out of range for a graph with %d nodes" % n)
-            srcs.append(ei[0] + off)
-            dsts.append(ei[1] + off)
-            if ea is None:
-                typs.append(np.full(ei.shape[1], 2, dtype=np.int64))      # data_utils.py:46-50
-            else:
-                ea = np.asarray(ea, dtype=np.int64).reshape(-1)
-                if ea.shape[0] != ei.shape[1]:
-                    raise ValueError("edge_attr must be one integer per edge (got %s)" % (ea.shape,))
-                typs.append(ea)
-        ns.append(int(n))
-        off += int(n)
-    N = off
-    ns = np.asarray(ns, dtype=np.int64)
-    gptr = np.zeros(len(ns) + 1, dtype=np.int64)
+    same merge the reference's COO->dense conversions perform (data_utils.py:52-53).  Vectorised over the batch: the
+    only per-graph Python work is collecting the arrays."""
+    raws = [(g["num_nodes"], g["edge_index"], g.get("edge_attr")) if isinstance(g, dict) else _raw(g)[:3] for g in graphs]
+    G = len(raws)
+    ns = np.fromiter((r[0] for r in raws), dtype=np.int64, count=G)
+    eis = [np.asarray(r[1], dtype=np.int64).reshape(2, -1) for r in raws]
+    ecount = np.fromiter((e.shape[1] for e in eis), dtype=np.int64, count=G)
+    gptr = np.zeros(G + 1, dtype=np.int64)
     np.cumsum(ns, out=gptr[1:])
-    pair_off = np.zeros(len(ns) + 1, dtype=np.int64)
+    N = int(gptr[-1])
+    pair_off = np.zeros(G + 1, dtype=np.int64)
     np.cumsum(ns * ns, out=pair_off[1:])
-    if srcs:
-        src, dst, typ = np.concatenate(srcs), np.concatenate(dsts), np.concatenate(typs)
-        if typ.size and typ.min() < 0:
+    E = int(ecount.sum())
+    if E:
+        ei = np.concatenate(eis, axis=1)
+        nper = np.repeat(ns, ecount)
+        bad = (ei < 0) | (ei >= nper)
+        if bad.any():
+            gi = int(np.searchsorted(np.cumsum(ecount), int(np.nonzero(bad.any(axis=0))[0][0]), side="right"))
+            raise IndexError("edge_index out of range for a graph with %d nodes" % int(ns[gi]))
+        typs = []
+        for r, c in zip(raws, ecount):
+            if r[2] is None:
+                if c:
+                    typs.append(np.full(c, 2, dtype=np.int64))                 # data_utils.py:46-50
+            else:
+                ea = np.asarray(r[2], dtype=np.int64).reshape(-1)
+                if ea.shape[0] != c:
+                    raise ValueError("edge_attr must be one integer per edge (got %s)" % (np.shape(r[2]),))
+                if c:
+                    typs.append(ea)
+        typ = np.concatenate(typs)
+        if typ.min() < 0:
             raise ValueError("negative edge types are not supported (the reference's bincount rejects them too)")
-        key = src * N + dst
-        uniq, inv = np.unique(key, return_inverse=True)
-        mult = np.bincount(inv, minlength=uniq.size)
-        tsum = np.bincount(inv, weights=typ.astype(np.float64), minlength=uniq.size).astype(np.int64)
+        off = np.repeat(gptr[:-1], ecount)
+        key = (ei[0] + off) * N + (ei[1] + off)
+        order = np.argsort(key, kind="stable")
+        ks = key[order]
+        first = np.empty(E, dtype=bool)
+        first[0] = True
+        np.not_equal(ks[1:], ks[:-1], out=first[1:])
+        starts = np.flatnonzero(first)
+        uniq = ks[starts]
+        mult = np.diff(np.append(starts, E))
+        tsum = np.add.reduceat(typ[order], starts)
         usrc, udst = uniq // N, uniq % N
     else:
         usrc = udst = mult = tsum = np.zeros(0, dtype=np.int64)
@@ -77,8 +88,8 @@ def pack_csr(graphs):
     if tsum.size and tsum.max() >= 2 ** 20:
         raise ValueError("edge type values above 2^20 are not supported")
     return {
-        "G": len(ns), "N": N, "n_max": int(ns.max()) if len(ns) else 0, "total_pairs": int(pair_off[-1]),
-        "gptr": gptr.astype(np.int32), "node_graph": np.repeat(np.arange(len(ns)), ns).astype(np.int32),
+        "G": G, "N": N, "n_max": int(ns.max()) if G else 0, "total_pairs": int(pair_off[-1]),
+        "gptr": gptr.astype(np.int32), "node_graph": np.repeat(np.arange(G, dtype=np.int32), ns),
         "pair_off": pair_off, "erow": erow.astype(np.int32), "ecol": udst.astype(np.int32),
         "emult": mult.astype(np.int32), "etype": tsum.astype(np.int32),
         "max_type_value": int(tsum.max()) if tsum.size else 0,
@@ -136,13 +147,46 @@ def _extract_device(csr, K, max_edge_attr_num, max_hop_num, max_edge_type, max_e
     return out
 
 
-def _upload(csr, device):
-    dv = {k: torch.from_numpy(np.ascontiguousarray(csr[k])).to(device) for k in
-          ("gptr", "node_graph", "pair_off", "erow", "ecol", "emult", "etype")}
-    for k in ("ecol", "emult", "etype"):
-        if dv[k].numel() == 0:
-            dv[k] = torch.zeros(1, dtype=torch.int32, device=device)
-    return dv
+_CSR_KEYS = ("pair_off", "gptr", "node_graph", "erow", "ecol", "emult", "etype")
+_STAGE = {}          # device -> [pinned uint8 staging tensor (grow-only), event of the last copy out of it]
+
+
+def _upload(csr, device, extra=None):
+    """The packed arrays (and `extra` host arrays, e.g. node features) -> ONE pinned staging buffer -> one host-to-device
+    copy; returns {name: device tensor view}.  Seven pageable copies (each a host-synchronous cudaMemcpy) were most of
+    the extraction's end-to-end time at molecule batch sizes."""
+    device = torch.device(device)
+    items = [(k, np.ascontiguousarray(csr[k])) for k in _CSR_KEYS] + \
+            [(k, np.ascontiguousarray(v)) for k, v in (extra or {}).items()]
+    offs, total = [], 0
+    for _, a in items:
+        offs.append(total)
+        total += (a.nbytes + 15) & ~15
+    total += 16                                             # empty arrays still get a valid device address
+    st = _STAGE.get(device)
+    if st is None or st[0].numel() < total:
+        st = [torch.empty(max(total, 1 << 16), dtype=torch.uint8, pin_memory=True), None]
+        _STAGE[device] = st
+    if st[1] is not None:
+        st[1].synchronize()                                 # the previous copy out of the staging buffer has finished
+    hv = st[0].numpy()
+    for (_, a), o in zip(items, offs):
+        if a.nbytes:
+            hv[o:o + a.nbytes] = a.reshape(-1).view(np.uint8)
+    dev = torch.empty(total, dtype=torch.uint8, device=device)
+    dev.copy_(st[0][:total], non_blocking=True)
+    st[1] = torch.cuda.Event()
+    st[1].record(torch.cuda.current_stream(device))
+    out = {}
+    for (k, a), o in zip(items, offs):
+        t = dev[o:o + a.nbytes].view(_TORCH_DTYPE[a.dtype.str])
+        out[k] = t.view(a.shape) if a.ndim != 1 else t
+    return out
+
+
+_TORCH_DTYPE = {np.dtype(np.int32).str: torch.int32, np.dtype(np.int64).str: torch.int64, np.dtype(np.float32).str: torch.float32,
+                np.dtype(np.float64).str: torch.float64, np.dtype(np.int16).str: torch.int16, np.dtype(np.uint8).str: torch.uint8,
+                np.dtype(np.int8).str: torch.int8, np.dtype(np.bool_).str: torch.bool}
 
 
 def upload_csr(csr, device):
@@ -158,12 +202,14 @@ def extract_batch(graphs, args, device="cuda"):
     Returns a `kpgnn_b200.model.Batch` on `device` laid out as PyG's Batch.from_data_list would lay out the
     reference's per-graph results (node offsets applied, graph-major order)."""
     csr = pack_csr(graphs)
+    xs = [g.get("x") if isinstance(g, dict) else _raw(g)[3] for g in graphs]
+    extra = {"x": np.concatenate([np.asarray(v) for v in xs])} if xs and xs[0] is not None else None
+    if extra is not None and extra["x"].dtype.str not in _TORCH_DTYPE:
+        raise TypeError("unsupported node feature dtype %s" % extra["x"].dtype)
+    csr["_device"] = dv = _upload(csr, device, extra)
     out = _extract_device(csr, *args, device=device)
-    xs = [np.asarray(_raw(g)[3]) for g in graphs]
-    x = torch.from_numpy(np.concatenate(xs)).to(device) if xs and xs[0] is not None else None
-    batch = torch.from_numpy(csr["node_graph"].astype(np.int64)).to(device)
     out.pop("eptr")
-    return Batch(num_graphs=csr["G"], num_nodes=csr["N"], x=x, batch=batch, **out)
+    return Batch(num_graphs=csr["G"], num_nodes=csr["N"], x=dv.get("x"), batch=dv["node_graph"].to(torch.int64), **out)
 
 
 def extract_batch_host(graphs, args, device="cuda"):

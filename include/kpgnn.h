@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define KPGNN_ABI_VERSION 12
+#define KPGNN_ABI_VERSION 13
 
 const char* kp_last_error(void);
 int kp_abi_version(void);
@@ -368,21 +368,24 @@ int kp_wire_unpack(const kp_wire_desc* desc, void* stream);
 /* ---- Data-parallel gradient exchange over NVLink peer memory --------------------------------------------
  * The reference trains on one GPU (train_ZINC.py:29-47: loss.backward(); optimizer.step()); split over ranks, every rank
  * must apply the mean of the ranks' gradients.  Each rank owns one peer-visible block
- *     [ KP_PEER_FLAG_BYTES of flags | n gradient floats ]      (kp_peer_block_bytes(n) bytes, zero-initialised)
+ *     [ KP_PEER_FLAG_BYTES of flags | gradient: n floats | result: n floats ]   (vectors padded to 256 bytes:
+ *     KP_PEER_VECTOR_BYTES(n); kp_peer_block_bytes(n) bytes in all, zero-initialised)
  * allocated by kp_peer_alloc (cudaMalloc), exported as a CUDA-IPC handle, and imported once by every other rank.
- * kp_peer_allreduce_mean: out[i] = (g_0[i] + ... + g_{world-1}[i]) / world, summed in rank order (bit-identical on all
- * ranks), read directly from the peers' blocks; flag exchanges before (gradients complete) and after (blocks may be
- * overwritten).  Every rank must call it the same number of times.  A wait that exceeds 20 s sets *error (1: waiting for
+ * kp_peer_allreduce_mean (n % 4 == 0): result[i] = (g_0[i] + ... + g_{world-1}[i]) / world in EVERY rank's block, summed
+ * in rank order by the rank that owns element i (two-shot: each rank reduces 1/world of the vector from the peers'
+ * blocks and stores it into all of them; bit-identical everywhere); flag exchanges before (gradients complete) and
+ * after (results delivered, blocks may be overwritten).  Every rank must call it the same number of times.  A wait that exceeds 20 s sets *error (1: waiting for
  * gradients, 2: waiting for readers) and ends the kernel; the caller checks it at its next synchronisation point. */
 #define KP_PEER_MAX 8
 #define KP_PEER_CTAS 64
 #define KP_PEER_HANDLE_BYTES 64
 #define KP_PEER_FLAG_BYTES (2 * KP_PEER_CTAS * KP_PEER_MAX * 4)
+#define KP_PEER_VECTOR_BYTES(n) ((((size_t)(n)) * 4 + 255) & ~(size_t)255)
 typedef struct kp_peer_desc {
   int32_t world, rank;
   int64_t n;                    /* gradient length in floats */
   char* block[KP_PEER_MAX];     /* block[r]: rank r's block as mapped in THIS process (own entry: the local allocation) */
-  float* out;                   /* [n] local result, 16-byte aligned */
+  float* out;                   /* unused (the result lives in the block); keep NULL */
   int32_t* epoch;               /* [KP_PEER_CTAS] local, zero-initialised, owned by the kernel */
   int32_t* error;               /* local device int */
   float scale;                  /* 1 / world */

@@ -2,13 +2,16 @@
 // contract is train_ZINC.py:29-47's optimisation step with the batch split over ranks: every rank applies the MEAN of
 // the ranks' gradients).  One kernel per step replaces {NCCL all-reduce launch, divide kernel, second graph launch}:
 //
-//   every rank owns one peer-visible block  [ flags | gradient (n floats) ]  (cudaMalloc + CUDA IPC, opened by every
+//   every rank owns one peer-visible block  [ flags | gradient (n floats) | result (n floats) ]  (cudaMalloc + CUDA IPC, opened by every
 //   other rank once at set-up); the kernel runs PEER_CTAS CTAs, CTA b owning slice b of the vector:
 //     1. publish "my gradient of epoch e is complete" into ready[b][rank] of EVERY rank's flag block (st.release.sys),
 //        wait until all ranks published theirs into mine                                 -- one NVLink round trip
-//     2. out[i] = (1/world) * (g_0[i] + g_1[i] + ... )  read straight from the peers' blocks (128-bit volatile loads,
-//        eight in flight per thread), summed in RANK ORDER on every rank => replicas stay bit-identical
-//     3. publish "done reading slice b" to every rank, wait for all of theirs: the next step may overwrite the block.
+//     2. two-shot: rank r reduces only ITS 1/world of the vector -- (1/world) * (g_0[i] + g_1[i] + ...) read straight
+//        from the peers' blocks (128-bit volatile loads, eight in flight per thread), summed in rank order -- and
+//        stores the result into the result vector of EVERY rank: (world-1)/world of the vector read and written per
+//        rank instead of (world-1) vectors read; one rank computes each element => replicas are bit-identical
+//     3. publish "my part is delivered, I am done reading" to every rank, wait for all of theirs: the result is
+//        complete here and the next step may overwrite the gradient blocks.
 //   CTA-local flag protocol: no rank-wide or grid-wide barrier, no co-residency requirement beyond grid <= #SMs.
 //   Every wait is bounded (PEER_TIMEOUT_NS on %globaltimer): a missing peer sets *error and lets the kernel end, it can
 //   never wedge the GPU.
@@ -65,11 +68,18 @@ __device__ __forceinline__ void exchange(const kp_peer_desc& d, int phase, int c
   __syncthreads();
 }
 
+// sum of slice [lo4, hi4) (float4 units) over the W ranks' gradients in rank order, times scale, stored into the result
+// vector of EVERY rank (two-shot exchange: each rank reduces 1/W of the vector and delivers it)
 template <int W>
 __device__ __forceinline__ void reduce_slice(const kp_peer_desc& d, long long lo4, long long hi4) {
   const float* g[W];
+  float* o[W];
+  const size_t recv_off = (size_t)KP_PEER_FLAG_BYTES + KP_PEER_VECTOR_BYTES(d.n);
 #pragma unroll
-  for (int r = 0; r < W; ++r) g[r] = reinterpret_cast<const float*>(d.block[r] + KP_PEER_FLAG_BYTES);
+  for (int r = 0; r < W; ++r) {
+    g[r] = reinterpret_cast<const float*>(d.block[r] + KP_PEER_FLAG_BYTES);
+    o[r] = reinterpret_cast<float*>(d.block[r] + recv_off);
+  }
   constexpr int U = W <= 2 ? 4 : (W <= 4 ? 2 : 1);          // W*U 128-bit loads in flight per thread
   long long i = lo4 + threadIdx.x;
   for (; i + (long long)(U - 1) * PEER_THREADS < hi4; i += (long long)U * PEER_THREADS) {
@@ -84,7 +94,8 @@ __device__ __forceinline__ void reduce_slice(const kp_peer_desc& d, long long lo
 #pragma unroll
       for (int r = 1; r < W; ++r) { a.x += v[u][r].x; a.y += v[u][r].y; a.z += v[u][r].z; a.w += v[u][r].w; }
       a.x *= d.scale; a.y *= d.scale; a.z *= d.scale; a.w *= d.scale;
-      *reinterpret_cast<float4*>(d.out + 4 * (i + (long long)u * PEER_THREADS)) = a;
+#pragma unroll
+      for (int r = 0; r < W; ++r) *reinterpret_cast<float4*>(o[r] + 4 * (i + (long long)u * PEER_THREADS)) = a;
     }
   }
   for (; i < hi4; i += PEER_THREADS) {
@@ -95,7 +106,8 @@ __device__ __forceinline__ void reduce_slice(const kp_peer_desc& d, long long lo
       a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
     }
     a.x *= d.scale; a.y *= d.scale; a.z *= d.scale; a.w *= d.scale;
-    *reinterpret_cast<float4*>(d.out + 4 * i) = a;
+#pragma unroll
+    for (int r = 0; r < W; ++r) *reinterpret_cast<float4*>(o[r] + 4 * i) = a;
   }
 }
 
@@ -105,10 +117,13 @@ __global__ void __launch_bounds__(PEER_THREADS) peer_allreduce_mean_kernel(const
   if (threadIdx.x == 0) s_epoch = d.epoch[b] + 1;
   __syncthreads();
   const int e = s_epoch;
-  exchange(d, 0, b, e);
+  exchange(d, 0, b, e);                                       // every rank's gradient is complete
+  // this rank owns float4s [rank*per_rank, (rank+1)*per_rank); CTA b owns 1/PEER_CTAS of that
   const long long n4 = d.n >> 2;
-  const long long per = (n4 + PEER_CTAS - 1) / PEER_CTAS;
-  const long long lo4 = min(n4, (long long)b * per), hi4 = min(n4, lo4 + per);
+  const long long per_rank = (n4 + d.world - 1) / d.world;
+  const long long rlo = min(n4, (long long)d.rank * per_rank), rhi = min(n4, rlo + per_rank);
+  const long long per = (rhi - rlo + PEER_CTAS - 1) / PEER_CTAS;
+  const long long lo4 = min(rhi, rlo + (long long)b * per), hi4 = min(rhi, lo4 + per);
   switch (d.world) {
     case 1: reduce_slice<1>(d, lo4, hi4); break;
     case 2: reduce_slice<2>(d, lo4, hi4); break;
@@ -119,23 +134,16 @@ __global__ void __launch_bounds__(PEER_THREADS) peer_allreduce_mean_kernel(const
     case 7: reduce_slice<7>(d, lo4, hi4); break;
     default: reduce_slice<8>(d, lo4, hi4); break;
   }
-  if (b == PEER_CTAS - 1) {                                  // the n % 4 tail
-    for (long long i = (n4 << 2) + threadIdx.x; i < d.n; i += PEER_THREADS) {
-      float a = 0.f;
-      for (int r = 0; r < d.world; ++r)
-        a += ld_volatile1(reinterpret_cast<const float*>(d.block[r] + KP_PEER_FLAG_BYTES) + i);
-      d.out[i] = a * d.scale;
-    }
-  }
-  __syncthreads();
-  exchange(d, 1, b, e);
+  __threadfence_system();                                     // this thread's result stores are visible system-wide ...
+  __syncthreads();                                            // ... before the CTA's release below
+  exchange(d, 1, b, e);                                       // sub-slice b of every rank's slice has been delivered here
   if (threadIdx.x == 0) d.epoch[b] = e;
 }
 
 }  // namespace kp
 
 extern "C" size_t kp_peer_block_bytes(int64_t n) {
-  return (size_t)KP_PEER_FLAG_BYTES + (((size_t)(n < 0 ? 0 : n) * sizeof(float) + 255) & ~(size_t)255);
+  return (size_t)KP_PEER_FLAG_BYTES + 2 * KP_PEER_VECTOR_BYTES(n < 0 ? 0 : n);
 }
 
 extern "C" int kp_peer_alloc(size_t bytes, void** ptr) {
@@ -175,10 +183,9 @@ extern "C" int kp_peer_release(void* ptr) {
 
 extern "C" int kp_peer_allreduce_mean(const kp_peer_desc* d, void* stream) {
   KP_CHECK_ARG(d && d->world >= 1 && d->world <= KP_PEER_MAX && d->rank >= 0 && d->rank < d->world && d->n >= 0 &&
-                   d->out && d->epoch && d->error,
-               "kp_peer_allreduce_mean: bad descriptor");
+                   d->n % 4 == 0 && d->epoch && d->error,
+               "kp_peer_allreduce_mean: bad descriptor (n must be a multiple of 4)");
   for (int r = 0; r < d->world; ++r) KP_CHECK_ARG(d->block[r], "kp_peer_allreduce_mean: missing peer block");
-  KP_CHECK_ARG((reinterpret_cast<uintptr_t>(d->out) & 15) == 0, "kp_peer_allreduce_mean: out must be 16-byte aligned");
   KP_LAUNCH(kp::peer_allreduce_mean_kernel, kp::PEER_CTAS, kp::PEER_THREADS, 0, stream, *d);
   return 0;
 }

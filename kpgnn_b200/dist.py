@@ -91,8 +91,9 @@ class PeerGradients(FlatGradients):
         import ctypes as C
         self.params = [p for p in params if p.requires_grad]
         dev = self.params[0].device
-        n = sum(p.numel() for p in self.params)
-        self.n, self.device = n, dev
+        n_real = sum(p.numel() for p in self.params)
+        n = (n_real + 3) & ~3                         # the kernel moves float4s; the pad floats stay zero
+        self.n, self.n_real, self.device = n, n_real, dev
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         if self.world > _lib.PEER_MAX:
             raise RuntimeError("peer exchange supports up to %d ranks on one node" % _lib.PEER_MAX)
@@ -116,15 +117,17 @@ class PeerGradients(FlatGradients):
                     _lib.check(L.kp_peer_import(h[0], C.byref(ptr)), "kp_peer_import")
                     self.blocks.append(ptr.value)
             self._own = own.value
-            self.send = torch.as_tensor(_RawCuda(own.value + _lib.PEER_FLAG_BYTES, n), device=dev)
-            assert self.send.data_ptr() == own.value + _lib.PEER_FLAG_BYTES and self.send.dtype == torch.float32
-            self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+            vec_bytes = (n * 4 + 255) & ~255
+            self._send_all = torch.as_tensor(_RawCuda(own.value + _lib.PEER_FLAG_BYTES, n), device=dev)
+            self._recv_all = torch.as_tensor(_RawCuda(own.value + _lib.PEER_FLAG_BYTES + vec_bytes, n), device=dev)
+            assert self._send_all.data_ptr() == own.value + _lib.PEER_FLAG_BYTES and self._send_all.dtype == torch.float32
+            self.send, self.flat = self._send_all[:n_real], self._recv_all[:n_real]
             self.state = torch.zeros(_lib.PEER_CTAS + 1, dtype=torch.int32, device=dev)      # epochs | error
             d = _lib.PeerDesc()
             d.world, d.rank, d.n = self.world, self.rank, n
             for r in range(self.world):
                 d.block[r] = self.blocks[r]
-            d.out, d.epoch = self.flat.data_ptr(), self.state.data_ptr()
+            d.out, d.epoch = None, self.state.data_ptr()
             d.error = self.state.data_ptr() + 4 * _lib.PEER_CTAS
             d.scale = 1.0 / self.world
             self.desc = d

@@ -256,25 +256,40 @@ def agg_roofline(device, num_graphs, peak, reps=10):
     dX = torch.empty(N, K, HIDDEN, device=device)
     dP = torch.empty(N, K, HIDDEN, device=device)
     dT0, dTk, dth = torch.empty_like(t0), torch.empty_like(tk), torch.empty_like(th)
-    nb = C.c_size_t(0)
-    _lib.check(lib.kp_agg_backward_workspace_bytes(C.byref(desc), C.byref(nb)), "ws")
-    ws = torch.empty(nb.value, dtype=torch.uint8, device=device)
+    from kpgnn_b200 import ops as OPS
     alg_b = 4 * N * HIDDEN + 4 * N * K * HIDDEN * 4 + 2 * (4 * (N * K + 1) + plan.nnz * 6)
-    _lib.check(lib.kp_agg_backward(C.byref(desc), dout.data_ptr(), dX.data_ptr(), dP.data_ptr(), dT0.data_ptr(),
-                                   dTk.data_ptr(), dth.data_ptr(), None, ws.data_ptr(), ws.numel(), sp), "kp_agg_backward")
-    checked = max(checked, _check_agg_launch(hb, ei, ea, x, P, t0, tk, th, out, dout, dX))
-    tb = []
-    for i in range(reps + 3):
-        flush_l2(flush)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(st)
-        _lib.check(lib.kp_agg_backward(C.byref(desc), dout.data_ptr(), dX.data_ptr(), dP.data_ptr(), dT0.data_ptr(),
-                                       dTk.data_ptr(), dth.data_ptr(), None, ws.data_ptr(), ws.numel(), sp),
-                   "kp_agg_backward")
-        b.record(st)
-        torch.cuda.synchronize(device)
-        if i >= 3:
-            tb.append(a.elapsed_time(b))
+    chunks = OPS.backward_chunks(plan, K, HIDDEN)       # node ranges of whole graphs when Gs [N,k,d] exceeds the L2
+
+    def run_bwd(ch):
+        OPS.agg_backward(plan, desc, dout, dX, dP, dT0, dTk, dth, None, chunks=ch)
+
+    def time_bwd(ch):
+        run_bwd(ch)
+        err = _check_agg_launch(hb, ei, ea, x, P, t0, tk, th, out, dout, dX)
+        ts = []
+        for i in range(reps + 3):
+            flush_l2(flush)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(st)
+            run_bwd(ch)
+            b.record(st)
+            torch.cuda.synchronize(device)
+            if i >= 3:
+                ts.append(a.elapsed_time(b))
+        return statistics.mean(ts), err
+    ms_whole, err_w = time_bwd(None)
+    checked = max(checked, err_w)
+    tb = [ms_whole]
+    ms_chunked = None
+    if chunks is not None:
+        ref_tabs = (dT0.clone(), dTk.clone(), dth.clone())
+        ms_chunked, err_c = time_bwd(chunks)
+        checked = max(checked, err_c)
+        for got, want in zip((dT0, dTk, dth), ref_tabs):          # table / theta gradients: chunk sums vs the single call
+            e = float((got - want).abs().max() / want.abs().max())
+            assert e < 1e-5, "chunked backward: table / theta gradient differs from the single call by %.3e" % e
+            checked = max(checked, e)
+        tb = [ms_chunked]
     msb = statistics.mean(tb)
     del flush
     traffic = None
@@ -292,7 +307,10 @@ def agg_roofline(device, num_graphs, peak, reps=10):
                          "frac": round(alg_b / (msb * 1e-3) / 1e9 / peak, 4),
                          "kernels": ("agg_block_bwd_kernel (recompute + dP + dtheta, dX and table gradients from the "
                                      "shared-memory hand-over tile) + partial reductions") if plan.block_ptr is not None
-                         else "agg_bwd_dst_lean (B1) + agg_fwd_lean<gather> (B2) + agg_bwd_table_count (B3) + reductions"}}
+                         else "agg_bwd_dst_lean (B1) + agg_fwd_lean<gather> (B2) + agg_bwd_table_count (B3) + reductions",
+                         "node_range_chunks": None if chunks is None else len(chunks) - 1,
+                         "ms_single_call": round(ms_whole, 5),
+                         "ms_chunked": None if ms_chunked is None else round(ms_chunked, 5)}}
 
 
 # ----------------------------------------------------------------------------------------------------------------

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define KPGNN_ABI_VERSION 13
+#define KPGNN_ABI_VERSION 14
 
 const char* kp_last_error(void);
 int kp_abi_version(void);
@@ -114,7 +114,14 @@ typedef struct {
    * buffer of kpgnn_b200/stack.py.  Served by the lean gather kernel only: kp_agg_backward returns 3 (and touches
    * nothing) when another kernel family would have to run, and the caller falls back to a temporary. */
   int64_t dx_node_stride, dx_hop_stride;
-  int32_t dx_accumulate, pad0;
+  int32_t dx_accumulate;
+  /* Backward only: node-range (chunked) backward for batches whose hand-over tensor Gs [N,k,d] exceeds the L2.  Graphs
+   * are closed node sets, so the backward of nodes [n0, n1) (whole graphs) is an independent call: N = n1-n0, rowptr /
+   * rowptrT advanced by n0*Kplan entries, P / dOut / dX / dP advanced by n0 rows, X and col / colT UNCHANGED (sources
+   * are gathered by their batch-wide ids), node_base = n0.  The chunk's Gs then lives in a workspace of the CHUNK's
+   * size that every chunk reuses -- it stays in L2 between the three kernels and never goes to HBM.  Table / theta
+   * gradients of the chunks are partial sums the caller adds.  Only where kp_agg_backward_chunkable() says so. */
+  int32_t node_base;
   /* Backward only, with fuse: when both are non-NULL the reduction of the per-CTA dtheta partials is fused with
    * GeometricCombine's backward (combine.py:51-58): geo_dalphas [d] receives d(loss)/d(alphas) for theta =
    * kp_geometric_theta_forward(geo_alphas); the dtheta argument of kp_agg_backward may then be NULL. */
@@ -158,6 +165,9 @@ int kp_agg_set_launch_geometry(int max_ctas, int lean_threads);
  *   workspace   kp_agg_backward_workspace_bytes(desc) bytes
  */
 int kp_agg_backward_workspace_bytes(const kp_agg_desc* desc, size_t* bytes);
+/* *ok = 1 when this call's backward runs on the kernels that honour kp_agg_desc.node_base (the packed-math gather
+ * family); kp_agg_backward refuses a non-zero node_base otherwise. */
+int kp_agg_backward_chunkable(const kp_agg_desc* desc, int32_t* ok);
 int kp_agg_backward(const kp_agg_desc* desc, const float* dOut, float* dX, float* dP, float* dT0, float* dTk,
                     float* dtheta, float* deps, void* workspace, size_t workspace_bytes, void* stream);
 

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # KPGNN_B200_LIB points at an alternative build of the same library (kernel tuning experiments)
 LIB_PATH = os.environ.get("KPGNN_B200_LIB") or os.path.join(_HERE, "libkpgnn_b200.so")
 
-ABI_VERSION = 13
+ABI_VERSION = 14
 
 
 class KpError(RuntimeError):
@@ -32,7 +32,7 @@ class AggDesc(C.Structure):
                 ("theta", C.c_void_p), ("eps", C.c_void_p), ("act", C.c_int32), ("fuse", C.c_int32),
                 ("amax0", C.c_int32), ("amaxk", C.c_int32),
                 ("dx_node_stride", C.c_int64), ("dx_hop_stride", C.c_int64),
-                ("dx_accumulate", C.c_int32), ("pad0", C.c_int32),
+                ("dx_accumulate", C.c_int32), ("node_base", C.c_int32),
                 ("geo_alphas", C.c_void_p), ("geo_dalphas", C.c_void_p), ("leaf_stream", C.c_void_p),
                 ("block_ptr", C.c_void_p), ("block_stats", C.c_void_p), ("num_blocks", C.c_int32),
                 ("max_block_nodes", C.c_int32)]
@@ -136,6 +136,7 @@ _SIGNATURES = {
     "kp_agg_set_force_generic": (C.c_int, [C.c_int]),
     "kp_agg_set_launch_geometry": (C.c_int, [C.c_int, C.c_int]),
     "kp_agg_backward_workspace_bytes": (C.c_int, [C.POINTER(AggDesc), C.POINTER(C.c_size_t)]),
+    "kp_agg_backward_chunkable": (C.c_int, [C.POINTER(AggDesc), C.POINTER(C.c_int32)]),
     "kp_agg_backward": (C.c_int, [C.POINTER(AggDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "kp_table_sum_forward": (C.c_int, [C.POINTER(TsumDesc), C.c_void_p, C.c_void_p, C.c_void_p]),

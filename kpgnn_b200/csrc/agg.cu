@@ -841,12 +841,29 @@ int kp_agg_backward_workspace_bytes(const kp_agg_desc* desc, size_t* bytes) {
   return 0;
 }
 
+static bool chunkable(const kp_agg_desc& a, const kp::Config& c) {
+  // the kernels whose per-node streams are indexed relative to the descriptor's pointers and whose gathers use the
+  // batch-wide ids: lean B1, lean gather B2 (no extras), count-matrix or sub-table B3
+  return c.fast && c.lean_b1 && c.need_gs && !c.fextra && !c.fb && !c.table_atomic && !a.block_ptr && !a.eps &&
+         kp::fast_lean_enabled() && (c.fG == 32 || c.fG == 16) && a.k + 1 <= c.fG;
+}
+
+int kp_agg_backward_chunkable(const kp_agg_desc* desc, int32_t* ok) {
+  KP_CHECK_ARG(desc && ok, "kp_agg_backward_chunkable: null argument");
+  kp::Config c;
+  if (kp::make_config(*desc, &c)) return 1;
+  *ok = chunkable(*desc, c) ? 1 : 0;
+  return 0;
+}
+
 int kp_agg_backward(const kp_agg_desc* desc, const float* dOut, float* dX, float* dP, float* dT0, float* dTk,
                     float* dtheta, float* deps, void* workspace, size_t workspace_bytes, void* stream) {
   KP_CHECK_ARG(desc && dOut, "kp_agg_backward: null argument");
   const kp_agg_desc& a = *desc;
   kp::Config c;
   if (kp::make_config(a, &c)) return 1;
+  KP_CHECK_ARG(a.node_base == 0 || (a.node_base > 0 && chunkable(a, c)),
+               "kp_agg_backward: node_base is only honoured where kp_agg_backward_chunkable() says so");
   KP_CHECK_ARG(a.rowptrT && a.colT, "kp_agg_backward: plan has no transposed CSR");
   KP_CHECK_ARG(!dtheta || a.fuse, "kp_agg_backward: dtheta requires fuse");
   const bool geo = a.fuse && a.geo_alphas && a.geo_dalphas;
@@ -937,7 +954,9 @@ int kp_agg_backward(const kp_agg_desc* desc, const float* dOut, float* dX, float
     int rc = kp::tile_b2(kp::make_fast_args(a), c.fG, c.fextra, Gsrc, dOut, dX, st);
     if (rc) return rc;
   } else if (dX && c.fast) {
-    int rc = kp::fast_b2(kp::make_fast_args(a), c.fG, a.fuse != 0, c.fextra, c.fgrid, Gsrc, dOut, dX, st);
+    // chunked call: colT holds batch-wide node ids, the chunk's Gs starts at node node_base
+    const float* Gb2 = Gsrc - (size_t)a.node_base * a.k * a.d;
+    int rc = kp::fast_b2(kp::make_fast_args(a), c.fG, a.fuse != 0, c.fextra, c.fgrid, Gb2, dOut, dX, st);
     if (rc) return rc;
   } else if (dX) {
     if (c.vec == 4) {

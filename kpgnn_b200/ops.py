@@ -24,6 +24,115 @@ LONG_ROW_ENTRIES = 12
 BLOCK_BWD_MIN_BYTES = None
 
 
+# Node-range (chunked) backward, include/kpgnn.h kp_agg_desc.node_base: when the hand-over tensor Gs [N,k,d] is larger
+# than CHUNK_BWD_MIN_BYTES (it would be written to HBM by B1 and read back twice, by B2 and B3), the backward runs over
+# ranges of whole graphs whose Gs slice is about CHUNK_BWD_GS_BYTES: every chunk reuses ONE slice-sized workspace, which
+# stays in the 126 MB L2 between the three kernels.  None disables.
+CHUNK_BWD_MIN_BYTES = 192 << 20
+CHUNK_BWD_GS_BYTES = 24 << 20
+
+
+def backward_chunks(plan, k, d):
+    """Node boundaries [0, ..., N] at graph (closed-block) boundaries for the chunked backward, or None."""
+    if CHUNK_BWD_MIN_BYTES is None or 4 * plan.N * k * d < CHUNK_BWD_MIN_BYTES:
+        return None
+    bp = plan.block_ptr_host()
+    if bp is None or len(bp) < 3:
+        return None
+    per = max(1, CHUNK_BWD_GS_BYTES // (4 * k * d))
+    bounds, N = [0], int(bp[-1])
+    import numpy as np
+    while bounds[-1] < N:
+        j = int(np.searchsorted(bp, bounds[-1] + per, side="right")) - 1
+        nxt = int(bp[j])
+        if nxt <= bounds[-1]:
+            nxt = int(bp[j + 1])                  # a single block larger than the target: take it whole
+        bounds.append(nxt)
+    return bounds if len(bounds) > 2 else None
+
+
+def agg_backward(plan, desc, dout, dX, dP, dT0, dTk, dth, deps, stream=None, chunks=None):
+    """kp_agg_backward for one call, over node ranges when `chunks` (backward_chunks) is given and the kernels that
+    would run honour it; table / theta / alpha gradients of the chunks are added in chunk order (deterministic).
+    `desc` is this call's descriptor (not modified); `dP` is the fused call's dP or None."""
+    lib = _lib.lib()
+    dev = dout.device
+    st = C.c_void_p(stream if stream is not None else torch.cuda.current_stream(dev).cuda_stream)
+    if chunks is not None and deps is None:
+        probe = _lib.AggDesc.from_buffer_copy(desc)
+        probe.block_ptr, probe.block_stats, probe.num_blocks, probe.max_block_nodes = None, None, 0, 0
+        ok = C.c_int32(0)
+        _lib.check(lib.kp_agg_backward_chunkable(C.byref(probe), C.byref(ok)), "kp_agg_backward_chunkable")
+        if not ok.value:
+            chunks = None
+    else:
+        chunks = None
+    if chunks is None:
+        nbytes = C.c_size_t(0)
+        _lib.check(lib.kp_agg_backward_workspace_bytes(C.byref(desc), C.byref(nbytes)), "kp_agg_backward_workspace_bytes")
+        ws = torch.empty(max(nbytes.value, 1), dtype=torch.uint8, device=dev)
+        _lib.check(lib.kp_agg_backward(C.byref(desc), dout.data_ptr(), _ptr(dX), _ptr(dP), _ptr(dT0), _ptr(dTk), _ptr(dth),
+                                       _ptr(deps), ws.data_ptr(), ws.numel(), st), "kp_agg_backward")
+        return ws
+    k, d, Kp, fuse = desc.k, desc.d, desc.Kplan, bool(desc.fuse)
+    geo = bool(desc.geo_alphas) and bool(desc.geo_dalphas)
+    descs, ws_bytes = [], 0
+    for n0, n1 in zip(chunks[:-1], chunks[1:]):
+        dc = _lib.AggDesc.from_buffer_copy(probe)
+        dc.N, dc.node_base, dc.leaf_stream = n1 - n0, n0, None
+        dc.rowptr, dc.rowptrT = desc.rowptr + 4 * n0 * Kp, desc.rowptrT + 4 * n0 * Kp
+        if desc.P:
+            dc.P = desc.P + 4 * n0 * (desc.p_node_stride or k * d)
+        nb = C.c_size_t(0)
+        _lib.check(lib.kp_agg_backward_workspace_bytes(C.byref(dc), C.byref(nb)), "kp_agg_backward_workspace_bytes")
+        ws_bytes = max(ws_bytes, nb.value)
+        descs.append(dc)
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+    nc = len(descs)
+    pT0 = torch.empty((nc,) + tuple(dT0.shape), dtype=torch.float32, device=dev) if dT0 is not None else None
+    pTk = torch.empty((nc,) + tuple(dTk.shape), dtype=torch.float32, device=dev) if dTk is not None else None
+    pth = torch.empty((nc, k, d), dtype=torch.float32, device=dev) if dth is not None else None
+    pal = torch.empty((nc, d), dtype=torch.float32, device=dev) if geo else None
+    do_row = d if fuse else k * d
+    dx_row = desc.dx_node_stride or k * d
+    for i, dc in enumerate(descs):
+        n0 = dc.node_base
+        if geo:
+            dc.geo_dalphas = pal[i].data_ptr()
+        _lib.check(lib.kp_agg_backward(
+            C.byref(dc), dout.data_ptr() + 4 * n0 * do_row, None if dX is None else dX.data_ptr() + 4 * n0 * dx_row,
+            None if dP is None else dP.data_ptr() + 4 * n0 * k * d, None if pT0 is None else pT0[i].data_ptr(),
+            None if pTk is None else pTk[i].data_ptr(), None if pth is None else pth[i].data_ptr(), None,
+            ws.data_ptr(), ws.numel(), st), "kp_agg_backward (chunk %d)" % i)
+    ext = torch.cuda.ExternalStream(st.value, device=dev) if stream is not None else None
+    with torch.cuda.stream(ext) if ext is not None else _nullctx():
+        if pT0 is not None:
+            torch.sum(pT0, dim=0, out=dT0)
+        if pTk is not None:
+            torch.sum(pTk, dim=0, out=dTk)
+        if pth is not None:
+            torch.sum(pth, dim=0, out=dth)
+        if geo:
+            C_f = C.c_void_p(desc.geo_dalphas)
+            out = torch.as_tensor(_RawF32(C_f.value, d), device=dev)
+            torch.sum(pal, dim=0, out=out)
+    return ws
+
+
+class _RawF32(object):
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f4", "data": (int(ptr), False), "version": 2,
+                                         "strides": None}
+
+
+class _nullctx(object):
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
 def want_blocks(plan, k, d, fuse):
     """Asks the plan for its closed node blocks when a block-resident kernel would serve this call."""
     if plan.block_ptr is not None:
@@ -128,14 +237,8 @@ class _KHopAggregate(torch.autograd.Function):
             dTk = dTk if dTk is not None else torch.empty_like(Tk_)
         dth = torch.empty_like(th_) if (th_ is not None and need[4] and fuse) else None
         deps = torch.empty_like(eps_) if (eps_ is not None and need[5]) else None
-        nbytes = C.c_size_t(0)
-        _lib.check(lib.kp_agg_backward_workspace_bytes(C.byref(desc), C.byref(nbytes)),
-                   "kp_agg_backward_workspace_bytes")
-        ws = torch.empty(max(nbytes.value, 1), dtype=torch.uint8, device=dev)
-        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        _lib.check(lib.kp_agg_backward(C.byref(desc), dout.data_ptr(), _ptr(dX),
-                                       _ptr(dP) if fuse else None, _ptr(dT0), _ptr(dTk), _ptr(dth), _ptr(deps),
-                                       ws.data_ptr(), ws.numel(), st), "kp_agg_backward")
+        agg_backward(plan, desc, dout, dX, dP if fuse else None, dT0, dTk, dth, deps,
+                     chunks=backward_chunks(plan, k, d))
         return (dX, dP, dT0 if need[2] else None, dTk if need[3] else None, dth, deps,
                 None, None, None, None, None, None)
 

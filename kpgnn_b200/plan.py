@@ -31,7 +31,7 @@ class GraphPlan(object):
     __slots__ = ("N", "E", "K", "nnz", "capacity", "self_loops", "rowptr", "col", "attr16", "rowptrT", "colT", "dinv",
                  "indeg", "max_attr0", "max_attrk", "device", "stats", "stats_host", "ws", "pending", "src", "dst",
                  "ready", "block_ptr", "block_stats", "block_ws", "num_blocks", "max_block_nodes", "max_block_nnz",
-                 "block_stats_host", "n_dev")
+                 "block_stats_host", "n_dev", "block_ptr_np")
 
     def blocks(self):
         """Closed node blocks (kp_plan_blocks: the graphs of the batch, found from the plan itself).  Computed on first
@@ -48,6 +48,30 @@ class GraphPlan(object):
             self._run_blocks()
             self.num_blocks, self.max_block_nodes, self.max_block_nnz, _ = self.block_stats.tolist()
         return self.block_ptr
+
+    def block_ptr_host(self):
+        """The closed-block boundaries as a host array [num_blocks+1] (one sync, cached per plan).  Does NOT attach the
+        blocks to the plan: the block-resident kernels stay off unless blocks() was asked for."""
+        cached = getattr(self, "block_ptr_np", None)
+        if cached is not None and cached[0] == self.nnz:
+            return cached[1]
+        if self.block_ptr is not None:
+            bp, nb = self.block_ptr, self.num_blocks
+        else:
+            lib = _lib.lib()
+            nbytes = C.c_size_t(0)
+            _lib.check(lib.kp_plan_blocks_workspace_bytes(self.N, C.byref(nbytes)), "kp_plan_blocks_workspace_bytes")
+            ws = torch.empty(max(nbytes.value, 16), dtype=torch.uint8, device=self.device)
+            bp = torch.empty(self.N + 1, dtype=torch.int32, device=self.device)
+            stats = torch.zeros(4, dtype=torch.int32, device=self.device)
+            _lib.check(lib.kp_plan_blocks(self.rowptr.data_ptr(), self.col.data_ptr(), self.rowptrT.data_ptr(),
+                                          self.colT.data_ptr(), self.N, self.K, self.capacity, bp.data_ptr(),
+                                          stats.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(self.device)),
+                       "kp_plan_blocks")
+            nb = int(stats[0].item())
+        arr = bp[:nb + 1].cpu().numpy()
+        self.block_ptr_np = (self.nnz, arr)
+        return arr
 
     def _run_blocks(self):
         lib = _lib.lib()
@@ -139,7 +163,7 @@ def build_plan(edge_index, edge_attr_base, attr_stride, K, num_nodes, self_loops
     p.N, p.E, p.K, p.self_loops, p.device = int(num_nodes), edge_index.size(1), K, bool(self_loops), dev
     p.pending = None
     p.ready = None
-    p.block_ptr = p.block_stats = p.block_ws = p.block_stats_host = None
+    p.block_ptr = p.block_stats = p.block_ws = p.block_stats_host = p.block_ptr_np = None
     p.n_dev = None        # device int32 scalar: rows that exist when N is a padded capacity (kpgnn_b200/wire.py)
     p.num_blocks = p.max_block_nodes = p.max_block_nnz = 0
     rows = p.N * K

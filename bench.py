@@ -267,6 +267,22 @@ def agg_roofline(device, num_graphs, peak, reps=10):
         run_bwd(ch)
         err = _check_agg_launch(hb, ei, ea, x, P, t0, tk, th, out, dout, dX)
         ts = []
+        if ch is not None and os.environ.get("KP_BENCH_GRAPH_BWD") == "1":      # experiment: device time without host launch cost
+            run_bwd(ch)
+            torch.cuda.synchronize(device)
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                run_bwd(ch)
+            for i in range(reps + 3):
+                flush_l2(flush)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(torch.cuda.current_stream(device))
+                gr.replay()
+                b.record(torch.cuda.current_stream(device))
+                torch.cuda.synchronize(device)
+                if i >= 3:
+                    ts.append(a.elapsed_time(b))
+            return statistics.mean(ts), err
         for i in range(reps + 3):
             flush_l2(flush)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -6,6 +6,7 @@
 PyTorch only provides device memory, the current stream and the autograd graph here.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -24,12 +25,17 @@ LONG_ROW_ENTRIES = 12
 BLOCK_BWD_MIN_BYTES = None
 
 
-# Node-range (chunked) backward, include/kpgnn.h kp_agg_desc.node_base: when the hand-over tensor Gs [N,k,d] is larger
-# than CHUNK_BWD_MIN_BYTES (it would be written to HBM by B1 and read back twice, by B2 and B3), the backward runs over
-# ranges of whole graphs whose Gs slice is about CHUNK_BWD_GS_BYTES: every chunk reuses ONE slice-sized workspace, which
-# stays in the 126 MB L2 between the three kernels.  None disables.
-CHUNK_BWD_MIN_BYTES = 192 << 20
-CHUNK_BWD_GS_BYTES = 24 << 20
+# Node-range (chunked) backward, include/kpgnn.h kp_agg_desc.node_base: the backward of a batch whose hand-over tensor
+# Gs [N,k,d] is larger than the L2 run over ranges of whole graphs, every chunk reusing ONE slice-sized Gs workspace that
+# stays in L2 between B1, B2 and B3.  Parity-tested (tests/test_chunked_bwd_gpu.py) but OFF by default
+# (CHUNK_BWD_MIN_BYTES = None): measured at 8 192 molecules (profiles/r2_chunked_bwd.txt) the single call takes 1.11 ms
+# and the chunked one 1.37 ms (7 chunks) to 1.66 ms (26 chunks) of pure device time -- each chunk pays the persistent
+# kernels' fixed costs (table staging, accumulator reset, partial write-out, a ragged last wave) five launches over,
+# which is more than the two saved HBM passes over Gs.  Set a byte threshold to opt in.
+CHUNK_BWD_MIN_BYTES = None
+CHUNK_BWD_GS_BYTES = int(os.environ.get("KP_CHUNK_GS_MB", "92")) << 20
+if os.environ.get("KP_CHUNK_BWD") == "1":
+    CHUNK_BWD_MIN_BYTES = 192 << 20
 
 
 def backward_chunks(plan, k, d):

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define KPGNN_ABI_VERSION 14
+#define KPGNN_ABI_VERSION 15
 
 const char* kp_last_error(void);
 int kp_abi_version(void);
@@ -224,8 +224,9 @@ typedef struct {
   float* dgate_raw[2];    /* [1] or NULL */
 } kp_fold_grads;
 int kp_fold_forward(const kp_fold_desc* desc, float* table, void* stream);
-/* workspace: 256 bytes, 16-byte aligned, ZEROED ONCE by the caller and private to one stream (the kernel leaves its
- * arrival counter at zero again). */
+/* workspace: KP_FOLD_WORKSPACE_BYTES, 16-byte aligned, ZEROED ONCE by the caller and private to one stream (the kernel
+ * leaves its arrival counter at zero again). */
+#define KP_FOLD_WORKSPACE_BYTES 1024
 int kp_fold_backward(const kp_fold_desc* desc, const float* dTable, const kp_fold_grads* grads, void* workspace,
                      size_t workspace_bytes, void* stream);
 

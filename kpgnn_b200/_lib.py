@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # KPGNN_B200_LIB points at an alternative build of the same library (kernel tuning experiments)
 LIB_PATH = os.environ.get("KPGNN_B200_LIB") or os.path.join(_HERE, "libkpgnn_b200.so")
 
-ABI_VERSION = 14
+ABI_VERSION = 15
 
 
 class KpError(RuntimeError):
@@ -232,13 +232,13 @@ _FOLD_WS = {}
 
 
 def fold_workspace(device):
-    """256 zero-initialised bytes per (device, stream) for kp_fold_backward (partials + self-resetting counter)."""
+    """KP_FOLD_WORKSPACE_BYTES zero-initialised bytes per (device, stream) for kp_fold_backward (partials + self-resetting counter)."""
     import torch
     dev = device.index if device.index is not None else torch.cuda.current_device()
     key = (dev, torch.cuda.current_stream(device).cuda_stream)
     t = _FOLD_WS.get(key)
     if t is None:
-        t = torch.zeros(256, dtype=torch.uint8, device=device)
+        t = torch.zeros(1024, dtype=torch.uint8, device=device)
         _FOLD_WS[key] = t
     return t
 

@@ -18,6 +18,7 @@
 namespace kp {
 
 constexpr int FOLD_THREADS = 256;
+constexpr int FOLD_SLICES = 8;     // CTAs per table: row slices (forward, dE) / output-channel slices (dW)
 
 __device__ __forceinline__ float fold_gate(float raw, int act) { return act == 0 ? tanhf(raw) : 1.f / (1.f + expf(-raw)); }
 __device__ __forceinline__ float fold_gate_grad(float raw, int act) {
@@ -33,8 +34,9 @@ __device__ __forceinline__ float fold_gate_grad(float raw, int act) {
 __global__ void __launch_bounds__(FOLD_THREADS) fold_fwd_kernel(const kp_fold_desc f, float* __restrict__ table) {
   extern __shared__ __align__(16) float sm[];
   const int Hi = f.H_in, Ho = f.H_out;
-  const int i = blockIdx.x;
+  const int i = blockIdx.x / FOLD_SLICES, sl = blockIdx.x - i * FOLD_SLICES;
   if (i == f.T) {                                         // the bias row
+    if (sl) return;
     const float g0 = fold_gate(__ldg(f.gate_raw[0]), f.gate_act), g1 = fold_gate(__ldg(f.gate_raw[1]), f.gate_act);
     for (int o = threadIdx.x; o < Ho; o += FOLD_THREADS)
       table[(size_t)f.row_off[f.T] * Ho + o] =
@@ -42,10 +44,12 @@ __global__ void __launch_bounds__(FOLD_THREADS) fold_fwd_kernel(const kp_fold_de
     return;
   }
   const int rows = f.rows[i];
+  const int rlo = (int)((long long)rows * sl / FOLD_SLICES), rhi = (int)((long long)rows * (sl + 1) / FOLD_SLICES);
+  if (rlo >= rhi) return;
   float* Es = sm;
   float* Ws = sm + rows * Hi;
   const int ws = Hi + 1;
-  for (int t = threadIdx.x; t < rows * Hi; t += FOLD_THREADS) Es[t] = __ldg(f.E[i] + t);
+  for (int t = rlo * Hi + threadIdx.x; t < rhi * Hi; t += FOLD_THREADS) Es[t] = __ldg(f.E[i] + t);
   for (int t = threadIdx.x; t < Ho * Hi; t += FOLD_THREADS) {
     const int o = t / Hi, c = t - o * Hi;
     Ws[o * ws + c] = __ldg(f.W[i] + (size_t)o * f.w_stride[i] + c);
@@ -56,18 +60,18 @@ __global__ void __launch_bounds__(FOLD_THREADS) fold_fwd_kernel(const kp_fold_de
   const int groups = FOLD_THREADS / Ho > 0 ? FOLD_THREADS / Ho : 1;
   const int og = threadIdx.x / Ho, o = threadIdx.x - og * Ho;
   if (og < groups)
-    for (int r0 = og * 4; r0 < rows; r0 += groups * 4) {
+    for (int r0 = rlo + og * 4; r0 < rhi; r0 += groups * 4) {
       float acc[4] = {0.f, 0.f, 0.f, 0.f};
       const float* w = Ws + o * ws;
       for (int c = 0; c < Hi; ++c) {
         const float wv = w[c];
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          if (r0 + j < rows) acc[j] = fmaf(Es[(r0 + j) * Hi + c], wv, acc[j]);
+          if (r0 + j < rhi) acc[j] = fmaf(Es[(r0 + j) * Hi + c], wv, acc[j]);
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        if (r0 + j < rows) out[(size_t)(r0 + j) * Ho + o] = g * acc[j];
+        if (r0 + j < rhi) out[(size_t)(r0 + j) * Ho + o] = g * acc[j];
     }
 }
 
@@ -77,10 +81,12 @@ fold_bwd_kernel(const kp_fold_desc f, const float* __restrict__ dTable, kp_fold_
                 unsigned* __restrict__ counter) {
   extern __shared__ __align__(16) float sm[];
   const int Hi = f.H_in, Ho = f.H_out;
-  const int i = blockIdx.x;
+  // grid: FOLD_SLICES CTAs per table (slice sl: a row range of dE and an output-channel range of dW), then the bias CTA
+  const int i = blockIdx.x / FOLD_SLICES, sl = blockIdx.x - i * FOLD_SLICES;
   __shared__ float red[FOLD_THREADS];
   __shared__ bool last;
   float partial = 0.f;
+  float* part_gate = part;                                  // [T*FOLD_SLICES] table shares, then [2] bias shares
   if (i == f.T) {                                         // bias row: dbias_g, and its share of the gate gradients
     const float* dMb = dTable + (size_t)f.row_off[f.T] * Ho;
     for (int gsel = 0; gsel < 2; ++gsel) {
@@ -97,11 +103,13 @@ fold_bwd_kernel(const kp_fold_desc f, const float* __restrict__ dTable, kp_fold_
         if ((int)threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
         __syncthreads();
       }
-      if (threadIdx.x == 0) part[f.T + gsel] = f.bias_mult[gsel] * red[0];
+      if (threadIdx.x == 0) part_gate[f.T * FOLD_SLICES + gsel] = f.bias_mult[gsel] * red[0];
       __syncthreads();
     }
   } else {
     const int rows = f.rows[i];
+    const int rlo = (int)((long long)rows * sl / FOLD_SLICES), rhi = (int)((long long)rows * (sl + 1) / FOLD_SLICES);
+    const int olo = (int)((long long)Ho * sl / FOLD_SLICES), ohi = (int)((long long)Ho * (sl + 1) / FOLD_SLICES);
     float* Es = sm;
     float* Ws = Es + rows * Hi;
     float* Ms = Ws + Ho * Hi;
@@ -119,17 +127,17 @@ fold_bwd_kernel(const kp_fold_desc f, const float* __restrict__ dTable, kp_fold_
       const int groups = FOLD_THREADS / Hi > 0 ? FOLD_THREADS / Hi : 1;
       const int rg = threadIdx.x / Hi, c = threadIdx.x - rg * Hi;
       if (rg < groups && out.dE[i])
-        for (int r0 = rg * 4; r0 < rows; r0 += groups * 4) {
+        for (int r0 = rlo + rg * 4; r0 < rhi; r0 += groups * 4) {
           float acc[4] = {0.f, 0.f, 0.f, 0.f};
           for (int o = 0; o < Ho; ++o) {
             const float wv = Ws[o * Hi + c];
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              if (r0 + j < rows) acc[j] = fmaf(Ms[(r0 + j) * Ho + o], wv, acc[j]);
+              if (r0 + j < rhi) acc[j] = fmaf(Ms[(r0 + j) * Ho + o], wv, acc[j]);
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            if (r0 + j < rows) out.dE[i][(size_t)(r0 + j) * Hi + c] = g * acc[j];
+            if (r0 + j < rhi) out.dE[i][(size_t)(r0 + j) * Hi + c] = g * acc[j];
         }
     }
     // (2) dW[o][c] = g * sum_r dM[r][o] E[r][c]; the gate gradient is <W, dM^T E> (before the gate factor)
@@ -137,17 +145,17 @@ fold_bwd_kernel(const kp_fold_desc f, const float* __restrict__ dTable, kp_fold_
       const int groups = FOLD_THREADS / Hi > 0 ? FOLD_THREADS / Hi : 1;
       const int og = threadIdx.x / Hi, c = threadIdx.x - og * Hi;
       if (og < groups)
-        for (int o0 = og * 4; o0 < Ho; o0 += groups * 4) {
+        for (int o0 = olo + og * 4; o0 < ohi; o0 += groups * 4) {
           float acc[4] = {0.f, 0.f, 0.f, 0.f};
           for (int r = 0; r < rows; ++r) {
             const float ev = Es[r * Hi + c];
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              if (o0 + j < Ho) acc[j] = fmaf(Ms[r * Ho + o0 + j], ev, acc[j]);
+              if (o0 + j < ohi) acc[j] = fmaf(Ms[r * Ho + o0 + j], ev, acc[j]);
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            if (o0 + j < Ho) {
+            if (o0 + j < ohi) {
               partial = fmaf(Ws[(o0 + j) * Hi + c], acc[j], partial);
               if (out.dW[i]) out.dW[i][(size_t)(o0 + j) * f.w_stride[i] + c] = g * acc[j];
             }
@@ -159,7 +167,7 @@ fold_bwd_kernel(const kp_fold_desc f, const float* __restrict__ dTable, kp_fold_
       if ((int)threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
       __syncthreads();
     }
-    if (threadIdx.x == 0) part[i] = red[0];
+    if (threadIdx.x == 0) part_gate[i * FOLD_SLICES + sl] = red[0];
   }
   // ---- the last CTA to arrive finishes the two gate gradients, adding the partials in table order
   if (threadIdx.x == 0) {
@@ -172,8 +180,9 @@ fold_bwd_kernel(const kp_fold_desc f, const float* __restrict__ dTable, kp_fold_
     const int gsel = threadIdx.x;
     float s = 0.f;
     for (int t = 0; t < f.T; ++t)
-      if (f.gate[t] == gsel) s += __ldcg(part + t);
-    s += __ldcg(part + f.T + gsel);
+      if (f.gate[t] == gsel)
+        for (int q = 0; q < FOLD_SLICES; ++q) s += __ldcg(part_gate + t * FOLD_SLICES + q);
+    s += __ldcg(part_gate + f.T * FOLD_SLICES + gsel);
     if (out.dgate_raw[gsel]) out.dgate_raw[gsel][0] = s * fold_gate_grad(__ldg(f.gate_raw[gsel]), f.gate_act);
     if (gsel == 0) *counter = 0u;                            // self-resetting: no memset before the next launch
   }
@@ -204,7 +213,7 @@ int kp_fold_forward(const kp_fold_desc* desc, float* table, void* stream) {
   KP_CHECK_ARG(smem <= 200 * 1024, "kp_fold_forward: a table needs %zu bytes of shared memory", smem);
   if (smem > 32 * 1024)
     KP_CUDA(cudaFuncSetAttribute(kp::fold_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  KP_LAUNCH(kp::fold_fwd_kernel, f.T + 1, kp::FOLD_THREADS, smem, stream, f, table);
+  KP_LAUNCH(kp::fold_fwd_kernel, f.T * kp::FOLD_SLICES + 1, kp::FOLD_THREADS, smem, stream, f, table);
   return 0;
 }
 
@@ -213,18 +222,20 @@ int kp_fold_backward(const kp_fold_desc* desc, const float* dTable, const kp_fol
   KP_CHECK_ARG(desc && dTable && grads && workspace, "kp_fold_backward: null argument");
   const kp_fold_desc& f = *desc;
   if (kp::fold_check(f)) return 1;
-  KP_CHECK_ARG(workspace_bytes >= 256 && (((uintptr_t)workspace) & 15) == 0, "kp_fold_backward: workspace needs 256 bytes");
+  KP_CHECK_ARG(workspace_bytes >= KP_FOLD_WORKSPACE_BYTES && (((uintptr_t)workspace) & 15) == 0,
+               "kp_fold_backward: workspace needs KP_FOLD_WORKSPACE_BYTES bytes");
   int maxrows = 0;
   for (int i = 0; i < f.T; ++i) maxrows = f.rows[i] > maxrows ? f.rows[i] : maxrows;
   const size_t smem = sizeof(float) * ((size_t)maxrows * f.H_in + (size_t)f.H_out * f.H_in + (size_t)maxrows * f.H_out);
   KP_CHECK_ARG(smem <= 200 * 1024, "kp_fold_backward: a table needs %zu bytes of shared memory", smem);
   if (smem > 32 * 1024)
     KP_CUDA(cudaFuncSetAttribute(kp::fold_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  // workspace: [0..63] float partials (T tables + 2 bias shares), then the arrival counter (zeroed ONCE by the caller;
-  // the kernel leaves it zero)
-  float* part = (float*)workspace;
-  unsigned* counter = (unsigned*)((char*)workspace + 128);
-  KP_LAUNCH(kp::fold_bwd_kernel, f.T + 1, kp::FOLD_THREADS, smem, stream, f, dTable, *grads, part, counter);
+  // workspace: the arrival counter (zeroed ONCE by the caller; the kernel leaves it zero), then at byte 256 the float
+  // partials of the gate gradients (T * FOLD_SLICES table shares + 2 bias shares)
+  unsigned* counter = (unsigned*)workspace;
+  float* part = (float*)((char*)workspace + 256);
+  static_assert(256 + 4 * (16 * kp::FOLD_SLICES + 2) <= KP_FOLD_WORKSPACE_BYTES, "fold workspace");
+  KP_LAUNCH(kp::fold_bwd_kernel, f.T * kp::FOLD_SLICES + 1, kp::FOLD_THREADS, smem, stream, f, dTable, *grads, part, counter);
   return 0;
 }
 

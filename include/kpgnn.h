@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define KPGNN_ABI_VERSION 15
+#define KPGNN_ABI_VERSION 16
 
 const char* kp_last_error(void);
 int kp_abi_version(void);
@@ -226,7 +226,7 @@ typedef struct {
 int kp_fold_forward(const kp_fold_desc* desc, float* table, void* stream);
 /* workspace: KP_FOLD_WORKSPACE_BYTES, 16-byte aligned, ZEROED ONCE by the caller and private to one stream (the kernel
  * leaves its arrival counter at zero again). */
-#define KP_FOLD_WORKSPACE_BYTES 1024
+#define KP_FOLD_WORKSPACE_BYTES 2048
 int kp_fold_backward(const kp_fold_desc* desc, const float* dTable, const kp_fold_grads* grads, void* workspace,
                      size_t workspace_bytes, void* stream);
 
@@ -287,6 +287,10 @@ typedef struct {
   const int32_t* n_dev;
 } kp_dense_desc;
 
+/* Test / A-B hook, process-wide: 1 = GEMM phases of the dense block on the tensor cores (mma.sync TF32 with error
+ * compensation, "3xTF32"; channel counts must be multiples of 8, otherwise the call keeps the fp32-FMA tiles), 0 = fp32
+ * FMA tiles everywhere, -1 = default (on; environment KP_DENSE_MMA=0 turns it off). */
+int kp_dense_block_set_mma(int mode);
 int kp_dense_block_max_rows(int32_t Cin, int32_t Cout);
 int kp_dense_block_workspace_bytes(const kp_dense_desc* desc, size_t* fwd_bytes, size_t* bwd_bytes);
 int kp_dense_block_forward(const kp_dense_desc* desc, float* out, void* workspace, size_t workspace_bytes,

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # KPGNN_B200_LIB points at an alternative build of the same library (kernel tuning experiments)
 LIB_PATH = os.environ.get("KPGNN_B200_LIB") or os.path.join(_HERE, "libkpgnn_b200.so")
 
-ABI_VERSION = 15
+ABI_VERSION = 16
 
 
 class KpError(RuntimeError):
@@ -151,6 +151,7 @@ _SIGNATURES = {
     "kp_bn_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "kp_dense_block_max_rows": (C.c_int, [C.c_int32, C.c_int32]),
+    "kp_dense_block_set_mma": (C.c_int, [C.c_int]),
     "kp_dense_block_workspace_bytes": (C.c_int, [C.POINTER(DenseDesc), C.POINTER(C.c_size_t),
                                                  C.POINTER(C.c_size_t)]),
     "kp_dense_block_forward": (C.c_int, [C.POINTER(DenseDesc), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
@@ -238,7 +239,7 @@ def fold_workspace(device):
     key = (dev, torch.cuda.current_stream(device).cuda_stream)
     t = _FOLD_WS.get(key)
     if t is None:
-        t = torch.zeros(1024, dtype=torch.uint8, device=device)
+        t = torch.zeros(2048, dtype=torch.uint8, device=device)
         _FOLD_WS[key] = t
     return t
 

@@ -80,6 +80,8 @@ __device__ __forceinline__ void db_cp_wait_all() { asm volatile("cp.async.wait_g
 // (conflict-free) although the rows are 4*stride apart -- and the copy from global memory is a pure 16-byte
 // permutation, so cp.async does it without a transposition pass through registers.
 __host__ __device__ __forceinline__ int db_wstride(int Kd) { return (((Kd >> 2) + 7) & ~7) << 2; }
+// allocation stride of a forward weight row: covers both the swizzled layout and the MMA path's [Kd+4] rows
+__host__ __device__ __forceinline__ int db_wstride_any(int Kd) { return db_wstride(Kd) > Kd + 4 ? db_wstride(Kd) : Kd + 4; }
 
 __device__ __forceinline__ void db_cp_weight_swizzled(const float* __restrict__ W, int Co, int Kd, float* __restrict__ Ws) {
   const int ck = Kd >> 2, ws = db_wstride(Kd);
@@ -251,6 +253,118 @@ __device__ __forceinline__ void db_gemm_AtB(const float* __restrict__ A, int lda
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Tensor-core variants of the three slab GEMMs: mma.sync m16n8k8 TF32 with error compensation ("3xTF32":
+// x = hi + lo with hi = tf32(x), lo = tf32(x - hi);  a*b ~ hi*hi + hi*lo + lo*hi, the two small terms in their own
+// accumulator) -- the dropped lo*lo term is 2^-22 relative, the same order as the rounding of an fp32 FMA chain of
+// length 104, so the 1e-5 parity bar holds (tests/test_dense_gpu.py runs both paths).  Why: with 4x4 register tiles the
+// SIMT phases are bound by shared-memory bandwidth (8 LDS.128 per 64 FMA: 3.4 us per 36x104x104 product); a warp-level
+// MMA needs 6 LDS.32 per 1024 MACs.  Same shared-memory layouts as the SIMT path except the forward weights, which
+// are kept [Co][Kd+4] (un-swizzled; +4 makes the B-fragment loads conflict-free).  Channels must be multiples of 8.
+// Rows / columns of a 16-wide tile that fall outside the operand read whatever follows it in shared memory (always
+// inside the kernel's allocation) and are never stored; a product row depends on its own operand row only.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void db_tf32_split(float x, unsigned& hi, unsigned& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  const float r = x - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+__device__ __forceinline__ void db_mma_tf32(float (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+constexpr int DB_MMA_NT = 3;     // 8-column tiles per warp unit: the A fragment (and its split) is reused across them
+
+// C[m][n] = init(n) + sum_k a(m,k) b(k,n) over Mt x Nt8 tiles of 16 x 8, Ksteps steps of 8.  fa(m,k), fb(k,n) fetch one
+// operand element; fstore(m, n, v0, v1) receives C[m][n], C[m][n+1].  A unit = one 16-row tile x DB_MMA_NT column tiles.
+template <typename FA, typename FB, typename FI, typename FS>
+__device__ __forceinline__ void db_mma_gemm(int Mt, int Nt8, int Ksteps, FA fa, FB fb, FI finit, FS fstore) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int ngroups = (Nt8 + DB_MMA_NT - 1) / DB_MMA_NT;
+  for (int u = warp; u < Mt * ngroups; u += DB_WARPS) {
+    const int mt = u % Mt, ng = u / Mt;
+    const int m0 = mt * 16, nt0 = ng * DB_MMA_NT;
+    float accM[DB_MMA_NT][4], accS[DB_MMA_NT][4];
+#pragma unroll
+    for (int j = 0; j < DB_MMA_NT; ++j) {
+      const int n = (nt0 + j) * 8 + 2 * t;
+      const bool on = nt0 + j < Nt8;
+      accM[j][0] = accM[j][2] = on ? finit(n) : 0.f;
+      accM[j][1] = accM[j][3] = on ? finit(n + 1) : 0.f;
+      accS[j][0] = accS[j][1] = accS[j][2] = accS[j][3] = 0.f;
+    }
+    for (int ks = 0; ks < Ksteps; ++ks) {
+      const int k0 = ks * 8;
+      unsigned ah[4], al[4];
+      db_tf32_split(fa(m0 + g, k0 + t), ah[0], al[0]);
+      db_tf32_split(fa(m0 + g + 8, k0 + t), ah[1], al[1]);
+      db_tf32_split(fa(m0 + g, k0 + t + 4), ah[2], al[2]);
+      db_tf32_split(fa(m0 + g + 8, k0 + t + 4), ah[3], al[3]);
+#pragma unroll
+      for (int j = 0; j < DB_MMA_NT; ++j) {
+        if (nt0 + j < Nt8) {                          // warp-uniform
+          const int n = (nt0 + j) * 8 + g;
+          unsigned bh0, bl0, bh1, bl1;
+          db_tf32_split(fb(k0 + t, n), bh0, bl0);
+          db_tf32_split(fb(k0 + t + 4, n), bh1, bl1);
+          db_mma_tf32(accS[j], al, bh0, bh1);
+          db_mma_tf32(accS[j], ah, bl0, bl1);
+          db_mma_tf32(accM[j], ah, bh0, bh1);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < DB_MMA_NT; ++j)
+      if (nt0 + j < Nt8) {
+        const int n = (nt0 + j) * 8 + 2 * t;
+        fstore(m0 + g, n, accM[j][0] + accS[j][0], accM[j][1] + accS[j][1]);
+        fstore(m0 + g + 8, n, accM[j][2] + accS[j][2], accM[j][3] + accS[j][3]);
+      }
+  }
+}
+
+__host__ __device__ __forceinline__ int db_wstride_mma(int Kd) { return Kd + 4; }
+// forward weights for the MMA path: row o of W [Co][Kd] at stride Kd+4 (16-byte chunks in order)
+__device__ __forceinline__ void db_cp_weight_padded(const float* __restrict__ W, int Co, int Kd, float* __restrict__ Ws) {
+  const int ck = Kd >> 2, ws = db_wstride_mma(Kd);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int o = warp; o < Co; o += DB_WARPS)
+    for (int kc = lane; kc < ck; kc += 32) db_cp16(Ws + o * ws + (kc << 2), W + (size_t)o * Kd + (kc << 2));
+}
+// out[r][o] = bias[o] + sum_k A[r][k] W[o][k], W at stride Kd+4
+__device__ __forceinline__ void db_mma_AWt(const float* __restrict__ A, int lda, int Kd, const float* __restrict__ Ws,
+                                           int Co, const float* __restrict__ bias, int nrp, float* __restrict__ out,
+                                           int ldo) {
+  const int ws = db_wstride_mma(Kd);
+  db_mma_gemm((nrp + 15) >> 4, Co >> 3, Kd >> 3,
+              [&](int r, int k) { return A[r * lda + k]; }, [&](int k, int n) { return Ws[n * ws + k]; },
+              [&](int n) { return __ldg(bias + n); },
+              [&](int r, int n, float v0, float v1) {
+                if (r < nrp) *reinterpret_cast<float2*>(out + r * ldo + n) = make_float2(v0, v1);
+              });
+}
+// out[r][n] = sum_k A[r][k] B[k][n]
+__device__ __forceinline__ void db_mma_AB(const float* __restrict__ A, int lda, int Kd, const float* __restrict__ B,
+                                          int Nn, int nrp, float* __restrict__ out, int ldo) {
+  db_mma_gemm((nrp + 15) >> 4, Nn >> 3, Kd >> 3,
+              [&](int r, int k) { return A[r * lda + k]; }, [&](int k, int n) { return B[k * Nn + n]; },
+              [&](int) { return 0.f; },
+              [&](int r, int n, float v0, float v1) {
+                if (r < nrp) *reinterpret_cast<float2*>(out + r * ldo + n) = make_float2(v0, v1);
+              });
+}
+// outg[m][n] = sum_{r<nr} A[r][m] B[r][n]  (global partial); operand rows >= nr are masked to zero
+__device__ __forceinline__ void db_mma_AtB(const float* __restrict__ A, int lda, int M, const float* __restrict__ B,
+                                           int ldb, int Nn, int nr, float* __restrict__ outg) {
+  db_mma_gemm((M + 15) >> 4, Nn >> 3, (nr + 7) >> 3,
+              [&](int m, int k) { return k < nr ? A[k * lda + m] : 0.f; },
+              [&](int k, int n) { return k < nr ? B[k * ldb + n] : 0.f; }, [&](int) { return 0.f; },
+              [&](int m, int n, float v0, float v1) {
+                if (m < M) __stcg(reinterpret_cast<float2*>(outg + (size_t)m * Nn + n), make_float2(v0, v1));
+              });
+}
+
 __device__ __forceinline__ void db_store_slab(const float* __restrict__ s, int r0, int nr, int C, float* __restrict__ g) {
   float* dst = g + (size_t)r0 * C;                      // the slab's rows are contiguous in the [N][C] matrix
   for (int i = threadIdx.x * 4; i < nr * C; i += DB_THREADS * 4)
@@ -410,7 +524,8 @@ __device__ __forceinline__ void db_bn_apply(const float* __restrict__ S, int C, 
 // forward
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(DB_THREADS, 1)
-dense_block_fwd_kernel(const kp_dense_desc m, float* __restrict__ out, float* __restrict__ part, unsigned* bar, int Rc) {
+dense_block_fwd_kernel(const kp_dense_desc m, float* __restrict__ out, float* __restrict__ part, unsigned* bar, int Rc,
+                       int mma) {
   extern __shared__ __align__(16) float smem[];
   DB_T_DECL
   DB_T(0);
@@ -424,18 +539,20 @@ dense_block_fwd_kernel(const kp_dense_desc m, float* __restrict__ out, float* __
   const int nr = max(0, min(Rc, N - r0));
   const int nr_cap = max(0, min(Rc, m.N - r0));
   const int Rp = (Rc + 3) & ~3;
-  float* W1s = smem;                         // [Co][wstride(Ci)] swizzled
-  float* W2s = W1s + Co * db_wstride(Ci);    // [Co][wstride(Co)] swizzled
-  float* A = W2s + Co * db_wstride(Co);      // [Rp][Ci]
+  float* W1s = smem;                         // [Co][wstride(Ci)] swizzled  (MMA path: [Co][Ci+4])
+  float* W2s = W1s + Co * db_wstride_any(Ci);    // [Co][wstride(Co)] swizzled  (MMA path: [Co][Co+4])
+  float* A = W2s + Co * db_wstride_any(Co);  // [Rp][Ci]
   float* Y = A + Rp * Ci;                    // [Rp][Co]
   float* Z = Y + Rp * Co;                    // [Rp][Co]
   float* red = Z + Rp * Co;                  // [DB_WARPS][3][Co]
   float* st = red + DB_WARPS * 3 * Co;       // [3][3][Co]: (mean, istd, var) of BN1, BN2, BN3
   // everything this CTA will read from global memory except the partials is requested now, asynchronously
   db_cp_slab(m.X, r0, nr, Rp, Ci, A);
-  db_cp_weight_swizzled(m.W1, Co, Ci, W1s);
+  if (mma) db_cp_weight_padded(m.W1, Co, Ci, W1s);
+  else db_cp_weight_swizzled(m.W1, Co, Ci, W1s);
   db_cp_commit();
-  db_cp_weight_swizzled(m.W2, Co, Co, W2s);              // second group: lands behind the first GEMM
+  if (mma) db_cp_weight_padded(m.W2, Co, Co, W2s);       // second group: lands behind the first GEMM
+  else db_cp_weight_swizzled(m.W2, Co, Co, W2s);
   db_cp_commit();
   for (int i = threadIdx.x * 4; i < Rp * Co; i += DB_THREADS * 4)
     *reinterpret_cast<float4*>(Z + i) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -447,7 +564,8 @@ dense_block_fwd_kernel(const kp_dense_desc m, float* __restrict__ out, float* __
   float* part2 = part1 + (size_t)grid * 2 * Co;
 
   // ---- Linear1 + BN1 + ReLU ----
-  db_gemm_AWt(A, Ci, Ci, W1s, Co, m.b1, Rp, Y, Co);
+  if (mma) db_mma_AWt(A, Ci, Ci, W1s, Co, m.b1, Rp, Y, Co);
+  else db_gemm_AWt(A, Ci, Ci, W1s, Co, m.b1, Rp, Y, Co);
   __syncthreads();
   DB_T(2);
   db_slab_stats(Y, Co, nr, red, part0 + (size_t)blockIdx.x * 2 * Co, part0 + (size_t)blockIdx.x * 2 * Co + Co);
@@ -463,7 +581,8 @@ dense_block_fwd_kernel(const kp_dense_desc m, float* __restrict__ out, float* __
   DB_T(6);
 
   // ---- Linear2 + BN2 + ReLU ----
-  db_gemm_AWt(Z, Co, Co, W2s, Co, m.b2, Rp, Y, Co);
+  if (mma) db_mma_AWt(Z, Co, Co, W2s, Co, m.b2, Rp, Y, Co);
+  else db_gemm_AWt(Z, Co, Co, W2s, Co, m.b2, Rp, Y, Co);
   __syncthreads();
   DB_T(7);
   db_slab_stats(Y, Co, nr, red, part1 + (size_t)blockIdx.x * 2 * Co, part1 + (size_t)blockIdx.x * 2 * Co + Co);
@@ -648,7 +767,8 @@ __device__ __forceinline__ void db_slab_colsum(const float* __restrict__ A, int 
 __global__ void __launch_bounds__(DB_THREADS, 1)
 dense_block_bwd_kernel(const kp_dense_desc m, const float* __restrict__ dOut, float* __restrict__ dX,
                        float* __restrict__ dW1, float* __restrict__ db1, float* __restrict__ dW2,
-                       float* __restrict__ db2, float* __restrict__ dbn, float* __restrict__ ws, unsigned* bar, int Rc) {
+                       float* __restrict__ db2, float* __restrict__ dbn, float* __restrict__ ws, unsigned* bar, int Rc,
+                       int mma) {
   extern __shared__ __align__(16) float smem[];
   DB_T_DECL
   DB_T(0);
@@ -766,7 +886,8 @@ dense_block_bwd_kernel(const kp_dense_desc m, const float* __restrict__ dOut, fl
   __syncthreads();
   DB_T(5);
   // ---- Linear2: dz1 = dy2 W2 first (critical path), then the dW2 / db2 partials ----
-  db_gemm_AB(D, Co, Co, W2, Co, Rp, E, Co);
+  if (mma) db_mma_AB(D, Co, Co, W2, Co, Rp, E, Co);
+  else db_gemm_AB(D, Co, Co, W2, Co, Rp, E, Co);
   __syncthreads();
   DB_T(6);
   db_relu_mask(E, X1, Co, nr, m.g1, m.be1);
@@ -779,7 +900,8 @@ dense_block_bwd_kernel(const kp_dense_desc m, const float* __restrict__ dOut, fl
   }
   ++phase;
   DB_T(7);
-  db_gemm_AtB(D, Co, Co, Z1, Co, Co, nr, pW2 + (size_t)blockIdx.x * Co * Co);
+  if (mma) db_mma_AtB(D, Co, Co, Z1, Co, Co, nr, pW2 + (size_t)blockIdx.x * Co * Co);
+  else db_gemm_AtB(D, Co, Co, Z1, Co, Co, nr, pW2 + (size_t)blockIdx.x * Co * Co);
   db_slab_colsum(D, Co, nr, red, pb2 + (size_t)blockIdx.x * Co);
   DB_T(8);
   if (threadIdx.x == 0) {
@@ -799,9 +921,11 @@ dense_block_bwd_kernel(const kp_dense_desc m, const float* __restrict__ dOut, fl
   __syncthreads();
   DB_T(10);
   // ---- Linear1: dX = dy1 W1, dW1 / db1 partials ----
-  db_gemm_AB(E, Co, Co, W1, Ci, Rp, D, Ci);
+  if (mma) db_mma_AB(E, Co, Co, W1, Ci, Rp, D, Ci);
+  else db_gemm_AB(E, Co, Co, W1, Ci, Rp, D, Ci);
   DB_T(11);
-  db_gemm_AtB(E, Co, Co, XS, Ci, Ci, nr, pW1 + (size_t)blockIdx.x * Co * Ci);
+  if (mma) db_mma_AtB(E, Co, Co, XS, Ci, Ci, nr, pW1 + (size_t)blockIdx.x * Co * Ci);
+  else db_gemm_AtB(E, Co, Co, XS, Ci, Ci, nr, pW1 + (size_t)blockIdx.x * Co * Ci);
   db_slab_colsum(E, Co, nr, red, pb1 + (size_t)blockIdx.x * Co);
   __syncthreads();
   DB_T(12);
@@ -879,7 +1003,7 @@ struct DbCfg {
 
 static size_t db_smem_fwd(int Ci, int Co, int Rc) {
   const int Rp = (Rc + 3) & ~3;
-  return sizeof(float) * ((size_t)Co * db_wstride(Ci) + (size_t)Co * db_wstride(Co) + (size_t)Rp * Ci +
+  return sizeof(float) * ((size_t)Co * db_wstride_any(Ci) + (size_t)Co * db_wstride_any(Co) + (size_t)Rp * Ci +
                           2 * (size_t)Rp * Co + (size_t)DB_WARPS * 3 * Co + 9 * (size_t)Co);
 }
 static size_t db_smem_bwd(int Ci, int Co, int Rc) {
@@ -888,6 +1012,14 @@ static size_t db_smem_bwd(int Ci, int Co, int Rc) {
                           (size_t)DB_WARPS * 2 * Co + 2 * (size_t)Co);
 }
 static const size_t kDbSmemBudget = 220 * 1024;
+
+// tensor-core GEMM phases (3xTF32) when every channel count is a multiple of 8; KP_DENSE_MMA=0 keeps the fp32-FMA tiles
+static int g_db_mma = -1;            // -1: environment / default; 0 / 1: kp_dense_block_set_mma
+static int db_use_mma(const kp_dense_desc& m) {
+  static const int env = getenv("KP_DENSE_MMA") ? atoi(getenv("KP_DENSE_MMA")) : 1;
+  const int on = g_db_mma >= 0 ? g_db_mma : env;
+  return (on && m.Cin % 8 == 0 && m.Cout % 8 == 0) ? 1 : 0;
+}
 
 static int db_max_rc(int Ci, int Co) {
   int rc = 0;
@@ -926,6 +1058,11 @@ static int db_config(const kp_dense_desc& m, DbCfg* c) {
 }  // namespace kp
 
 extern "C" {
+
+int kp_dense_block_set_mma(int mode) {
+  kp::g_db_mma = mode < 0 ? -1 : (mode ? 1 : 0);
+  return 0;
+}
 
 int kp_dense_block_max_rows(int32_t Cin, int32_t Cout) {
   if (Cin < 4 || Cout < 4 || Cin % 4 || Cout % 4 || Cin > 128 || Cout > 128 || Cin > Cout) return 0;
@@ -971,7 +1108,8 @@ int kp_dense_block_forward(const kp_dense_desc* desc, float* out, void* workspac
     kp_dense_desc marg = m;
     float* part = (float*)((char*)workspace + 256);
     int rc_rows = c.Rc;
-    void* args[] = {&marg, &out, &part, &bar, &rc_rows};
+    int mma = kp::db_use_mma(m);
+    void* args[] = {&marg, &out, &part, &bar, &rc_rows, &mma};
     KP_LAUNCH_COOP(kp::dense_block_fwd_kernel, c.grid, kp::DB_THREADS, c.smem_fwd, st, args);
   }
   return 0;
@@ -999,7 +1137,8 @@ int kp_dense_block_backward(const kp_dense_desc* desc, const float* dOut, float*
     kp_dense_desc marg = m;
     float* part = (float*)((char*)workspace + 256);
     int rc_rows = c.Rc;
-    void* args[] = {&marg, (void*)&dOut, &dX, &dW1, &db1, &dW2, &db2, &dbn, &part, &bar, &rc_rows};
+    int mma = kp::db_use_mma(m);
+    void* args[] = {&marg, (void*)&dOut, &dX, &dW1, &db1, &dW2, &db2, &dbn, &part, &bar, &rc_rows, &mma};
     KP_LAUNCH_COOP(kp::dense_block_bwd_kernel, c.grid, kp::DB_THREADS, c.smem_bwd, st, args);
   }
   {

@@ -18,7 +18,7 @@
 namespace kp {
 
 constexpr int FOLD_THREADS = 256;
-constexpr int FOLD_SLICES = 8;     // CTAs per table: row slices (forward, dE) / output-channel slices (dW)
+constexpr int FOLD_SLICES = 13;    // CTAs per table: row slices (forward, dE) / output-channel slices (dW)
 
 __device__ __forceinline__ float fold_gate(float raw, int act) { return act == 0 ? tanhf(raw) : 1.f / (1.f + expf(-raw)); }
 __device__ __forceinline__ float fold_gate_grad(float raw, int act) {
@@ -50,9 +50,9 @@ __global__ void __launch_bounds__(FOLD_THREADS) fold_fwd_kernel(const kp_fold_de
   float* Ws = sm + rows * Hi;
   const int ws = Hi + 1;
   for (int t = rlo * Hi + threadIdx.x; t < rhi * Hi; t += FOLD_THREADS) Es[t] = __ldg(f.E[i] + t);
-  for (int t = threadIdx.x; t < Ho * Hi; t += FOLD_THREADS) {
-    const int o = t / Hi, c = t - o * Hi;
-    Ws[o * ws + c] = __ldg(f.W[i] + (size_t)o * f.w_stride[i] + c);
+  for (int o = threadIdx.x >> 5; o < Ho; o += FOLD_THREADS / 32) {
+    const float* wrow = f.W[i] + (size_t)o * f.w_stride[i];
+    for (int c = threadIdx.x & 31; c < Hi; c += 32) Ws[o * ws + c] = __ldg(wrow + c);
   }
   __syncthreads();
   const float g = fold_gate(__ldg(f.gate_raw[f.gate[i]]), f.gate_act);
@@ -115,9 +115,9 @@ fold_bwd_kernel(const kp_fold_desc f, const float* __restrict__ dTable, kp_fold_
     float* Ms = Ws + Ho * Hi;
     const float* dM = dTable + (size_t)f.row_off[i] * Ho;
     for (int t = threadIdx.x; t < rows * Hi; t += FOLD_THREADS) Es[t] = __ldg(f.E[i] + t);
-    for (int t = threadIdx.x; t < Ho * Hi; t += FOLD_THREADS) {
-      const int o = t / Hi, c = t - o * Hi;
-      Ws[t] = __ldg(f.W[i] + (size_t)o * f.w_stride[i] + c);
+    for (int o = threadIdx.x >> 5; o < Ho; o += FOLD_THREADS / 32) {          // a warp per weight row: no index division
+      const float* wrow = f.W[i] + (size_t)o * f.w_stride[i];
+      for (int c = threadIdx.x & 31; c < Hi; c += 32) Ws[o * Hi + c] = __ldg(wrow + c);
     }
     for (int t = threadIdx.x; t < rows * Ho; t += FOLD_THREADS) Ms[t] = __ldg(dM + t);
     __syncthreads();

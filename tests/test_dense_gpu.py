@@ -52,12 +52,22 @@ def _run(mods, x0, r0, gy, fused, use_bn3, use_res, steps=2):
     return out
 
 
+@pytest.fixture(params=[1, 0], ids=["mma-3xtf32", "fp32-fma"])
+def gemm_path(request, lib):
+    """Both GEMM implementations of the dense block: tensor-core 3xTF32 (default) and the fp32-FMA register tiles."""
+    lib.kp_dense_block_set_mma(request.param)
+    yield request.param
+    lib.kp_dense_block_set_mma(-1)
+
+
 @pytest.mark.parametrize("N", [3, 37, 300, 2952, 5000])
-@pytest.mark.parametrize("C", [(104, 104), (32, 64), (128, 128)])
+@pytest.mark.parametrize("C", [(104, 104), (32, 64), (128, 128), (100, 100)])
 @pytest.mark.parametrize("tail", ["bn3+res", "bn3", "res", "none"])
-def test_dense_block_matches_torch(lib, N, C, tail):
+def test_dense_block_matches_torch(lib, gemm_path, N, C, tail):
     dev = torch.device("cuda:0")
     Cin, Cout = C
+    if gemm_path == 1 and (Cin % 8 or Cout % 8):
+        pytest.skip("channel counts not multiples of 8 always run the fp32-FMA tiles")
     if N > lib.kp_dense_block_max_rows(Cin, Cout):
         pytest.skip("more rows than one slab per SM")
     use_bn3, use_res = "bn3" in tail, "res" in tail
@@ -76,7 +86,7 @@ def test_dense_block_matches_torch(lib, N, C, tail):
         assert float((a - b).abs().max()) / scale < tol, (k, float((a - b).abs().max()), scale)
 
 
-def test_dense_block_deterministic(lib):
+def test_dense_block_deterministic(lib, gemm_path):
     dev = torch.device("cuda:0")
     g = torch.Generator().manual_seed(5)
     x0 = torch.randn(2952, 104, generator=g).to(dev)

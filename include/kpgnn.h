@@ -289,7 +289,8 @@ typedef struct {
 
 /* Test / A-B hook, process-wide: 1 = GEMM phases of the dense block on the tensor cores (mma.sync TF32 with error
  * compensation, "3xTF32"; channel counts must be multiples of 8, otherwise the call keeps the fp32-FMA tiles), 0 = fp32
- * FMA tiles everywhere, -1 = default (on; environment KP_DENSE_MMA=0 turns it off). */
+ * FMA tiles everywhere, -1 = default (off: measured slower than the FMA tiles, profiles/r2_dense_mma.txt; environment
+ * KP_DENSE_MMA=1 turns it on). */
 int kp_dense_block_set_mma(int mode);
 int kp_dense_block_max_rows(int32_t Cin, int32_t Cout);
 int kp_dense_block_workspace_bytes(const kp_dense_desc* desc, size_t* fwd_bytes, size_t* bwd_bytes);

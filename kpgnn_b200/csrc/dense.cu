@@ -1013,10 +1013,15 @@ static size_t db_smem_bwd(int Ci, int Co, int Rc) {
 }
 static const size_t kDbSmemBudget = 220 * 1024;
 
-// tensor-core GEMM phases (3xTF32) when every channel count is a multiple of 8; KP_DENSE_MMA=0 keeps the fp32-FMA tiles
+// tensor-core GEMM phases (3xTF32, channel counts multiples of 8): OPT-IN (KP_DENSE_MMA=1 / kp_dense_block_set_mma(1)).
+// Measured inside the training step (profiles/r2_dense_mma.txt): as accurate as the fp32-FMA tiles (3.3e-7 vs 4.3e-7
+// against float64 at the bench shape) but SLOWER -- forward 295-307 us vs 280 us per step, backward 353-387 vs 302-334:
+// legacy mma.sync TF32 issues at a fraction of the tcgen05 rate, and three MMAs plus the register-side hi/lo split per
+// 16x8x8 tile cost more issue slots than the 4x4 FMA tiles they replace.  A win would need tcgen05 (operands from
+// shared-memory descriptors, hi/lo planes pre-split in shared memory, TMEM accumulators, M = 64 row tiles).
 static int g_db_mma = -1;            // -1: environment / default; 0 / 1: kp_dense_block_set_mma
 static int db_use_mma(const kp_dense_desc& m) {
-  static const int env = getenv("KP_DENSE_MMA") ? atoi(getenv("KP_DENSE_MMA")) : 1;
+  static const int env = getenv("KP_DENSE_MMA") ? atoi(getenv("KP_DENSE_MMA")) : 0;
   const int on = g_db_mma >= 0 ? g_db_mma : env;
   return (on && m.Cin % 8 == 0 && m.Cout % 8 == 0) ? 1 : 0;
 }

@@ -19,7 +19,9 @@ namespace kp {
 
 constexpr int DB_THREADS = 512;   // 16 warps: the block is a chain of short phases, warps are the only latency hiding
 constexpr int DB_WARPS = DB_THREADS / 32;
-constexpr int DB_ROWS = 36;          // target rows per CTA: 18 row pairs x 26 channel quads <= 512 threads at 104 channels
+constexpr int DB_ROWS = 32;          // target rows per CTA (8 row quads x 26 channel quads = 208 of 512 threads own a GEMM tile at
+                                     // 104 channels); measured inside the step: backward 302 us / 8 kernels vs 316 at 36 rows
+                                     // and 292 at 28 (where the forward loses 3 us), profiles/r2_dense_mma.txt
 constexpr int DB_MAX_GRID = kNumSMs; // every CTA must be resident: one per SM
 
 __device__ __forceinline__ unsigned db_ld_acquire(const unsigned* p) {

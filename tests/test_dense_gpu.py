@@ -32,13 +32,18 @@ def _run(mods, x0, r0, gy, fused, use_bn3, use_res, steps=2):
             y = fused_dense_block(x, lin1, bn1, lin2, bn2, bn3 if use_bn3 else None, r)
             assert y is not None
         else:
-            y = torch.relu(bn2(lin2(torch.relu(bn1(lin1(x))))))
+            a1 = bn1(lin1(x))
+            a2 = bn2(lin2(torch.relu(a1)))
+            kink = min(float(a1.detach().abs().min()), float(a2.detach().abs().min()))
+            y = torch.relu(a2)
             if use_bn3:
                 y = bn3(y)
             if use_res:
                 y = y + r
     y.backward(gy)
     out = {"y": y.detach(), "dx": x.grad}
+    if not fused:
+        out["_kink"] = kink       # smallest |pre-ReLU value| of the last step: a mask flip away from another fp32 evaluation?
     if use_res:
         out["dr"] = r.grad
     for name, m in zip(("lin1", "bn1", "lin2", "bn2", "bn3"), mods):
@@ -70,15 +75,24 @@ def test_dense_block_matches_torch(lib, gemm_path, N, C, tail):
         pytest.skip("channel counts not multiples of 8 always run the fp32-FMA tiles")
     if gemm_path == 1 and N == 3:
         pytest.skip("opt-in tensor-core path: the 3-row case (BatchNorm over three samples, gradients that cancel to "
-                    "rounding level) differed from torch by 2e-2 on dX at C = 128 and was not investigated")
+                    "rounding level) missed the 1e-4 bar at C = 128 and was not investigated")
     if N > lib.kp_dense_block_max_rows(Cin, Cout):
         pytest.skip("more rows than one slab per SM")
     use_bn3, use_res = "bn3" in tail, "res" in tail
-    g = torch.Generator().manual_seed(N + Cin)
-    x0 = (torch.randn(N, Cin, generator=g) * 2 + 0.5).to(dev)
-    r0 = torch.randn(N, Cout, generator=g).to(dev)
-    gy = torch.randn(N, Cout, generator=g).to(dev)
-    ref = _run(_modules(Cin, Cout, 1, dev), x0, r0, gy, False, use_bn3, use_res)
+    # Two fp32 evaluations of a pre-ReLU value within rounding of zero can land on opposite sides of the kink; the
+    # gradient of that row then differs by a whole term (seen: N=5000, C=100, one row with |BN2 out| = 6e-7, dX off
+    # by 1.6e-2 in that row only -- profiles/dense_kink.py).  That is not what this test measures: draw inputs whose
+    # reference stays clear of the kinks.
+    for attempt in range(16):
+        g = torch.Generator().manual_seed(N + Cin + 1000 * attempt)
+        x0 = (torch.randn(N, Cin, generator=g) * 2 + 0.5).to(dev)
+        r0 = torch.randn(N, Cout, generator=g).to(dev)
+        gy = torch.randn(N, Cout, generator=g).to(dev)
+        ref = _run(_modules(Cin, Cout, 1, dev), x0, r0, gy, False, use_bn3, use_res)
+        if ref.pop("_kink") >= 1.5e-6:
+            break
+    else:
+        pytest.skip("no kink-free draw in 16 attempts")
     got = _run(_modules(Cin, Cout, 1, dev), x0, r0, gy, True, use_bn3, use_res)
     wscale = max(float(ref["lin1.dw"].abs().max()), float(ref["lin2.dw"].abs().max()))
     for k, a in ref.items():

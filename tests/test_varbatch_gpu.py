@@ -83,6 +83,12 @@ def test_dense_block_device_row_count(lib, N, cap):
         if i < 3:
             assert float(b[N:].abs().max()) == 0.0 if b.size(0) > N and i < 2 else True
             b = b[:N]
+        if i in (4, 8):
+            # lin1.bias / lin2.bias feed a BatchNorm: their gradient is analytically zero, both sides are rounding noise
+            # whose pattern depends on the slab decomposition (capacity vs exact row count) -- hold it to the weight scale
+            w = res[0][i - 1]
+            assert float((a - b).abs().max()) < 2e-6 * float(w.abs().max()), (i, float((a - b).abs().max()))
+            continue
         assert rel_err(b, a) < 2e-6, (i, rel_err(b, a))
 
 

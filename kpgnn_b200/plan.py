@@ -31,7 +31,7 @@ class GraphPlan(object):
     __slots__ = ("N", "E", "K", "nnz", "capacity", "self_loops", "rowptr", "col", "attr16", "rowptrT", "colT", "dinv",
                  "indeg", "max_attr0", "max_attrk", "device", "stats", "stats_host", "ws", "pending", "src", "dst",
                  "ready", "block_ptr", "block_stats", "block_ws", "num_blocks", "max_block_nodes", "max_block_nnz",
-                 "block_stats_host", "n_dev", "block_ptr_np")
+                 "block_stats_host", "n_dev", "block_ptr_np", "arrays_ready", "tail")
 
     def blocks(self):
         """Closed node blocks (kp_plan_blocks: the graphs of the batch, found from the plan itself).  Computed on first
@@ -163,6 +163,7 @@ def build_plan(edge_index, edge_attr_base, attr_stride, K, num_nodes, self_loops
     p.N, p.E, p.K, p.self_loops, p.device = int(num_nodes), edge_index.size(1), K, bool(self_loops), dev
     p.pending = None
     p.ready = None
+    p.arrays_ready = p.tail = None
     p.block_ptr = p.block_stats = p.block_ws = p.block_stats_host = p.block_ptr_np = None
     p.n_dev = None        # device int32 scalar: rows that exist when N is a padded capacity (kpgnn_b200/wire.py)
     p.num_blocks = p.max_block_nodes = p.max_block_nnz = 0
@@ -203,6 +204,11 @@ def refresh_plan(p, edge_index, edge_attr_base, attr_stride):
                                             _stream_ptr(p.device)), "kp_plan_clamp")
         if p.block_ptr is not None:
             p._run_blocks()
+        # consumers need the arrays, not the host copies of the statistics: their event is recorded BEFORE the
+        # device-to-host copies (a pinned write-back costs ~10 us of latency that sat on the step's critical path)
+        p.arrays_ready = torch.cuda.Event()
+        p.arrays_ready.record(torch.cuda.current_stream(p.device))
+        if p.block_ptr is not None:
             p.block_stats_host.copy_(p.block_stats, non_blocking=True)
         p.stats_host.copy_(p.stats, non_blocking=True)
         if torch.cuda.is_current_stream_capturing():
@@ -278,10 +284,14 @@ def refresh_plan_async(p, edge_index, edge_attr_base, attr_stride, stream):
     cur = torch.cuda.current_stream(p.device)
     stream.wait_stream(cur)
     with torch.cuda.stream(stream):
+        p.arrays_ready = None
         ok = refresh_plan(p, edge_index, edge_attr_base, attr_stride)
         ev = torch.cuda.Event()
         ev.record(stream)
-    p.ready = ev
+    # the first consumer waits for the arrays only; the caller joins `p.tail` (statistics copied to the host) before its
+    # region ends -- a captured graph must not leave the side stream unjoined
+    p.ready = p.arrays_ready if p.arrays_ready is not None else ev
+    p.tail = ev
     return ok
 
 

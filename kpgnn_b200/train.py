@@ -128,6 +128,9 @@ class Trainer(object):
         self._zero()
         loss = self.loss_fn(self.model(self.dev), self.dev.y)
         loss.backward()
+        if self.plan_obj is not None and self.plan_obj.tail is not None:     # late join of the plan stream (host statistics)
+            torch.cuda.current_stream(self.device).wait_event(self.plan_obj.tail)
+            self.plan_obj.tail = None
         if self.grads is not None:
             self.grads.gather_()
         return loss.detach()

@@ -30,13 +30,31 @@ def kernel_path(request, lib):
 
 
 def _run_pair(mine, ora, batch, make_x, P_shape, use_pe, gine=False):
-    dev = torch.device("cuda:0")
+    """Compares the two layers on seeded inputs.  A ReLU inside the layer (KP-GIN+'s MLP) makes the gradient
+    discontinuous where a pre-activation is within rounding of zero: two correct fp32 / fp64 evaluations can then take
+    different branches, and ONE node's input gradient differs by a whole term (diagnosed with profiles/dense_kink.py: one
+    row off by 1e-2, every other row at 1e-6).  Such a draw says nothing about the kernels: when the forward matches and
+    the mismatch is confined to a few rows of dX, the comparison is repeated on a fresh draw (which must then pass
+    outright); any other mismatch fails immediately."""
     ora.load_state_dict(mine.state_dict())
+    for attempt in range(3):
+        fails, kink_like = _compare_once(mine, ora, batch, make_x, P_shape, use_pe, gine, seed=7 + 100 * attempt)
+        if not fails:
+            return
+        if not kink_like:
+            break
+    raise AssertionError(fails)
+
+
+def _compare_once(mine, ora, batch, make_x, P_shape, use_pe, gine, seed):
+    dev = torch.device("cuda:0")
     mine = mine.to(dev)
     ora = ora.to(dev)
     mine.train()
     ora.train()
-    g = torch.Generator().manual_seed(7)
+    for layer in (mine, ora):
+        layer.zero_grad(set_to_none=True)
+    g = torch.Generator().manual_seed(seed)
     x0 = make_x(g)
     P0 = torch.randn(*P_shape, generator=g) if P_shape is not None else None
     N = batch["num_nodes"]
@@ -71,7 +89,9 @@ def _run_pair(mine, ora, batch, make_x, P_shape, use_pe, gine=False):
             grads[n] = p.grad
         outs.append((y, grads))
     (y0, g0), (y1, g1) = outs
-    assert rel_err(y1, y0) < RTOL, ("forward", rel_err(y1, y0))
+    fails = []
+    if not rel_err(y1, y0) < RTOL:
+        return [("forward", rel_err(y1, y0))], False
     # gradients that are analytically zero (a Linear bias feeding BatchNorm) are pure rounding noise in both
     # implementations: give every tensor a floor of 1e-3 x the largest gradient in the layer
     gmax = max(float(v.abs().max()) for v in g0.values() if v is not None)
@@ -81,10 +101,20 @@ def _run_pair(mine, ora, batch, make_x, P_shape, use_pe, gine=False):
                 assert t is None or float(t.abs().max()) == 0.0, n
             continue
         if n in NOISE_ONLY:
-            assert float((g1[n] - g0[n]).abs().max()) < 1e-4 * gmax, n
+            if not float((g1[n] - g0[n]).abs().max()) < 1e-4 * gmax:
+                fails.append((n, "noise-only gradient above 1e-4 of the layer's largest"))
             continue
         err = rel_err(g1[n], g0[n], floor=1e-3 * gmax)
-        assert err < RTOL, (n, err)
+        if not err < RTOL:
+            fails.append((n, err))
+    kink_like = False
+    if fails and any(n == "x" for n, _ in fails):
+        dx0, dx1 = g0["x"].double(), g1["x"].double()
+        scale = max(float(dx0.abs().max()), 1e-3 * gmax)
+        row_err = (dx1 - dx0).abs().reshape(dx0.size(0), -1).max(dim=1).values / scale
+        bad = int((row_err > RTOL).sum())
+        kink_like = 0 < bad <= max(1, dx0.size(0) // 50) and float(row_err.median()) < RTOL
+    return fails, kink_like
 
 
 CASES = [(K, kern, comb, pe) for K in (1, 3, 8) for kern in ("spd", "gd") for comb in ("geometric", "attention")

@@ -33,9 +33,10 @@ def _run_pair(mine, ora, batch, make_x, P_shape, use_pe, gine=False):
     """Compares the two layers on seeded inputs.  A ReLU inside the layer (KP-GIN+'s MLP) makes the gradient
     discontinuous where a pre-activation is within rounding of zero: two correct fp32 / fp64 evaluations can then take
     different branches, and ONE node's input gradient differs by a whole term (diagnosed with profiles/dense_kink.py: one
-    row off by 1e-2, every other row at 1e-6).  Such a draw says nothing about the kernels: when the forward matches and
-    the mismatch is confined to a few rows of dX, the comparison is repeated on a fresh draw (which must then pass
-    outright); any other mismatch fails immediately."""
+    row off by 1e-2 at N = 5 000; at N = 70 the BatchNorm backward spreads it over every row).  Such a draw says nothing
+    about the kernels: when the ORACLE itself reports a pre-ReLU value within 2e-6 of zero (forward hooks on its ReLU
+    modules, float64 where the oracle runs in float64) and the forward matches, the comparison is repeated on a fresh
+    draw; any mismatch on a draw that is clear of the kinks fails immediately."""
     ora.load_state_dict(mine.state_dict())
     for attempt in range(3):
         fails, kink_like = _compare_once(mine, ora, batch, make_x, P_shape, use_pe, gine, seed=7 + 100 * attempt)
@@ -69,25 +70,40 @@ def _compare_once(mine, ora, batch, make_x, P_shape, use_pe, gine, seed):
     f64 = any("attention_lstm" in n for n, _ in ora.named_parameters())
     if f64:
         ora = ora.double()
+    kink = [float("inf")]
+    hooks = [m.register_forward_pre_hook(lambda mod, inp: kink.__setitem__(0, min(kink[0], float(inp[0].detach().abs().min()))))
+             for m in ora.modules() if isinstance(m, torch.nn.ReLU)]
+    import torch.nn.functional as F_
+    f_relu = F_.relu
+
+    def relu_probe(inp, *a, **k):
+        kink[0] = min(kink[0], float(inp.detach().abs().min())) if inp.numel() else kink[0]
+        return f_relu(inp, *a, **k)
     outs = []
-    for layer in (ora, mine):
-        d = dev
-        dt = torch.float64 if (f64 and layer is ora) else torch.float32
-        x = x0.clone().to(d, dt).requires_grad_(True)
-        P = P0.clone().to(d, dt).requires_grad_(True) if P0 is not None else None
-        ei, ea = batch["edge_index"].to(d), batch["edge_attr"].to(d)
-        if gine:
-            y = layer(x * 1.0, ei, ea[:, :1])
-        else:
-            y = layer(x * 1.0, ei, ea, pe.to(d) if pe is not None else None, P)
-        gy = torch.randn(y.shape, generator=torch.Generator().manual_seed(11)).to(d, dt)
-        y.backward(gy)
-        grads = {"x": x.grad}
-        if P is not None:
-            grads["P"] = P.grad
-        for n, p in layer.named_parameters():
-            grads[n] = p.grad
-        outs.append((y, grads))
+    try:
+        for layer in (ora, mine):
+            F_.relu = relu_probe if layer is ora else f_relu          # the oracle's functional ReLUs report too
+            d = dev
+            dt = torch.float64 if (f64 and layer is ora) else torch.float32
+            x = x0.clone().to(d, dt).requires_grad_(True)
+            P = P0.clone().to(d, dt).requires_grad_(True) if P0 is not None else None
+            ei, ea = batch["edge_index"].to(d), batch["edge_attr"].to(d)
+            if gine:
+                y = layer(x * 1.0, ei, ea[:, :1])
+            else:
+                y = layer(x * 1.0, ei, ea, pe.to(d) if pe is not None else None, P)
+            gy = torch.randn(y.shape, generator=torch.Generator().manual_seed(11)).to(d, dt)
+            y.backward(gy)
+            grads = {"x": x.grad}
+            if P is not None:
+                grads["P"] = P.grad
+            for n, p in layer.named_parameters():
+                grads[n] = p.grad
+            outs.append((y, grads))
+    finally:
+        F_.relu = f_relu
+    for h in hooks:
+        h.remove()
     (y0, g0), (y1, g1) = outs
     fails = []
     if not rel_err(y1, y0) < RTOL:
@@ -107,13 +123,9 @@ def _compare_once(mine, ora, batch, make_x, P_shape, use_pe, gine, seed):
         err = rel_err(g1[n], g0[n], floor=1e-3 * gmax)
         if not err < RTOL:
             fails.append((n, err))
-    kink_like = False
-    if fails and any(n == "x" for n, _ in fails):
-        dx0, dx1 = g0["x"].double(), g1["x"].double()
-        scale = max(float(dx0.abs().max()), 1e-3 * gmax)
-        row_err = (dx1 - dx0).abs().reshape(dx0.size(0), -1).max(dim=1).values / scale
-        bad = int((row_err > RTOL).sum())
-        kink_like = 0 < bad <= max(1, dx0.size(0) // 50) and float(row_err.median()) < RTOL
+    kink_like = bool(fails) and kink[0] < 2e-6
+    if fails:
+        fails.append(("smallest |pre-ReLU| in the oracle", kink[0]))
     return fails, kink_like
 
 

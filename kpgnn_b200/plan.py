@@ -31,7 +31,8 @@ class GraphPlan(object):
     __slots__ = ("N", "E", "K", "nnz", "capacity", "self_loops", "rowptr", "col", "attr16", "rowptrT", "colT", "dinv",
                  "indeg", "max_attr0", "max_attrk", "device", "stats", "stats_host", "ws", "pending", "src", "dst",
                  "ready", "block_ptr", "block_stats", "block_ws", "num_blocks", "max_block_nodes", "max_block_nnz",
-                 "block_stats_host", "n_dev", "block_ptr_np", "arrays_ready", "tail")
+                 "block_stats_host", "n_dev", "block_ptr_np", "arrays_ready", "tail",
+                 "sticky", "sticky_host")
 
     def blocks(self):
         """Closed node blocks (kp_plan_blocks: the graphs of the batch, found from the plan itself).  Computed on first
@@ -86,6 +87,19 @@ class GraphPlan(object):
             raise IndexError("edge_attr[:,0] has value %d but hop1_edge_emb has %d rows" % (self.max_attr0, rows0))
         if k > 1 and self.max_attrk >= rowsk:
             raise IndexError("edge_attr[:,1:] has value %d but hopk_edge_emb has %d rows" % (self.max_attrk, rowsk))
+
+    def validate_lagged(self):
+        """For pipelined loops: checks the STICKY statistics (running maxima over all refreshes so far) as they are in
+        host memory right now, without waiting for the stream.  The caller has synchronised on the end of an earlier
+        step; whatever later steps have added since is checked too, nothing is ever missed."""
+        nnz, m0, mk, bad = self.sticky_host.tolist()
+        if bad:
+            raise IndexError("edge_index / edge_attr out of range in %d entries" % bad)
+        if nnz > self.capacity:
+            raise _lib.KpError("in-place plan refresh overflowed: nnz %d > capacity %d" % (nnz, self.capacity))
+        if m0 > self.max_attr0 or mk > self.max_attrk:
+            raise IndexError("refreshed batch has edge attrs (%d,%d) above those the plan was validated for (%d,%d)"
+                             % (m0, mk, self.max_attr0, self.max_attrk))
 
     def validate(self):
         """Completes a deferred refresh: waits for its statistics and raises on overflow / bad indices."""
@@ -176,6 +190,10 @@ def build_plan(edge_index, edge_attr_base, attr_stride, K, num_nodes, self_loops
     p.indeg = torch.empty(max(p.N, 1), dtype=torch.int32, device=dev)
     p.stats = torch.empty(4, dtype=torch.int32, device=dev)
     p.stats_host = torch.empty(4, dtype=torch.int32, pin_memory=True)
+    # running maximum of the statistics over every deferred refresh (never reset): a host that reads it late -- a loop
+    # that validates batch i while batch i+1 is already running -- cannot miss an overflow / bad index / attr bound
+    p.sticky = torch.zeros(4, dtype=torch.int32, device=dev)
+    p.sticky_host = torch.zeros(4, dtype=torch.int32).pin_memory()
     p.dinv = torch.empty(max(rows, 1), dtype=torch.float32, device=dev) if self_loops else None
     pin = _plan_input(p, edge_index, edge_attr_base, attr_stride)
     _run_count(p, pin)
@@ -211,6 +229,8 @@ def refresh_plan(p, edge_index, edge_attr_base, attr_stride):
         if p.block_ptr is not None:
             p.block_stats_host.copy_(p.block_stats, non_blocking=True)
         p.stats_host.copy_(p.stats, non_blocking=True)
+        torch.maximum(p.sticky, p.stats, out=p.sticky)
+        p.sticky_host.copy_(p.sticky, non_blocking=True)
         if torch.cuda.is_current_stream_capturing():
             p.pending = "captured"              # every replay refreshes stats_host; validate() syncs the stream
         else:

@@ -70,6 +70,8 @@ class Trainer(object):
         self.launches_per_step = 0
         self.idx_buf = peripheral_index(self.dev.peripheral_edge_attr, self.dev.peripheral_configuration_attr)
         self.plan_obj = None
+        self._loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+        self._e2e_i, self._e2e_prev = 0, None
 
     def _make_grads(self):
         """world > 1: the library's peer-memory exchange (csrc/peer.cu) when every rank can open every other rank's
@@ -235,6 +237,46 @@ class Trainer(object):
         val = self.loss.item()
         self.validate()
         return val
+
+    def step_e2e_pipelined(self, next_host_flat):
+        """step_e2e without a host stall per step: the loss of step i is copied to pinned memory behind step i and READ
+        while step i+1 runs (one value per step, one step late -- the accumulation of train_ZINC.py:45 is unchanged); the
+        deferred plan checks read the sticky statistics the same way.  Returns the previous step's loss (None on the
+        first call); drain() returns the last one."""
+        self.hand_over()
+        self.replay()
+        st = torch.cuda.current_stream(self.device)
+        slot = self._e2e_i & 1
+        self._loss_host[slot].copy_(self.loss, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(st)
+        self.prefetch(next_host_flat)
+        prev, self._e2e_prev = self._e2e_prev, (ev, slot)
+        self._e2e_i += 1
+        if prev is None:
+            return None
+        prev[0].synchronize()
+        val = float(self._loss_host[prev[1]])
+        self._validate_lagged()
+        return val
+
+    def drain(self):
+        """Loss of the last pipelined step (waits for it) + a full validation."""
+        prev, self._e2e_prev = self._e2e_prev, None
+        if prev is None:
+            return None
+        prev[0].synchronize()
+        val = float(self._loss_host[prev[1]])
+        self.validate()
+        return val
+
+    def _validate_lagged(self):
+        if self.plan_obj is not None:
+            self.plan_obj.validate_lagged()
+        if isinstance(self.grads, PeerGradients):
+            self._validations = getattr(self, "_validations", 0) + 1
+            if self._validations % 64 == 1:
+                self.grads.check()
 
     def validate(self):
         if self.plan_obj is not None:

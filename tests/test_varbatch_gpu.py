@@ -195,3 +195,48 @@ def test_captured_step_over_distinct_batches_matches_oracle(lib):
     # the two runs' means over the 20 steps are within 25 % of each other
     assert np.mean(mine_all[-6:]) < np.mean(mine_all[:6]) and np.mean(ref_all[-6:]) < np.mean(ref_all[:6])
     assert abs(np.mean(mine_all) - np.mean(ref_all)) < 0.25 * np.mean(ref_all), (mine_all, ref_all)
+
+
+def test_pipelined_e2e_steps_equal_synchronous_steps(lib):
+    """Trainer.step_e2e_pipelined (loss of step i read while step i+1 runs, sticky plan statistics checked one step late)
+    must produce the loss sequence of the synchronous step_e2e bit for bit, and still catch a batch that overflows the
+    plan capacity."""
+    from kpgnn_b200.model import zinc_kpginplus
+    from kpgnn_b200.train import Trainer, fit_spec
+    dev = torch.device("cuda:0")
+    hbs = [_host_batch(16, 300 + s) for s in range(4)]
+    spec, bounds = fit_spec(hbs, 8, 3, 6)
+    flats = [spec.pack(b, spec.host_buffer()) for b in hbs]
+    seqs = []
+    for pipelined in (False, True):
+        torch.manual_seed(0)
+        model = zinc_kpginplus(8, 4, 64).to(dev).train()
+        tr = Trainer(model, spec, bounds, dev)
+        sd = {k: v.clone() for k, v in model.state_dict().items()}
+        tr.capture(flats[0])
+        model.load_state_dict(sd)
+        tr.opt.state.zero_()
+        tr.opt.m.zero_()
+        tr.opt.v.zero_()
+        tr.prefetch(flats[0])
+        out = []
+        for step in range(10):
+            nxt = flats[(step + 1) % 4]
+            if pipelined:
+                v = tr.step_e2e_pipelined(nxt)
+                if v is not None:
+                    out.append(v)
+            else:
+                out.append(tr.step_e2e(nxt))
+        if pipelined:
+            out.append(tr.drain())
+        seqs.append(out)
+    assert len(seqs[0]) == len(seqs[1]) == 10
+    assert seqs[0] == seqs[1], (seqs[0], seqs[1])
+    # overflow: shrink the validated capacity below what the batches need; the lagged check must raise within two steps
+    tr.plan_obj.capacity = 8
+    tr.prefetch(flats[0])
+    with pytest.raises(Exception):
+        for step in range(3):
+            tr.step_e2e_pipelined(flats[(step + 1) % 4])
+        tr.drain()

@@ -210,7 +210,7 @@ def test_pipelined_e2e_steps_equal_synchronous_steps(lib):
     seqs = []
     for pipelined in (False, True):
         torch.manual_seed(0)
-        model = zinc_kpginplus(8, 4, 64).to(dev).train()
+        model = zinc_kpginplus(8, 8, 64).to(dev).train()
         tr = Trainer(model, spec, bounds, dev)
         sd = {k: v.clone() for k, v in model.state_dict().items()}
         tr.capture(flats[0])

@@ -230,6 +230,7 @@ __global__ void __launch_bounds__(1024, 1)      // <= 64 registers; launched wit
 agg_fwd_lean_kernel(const FastArgs fa, float* __restrict__ out, unsigned pf_x_lines, unsigned pf_p_lines, int pf_dist,
                     unsigned pf_bulk_bytes) {
   extern __shared__ __align__(16) float sm[];
+  kp_pdl_trigger();      // a kernel launched behind this one with the PDL attribute (the dense block) may start its prologue
   const kp_agg_desc& a = fa.d;
   const int staged = stage_tables<TAB, FUSE>(a, sm);
   const int d = a.d, k = a.k, Kp = a.Kplan, N = a.N;

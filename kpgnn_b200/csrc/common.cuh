@@ -41,19 +41,42 @@ extern std::atomic<uint64_t> g_launches;
 // Kernels that spin on a grid-wide barrier: a cooperative launch makes the driver guarantee that every CTA of the grid
 // is co-resident (it fails with cudaErrorCooperativeLaunchTooLarge instead of deadlocking on a smaller part / MIG
 // slice); capturable in CUDA graphs like a plain launch.  `args` is the usual array of pointers to the arguments.
-#define KP_LAUNCH_COOP(kernel, grid, block, smem, stream, args)                                             \
+#define KP_LAUNCH_COOP(kernel, grid, block, smem, strm_, args)                                             \
   do {                                                                                                      \
     static const bool _plain = getenv("KP_DENSE_COOP") && atoi(getenv("KP_DENSE_COOP")) == 0;               \
-    cudaError_t _le = _plain ? cudaLaunchKernel((const void*)(kernel), dim3(grid), dim3(block), (args),     \
-                                                (size_t)(smem), (cudaStream_t)(stream))                     \
-                             : cudaLaunchCooperativeKernel((const void*)(kernel), dim3(grid), dim3(block), (args),   \
-                                                  (size_t)(smem), (cudaStream_t)(stream));                  \
+    static const bool _pdl = getenv("KP_DENSE_PDL") && atoi(getenv("KP_DENSE_PDL")) == 1;                   \
+    cudaLaunchConfig_t _cfg = {};                                                                           \
+    _cfg.gridDim = dim3(grid);                                                                              \
+    _cfg.blockDim = dim3(block);                                                                            \
+    _cfg.dynamicSmemBytes = (size_t)(smem);                                                                 \
+    _cfg.stream = (cudaStream_t)(strm_);                                                                    \
+    cudaLaunchAttribute _at[2];                                                                             \
+    unsigned _na = 0;                                                                                       \
+    if (!_plain) {                                                                                          \
+      _at[_na].id = cudaLaunchAttributeCooperative;                                                         \
+      _at[_na].val.cooperative = 1;                                                                         \
+      ++_na;                                                                                                \
+    }                                                                                                       \
+    if (_pdl) { /* programmatic dependent launch: the kernel may start while its predecessor drains; it   */ \
+      _at[_na].id = cudaLaunchAttributeProgrammaticStreamSerialization; /* calls griddepcontrol.wait before */ \
+      _at[_na].val.programmaticStreamSerializationAllowed = 1;          /* touching the predecessor's data  */ \
+      ++_na;                                                                                                \
+    }                                                                                                       \
+    _cfg.attrs = _at;                                                                                       \
+    _cfg.numAttrs = _na;                                                                                    \
+    cudaError_t _le = cudaLaunchKernelExC(&_cfg, (const void*)(kernel), (args));                            \
     kp::g_launches.fetch_add(1, std::memory_order_relaxed);                                                 \
     if (_le != cudaSuccess) {                                                                               \
       kp::set_error("cooperative launch of %s failed: %s (%s:%d)", #kernel, cudaGetErrorString(_le), __FILE__, __LINE__); \
       return 2;                                                                                             \
     }                                                                                                       \
   } while (0)
+
+// Programmatic dependent launch, device side.  kp_pdl_wait(): every memory operation of the preceding kernel in the stream
+// is complete and visible (a no-op when the kernel was launched normally).  kp_pdl_trigger(): kernels launched behind
+// this one with the PDL attribute may start now (they still wait in kp_pdl_wait for this grid to finish).
+__device__ __forceinline__ void kp_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void kp_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // Fork helper: make `to` wait for everything enqueued on `from` so far.  Events come from a small per-thread ring and
 // are never destroyed while in flight (create + record + wait + destroy around every fork is legal, but keeping the

@@ -549,11 +549,16 @@ dense_block_fwd_kernel(const kp_dense_desc m, float* __restrict__ out, float* __
   float* red = Z + Rp * Co;                  // [DB_WARPS][3][Co]
   float* st = red + DB_WARPS * 3 * Co;       // [3][3][Co]: (mean, istd, var) of BN1, BN2, BN3
   // everything this CTA will read from global memory except the partials is requested now, asynchronously
-  db_cp_slab(m.X, r0, nr, Rp, Ci, A);
+  // The first weight matrix does not depend on the preceding kernel: under programmatic dependent launch
+  // (KP_DENSE_PDL=1) its copy is in flight while that kernel drains; the X slab (the predecessor's output) is requested
+  // behind kp_pdl_wait().  The row count was written at the head of the step.
   if (mma) db_cp_weight_padded(m.W1, Co, Ci, W1s);
   else db_cp_weight_swizzled(m.W1, Co, Ci, W1s);
   db_cp_commit();
-  if (mma) db_cp_weight_padded(m.W2, Co, Co, W2s);       // second group: lands behind the first GEMM
+  kp_pdl_wait();
+  db_cp_slab(m.X, r0, nr, Rp, Ci, A);
+  db_cp_commit();
+  if (mma) db_cp_weight_padded(m.W2, Co, Co, W2s);       // third group: lands behind the first GEMM
   else db_cp_weight_swizzled(m.W2, Co, Co, W2s);
   db_cp_commit();
   for (int i = threadIdx.x * 4; i < Rp * Co; i += DB_THREADS * 4)
@@ -803,7 +808,17 @@ dense_block_bwd_kernel(const kp_dense_desc m, const float* __restrict__ dOut, fl
   const float* mean1 = m.stats, *istd1 = m.stats + Co, *mean2 = m.stats + 2 * Co, *istd2 = m.stats + 3 * Co;
   const float* mean3 = m.stats + 4 * Co, *istd3 = m.stats + 5 * Co;
 
-  // every slab and both weight matrices are requested now, asynchronously: one round trip to L2 / HBM
+  // every slab and both weight matrices are requested now, asynchronously: one round trip to L2 / HBM.  Saved
+  // activations and weights first -- they do not depend on the preceding kernel, so under programmatic dependent launch
+  // (KP_DENSE_PDL=1) they are in flight while it drains -- then, behind kp_pdl_wait(), the incoming gradient.
+  if (m.g3) db_cp_slab(m.Z2, r0, nr, Rp, Co, X3);
+  db_cp_slab(m.Y2, r0, nr, Rp, Co, X2);
+  db_cp_slab(m.Y1, r0, nr, Rp, Co, X1);
+  db_cp_slab(m.X, r0, nr, Rp, Ci, XS);
+  db_cp_rows(m.W2, Co * Co, W2);
+  db_cp_rows(m.W1, Co * Ci, W1);
+  db_cp_commit();
+  kp_pdl_wait();
   {
     const size_t sd = m.dout_stride ? (size_t)m.dout_stride : (size_t)Co;
     const int warp = threadIdx.x >> 5, c = (threadIdx.x & 31) * 4;
@@ -813,12 +828,6 @@ dense_block_bwd_kernel(const kp_dense_desc m, const float* __restrict__ dOut, fl
         else *reinterpret_cast<float4*>(D + r * Co + c) = make_float4(0.f, 0.f, 0.f, 0.f);
       }
   }
-  if (m.g3) db_cp_slab(m.Z2, r0, nr, Rp, Co, X3);
-  db_cp_slab(m.Y2, r0, nr, Rp, Co, X2);
-  db_cp_slab(m.Y1, r0, nr, Rp, Co, X1);
-  db_cp_slab(m.X, r0, nr, Rp, Ci, XS);
-  db_cp_rows(m.W2, Co * Co, W2);
-  db_cp_rows(m.W1, Co * Ci, W1);
   db_cp_commit();
   db_cp_wait_all();
   __syncthreads();

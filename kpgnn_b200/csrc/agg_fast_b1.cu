@@ -20,7 +20,7 @@ static int launch_lean(const FastArgs& fa, int grid, int threads, size_t smem, c
   if (smem > 32 * 1024)
     KP_CUDA(cudaFuncSetAttribute(agg_bwd_dst_lean_kernel<G, ACT, FUSE, TAB>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  KP_LAUNCH((agg_bwd_dst_lean_kernel<G, ACT, FUSE, TAB>), grid, threads, smem, st, fa, dOut, Gs, dP, dth);
+  KP_LAUNCH_PDL((agg_bwd_dst_lean_kernel<G, ACT, FUSE, TAB>), grid, threads, smem, st, fa, dOut, Gs, dP, dth);
   return 0;
 }
 template <int G>

@@ -58,7 +58,7 @@ static int launch_lean(const FastArgs& fa, int grid, size_t smem, float* out, cu
   if (total > 32 * 1024)
     KP_CUDA(cudaFuncSetAttribute(agg_fwd_lean_kernel<G, ACT, FUSE, TAB, EXTRA>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total));
-  KP_LAUNCH((agg_fwd_lean_kernel<G, ACT, FUSE, TAB, EXTRA>), grid, threads, total, st, fa, out, pfx_, pfp_, dist, bulk);
+  KP_LAUNCH_PDL((agg_fwd_lean_kernel<G, ACT, FUSE, TAB, EXTRA>), grid, threads, total, st, fa, out, pfx_, pfp_, dist, bulk);
   return 0;
 }
 

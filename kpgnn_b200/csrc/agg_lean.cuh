@@ -230,9 +230,14 @@ __global__ void __launch_bounds__(1024, 1)      // <= 64 registers; launched wit
 agg_fwd_lean_kernel(const FastArgs fa, float* __restrict__ out, unsigned pf_x_lines, unsigned pf_p_lines, int pf_dist,
                     unsigned pf_bulk_bytes) {
   extern __shared__ __align__(16) float sm[];
-  kp_pdl_trigger();      // a kernel launched behind this one with the PDL attribute (the dense block) may start its prologue
   const kp_agg_desc& a = fa.d;
+  // Programmatic dependent launch: the tables / theta (parameters and step-head products) are staged while the
+  // preceding kernel (the dense block) is still running; X and P are touched behind kp_pdl_wait().  Dependents are
+  // released only after this CTA's own wait, so a dependent's prologue never overlaps more than one kernel back and
+  // never competes with CTAs of this grid that are not resident yet.
   const int staged = stage_tables<TAB, FUSE>(a, sm);
+  kp_pdl_wait();
+  kp_pdl_trigger();
   const int d = a.d, k = a.k, Kp = a.Kplan, N = a.N;
   const unsigned xs = fa.xs, d4 = (unsigned)d * 4u;
   const int lane = threadIdx.x & (G - 1);
@@ -525,6 +530,8 @@ agg_bwd_dst_lean_kernel(const FastArgs fa, const float* __restrict__ dOut, float
     for (int i = threadIdx.x * 4; i < gpb * k * (int)dpad; i += blockDim.x * 4) st4(acc_all + i, make_float4(0.f, 0.f, 0.f, 0.f));
     __syncthreads();
   }
+  kp_pdl_wait();         // prologue (tables, accumulators) overlapped the preceding kernel; dOut / X / P from here on
+  kp_pdl_trigger();
   const float* Xc = opaque_ptr(a.X + c);
   const bool hasP = need_z && a.P != nullptr;
   const float* Pc = opaque_ptr(hasP ? a.P + c : a.X + c);

@@ -38,13 +38,34 @@ extern std::atomic<uint64_t> g_launches;
     KP_CUDA(cudaGetLastError());                                                           \
   } while (0)
 
+// Launch with the programmatic-dependent-launch attribute (KP_AGG_PDL=0 turns it off): the kernel may be scheduled
+// while the preceding kernel of the stream is still running, once every CTA of that kernel has called
+// kp_pdl_trigger() (or exited); it must call kp_pdl_wait() before touching anything the predecessor writes.
+#define KP_LAUNCH_PDL(kernel, grid, block, smem, strm_, ...)                                                \
+  do {                                                                                                      \
+    static const bool _pdl = !(getenv("KP_AGG_PDL") && atoi(getenv("KP_AGG_PDL")) == 0);                    \
+    cudaLaunchConfig_t _cfg = {};                                                                           \
+    _cfg.gridDim = dim3(grid);                                                                              \
+    _cfg.blockDim = dim3(block);                                                                            \
+    _cfg.dynamicSmemBytes = (size_t)(smem);                                                                 \
+    _cfg.stream = (cudaStream_t)(strm_);                                                                    \
+    cudaLaunchAttribute _at[1];                                                                             \
+    _at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                         \
+    _at[0].val.programmaticStreamSerializationAllowed = 1;                                                  \
+    _cfg.attrs = _at;                                                                                       \
+    _cfg.numAttrs = _pdl ? 1 : 0;                                                                           \
+    cudaError_t _le = cudaLaunchKernelEx(&_cfg, kernel, __VA_ARGS__);                                       \
+    kp::g_launches.fetch_add(1, std::memory_order_relaxed);                                                 \
+    KP_CUDA(_le);                                                                                           \
+  } while (0)
+
 // Kernels that spin on a grid-wide barrier: a cooperative launch makes the driver guarantee that every CTA of the grid
 // is co-resident (it fails with cudaErrorCooperativeLaunchTooLarge instead of deadlocking on a smaller part / MIG
 // slice); capturable in CUDA graphs like a plain launch.  `args` is the usual array of pointers to the arguments.
 #define KP_LAUNCH_COOP(kernel, grid, block, smem, strm_, args)                                             \
   do {                                                                                                      \
     static const bool _plain = getenv("KP_DENSE_COOP") && atoi(getenv("KP_DENSE_COOP")) == 0;               \
-    static const bool _pdl = getenv("KP_DENSE_PDL") && atoi(getenv("KP_DENSE_PDL")) == 1;                   \
+    static const bool _pdl = !(getenv("KP_DENSE_PDL") && atoi(getenv("KP_DENSE_PDL")) == 0);                  \
     cudaLaunchConfig_t _cfg = {};                                                                           \
     _cfg.gridDim = dim3(grid);                                                                              \
     _cfg.blockDim = dim3(block);                                                                            \

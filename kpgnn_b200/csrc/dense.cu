@@ -556,6 +556,7 @@ dense_block_fwd_kernel(const kp_dense_desc m, float* __restrict__ out, float* __
   else db_cp_weight_swizzled(m.W1, Co, Ci, W1s);
   db_cp_commit();
   kp_pdl_wait();
+  kp_pdl_trigger();      // dependents (the next aggregation kernel) may run their prologue from here on
   db_cp_slab(m.X, r0, nr, Rp, Ci, A);
   db_cp_commit();
   if (mma) db_cp_weight_padded(m.W2, Co, Co, W2s);       // third group: lands behind the first GEMM
@@ -819,6 +820,7 @@ dense_block_bwd_kernel(const kp_dense_desc m, const float* __restrict__ dOut, fl
   db_cp_rows(m.W1, Co * Ci, W1);
   db_cp_commit();
   kp_pdl_wait();
+  kp_pdl_trigger();      // dependents (the next aggregation kernel) may run their prologue from here on
   {
     const size_t sd = m.dout_stride ? (size_t)m.dout_stride : (size_t)Co;
     const int warp = threadIdx.x >> 5, c = (threadIdx.x & 31) * 4;

@@ -38,12 +38,15 @@ extern std::atomic<uint64_t> g_launches;
     KP_CUDA(cudaGetLastError());                                                           \
   } while (0)
 
-// Launch with the programmatic-dependent-launch attribute (KP_AGG_PDL=0 turns it off): the kernel may be scheduled
+// Launch with the programmatic-dependent-launch attribute -- OPT-IN (KP_AGG_PDL=1 for the aggregation kernels,
+// KP_DENSE_PDL=1 for the dense block): parity-tested with both on (full GPU suite), but measured with CUDA events
+// inside the captured step it gains nothing (dense: 1.1786 vs 1.1748 ms) or loses (aggregation: 1.1913 ms) --
+// profiles/r2_pdl.txt.  With the attribute the kernel may be scheduled
 // while the preceding kernel of the stream is still running, once every CTA of that kernel has called
 // kp_pdl_trigger() (or exited); it must call kp_pdl_wait() before touching anything the predecessor writes.
 #define KP_LAUNCH_PDL(kernel, grid, block, smem, strm_, ...)                                                \
   do {                                                                                                      \
-    static const bool _pdl = !(getenv("KP_AGG_PDL") && atoi(getenv("KP_AGG_PDL")) == 0);                    \
+    static const bool _pdl = getenv("KP_AGG_PDL") && atoi(getenv("KP_AGG_PDL")) == 1;                     \
     cudaLaunchConfig_t _cfg = {};                                                                           \
     _cfg.gridDim = dim3(grid);                                                                              \
     _cfg.blockDim = dim3(block);                                                                            \
@@ -65,7 +68,7 @@ extern std::atomic<uint64_t> g_launches;
 #define KP_LAUNCH_COOP(kernel, grid, block, smem, strm_, args)                                             \
   do {                                                                                                      \
     static const bool _plain = getenv("KP_DENSE_COOP") && atoi(getenv("KP_DENSE_COOP")) == 0;               \
-    static const bool _pdl = !(getenv("KP_DENSE_PDL") && atoi(getenv("KP_DENSE_PDL")) == 0);                  \
+    static const bool _pdl = getenv("KP_DENSE_PDL") && atoi(getenv("KP_DENSE_PDL")) == 1;                   \
     cudaLaunchConfig_t _cfg = {};                                                                           \
     _cfg.gridDim = dim3(grid);                                                                              \
     _cfg.blockDim = dim3(block);                                                                            \

@@ -157,6 +157,24 @@ class PeerGradients(FlatGradients):
                    "kp_peer_allreduce_mean")
         return self.flat
 
+    def close(self):
+        """Unmaps the peers' blocks and frees this rank's (call on every rank, after a barrier: a peer may still be
+        reading until its last exchange has returned).  The object is unusable afterwards."""
+        from . import _lib
+        L = _lib.lib()
+        if getattr(self, "blocks", None) is None:
+            return
+        torch.cuda.synchronize(self.device)
+        with torch.cuda.device(self.device):
+            for r, ptr in enumerate(self.blocks):
+                if r != self.rank and ptr:
+                    L.kp_peer_release(ptr)
+            self.send = self.flat = self._send_all = self._recv_all = None
+            for p in self.params:
+                p.grad = None
+            L.kp_peer_free(self._own)
+        self.blocks = None
+
     def check(self):
         """After a synchronisation point: did an exchange time out waiting for a peer?"""
         err = int(self.state[-1].item())

@@ -126,5 +126,10 @@ class DeviceWire(object):
         if not torch.cuda.is_current_stream_capturing():
             ts = [t for t in (self.batch.edge_index, self.batch.edge_attr, self.batch.peripheral_edge_attr,
                               self.batch.peripheral_configuration_attr, self.batch.x, self.batch.batch)]
-            torch._C._autograd._unsafe_set_version_counter(ts, [t._version + 1 for t in ts])
+            bump = getattr(torch._C._autograd, "_unsafe_set_version_counter", None)
+            if bump is not None:
+                bump(ts, [t._version + 1 for t in ts])
+            else:                       # older / newer torch without the hook: an in-place no-op bumps the counter too
+                for t in ts:
+                    t.add_(0)
         return self.batch

@@ -23,19 +23,20 @@ def main():
         for _ in range(3):
             bs.step_resident()
         torch.cuda.synchronize()
-    evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
-    evs.sort(key=lambda e: e.time_range.start)
-    # last replay: from the last wire_unpack kernel on
-    starts = [i for i, e in enumerate(evs) if "wire_unpack" in e.name]
+    # raw Kineto records carry the stream id (device_resource_id); FunctionEvent does not
+    evs = [e for e in prof.profiler.kineto_results.events()
+           if e.device_type() == torch.autograd.DeviceType.CUDA and e.duration_ns() > 0]
+    evs.sort(key=lambda e: e.start_ns())
+    starts = [i for i, e in enumerate(evs) if "wire_unpack" in e.name()]
     seg = evs[starts[-1]:]
-    t0 = seg[0].time_range.start
-    end = max(e.time_range.end for e in seg)
-    print("# one step: %d device activities, %.1f us from first start to last end" % (len(seg), end - t0))
+    t0 = seg[0].start_ns()
+    end = max(e.start_ns() + e.duration_ns() for e in seg)
+    print("# one step: %d device activities, %.1f us from first start to last end" % (len(seg), (end - t0) / 1e3))
     tot = {}
     for e in seg:
-        dur = e.time_range.end - e.time_range.start
-        print("%8.1f %7.1f  s%-3d %s" % (e.time_range.start - t0, dur, e.device_index if False else getattr(e, "stream", 0) or 0, e.name[:110]))
-        key = e.name.split("(")[0][:60]
+        dur = e.duration_ns() / 1e3
+        print("%8.1f %7.1f  s%-3d %s" % ((e.start_ns() - t0) / 1e3, dur, e.device_resource_id(), e.name()[:110]))
+        key = e.name().split("(")[0][:60]
         tot[key] = tot.get(key, 0.0) + dur
     print("# totals")
     for k, v in sorted(tot.items(), key=lambda kv: -kv[1])[:30]:

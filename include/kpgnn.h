@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define KPGNN_ABI_VERSION 16
+#define KPGNN_ABI_VERSION 17
 
 const char* kp_last_error(void);
 int kp_abi_version(void);
@@ -413,6 +413,27 @@ int kp_peer_export(const void* ptr, unsigned char handle[KP_PEER_HANDLE_BYTES]);
 int kp_peer_import(const unsigned char handle[KP_PEER_HANDLE_BYTES], void** ptr);
 int kp_peer_release(void* ptr);
 int kp_peer_allreduce_mean(const kp_peer_desc* desc, void* stream);
+
+/* Graph-regression head as one kernel each way: h = relu(rep); pooled[g] = sum (mean != 0: mean) of h over the rows of
+ * graph g; score[g] = <w, pooled[g]> + b; loss = mean_g |score - y| (loss_kind 0, train_ZINC.py:42) or mean_g (score - y)^2
+ * (loss_kind 1) -- models/GNNs.py:276-277 (ReLU of the output projection, dropout 0), models/GraphRegression.py:26 and its
+ * Linear(H,1) regressor.  batch is int64, non-decreasing, graph ids in [0,G) (rows with id >= G, the padding of a capacity
+ * batch, contribute nothing and receive zero gradient); n_dev as in kp_dense_desc.  Fixed-order sums, no float atomics.
+ * workspace: kp_head_workspace_bytes(G), 16-byte aligned, ZEROED ONCE by the caller and private to one stream. */
+typedef struct kp_head_desc {
+  int32_t N, H, G, mean, loss_kind, pad;
+  const float* rep; int64_t rep_stride;      /* [N,H] pre-activation of the output projection */
+  int64_t rep_stride_out;                    /* backward: row stride of drep */
+  const int64_t* batch;
+  const int32_t* n_dev;                      /* live row count (device) or NULL */
+  const float* w; const float* b;            /* regressor weight [H] and bias [1] */
+  const float* y;                            /* targets [G] */
+} kp_head_desc;
+size_t kp_head_workspace_bytes(int32_t G);
+int kp_head_forward(const kp_head_desc* desc, float* pooled, float* score, float* loss, void* workspace,
+                    size_t workspace_bytes, void* stream);
+int kp_head_backward(const kp_head_desc* desc, const float* pooled, const float* score, const float* dloss, float* drep,
+                     float* dw, float* db, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Graph readout over a sorted segment vector: PyG global_add_pool / global_mean_pool on `data.batch`
  * (models/GraphRegression.py:26, models/GraphClassification.py:30).  out[g,:] = sum (mean != 0: mean) of the rows i of

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # KPGNN_B200_LIB points at an alternative build of the same library (kernel tuning experiments)
 LIB_PATH = os.environ.get("KPGNN_B200_LIB") or os.path.join(_HERE, "libkpgnn_b200.so")
 
-ABI_VERSION = 16
+ABI_VERSION = 17
 
 
 class KpError(RuntimeError):
@@ -97,6 +97,12 @@ class PeerDesc(C.Structure):
                 ("out", C.c_void_p), ("epoch", C.c_void_p), ("error", C.c_void_p), ("scale", C.c_float)]
 
 
+class HeadDesc(C.Structure):
+    _fields_ = [("N", C.c_int32), ("H", C.c_int32), ("G", C.c_int32), ("mean", C.c_int32), ("loss_kind", C.c_int32),
+                ("pad", C.c_int32), ("rep", C.c_void_p), ("rep_stride", C.c_int64), ("rep_stride_out", C.c_int64),
+                ("batch", C.c_void_p), ("n_dev", C.c_void_p), ("w", C.c_void_p), ("b", C.c_void_p), ("y", C.c_void_p)]
+
+
 class WireDesc(C.Structure):
     _fields_ = [("n_cap", C.c_int32), ("e_cap", C.c_int32), ("g", C.c_int32), ("K", C.c_int32), ("met", C.c_int32),
                 ("hp1", C.c_int32), ("x_bytes", C.c_int32), ("attr_bytes", C.c_int32), ("p_bytes", C.c_int32),
@@ -176,6 +182,11 @@ _SIGNATURES = {
     "kp_peer_import": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
     "kp_peer_release": (C.c_int, [C.c_void_p]),
     "kp_peer_allreduce_mean": (C.c_int, [C.POINTER(PeerDesc), C.c_void_p]),
+    "kp_head_workspace_bytes": (C.c_size_t, [C.c_int32]),
+    "kp_head_forward": (C.c_int, [C.POINTER(HeadDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                  C.c_void_p]),
+    "kp_head_backward": (C.c_int, [C.POINTER(HeadDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "kp_segment_sum": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                 C.c_void_p, C.c_void_p]),
     "kp_peripheral_grad": (C.c_int, [C.POINTER(PgradDesc), C.c_void_p, C.c_void_p]),

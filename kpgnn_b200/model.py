@@ -175,11 +175,23 @@ class KPGNNPlusBackbone(nn.Module):
             return _TableSum.apply(w, xin.view(-1, 1), [0], [0, 1], [0, w.size(0)])
         return self.init_proj(data).squeeze()
 
-    def forward(self, data):
+    def _tail_fusable(self):
+        """Is the tail Linear -> ReLU -> identity dropout (what the fused regression head can absorb)?"""
+        mods = list(self.output_proj)
+        return len(mods) == 3 and isinstance(mods[1], nn.ReLU) and isinstance(mods[2], nn.Dropout) and \
+            (mods[2].p == 0.0 or not self.training)
+
+    def _tail(self, rep_in, pre_activation):
+        """output_proj on the JK representation; with pre_activation only its Linear (the fused head applies the ReLU)."""
+        return self.output_proj[0](rep_in) if pre_activation else self.output_proj(rep_in)
+
+    def forward(self, data, pre_activation=False):
+        if pre_activation and not self._tail_fusable():
+            return None
         x = self.input_embedding(data)
         N = x.size(0)
         P = self.peripheral(data, N, x)
-        fused = self._forward_stack(data, x, P)
+        fused = self._forward_stack(data, x, P, pre_activation)
         if fused is not None:
             return fused
         h_list = [x]
@@ -213,11 +225,11 @@ class KPGNNPlusBackbone(nn.Module):
             rep = torch.stack(h_list, 0).sum(0)
         else:
             raise ValueError("JK=%r not supported by this backbone" % (self.JK,))
-        return self.output_proj(rep)
+        return self._tail(rep, pre_activation)
 
     use_stack = True          # tests switch this off to compare against the layer-by-layer path
 
-    def _forward_stack(self, data, x, P):
+    def _forward_stack(self, data, x, P, pre_activation=False):
         """All layers as one autograd node over a layer-history buffer (kpgnn_b200/stack.py); None if not applicable."""
         from .stack import kpginplus_stack, stack_applicable
         from .layers._base import _all_zero, SplitKLinear  # noqa: F401
@@ -238,12 +250,14 @@ class KPGNNPlusBackbone(nn.Module):
         Hn = kpginplus_stack(self.gnns, norms, x, P, plan, self.residual)      # [N, L+1, H], slot L-j = h_j
         lin = self.output_proj[0]
         if self.JK == "last":
-            return self.output_proj(Hn[:, 0])
+            return self._tail(Hn[:, 0], pre_activation)
         H, L1 = self.hidden_size, self.num_layer + 1
         # JK concat (GNNs.py:455): Hn viewed [N, (L+1)H] holds the layer outputs newest first, so the projection's
         # column blocks are flipped instead of the activations
         Wf = lin.weight.view(lin.out_features, L1, H).flip(1).reshape(lin.out_features, L1 * H)
         rep = _SplitKLinearFn.apply(Hn.view(x.size(0), L1 * H), Wf, lin.bias)
+        if pre_activation:
+            return rep
         for m in list(self.output_proj)[1:]:
             rep = m(rep)
         return rep
@@ -260,6 +274,17 @@ class KPGNNPlusRegressor(nn.Module):
     def forward(self, data):
         h = self.embedding_model(data)
         return self.regressor(segment_sum(h, data.batch, data.num_graphs)).squeeze()
+
+    def fused_loss(self, data, kind="l1"):
+        """loss(self(data), data.y) for the L1 (train_ZINC.py:42) or MSE loss with the ReLU of the output projection, the
+        pooling, the regressor and the loss in ONE kernel each way (kp_head_*).  None when the backbone's tail is not
+        Linear -> ReLU -> identity dropout (the caller then evaluates the loss the usual way)."""
+        from .head import fused_regression_loss
+        rep = self.embedding_model(data, pre_activation=True)
+        if rep is None:
+            return None
+        return fused_regression_loss(rep, self.regressor.weight, self.regressor.bias, data.y, data.batch,
+                                     data.num_graphs, mean=False, kind=kind, n_dev=getattr(data, "n_dev", None))
 
 
 def zinc_kpginplus(K=8, num_layer=8, hidden=104, combine="geometric"):

@@ -70,6 +70,7 @@ class Trainer(object):
         self.launches_per_step = 0
         self.idx_buf = peripheral_index(self.dev.peripheral_edge_attr, self.dev.peripheral_configuration_attr)
         self.plan_obj = None
+        self.fuse_head = os.environ.get("KP_FUSED_HEAD", "1") != "0"
         self._loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
         self._e2e_i, self._e2e_prev = 0, None
 
@@ -128,7 +129,11 @@ class Trainer(object):
         self.wire.unpack()
         self.refresh_derived()
         self._zero()
-        loss = self.loss_fn(self.model(self.dev), self.dev.y)
+        loss = None
+        if self.loss_fn is l1_loss and self.fuse_head and hasattr(self.model, "fused_loss"):
+            loss = self.model.fused_loss(self.dev, "l1")          # head + loss as one kernel each way (kp_head_*)
+        if loss is None:
+            loss = self.loss_fn(self.model(self.dev), self.dev.y)
         loss.backward()
         if self.plan_obj is not None and self.plan_obj.tail is not None:     # late join of the plan stream (host statistics)
             torch.cuda.current_stream(self.device).wait_event(self.plan_obj.tail)

@@ -67,7 +67,7 @@ def test_struct_layouts_match_header(tmp_path):
     from kpgnn_b200 import _lib
     mirrors = {"kp_plan_input": _lib.PlanInput, "kp_agg_desc": _lib.AggDesc, "kp_extract_input": _lib.ExtractInput,
                "kp_tsum_desc": _lib.TsumDesc, "kp_dense_desc": _lib.DenseDesc, "kp_theta_batch": _lib.ThetaBatch,
-               "kp_pgrad_desc": _lib.PgradDesc, "kp_attn_desc": _lib.AttnDesc, "kp_wire_desc": _lib.WireDesc, "kp_peer_desc": _lib.PeerDesc, "kp_fold_desc": _lib.FoldDesc,
+               "kp_pgrad_desc": _lib.PgradDesc, "kp_attn_desc": _lib.AttnDesc, "kp_wire_desc": _lib.WireDesc, "kp_peer_desc": _lib.PeerDesc, "kp_head_desc": _lib.HeadDesc, "kp_fold_desc": _lib.FoldDesc,
                "kp_fold_grads": _lib.FoldGrads}
     header = open(os.path.join(ROOT, "include", "kpgnn.h")).read()
     declared = set(re.findall(r"^\}\s*(kp_[a-z0-9_]+)\s*;", header, flags=re.M))

@@ -477,14 +477,23 @@ def other_model_steps(device):
             loss = l1_loss(model(b), y)
             loss.backward()
             opt.step()
-        return _events_ms(step, steps, device, warm=3)
+        ms_eager = _events_ms(step, steps, device, warm=3)
+        ms_graph = None
+        try:                                    # the same step as ONE CUDA graph (kpgnn_b200.train.GraphedStep)
+            from kpgnn_b200.train import GraphedStep
+            gs = GraphedStep(model, b, y, l1_loss)
+            ms_graph = _events_ms(gs.replay, steps, device, warm=3)
+        except Exception as e:                  # diagnostics only
+            log("GraphedStep failed: %r" % (e,))
+        return ms_eager, ms_graph
     # configs[2]: KPGINPrime K=16, 17 layers, hidden 96 (README.md:128)
     b16 = extract_batch(graphs, (16, 50, 6, 3, 50, 50, "spd"), device)
     torch.manual_seed(0)
     prime = backbones.make_model("KPGINPrime", 96, 16, 17, 21, 3, 50, 50, 6, 50, JK="concat", residual=True).to(device).train()
-    ms = time_model(prime, b16)
+    ms, msg = time_model(prime, b16)
     res["kpginprime_K16_L17_H96_batch128"] = {"ms_per_step_eager": round(ms, 3),
-                                              "graphs_per_s": round(GRAPHS_PER_GPU / (ms * 1e-3), 1)}
+                                              "ms_per_step_cuda_graph": None if msg is None else round(msg, 3),
+                                              "graphs_per_s": round(GRAPHS_PER_GPU / ((msg or ms) * 1e-3), 1)}
     try:
         from oracle import refimport
         if refimport.available():
@@ -502,11 +511,13 @@ def other_model_steps(device):
                                       max_hop_num=6, max_distance_count=50, wo_peripheral_edge=False,
                                       wo_peripheral_configuration=False, drop_prob=0.0)
             model = dropin.GraphRegression.GraphRegression(embedding_model=gnn, pooling_method="sum").to(device).train()
-            ms = time_model(model, b8)
+            ms, msg = time_model(model, b8)
             res["reference_GNNPlus_unmodified_over_dropin_layers_batch128"] = {
-                "ms_per_step_eager": round(ms, 3), "graphs_per_s": round(GRAPHS_PER_GPU / (ms * 1e-3), 1),
-                "note": "the reference's own models/GNNs.py + GraphRegression.py (staged copy), layer by layer, no CUDA "
-                        "graph, no stack node: what a reference user gets from install_dropin() alone"}
+                "ms_per_step_eager": round(ms, 3), "ms_per_step_cuda_graph": None if msg is None else round(msg, 3),
+                "graphs_per_s": round(GRAPHS_PER_GPU / ((msg or ms) * 1e-3), 1),
+                "note": "the reference's own models/GNNs.py + GraphRegression.py (staged copy), layer by layer, no stack "
+                        "node: what a reference user gets from install_dropin() alone (eager), and with the step "
+                        "captured by kpgnn_b200.train.GraphedStep"}
     except Exception as e:      # diagnostics must never take the bench line down
         res["reference_GNNPlus_unmodified_over_dropin_layers_batch128"] = {"error": repr(e)[:200]}
     return res

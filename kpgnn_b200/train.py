@@ -290,3 +290,40 @@ class Trainer(object):
             self._validations = getattr(self, "_validations", 0) + 1
             if self._validations % 16 == 1:
                 self.grads.check()
+
+
+class GraphedStep(object):
+    """forward + backward + Adam of ANY model built on the drop-in layers (the native backbones, or the reference's own
+    unmodified models/GNNs.py after install_dropin()) on a FIXED-SHAPE batch as one CUDA graph: the eager step of these
+    models is launch-bound (hundreds of 2-10 us kernels), a graph replay is not.  `batch` and `y` are the static inputs:
+    copy a new batch of the same shapes INTO their tensors between replays (the plan cache follows the tensors' version
+    counters outside capture only, so contents that change the K-hop structure need kpgnn_b200.plan.refresh_plan +
+    mark_current, as Trainer does; identical structure -- e.g. new node features / targets -- needs nothing)."""
+
+    def __init__(self, model, batch, y, loss_fn=l1_loss, lr=1e-3, warmup=3):
+        self.model, self.batch, self.y, self.loss_fn = model, batch, y, loss_fn
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        self.opt = FusedAdam(self.params, lr=lr)
+        dev = self.params[0].device
+        s = torch.cuda.Stream(dev)
+        s.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self._step()
+        torch.cuda.current_stream(dev).wait_stream(s)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._step()
+
+    def _step(self):
+        for p in self.params:
+            p.grad = None
+        loss = self.loss_fn(self.model(self.batch), self.y)
+        loss.backward()
+        self.opt.step()
+        return loss.detach()
+
+    def replay(self):
+        self.graph.replay()
+        return self.loss

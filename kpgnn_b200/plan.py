@@ -148,10 +148,16 @@ def _run_fill(p, pin):
 
 
 def _plan_input(p, edge_index, edge_attr_base, attr_stride):
-    p.src = edge_index[0].contiguous()
-    p.dst = edge_index[1].contiguous()
-    return _lib.PlanInput(p.src.data_ptr(), p.dst.data_ptr(), edge_attr_base.data_ptr(), attr_stride, p.N, p.E, p.K,
-                          1 if p.self_loops else 0)
+    # The plan is cached ON the edge_index tensor (edge_index._kpgnn_plans), so it must not hold a view of it: a view's
+    # ._base is the tensor object itself -- a reference cycle that only the cyclic GC breaks, i.e. every batch's plan,
+    # wire tensors and extraction outputs stayed allocated until a collection ran (1.7 GB per configs[4] step, the
+    # allocator fell back to cudaMalloc at 85 ms a call).  Rows of a contiguous [2,E] tensor are used in place (the caller
+    # keeps edge_index alive across the launch); only a real copy of a strided input is kept.
+    src, dst = edge_index[0], edge_index[1]
+    p.src = None if src.is_contiguous() else src.contiguous()
+    p.dst = None if dst.is_contiguous() else dst.contiguous()
+    return _lib.PlanInput((p.src if p.src is not None else src).data_ptr(), (p.dst if p.dst is not None else dst).data_ptr(),
+                          edge_attr_base.data_ptr(), attr_stride, p.N, p.E, p.K, 1 if p.self_loops else 0)
 
 
 _CAPACITY_HINT = 0

@@ -74,3 +74,28 @@ def test_plan_empty(lib):
     plan, k = get_plan(ei, ea, 4)
     assert plan.nnz == 0 and k == 3
     assert int(plan.rowptr.abs().sum()) == 0
+
+
+def test_plans_of_discarded_batches_are_freed_without_the_cyclic_gc(lib):
+    """The plan is cached on the edge_index tensor object; it must not reference that tensor back (a view's ._base is the
+    tensor itself), or every batch of a per-step collation loop (train_ZINC.py:33: a new Batch every step) stays allocated
+    until the cyclic garbage collector happens to run."""
+    import gc
+    from kpgnn_b200.plan import get_plan
+    dev = torch.device("cuda:0")
+    b = zinc_batch(24, 6, "spd", seed=5)
+    N = b["num_nodes"]
+    gc.collect()
+    gc.disable()
+    try:
+        sizes = []
+        for step in range(6):
+            ei, ea = b["edge_index"].to(dev), b["edge_attr"].to(dev)          # fresh tensor objects, as a loader delivers
+            plan, _ = get_plan(ei, ea, N)
+            plan.blocks()
+            del plan, ei, ea
+            torch.cuda.synchronize()
+            sizes.append(torch.cuda.memory_allocated())
+    finally:
+        gc.enable()
+    assert sizes[-1] <= sizes[1], sizes

@@ -83,19 +83,22 @@ fold_bwd_kernel(const kp_fold_desc f, const float* __restrict__ dTable, kp_fold_
   const int Hi = f.H_in, Ho = f.H_out;
   // grid: FOLD_SLICES CTAs per table (slice sl: a row range of dE and an output-channel range of dW), then the bias CTA
   const int i = blockIdx.x / FOLD_SLICES, sl = blockIdx.x - i * FOLD_SLICES;
-  __shared__ float red[FOLD_THREADS];
+  // The gate gradients are sums of ~rows*H*H signed products that cancel to a few per cent of their running partial
+  // sums: they are accumulated in double (a few dozen DFMA per thread), so that neither the slicing nor the order of
+  // the partials shows in the result.
+  __shared__ double red[FOLD_THREADS];
   __shared__ bool last;
-  float partial = 0.f;
-  float* part_gate = part;                                  // [T*FOLD_SLICES] table shares, then [2] bias shares
+  double partial = 0.0;
+  double* part_gate = reinterpret_cast<double*>(part);      // [T*FOLD_SLICES] table shares, then [2] bias shares
   if (i == f.T) {                                         // bias row: dbias_g, and its share of the gate gradients
     const float* dMb = dTable + (size_t)f.row_off[f.T] * Ho;
     for (int gsel = 0; gsel < 2; ++gsel) {
       const float g = fold_gate(__ldg(f.gate_raw[gsel]), f.gate_act);
-      float s = 0.f;
+      double s = 0.0;
       for (int o = threadIdx.x; o < Ho; o += FOLD_THREADS) {
         const float dm = __ldg(dMb + o);
         if (out.dbias[gsel]) out.dbias[gsel][o] = f.bias_mult[gsel] * g * dm;
-        s = fmaf(dm, __ldg(f.bias[gsel] + o), s);
+        s = fma((double)dm, (double)__ldg(f.bias[gsel] + o), s);
       }
       red[threadIdx.x] = s;
       __syncthreads();
@@ -156,7 +159,7 @@ fold_bwd_kernel(const kp_fold_desc f, const float* __restrict__ dTable, kp_fold_
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             if (o0 + j < ohi) {
-              partial = fmaf(Ws[(o0 + j) * Hi + c], acc[j], partial);
+              partial = fma((double)Ws[(o0 + j) * Hi + c], (double)acc[j], partial);
               if (out.dW[i]) out.dW[i][(size_t)(o0 + j) * f.w_stride[i] + c] = g * acc[j];
             }
         }
@@ -178,12 +181,12 @@ fold_bwd_kernel(const kp_fold_desc f, const float* __restrict__ dTable, kp_fold_
   if (last && threadIdx.x < 2) {
     __threadfence();
     const int gsel = threadIdx.x;
-    float s = 0.f;
+    double s = 0.0;
     for (int t = 0; t < f.T; ++t)
       if (f.gate[t] == gsel)
         for (int q = 0; q < FOLD_SLICES; ++q) s += __ldcg(part_gate + t * FOLD_SLICES + q);
     s += __ldcg(part_gate + f.T * FOLD_SLICES + gsel);
-    if (out.dgate_raw[gsel]) out.dgate_raw[gsel][0] = s * fold_gate_grad(__ldg(f.gate_raw[gsel]), f.gate_act);
+    if (out.dgate_raw[gsel]) out.dgate_raw[gsel][0] = (float)s * fold_gate_grad(__ldg(f.gate_raw[gsel]), f.gate_act);
     if (gsel == 0) *counter = 0u;                            // self-resetting: no memset before the next launch
   }
 }
@@ -230,11 +233,11 @@ int kp_fold_backward(const kp_fold_desc* desc, const float* dTable, const kp_fol
   KP_CHECK_ARG(smem <= 200 * 1024, "kp_fold_backward: a table needs %zu bytes of shared memory", smem);
   if (smem > 32 * 1024)
     KP_CUDA(cudaFuncSetAttribute(kp::fold_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  // workspace: the arrival counter (zeroed ONCE by the caller; the kernel leaves it zero), then at byte 256 the float
+  // workspace: the arrival counter (zeroed ONCE by the caller; the kernel leaves it zero), then at byte 256 the DOUBLE
   // partials of the gate gradients (T * FOLD_SLICES table shares + 2 bias shares)
   unsigned* counter = (unsigned*)workspace;
   float* part = (float*)((char*)workspace + 256);
-  static_assert(256 + 4 * (16 * kp::FOLD_SLICES + 2) <= KP_FOLD_WORKSPACE_BYTES, "fold workspace");
+  static_assert(256 + 8 * (16 * kp::FOLD_SLICES + 2) <= KP_FOLD_WORKSPACE_BYTES, "fold workspace");
   KP_LAUNCH(kp::fold_bwd_kernel, f.T * kp::FOLD_SLICES + 1, kp::FOLD_THREADS, smem, stream, f, dTable, *grads, part, counter);
   return 0;
 }

@@ -72,6 +72,7 @@ def _compare(cfg, ref_model, my_model, batch_cpu, dev):
     assert rel_err(p1, p0) < bar(rel_err(p32, p0)), ("prediction", rel_err(p1, p0), rel_err(p32, p0))
     assert abs(l1 - l0) <= bar(abs(l32 - l0) / max(abs(l0), 1e-6)) * max(abs(l0), 1e-6), ("loss", l0, l1, l32)
     gmax = max(float(v.abs().max()) for v in g0.values() if v is not None)
+    fails = []
     for n in g0:
         a, c, r = g1[n], g0[n], g32[n]
         if a is None or c is None:
@@ -82,7 +83,9 @@ def _compare(cfg, ref_model, my_model, batch_cpu, dev):
             assert float((a - c).abs().max()) < 1e-4 * gmax, n
             continue
         err, own = rel_err(a, c, floor=1e-2 * gmax), rel_err(r, c, floor=1e-2 * gmax)
-        assert err < bar(own), (n, err, own)
+        if not err < bar(own):
+            fails.append((n, tuple(a.shape), "%.2e" % err, "own %.2e" % own))
+    assert not fails, fails
 
 
 @pytest.mark.parametrize("name,combine,virtual_node", [

@@ -88,7 +88,7 @@ def _compare(cfg, ref_model, my_model, batch_cpu, dev):
             # scalar gates (pew / pcw): one sum over ~N*K*H signed products that cancels to a few per cent of its partial
             # sums.  The reference model's own torch ops around the drop-in layers (index_add_ pooling of the virtual
             # node: float atomics) are not run-to-run reproducible, and this sum amplifies their 1e-7 jitter: the SAME
-            # test case gave 5.7e-5 and 6.4e-5 in two full-suite runs and < 1.4e-5 in ten others, with a bit-reproducible
+            # test case gave 5.7e-5 and 6.4e-5 in two runs and stayed below 1.4e-5 in every other run, with a bit-reproducible
             # product path.  One fp32 evaluation of the reference is too small a sample for "its own error" here.
             limit = max(limit, 2e-4)
         if not err < limit:

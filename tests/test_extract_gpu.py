@@ -94,6 +94,35 @@ def test_random_typed_directed_multigraphs_vs_oracle(lib):
         _check_batch(graphs, args)
 
 
+def test_cutoff_one_configuration_vs_oracle(lib):
+    """max_hop_num = 1 (run_simulation.py:103) takes the lane-per-member path of extract_peripheral_kernel: typed, directed,
+    duplicate and self-loop edges, dense and sparse graphs, both kernels -- bit-exact against the oracle."""
+    import networkx as nx
+    rng = np.random.default_rng(11)
+    for it in range(10):
+        graphs = []
+        for i in range(6):
+            g = synth.random_typed_graph(rng, int(rng.integers(2, 48)), float(rng.uniform(0.05, 0.6)),
+                                         num_types=int(rng.integers(1, 6)), directed=bool(rng.integers(0, 2)), typed=True)
+            if g["edge_index"].shape[1] and it % 2 == 0:
+                ei, ea = g["edge_index"], g["edge_attr"]
+                dup = rng.integers(0, ei.shape[1], size=4)
+                loops = rng.integers(0, g["num_nodes"], size=3)
+                g["edge_index"] = np.concatenate([ei, ei[:, dup], np.stack([loops, loops])], 1)
+                g["edge_attr"] = np.concatenate([ea, ea[dup], np.full(3, 2)])
+            graphs.append(g)
+        args = (int(rng.integers(1, 7)), int(rng.choice([1, 3, 50])), 1, int(rng.integers(1, 5)),
+                int(rng.choice([1, 3, 50])), int(rng.choice([1, 3, 50])), "spd" if it % 2 else "gd")
+        _check_batch(graphs, args)
+    dense = []
+    for s in range(3):
+        G = nx.random_regular_graph(12, 25, seed=s)
+        e = np.array(list(G.to_directed().edges)).T
+        e = e[:, np.lexsort((e[1], e[0]))]
+        dense.append({"num_nodes": 25, "x": np.ones(25, dtype=np.int64), "edge_index": e.astype(np.int64), "edge_attr": None})
+    _check_batch(dense, (4, 1000, 1, 2, 1000, 1000, "spd"))
+
+
 def test_dense_regular_gd_saturation_vs_oracle(lib):
     """SR25-shape: 25 nodes, 12-regular, gd K=4 -- walk counts reach the hundreds (int16 attrs, cap 1000)."""
     import networkx as nx

@@ -746,6 +746,9 @@ def main():
         workloads["extract"] = [
             extraction_metrics(device, peak, "configs[1] zinc128 K=8 spd", zg, EXTRACT_ARGS),
             extraction_metrics(device, peak, "configs[2] zinc128 K=16 spd", zg, (16, 50, 6, 3, 50, 50, "spd")),
+            # the same extraction at the roofline launch's size: what the kernels reach when they are not latency-bound
+            extraction_metrics(device, peak, "configs[1] zinc%d K=8 spd" % ROOFLINE_GRAPHS,
+                               synth.zinc_like_graphs(ROOFLINE_GRAPHS, seed=1000 + ROOFLINE_GRAPHS), EXTRACT_ARGS, reps=3),
             extraction_metrics(device, peak, "configs[4] regular1280 x16 K=6 spd",
                                [synth.regular_graph(REG_N, 3, s) for s in range(16)], REG_EXTRACT, reps=3)]
         workloads["model_steps"] = other_model_steps(device)

@@ -4,7 +4,7 @@
 //
 // Why: at molecule-batch sizes (N ~ 3 000 rows, 104 channels) the step was a chain of ~45 kernels of 2-11 us each
 // per layer around the aggregation (2 + 4 SIMT GEMMs, 3 + 3 BatchNorm kernels, 4 column sums, bias / residual
-// adds; profiles/r1v_step_kineto.txt) -- all latency, no bandwidth.  Here each CTA keeps a slab of ~36 rows and
+// adds; profiles/r1v_step_kineto.txt) -- all latency, no bandwidth.  Here each CTA keeps a slab of ~32 rows and
 // BOTH weight matrices in shared memory for the whole block; the only cross-CTA dependencies are the three batch
 // statistics (and, backward, the weight-gradient sums), exchanged through small per-CTA partials in L2 behind a
 // grid-wide barrier.  Statistics use Chan's parallel variance (per-slab mean / M2 merged in a fixed order), the

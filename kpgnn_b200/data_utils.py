@@ -246,6 +246,46 @@ def extract_multi_hop_neighbors(data, K, max_edge_attr_num, max_hop_num, max_edg
     return data
 
 
+def extract_many(data_list, K, max_edge_attr_num, max_hop_num, max_edge_type, max_edge_count, max_distance_count, kernel,
+                 chunk=1024, device="cuda"):
+    """extract_multi_hop_neighbors over a LIST of graphs -- what a dataset's process() does with its pre_transform
+    (datasets/ZINC_dataset.py:100-140, PlanarSATPairsDataset.py:28-39: `[self.pre_transform(d) for d in data_list]`) -- with
+    the graphs extracted `chunk` at a time in one batched GPU call instead of one call per graph.  Mutates and returns the
+    same objects with exactly the fields, dtypes and quirks of the per-graph function (graphs without edges take the
+    reference's early-return branch, data_utils.py:37-44)."""
+    args = (K, max_edge_attr_num, max_hop_num, max_edge_type, max_edge_count, max_distance_count, kernel)
+    todo = []
+    for d in data_list:
+        if d.edge_index.size(1) == 0:
+            extract_multi_hop_neighbors(d, *args)                    # two zero fields, no kernel involved
+        else:
+            todo.append(d)
+    for c0 in range(0, len(todo), chunk):
+        part = todo[c0:c0 + chunk]
+        raws = []
+        for d in part:
+            has_attr = ("edge_attr" in d) if hasattr(d, "__contains__") else getattr(d, "edge_attr", None) is not None
+            raws.append({"num_nodes": d.num_nodes, "edge_index": d.edge_index.cpu().numpy(),
+                         "edge_attr": d.edge_attr.cpu().numpy() if has_attr else None})
+        csr = pack_csr(raws)
+        csr["_device"] = _upload(csr, device)
+        out = _extract_device(csr, *args, device=device)
+        ei, ea = out["edge_index"].cpu(), out["edge_attr"].cpu()
+        pea = None if out["peripheral_edge_attr"] is None else out["peripheral_edge_attr"].cpu()
+        pca = None if out["peripheral_configuration_attr"] is None else out["peripheral_configuration_attr"].cpu()
+        gptr = torch.from_numpy(csr["gptr"].astype(np.int64))
+        eptr = torch.searchsorted(ei[0].contiguous(), gptr)         # K-hop edges are sorted by (graph, source, target)
+        for g, d in enumerate(part):
+            n0, n1, e0, e1 = int(gptr[g]), int(gptr[g + 1]), int(eptr[g]), int(eptr[g + 1])
+            back = d.edge_index.device
+            d.edge_index = (ei[:, e0:e1] - n0).to(back)
+            d.edge_attr = ea[e0:e1].clone().to(back)
+            d.peripheral_edge_attr = None if pea is None else pea[n0:n1].clone().to(back)
+            d.peripheral_configuration_attr = None if pca is None else pca[n0:n1].clone().to(back)
+            d.pe_attr = torch.zeros((n1 - n0, K - 1), dtype=torch.int64, device=back) if K > 1 else None
+    return data_list
+
+
 def post_transform(wo_path_encoding, wo_edge_feature):
     """Ablation clamps applied per access (data_utils.py:306-347): plain elementwise host ops, kept for import
     compatibility with the reference's train scripts."""

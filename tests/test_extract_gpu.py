@@ -217,3 +217,27 @@ def test_reference_goldens_full_configs_bit_exact(lib):
             ref = np.concatenate(parts, axis=1 if f == "edge_index" else 0)
             got = getattr(b, f).cpu().numpy()
             assert got.shape == ref.shape and np.array_equal(got, ref), (args, f)
+
+
+def test_extract_many_equals_per_graph_calls(lib):
+    """The batched dataset pre-transform (kpgnn_b200.data_utils.extract_many, what datasets/*.py process() runs over a whole
+    data list) gives every graph exactly the fields of the per-graph drop-in -- including graphs without edges, which take
+    the reference's early-return branch (data_utils.py:37-44) -- for typed, untyped, directed and duplicate-edge inputs."""
+    from kpgnn_b200.data_utils import extract_many, extract_multi_hop_neighbors
+    rng = np.random.default_rng(3)
+    graphs = synth.zinc_like_graphs(20, seed=9)
+    for i in range(8):
+        graphs.append(synth.random_typed_graph(rng, int(rng.integers(2, 30)), float(rng.uniform(0.05, 0.5)),
+                                               num_types=3, directed=bool(i % 2), typed=bool(i % 3)))
+    graphs.insert(5, {"num_nodes": 4, "x": np.zeros(4, dtype=np.int64), "edge_index": np.zeros((2, 0), dtype=np.int64),
+                      "edge_attr": np.zeros(0, dtype=np.int64)})
+    for args in ((4, 50, 6, 3, 50, 50, "spd"), (3, 10, 1, 1, 1, 1, "gd"), (1, 50, 2, 2, 50, 50, "spd")):
+        one = [extract_multi_hop_neighbors(_data(g), *args) for g in graphs]
+        many = extract_many([_data(g) for g in graphs], *args, chunk=7)
+        for a, b in zip(one, many):
+            for f in ("edge_index", "edge_attr", "pe_attr", "peripheral_edge_attr", "peripheral_configuration_attr",
+                      "peripheral_configuration"):
+                va, vb = getattr(a, f, None), getattr(b, f, None)
+                assert (va is None) == (vb is None), f
+                if va is not None:
+                    assert va.dtype == vb.dtype and va.shape == vb.shape and torch.equal(va, vb), f

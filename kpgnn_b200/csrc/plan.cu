@@ -76,6 +76,63 @@ __global__ void plan_nnz_kernel(const int* __restrict__ rowptr, int rows, int* _
   stats[0] = rowptr[rows];
 }
 
+// ---- small-batch head of the plan build: at a few thousand nodes the count phase was seven launches (4 memsets, the
+// count kernel, 2 x {CUB scan init + scan}, the nnz read) whose launch gaps sat on the critical path of the training
+// step.  One kernel zeroes all four arrays; one kernel (a CTA per array) does both exclusive scans in place and writes nnz.
+__global__ void __launch_bounds__(256) plan_zero_kernel(int* __restrict__ a, int* __restrict__ b, long long nab,
+                                                        int* __restrict__ c, long long nc, int* __restrict__ stats) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nab; i += stride) {
+    a[i] = 0;
+    b[i] = 0;
+  }
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nc; i += stride) c[i] = 0;
+  if (blockIdx.x == 0 && threadIdx.x < 4) stats[threadIdx.x] = 0;
+}
+
+constexpr int PLAN_SCAN_THREADS = 1024;
+constexpr int PLAN_SCAN_MAX = PLAN_SCAN_THREADS * 64;        // elements one CTA scans (64 per thread)
+
+// in-place exclusive scan of n ints by ONE CTA: thread t owns the contiguous chunk [t*per, (t+1)*per)
+__global__ void __launch_bounds__(PLAN_SCAN_THREADS)
+plan_scan2_kernel(int* __restrict__ a0, int* __restrict__ a1, int n, int* __restrict__ stats) {
+  __shared__ int wsum[PLAN_SCAN_THREADS / 32];
+  int* a = blockIdx.x == 0 ? a0 : a1;
+  const int per = (n + PLAN_SCAN_THREADS - 1) / PLAN_SCAN_THREADS;
+  const int lo = min(n, (int)threadIdx.x * per), hi = min(n, lo + per);
+  int s = 0;
+  for (int i = lo; i < hi; ++i) s += a[i];
+  // block-wide exclusive scan of the per-thread sums
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int incl = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) wsum[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int w = wsum[lane];
+    int wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += v;
+    }
+    wsum[lane] = wi - w;                                       // exclusive prefix of the warp sums
+  }
+  __syncthreads();
+  int run = wsum[warp] + incl - s;
+  for (int i = lo; i < hi; ++i) {
+    const int v = a[i];
+    a[i] = run;
+    run += v;
+  }
+  // the last element's output is the grand total when its input is 0 (the arrays carry one slot past the rows)
+  if (blockIdx.x == 0 && hi == n && lo < n) stats[0] = a[n - 1];
+}
+
 __global__ void plan_scatter_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
                                     const int64_t* __restrict__ attr, int64_t attr_stride, int N, int E, int K,
                                     const int* __restrict__ rowptr, const int* __restrict__ rowptrT,
@@ -311,10 +368,16 @@ int kp_plan_count(const kp_plan_input* in, int32_t* rowptr, int32_t* rowptrT, in
   KP_CHECK_ARG(workspace_bytes >= need && (workspace || need == 0), "kp_plan_count: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   long long rows = (long long)N * K;
-  KP_CUDA(cudaMemsetAsync(rowptr, 0, sizeof(int) * (rows + 1), st));
-  KP_CUDA(cudaMemsetAsync(rowptrT, 0, sizeof(int) * (rows + 1), st));
-  KP_CUDA(cudaMemsetAsync(indeg, 0, sizeof(int) * (size_t)(N > 0 ? N : 1), st));
-  KP_CUDA(cudaMemsetAsync(stats, 0, sizeof(int) * 4, st));
+  const bool small = rows + 1 <= kp::PLAN_SCAN_MAX;             // one-CTA scans, fused zeroing (see plan_scan2_kernel)
+  if (small) {
+    KP_LAUNCH(kp::plan_zero_kernel, kp::ceil_div(rows + 1, 256 * 4), 256, 0, st, rowptr, rowptrT, rows + 1, indeg,
+              (long long)(N > 0 ? N : 1), stats);
+  } else {
+    KP_CUDA(cudaMemsetAsync(rowptr, 0, sizeof(int) * (rows + 1), st));
+    KP_CUDA(cudaMemsetAsync(rowptrT, 0, sizeof(int) * (rows + 1), st));
+    KP_CUDA(cudaMemsetAsync(indeg, 0, sizeof(int) * (size_t)(N > 0 ? N : 1), st));
+    KP_CUDA(cudaMemsetAsync(stats, 0, sizeof(int) * 4, st));
+  }
   long long total = (long long)E * K;
   if (total > 0) {
     KP_LAUNCH(kp::plan_count_kernel, kp::ceil_div(total, 256), 256, 0, st, in->src, in->dst, in->attr,
@@ -322,6 +385,10 @@ int kp_plan_count(const kp_plan_input* in, int32_t* rowptr, int32_t* rowptrT, in
   }
   if (in->self_loops && rows > 0) {
     KP_LAUNCH(kp::plan_add_loops_kernel, kp::ceil_div(rows, 256), 256, 0, st, rowptr, rowptrT, (int)rows);
+  }
+  if (small) {
+    KP_LAUNCH(kp::plan_scan2_kernel, 2, kp::PLAN_SCAN_THREADS, 0, st, rowptr, rowptrT, (int)rows + 1, stats);
+    return 0;
   }
   size_t temp = workspace_bytes;
   KP_CUDA(cub::DeviceScan::ExclusiveSum(workspace, temp, rowptr, rowptr, (int)rows + 1, st));

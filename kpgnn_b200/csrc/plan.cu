@@ -7,6 +7,8 @@
 // segment sort so that the float summation order downstream is reproducible.
 #include <cub/device/device_scan.cuh>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace kp {
@@ -368,7 +370,8 @@ int kp_plan_count(const kp_plan_input* in, int32_t* rowptr, int32_t* rowptrT, in
   KP_CHECK_ARG(workspace_bytes >= need && (workspace || need == 0), "kp_plan_count: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   long long rows = (long long)N * K;
-  const bool small = rows + 1 <= kp::PLAN_SCAN_MAX;             // one-CTA scans, fused zeroing (see plan_scan2_kernel)
+  static const bool small_off = getenv("KP_PLAN_SMALL") && atoi(getenv("KP_PLAN_SMALL")) == 0;     // A/B switch
+  const bool small = !small_off && rows + 1 <= kp::PLAN_SCAN_MAX;   // one-CTA scans, fused zeroing (see plan_scan2_kernel)
   if (small) {
     KP_LAUNCH(kp::plan_zero_kernel, kp::ceil_div(rows + 1, 256 * 4), 256, 0, st, rowptr, rowptrT, rows + 1, indeg,
               (long long)(N > 0 ? N : 1), stats);

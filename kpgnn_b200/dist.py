@@ -86,7 +86,7 @@ class PeerGradients(FlatGradients):
     Set-up needs a process group for the one-time handle exchange only (any backend).  Raises when a peer block cannot
     be opened (no P2P path between the devices) -- the caller then keeps FlatGradients + the backend's all-reduce."""
 
-    def __init__(self, params, group=None):
+    def __init__(self, params, group=None, barrier=True):
         from . import _lib
         import ctypes as C
         self.params = [p for p in params if p.requires_grad]
@@ -95,19 +95,28 @@ class PeerGradients(FlatGradients):
         n = (n_real + 3) & ~3                         # the kernel moves float4s; the pad floats stay zero
         self.n, self.n_real, self.device = n, n_real, dev
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
-        if self.world > _lib.PEER_MAX:
-            raise RuntimeError("peer exchange supports up to %d ranks on one node" % _lib.PEER_MAX)
         L = _lib.lib()
         with torch.cuda.device(dev):
-            nbytes = L.kp_peer_block_bytes(n)
-            own = C.c_void_p()
-            _lib.check(L.kp_peer_alloc(nbytes, C.byref(own)), "kp_peer_alloc")
-            handle = C.create_string_buffer(_lib.PEER_HANDLE_BYTES)
-            _lib.check(L.kp_peer_export(own, handle), "kp_peer_export")
+            # Every rank takes part in the handle exchange even when its own allocation failed (payload None), and every
+            # rank then sees the same list: either all raise here or none does -- no rank is left waiting in a collective.
+            own, payload, err = C.c_void_p(), None, None
+            try:
+                if self.world > _lib.PEER_MAX:
+                    raise RuntimeError("peer exchange supports up to %d ranks on one node" % _lib.PEER_MAX)
+                nbytes = L.kp_peer_block_bytes(n)
+                _lib.check(L.kp_peer_alloc(nbytes, C.byref(own)), "kp_peer_alloc")
+                handle = C.create_string_buffer(_lib.PEER_HANDLE_BYTES)
+                _lib.check(L.kp_peer_export(own, handle), "kp_peer_export")
+                payload = (bytes(handle.raw), n, int(dev.index))
+            except Exception as e:                      # noqa: BLE001 -- reported to every rank through the exchange
+                err = e
             handles = [None] * self.world
-            dist.all_gather_object(handles, (bytes(handle.raw), n, int(dev.index)), group=group)
-            if any(h[1] != n for h in handles):
-                raise RuntimeError("ranks disagree on the gradient length")
+            dist.all_gather_object(handles, payload, group=group)
+            bad = [r for r, h in enumerate(handles) if h is None or h[1] != n]
+            if bad:
+                if own.value:
+                    L.kp_peer_free(own)
+                raise RuntimeError("peer gradient blocks unavailable on rank(s) %s%s" % (bad, ": %s" % err if err else ""))
             self.blocks = []
             for r, h in enumerate(handles):
                 if r == self.rank:
@@ -132,7 +141,11 @@ class PeerGradients(FlatGradients):
             d.scale = 1.0 / self.world
             self.desc = d
         self._point_grads()
-        dist.barrier(group=group)           # every rank has opened every block before the first exchange
+        # every rank must have opened every block before the first exchange.  A caller that follows the construction with
+        # its own collective on all ranks (Trainer: the all-or-none agreement, which also covers a rank whose set-up
+        # raised) passes barrier=False -- a barrier here would pair with that rank's agreement call and desynchronise.
+        if barrier:
+            dist.barrier(group=group)
 
     def _point_grads(self):
         o = 0

@@ -82,7 +82,7 @@ class Trainer(object):
         grads, err = None, None
         if want:
             try:
-                grads = PeerGradients(self.params)
+                grads = PeerGradients(self.params, barrier=False)    # the agreement below is the barrier
             except Exception as e:                      # noqa: BLE001 -- any set-up failure selects the NCCL exchange
                 err = e
         ok = torch.tensor([1 if grads is not None else 0], device=self.device if dist.get_backend() == "nccl" else "cpu")

@@ -72,3 +72,55 @@ def test_pack_edge_cases():
         DU.pack_csr([{"num_nodes": 2, "edge_index": np.array([[0], [1]]), "edge_attr": np.array([1, 2])}])
     with pytest.raises(ValueError):
         DU.pack_csr([{"num_nodes": 2, "edge_index": np.array([[0], [1]]), "edge_attr": np.array([-1])}])
+
+
+def test_extract_many_splits_a_collated_result_per_graph(monkeypatch):
+    """Host logic of kpgnn_b200.data_utils.extract_many (chunking, per-graph node / edge ranges, un-offsetting, the
+    edge-less branch) with the device extraction replaced by the numpy oracle: runs without a GPU."""
+    import os
+    import sys
+    import torch
+    from kpgnn_b200 import synth
+    from oracle.extract_np import extract_multi_hop_neighbors_np
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "pyg_standin"))
+    from torch_geometric.data import Data
+    args = (3, 50, 2, 2, 50, 50, "spd")
+    graphs = synth.zinc_like_graphs(9, seed=4)
+    graphs.insert(3, {"num_nodes": 2, "x": np.zeros(2, dtype=np.int64), "edge_index": np.zeros((2, 0), dtype=np.int64),
+                      "edge_attr": np.zeros(0, dtype=np.int64)})
+    per_graph = {}
+
+    def fake_upload(csr, device, extra=None):
+        return {}
+
+    def fake_extract(csr, K, a1, a2, a3, a4, a5, kern, device=None):
+        # collate the oracle's per-graph outputs the way the device path lays them out: node offsets applied, graph-major
+        chunk = fake_extract.chunks.pop(0)
+        ei, ea, pea, pca, off = [], [], [], [], 0
+        for g in chunk:
+            o = extract_multi_hop_neighbors_np(g["num_nodes"], g["edge_index"], g["edge_attr"], K, a1, a2, a3, a4, a5, kern)
+            ei.append(torch.from_numpy(o["edge_index"]) + off)
+            ea.append(torch.from_numpy(o["edge_attr"]))
+            pea.append(torch.from_numpy(o["peripheral_edge_attr"]))
+            pca.append(torch.from_numpy(o["peripheral_configuration_attr"]))
+            off += g["num_nodes"]
+        return {"edge_index": torch.cat(ei, 1), "edge_attr": torch.cat(ea), "peripheral_edge_attr": torch.cat(pea),
+                "peripheral_configuration_attr": torch.cat(pca), "pe_attr": None, "eptr": None}
+    with_edges = [g for g in graphs if g["edge_index"].shape[1]]
+    fake_extract.chunks = [with_edges[i:i + 4] for i in range(0, len(with_edges), 4)]
+    monkeypatch.setattr(DU, "_upload", fake_upload)
+    monkeypatch.setattr(DU, "_extract_device", fake_extract)
+    datas = [Data(x=torch.from_numpy(g["x"]), edge_index=torch.from_numpy(g["edge_index"]),
+                  edge_attr=torch.from_numpy(g["edge_attr"])) for g in graphs]
+    for d, g in zip(datas, graphs):
+        d.num_nodes_ = g["num_nodes"]
+    out = DU.extract_many(datas, *args, chunk=4, device="cpu")
+    for d, g in zip(out, graphs):
+        if g["edge_index"].shape[1] == 0:
+            assert d.peripheral_edge_attr.shape == (2, 3, 2, 2) and d.peripheral_configuration.shape == (2, 3, 2)
+            continue
+        o = extract_multi_hop_neighbors_np(g["num_nodes"], g["edge_index"], g["edge_attr"], *args)
+        assert np.array_equal(d.edge_index.numpy(), o["edge_index"]) and np.array_equal(d.edge_attr.numpy(), o["edge_attr"])
+        assert np.array_equal(d.peripheral_edge_attr.numpy(), o["peripheral_edge_attr"])
+        assert np.array_equal(d.peripheral_configuration_attr.numpy(), o["peripheral_configuration_attr"])
+        assert d.pe_attr.shape == (g["num_nodes"], 2) and int(d.pe_attr.abs().sum()) == 0
